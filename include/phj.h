@@ -1,0 +1,194 @@
+/* include/phj.h -- C ABI of the B200-native hash-join engine (libphj_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of ragoragino/partitionedhashjoin ("phjoin"):
+ * the count-only equi-join of two relations of 16-byte {int64 key, int64 payload} tuples, as a
+ * no-partitioning join or a radix-partitioned join. The reference has no FFI today -- its joiners
+ * are C++ templates called only from src/main.cpp:81-139 -- so each entry point below names the
+ * reference interface it stands in for (file:line under /root/reference/). The C++ host mirror of
+ * those interfaces lives in partitionedhashjoin_b200/host/ and is what INTEGRATION.md shows a
+ * maintainer how to bind.
+ *
+ * Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary. Every function
+ * returns 0 on success and a non-zero phj_status otherwise; phj_last_error() then describes the
+ * failure (thread-local). There is NO CPU fallback: without a CUDA device every compute entry
+ * point fails with PHJ_ERR_CUDA.
+ */
+#ifndef PHJ_H
+#define PHJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHJ_ABI_VERSION 1
+
+/* Common::Tuple (src/Common/Table.hpp:20-25): alignas(16) {int64 id; int64 payload}. */
+typedef struct {
+    int64_t id;
+    int64_t payload;
+} phj_tuple;
+
+/* Common::JoinedTuple (src/Common/Table.hpp:27-33). */
+typedef struct {
+    int64_t id;
+    int64_t payloadA;
+    int64_t payloadB;
+} phj_joined_tuple;
+
+/* Common::JoinAlgorithmType (src/Common/Configuration.hpp:12-15). */
+enum { PHJ_ALGO_NO_PARTITIONING = 0, PHJ_ALGO_RADIX_PARTITIONING = 1 };
+
+/* Hasher behind Common::IHasher (src/Common/IHasher.hpp:6-11). The reference ships only XXH3
+ * (src/Common/XXHasher.hpp:19-22); MURMUR3 and CITY are extensions named by the north star:
+ *   MURMUR3 = low 64 bits of MurmurHash3_x64_128(&key, 8, (uint32)seed)
+ *   CITY    = CityHash64WithSeed(&key, 8, seed), CityHash v1.0 short-key path (libc++ flavour) */
+enum { PHJ_HASH_XXH3 = 0, PHJ_HASH_MURMUR3 = 1, PHJ_HASH_CITY = 2 };
+
+enum {
+    PHJ_OK = 0,
+    PHJ_ERR_INVALID = 1, /* bad argument / configuration (std::invalid_argument in the reference) */
+    PHJ_ERR_CUDA = 2,    /* CUDA runtime error, or no usable device */
+    PHJ_ERR_STATE = 3,   /* call sequence error (e.g. join before upload) */
+    PHJ_ERR_NOMEM = 4    /* device or pinned-host allocation failed */
+};
+
+/* Construction parameters: the union of what the reference passes to its two joiners --
+ * NoPartitioning::Configuration / RadixClustering::Configuration (NumberOfPartitions,
+ * src/RadixCluster/Configuration.hpp:6-9), the partition hasher and the table hasher
+ * (src/main.cpp:213-217,267) -- plus the device. Zero-initialise, then set what you need. */
+typedef struct {
+    int32_t algo;        /* PHJ_ALGO_* */
+    int32_t hash;        /* PHJ_HASH_* */
+    uint64_t partitions; /* NumberOfPartitions; 0 = engine default. A power of two is split into
+                            radix passes; any other value uses the reference's `hash % P` in one
+                            pass (src/Common/XXHasher.hpp:21). Must be 0 for NO_PARTITIONING
+                            (src/Arguments.hpp:12-17 rejects --partitions there). */
+    uint32_t radix_bits[2]; /* optional: bits of pass 1 / pass 2 (most significant digit first);
+                               {0,0} = derive from `partitions`. Sum must equal log2(partitions)
+                               when both are given. */
+    uint64_t hash_seed;  /* seed of the partitioning hasher (XXHasher::m_seed) */
+    uint64_t table_seed; /* seed of the hash-table hasher; only observable through timing */
+    int32_t device;      /* CUDA device ordinal */
+    uint32_t flags;      /* PHJ_FLAG_* */
+    uint64_t reserve_build; /* optional capacity hints (tuples); 0 = size on first upload */
+    uint64_t reserve_probe;
+} phj_config;
+
+#define PHJ_FLAG_KEEP_PARTITIONS 0x1u /* retain the partitioned relations for phj_read_partitions */
+#define PHJ_FLAG_NO_TMA_STORE 0x2u    /* scatter flush with st.global.v4 instead of bulk stores */
+
+/* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the
+ * count it only logs (src/NoPartitioning/HashJoin.hpp:184, src/RadixCluster/HashJoin.hpp:320). */
+typedef struct {
+    uint64_t matches;      /* probe tuples with at least one build match */
+    uint64_t partition_ns; /* device time: first partitioning kernel .. last scatter */
+    uint64_t build_ns;     /* NPJ: table clear + build kernel. Radix: build share of the CTA with
+                              the largest build+probe (RadixCluster/HashJoin.hpp:67-87,308-309) */
+    uint64_t probe_ns;     /* NPJ: probe kernel only (the reference's figure also contains the
+                              build, Results.hpp:202). Radix: probe share of that same CTA */
+    uint64_t join_ns;      /* radix: device time of the fused build+probe kernel(s) */
+    uint64_t total_ns;     /* device time, first kernel .. match count resident on the host */
+    uint64_t h2d_ns;       /* device time of the uploads done by phj_join_host, else 0 */
+    uint64_t hbm_bytes_alg; /* algorithmic HBM bytes of this join */
+    uint32_t kernel_launches;
+    uint32_t passes; /* radix passes actually run */
+    uint64_t partitions; /* fan-out actually used */
+    uint64_t fallback_partitions; /* partitions whose build side exceeded the shared-memory table
+                                     and went through the global table instead */
+} phj_result;
+
+typedef struct phj_handle phj_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Stands in for constructing NoPartitioning::HashJoiner (src/NoPartitioning/HashJoin.hpp:43-52) /
+ * RadixClustering::HashJoiner (src/RadixCluster/HashJoin.hpp:137-147) together with its hash-table
+ * factory (src/main.cpp:216-217). */
+int phj_create(const phj_config* config, phj_handle** out);
+void phj_destroy(phj_handle* h);
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* phj_last_error(void);
+uint32_t phj_abi_version(void);
+
+/* ---- data ------------------------------------------------------------------------------------ */
+
+/* Copy the build relation R (tableA) and probe relation S (tableB) to the device. Host pointers
+ * are what a reference caller holds as &(*table)[0] of a Common::Table<Common::Tuple>
+ * (src/Common/Table.hpp:35-57); the caller keeps ownership, the inputs are never modified.
+ * Device arenas are (re)allocated here, i.e. outside phj_join's timed region, mirroring the
+ * reference, which allocates its partition buffers before starting the timer
+ * (src/RadixCluster/HashJoin.hpp:195-208). */
+int phj_upload(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
+               size_t n_probe);
+
+/* Same, for relations that already live in device memory of config.device (zero-copy: the engine
+ * reads them in place and never writes them). */
+int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
+                    size_t n_probe);
+
+/* ---- the join ---------------------------------------------------------------------------------
+ * Stands in for HashJoiner::Run(tableA, tableB, timer) (src/NoPartitioning/HashJoin.hpp:54-74,
+ * src/RadixCluster/HashJoin.hpp:190-241) on the relations given to phj_upload / phj_bind_device.
+ * Synchronous; may be called repeatedly (the inputs stay resident). Not re-entrant per handle. */
+int phj_join(phj_handle* h, phj_result* out);
+
+/* Upload + join in one call, the end-to-end path (host buffers in, count out). */
+int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
+                  size_t n_probe, phj_result* out);
+
+/* ---- introspection / test hooks --------------------------------------------------------------- */
+
+/* Device evaluation of the raw 64-bit hash (before `% cardinality`) of n host keys: pins the
+ * __device__ hash functions bit-exactly against src/Common/XXHasher.hpp:19-22 from the host. */
+int phj_hash_batch(int32_t hash, uint64_t seed, const int64_t* keys, size_t n, uint64_t* out,
+                   int32_t device);
+/* Host evaluation of the same function (the same source compiled for the host). */
+uint64_t phj_hash_host(int32_t hash, uint64_t seed, int64_t key);
+
+/* After a radix join on a handle created with PHJ_FLAG_KEEP_PARTITIONS: copy out the partitioned
+ * relation (`which` 0 = build, 1 = probe; n tuples) and the partitions+1 partition boundaries --
+ * the device analogue of partitionedTable + PartitionsInfo (src/RadixCluster/HashJoin.hpp:16-33,
+ * 195-198). For a power-of-two fan-out the layout is the reference's: partition p = hash % P at
+ * [bounds[p], bounds[p+1]), tuples in input order within a partition. */
+int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* bounds);
+
+/* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
+ * names[i] points to a static string. */
+int phj_kernel_times(phj_handle* h, const char** names, uint64_t* ns, uint32_t cap);
+
+/* Device facts the host side prints next to results (SM count, L2, HBM, clocks). */
+typedef struct {
+    char name[128];
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    uint64_t global_mem_bytes;
+    uint64_t l2_bytes;
+    uint64_t smem_per_block_optin;
+    int32_t sm_clock_khz, mem_clock_khz, mem_bus_bits;
+} phj_device_info;
+int phj_get_device_info(int32_t device, phj_device_info* out);
+int phj_device_count(void);
+
+/* ---- data generators (host side) ---------------------------------------------------------------
+ * DataGenerator::Sequential / DataGenerator::Zipf (src/DataGenerator/Sequential.cpp:6-40,
+ * src/DataGenerator/Zipf.cpp:14-108) and the Park-Miller LCG (src/Common/Random.cpp:9-30). They
+ * produce the join's INPUT on the host exactly as the reference does (device pow() is not
+ * bit-identical to glibc's), with the seeding made explicit: the table is cut into `batches`
+ * equal slices (the last takes the remainder) and slice b draws from an LCG seeded
+ * base_seed + b. `threads` <= 0 uses all hardware threads. */
+int phj_fill_sequential(phj_tuple* out, size_t n, int64_t start, int32_t threads);
+int phj_fill_zipf(phj_tuple* out, size_t n, double alpha, int64_t range_first, int64_t range_second,
+                  int64_t base_seed, size_t batches, int32_t threads);
+
+/* Pinned host memory for relations that are uploaded repeatedly (phj_join_host). */
+int phj_host_alloc(void** out, size_t bytes);
+int phj_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHJ_H */

@@ -1,0 +1,1014 @@
+// phj_engine.cu -- device arenas, launch plan and the C ABI of include/phj.h.
+//
+// Replaces, for the B200, the orchestration the reference does in
+//   RadixClustering::HashJoiner::Run / Partition / Join   src/RadixCluster/HashJoin.hpp:190-440
+//   NoPartitioning::HashJoiner::Run / Build / Probe       src/NoPartitioning/HashJoin.hpp:54-187
+// The reference's thread pool + 3-stage Pipeline (src/Common/ThreadPool.cpp:99-146) becomes one
+// CUDA stream: kernel order on the stream is the pipeline barrier, the grid is the worker set.
+// Nothing in the timed region waits for the host: segment plans, cursors and partition boundaries
+// are produced and consumed on the device; the host reads back 16 bytes at the end.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phj.h"
+#include "phj_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define PHJ_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? PHJ_ERR_NOMEM : PHJ_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,       \
+                        __LINE__);                                                              \
+    } while (0)
+
+// Tile shapes of the partitioning kernels (tuples per tile = TPB * IPT).
+#ifndef PHJ_HIST_TPB
+#define PHJ_HIST_TPB 512
+#endif
+#ifndef PHJ_HIST_IPT
+#define PHJ_HIST_IPT 8
+#endif
+#ifndef PHJ_SCAT_TPB
+#define PHJ_SCAT_TPB 512
+#endif
+#ifndef PHJ_SCAT_IPT
+#define PHJ_SCAT_IPT 8
+#endif
+#ifndef PHJ_JOIN_TPB
+#define PHJ_JOIN_TPB 512
+#endif
+constexpr int kScatTile = PHJ_SCAT_TPB * PHJ_SCAT_IPT;
+constexpr int kMaxBitsPerPass = 8;
+constexpr int kMaxKernelTimes = 24;
+
+enum Scalar : int {  // device-resident uint32 scalars
+    kNsegs1 = 0,
+    kNcounts1,
+    kNsegs2,
+    kNcounts2,
+    kOversize,
+    kGtFlags,
+    kNumScalars = 8
+};
+
+struct KernelTime {
+    const char* name;
+    cudaEvent_t begin, end;
+    bool used;
+};
+
+}  // namespace
+
+struct phj_handle {
+    phj_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+
+    // relations: 0 = build (R), 1 = probe (S)
+    ulonglong2* d_in[2] = {nullptr, nullptr};
+    bool owns_in[2] = {false, false};
+    size_t cap_in[2] = {0, 0};
+    size_t n[2] = {0, 0};
+    bool have_data = false;
+    ulonglong2* d_buf_a[2] = {nullptr, nullptr};  // pass-1 output
+    ulonglong2* d_buf_b[2] = {nullptr, nullptr};  // pass-2 output
+    size_t cap_buf[2] = {0, 0};
+
+    // radix plan
+    bool pow2 = true;
+    uint64_t P = 0;     // reference fan-out (hash % P)
+    int bits_total = 0; // bits of the full digit space (ceil(log2 P))
+    int b1 = 0, b2 = 0;
+    uint32_t d1 = 0, d2 = 0;  // digits actually used per pass
+    uint64_t nparts = 0;      // d1 * d2 (>= P)
+    uint32_t nsegs1 = 0, max_segs2 = 0, target_segs2[2] = {0, 0};
+    phj::Segment* d_segs1 = nullptr;
+    phj::Segment* d_segs2 = nullptr;
+    size_t cap_segs1 = 0, cap_segs2 = 0;
+    uint32_t* d_scalars = nullptr;
+    uint32_t* d_counts = nullptr;
+    uint64_t* d_cursors = nullptr;
+    uint64_t* d_chunk_sums = nullptr;
+    size_t cap_counts = 0, cap_cursors = 0, cap_chunk_sums = 0;
+    uint64_t* d_bounds1[2] = {nullptr, nullptr};
+    uint64_t* d_bounds2[2] = {nullptr, nullptr};
+    size_t cap_bounds1 = 0, cap_bounds2 = 0;
+
+    // join
+    unsigned long long* d_matches = nullptr;
+    uint64_t* d_cta_times = nullptr;
+    size_t cap_cta_times = 0;
+    uint32_t join_grid = 0, join_slots = 0, join_max_keys = 0;
+    uint64_t* d_gt = nullptr;
+    uint64_t gt_buckets = 0;
+
+    // host staging (pinned)
+    uint64_t* h_out = nullptr;  // [0] matches, [1] scalars copy...
+    uint64_t* h_cta_times = nullptr;
+
+    cudaEvent_t ev[6] = {};
+    KernelTime ktimes[kMaxKernelTimes] = {};
+    int n_ktimes = 0;
+    bool time_kernels = false;
+    bool joined_radix = false;
+    uint32_t launches = 0;
+};
+
+namespace {
+
+using namespace phj;
+
+int ilog2_ceil(uint64_t x) {
+    int b = 0;
+    while ((1ull << b) < x) ++b;
+    return b;
+}
+
+template <typename T>
+int dev_reserve(T** p, size_t* cap, size_t want) {
+    if (want <= *cap && *p) return PHJ_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (want == 0) want = 1;
+    PHJ_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)));
+    *cap = want;
+    return PHJ_OK;
+}
+
+// ---- kernel-time bookkeeping --------------------------------------------------------------------
+struct KernelScope {
+    phj_handle* h;
+    int idx;
+    KernelScope(phj_handle* h_, const char* name) : h(h_), idx(-1) {
+        ++h->launches;
+        if (h->time_kernels && h->n_ktimes < kMaxKernelTimes) {
+            idx = h->n_ktimes++;
+            h->ktimes[idx].name = name;
+            h->ktimes[idx].used = true;
+            cudaEventRecord(h->ktimes[idx].begin, h->stream);
+        }
+    }
+    ~KernelScope() {
+        if (idx >= 0) cudaEventRecord(h->ktimes[idx].end, h->stream);
+    }
+};
+
+// ---- template dispatch ---------------------------------------------------------------------------
+template <int BITS, int HASH, bool POW2>
+void launch_hist_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    radix_histogram<BITS, HASH, POW2, PHJ_HIST_TPB, PHJ_HIST_IPT>
+        <<<grid, PHJ_HIST_TPB, 0, h->stream>>>(pp);
+}
+
+template <int BITS, int HASH, bool POW2, bool TMA>
+cudaError_t launch_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    using L = ScatterSmem<BITS, PHJ_SCAT_TPB, PHJ_SCAT_IPT>;
+    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA>;
+    static bool configured[16] = {};
+    if (!configured[h->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)L::total);
+        if (e != cudaSuccess) return e;
+        configured[h->device & 15] = true;
+    }
+    kern<<<grid, PHJ_SCAT_TPB, L::total, h->stream>>>(pp);
+    return cudaSuccess;
+}
+
+template <int BITS, int HASH>
+cudaError_t launch_pass_hp(phj_handle* h, bool scatter, const PassParams& pp, uint32_t grid) {
+    const bool tma = !(h->cfg.flags & PHJ_FLAG_NO_TMA_STORE);
+    if (!scatter) {
+        if (h->pow2) launch_hist_t<BITS, HASH, true>(h, pp, grid);
+        else launch_hist_t<BITS, HASH, false>(h, pp, grid);
+        return cudaSuccess;
+    }
+    if (h->pow2)
+        return tma ? launch_scatter_t<BITS, HASH, true, true>(h, pp, grid)
+                   : launch_scatter_t<BITS, HASH, true, false>(h, pp, grid);
+    return tma ? launch_scatter_t<BITS, HASH, false, true>(h, pp, grid)
+               : launch_scatter_t<BITS, HASH, false, false>(h, pp, grid);
+}
+
+template <int BITS>
+cudaError_t launch_pass_b(phj_handle* h, bool scatter, const PassParams& pp, uint32_t grid) {
+    switch (h->cfg.hash) {
+        case PHJ_HASH_MURMUR3: return launch_pass_hp<BITS, kMurmur3>(h, scatter, pp, grid);
+        case PHJ_HASH_CITY: return launch_pass_hp<BITS, kCity>(h, scatter, pp, grid);
+        default: return launch_pass_hp<BITS, kXXH3>(h, scatter, pp, grid);
+    }
+}
+
+// A pass with `bits` digit bits runs on the smallest instantiated shape that holds them.
+cudaError_t launch_pass(phj_handle* h, bool scatter, int bits, const PassParams& pp, uint32_t grid) {
+    if (bits <= 6) return launch_pass_b<6>(h, scatter, pp, grid);
+    return launch_pass_b<8>(h, scatter, pp, grid);
+}
+
+template <int HASH>
+cudaError_t launch_join_t(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
+    auto kern = join_partitions<HASH, PHJ_JOIN_TPB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, PHJ_JOIN_TPB, smem, h->stream>>>(jp);
+    return cudaSuccess;
+}
+
+cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
+    switch (h->cfg.hash) {
+        case PHJ_HASH_MURMUR3: return launch_join_t<kMurmur3>(h, jp, grid, smem);
+        case PHJ_HASH_CITY: return launch_join_t<kCity>(h, jp, grid, smem);
+        default: return launch_join_t<kXXH3>(h, jp, grid, smem);
+    }
+}
+
+template <int HASH>
+void launch_gt_t(phj_handle* h, bool build, const GtParams& gp, uint32_t grid) {
+    if (h->pow2) {
+        if (build) gt_build<HASH, true><<<grid, 256, 0, h->stream>>>(gp);
+        else gt_probe<HASH, true><<<grid, 256, 0, h->stream>>>(gp);
+    } else {
+        if (build) gt_build<HASH, false><<<grid, 256, 0, h->stream>>>(gp);
+        else gt_probe<HASH, false><<<grid, 256, 0, h->stream>>>(gp);
+    }
+}
+
+void launch_gt(phj_handle* h, bool build, const GtParams& gp, uint32_t grid) {
+    switch (h->cfg.hash) {
+        case PHJ_HASH_MURMUR3: launch_gt_t<kMurmur3>(h, build, gp, grid); break;
+        case PHJ_HASH_CITY: launch_gt_t<kCity>(h, build, gp, grid); break;
+        default: launch_gt_t<kXXH3>(h, build, gp, grid); break;
+    }
+}
+
+// ---- planning -----------------------------------------------------------------------------------
+// Fan-out plan from config + |R|: the reference exposes one knob, NumberOfPartitions
+// (src/RadixCluster/Configuration.hpp:8); a power of two is split most-significant-digit first
+// into <= 2 passes of <= 8 bits so that the final order is the reference's partition order.
+int plan_radix(phj_handle* h) {
+    const phj_config& c = h->cfg;
+    uint64_t P = c.partitions;
+    if (P == 0) {
+        // engine default: build partitions of ~2.4 K keys (a 4 K-slot shared-memory table)
+        uint64_t want = (h->n[0] + 2399) / 2400;
+        int b = ilog2_ceil(std::max<uint64_t>(want, 1));
+        b = std::min(b, 2 * kMaxBitsPerPass);
+        P = 1ull << b;
+    }
+    h->P = P;
+    h->pow2 = (P & (P - 1)) == 0;
+    h->bits_total = ilog2_ceil(P);
+    if (h->bits_total > 2 * kMaxBitsPerPass)
+        return fail(PHJ_ERR_INVALID, "partitions=%llu exceeds the supported fan-out of %llu",
+                    (unsigned long long)P, 1ull << (2 * kMaxBitsPerPass));
+    int b1 = (int)c.radix_bits[0], b2 = (int)c.radix_bits[1];
+    if (b1 == 0 && b2 == 0) {
+        if (h->bits_total <= 7) {
+            b1 = h->bits_total;
+            b2 = 0;
+        } else {
+            b1 = (h->bits_total + 1) / 2;
+            b2 = h->bits_total - b1;
+        }
+    } else {
+        if (b1 + b2 != h->bits_total || b1 > kMaxBitsPerPass || b2 > kMaxBitsPerPass || b1 < 0 ||
+            b2 < 0 || (b1 == 0 && h->bits_total > 0))
+            return fail(PHJ_ERR_INVALID,
+                        "radix_bits {%d,%d} must each be <= %d and sum to log2(partitions) = %d", b1,
+                        b2, kMaxBitsPerPass, h->bits_total);
+    }
+    h->b1 = b1;
+    h->b2 = b2;
+    h->d2 = 1u << b2;
+    h->d1 = (uint32_t)((P + h->d2 - 1) >> b2);  // pass-1 digits actually populated
+    h->nparts = (uint64_t)h->d1 * h->d2;
+    return PHJ_OK;
+}
+
+DigitFn digit_fn(const phj_handle* h, int pass) {
+    DigitFn f;
+    f.pmask = h->pow2 ? h->P - 1 : ~0ull;
+    f.modulus = h->P;
+    if (pass == 1) {
+        f.shift = (uint32_t)h->b2;
+        f.mask = (1u << std::max(h->b1, 1)) - 1;  // b1 == 0 only when P == 1 (digit always 0)
+        if (h->b1 == 0) f.mask = 0;
+    } else {
+        f.shift = 0;
+        f.mask = (1u << h->b2) - 1;
+    }
+    return f;
+}
+
+uint32_t segments_for(const phj_handle* h, size_t n, int tile) {
+    if (n == 0) return 0;
+    // ~8 segments per SM for the big relation; never shorter than 4 tiles
+    uint64_t target = (uint64_t)h->sm_count * 8;
+    uint64_t by_len = (n + (uint64_t)tile * 4 - 1) / ((uint64_t)tile * 4);
+    return (uint32_t)std::max<uint64_t>(1, std::min(target, by_len));
+}
+
+int build_plan(phj_handle* h) {
+    int rc;
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING) {
+        h->P = 1;
+        h->pow2 = true;
+        h->nparts = 1;
+    } else {
+        if ((rc = plan_radix(h)) != PHJ_OK) return rc;
+        // ---- pass 1 segments (host-built: sizes are known) ----
+        std::vector<Segment> segs;
+        uint32_t nseg[2];
+        uint32_t cnt_base = 0;
+        for (int rel = 0; rel < 2; ++rel) {
+            nseg[rel] = segments_for(h, h->n[rel], kScatTile);
+            uint64_t len = nseg[rel] ? (h->n[rel] + nseg[rel] - 1) / nseg[rel] : 0;
+            len = ((len + kScatTile - 1) / kScatTile) * kScatTile;
+            nseg[rel] = len ? (uint32_t)((h->n[rel] + len - 1) / len) : 0;
+            for (uint32_t s = 0; s < nseg[rel]; ++s) {
+                Segment sg;
+                sg.begin = (uint64_t)s * len;
+                sg.end = std::min<uint64_t>(h->n[rel], sg.begin + len);
+                sg.cnt_index = cnt_base + s;
+                sg.cnt_stride = nseg[rel];
+                sg.rel = rel;
+                sg.parent_first = (s == 0 ? 0x80000000u : 0u);
+                segs.push_back(sg);
+            }
+            cnt_base += nseg[rel] * h->d1;
+        }
+        h->nsegs1 = (uint32_t)segs.size();
+        uint32_t ncounts1 = cnt_base;
+        if ((rc = dev_reserve(&h->d_segs1, &h->cap_segs1, segs.size())) != PHJ_OK) return rc;
+        if (!segs.empty())
+            PHJ_CUDA(cudaMemcpyAsync(h->d_segs1, segs.data(), segs.size() * sizeof(Segment),
+                                     cudaMemcpyHostToDevice, h->stream));
+        // ---- pass 2 capacity ----
+        size_t ncounts_max = ncounts1;
+        if (h->b2 > 0) {
+            for (int rel = 0; rel < 2; ++rel)
+                h->target_segs2[rel] = std::max<uint32_t>(1, segments_for(h, h->n[rel], kScatTile));
+            h->max_segs2 = h->target_segs2[0] + h->target_segs2[1] + 2 * h->d1;
+            if ((rc = dev_reserve(&h->d_segs2, &h->cap_segs2, h->max_segs2)) != PHJ_OK) return rc;
+            ncounts_max = std::max<size_t>(ncounts_max, (size_t)h->max_segs2 * h->d2);
+        }
+        if (ncounts_max > (size_t)kScanChunk * 1024)
+            return fail(PHJ_ERR_INVALID, "internal: %zu counters exceed the scan capacity", ncounts_max);
+        if ((rc = dev_reserve(&h->d_counts, &h->cap_counts, ncounts_max)) != PHJ_OK) return rc;
+        if ((rc = dev_reserve(&h->d_cursors, &h->cap_cursors, ncounts_max)) != PHJ_OK) return rc;
+        if ((rc = dev_reserve(&h->d_chunk_sums, &h->cap_chunk_sums, 1024)) != PHJ_OK) return rc;
+        // ---- boundaries ----
+        const size_t nb1 = (size_t)h->d1 + 1, nb2 = (size_t)h->nparts + 1;
+        if (nb1 > h->cap_bounds1 || !h->d_bounds1[0]) {
+            for (int rel = 0; rel < 2; ++rel) {
+                if (h->d_bounds1[rel]) cudaFree(h->d_bounds1[rel]);
+                PHJ_CUDA(cudaMalloc(&h->d_bounds1[rel], nb1 * 8));
+            }
+            h->cap_bounds1 = nb1;
+        }
+        if (nb2 > h->cap_bounds2 || !h->d_bounds2[0]) {
+            for (int rel = 0; rel < 2; ++rel) {
+                if (h->d_bounds2[rel]) cudaFree(h->d_bounds2[rel]);
+                PHJ_CUDA(cudaMalloc(&h->d_bounds2[rel], nb2 * 8));
+            }
+            h->cap_bounds2 = nb2;
+        }
+        for (int rel = 0; rel < 2; ++rel) {
+            // a relation without tuples launches no segment: its boundaries are all zero. The last
+            // boundary (= n) is never written by a kernel.
+            PHJ_CUDA(cudaMemsetAsync(h->d_bounds1[rel], 0, nb1 * 8, h->stream));
+            PHJ_CUDA(cudaMemsetAsync(h->d_bounds2[rel], 0, nb2 * 8, h->stream));
+            uint64_t nn = h->n[rel];
+            PHJ_CUDA(cudaMemcpyAsync(h->d_bounds1[rel] + h->d1, &nn, 8, cudaMemcpyHostToDevice, h->stream));
+            PHJ_CUDA(cudaMemcpyAsync(h->d_bounds2[rel] + h->nparts, &nn, 8, cudaMemcpyHostToDevice, h->stream));
+            PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        uint32_t sc[kNumScalars] = {};
+        sc[kNsegs1] = h->nsegs1;
+        sc[kNcounts1] = ncounts1;
+        PHJ_CUDA(cudaMemcpyAsync(h->d_scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+
+        // ---- partition buffers ----
+        for (int rel = 0; rel < 2; ++rel) {
+            if (h->n[rel] > h->cap_buf[rel] || !h->d_buf_a[rel]) {
+                if (h->d_buf_a[rel]) cudaFree(h->d_buf_a[rel]);
+                if (h->d_buf_b[rel]) cudaFree(h->d_buf_b[rel]);
+                h->d_buf_a[rel] = h->d_buf_b[rel] = nullptr;
+                size_t want = std::max<size_t>(h->n[rel], 1);
+                PHJ_CUDA(cudaMalloc(&h->d_buf_a[rel], want * 16));
+                PHJ_CUDA(cudaMalloc(&h->d_buf_b[rel], want * 16));
+                h->cap_buf[rel] = want;
+            }
+        }
+        // ---- join geometry ----
+        uint64_t mean = std::max<uint64_t>(1, h->n[0] / std::max<uint64_t>(1, h->P));
+        uint32_t slots = 1024;
+        while (slots < 16384 && (double)slots < 1.6 * (double)mean) slots <<= 1;
+        h->join_slots = slots;
+        h->join_max_keys = slots / 4 * 3;
+        const size_t smem = (size_t)slots * 8;
+        uint32_t resident = (uint32_t)std::max<size_t>(1, std::min<size_t>((h->smem_optin) / (smem + 1024), 2048 / PHJ_JOIN_TPB));
+        h->join_grid = (uint32_t)h->sm_count * resident * 4;
+        size_t cap = h->cap_cta_times;
+        if ((rc = dev_reserve(&h->d_cta_times, &cap, (size_t)h->join_grid * 2)) != PHJ_OK) return rc;
+        if (cap != h->cap_cta_times) {
+            if (h->h_cta_times) cudaFreeHost(h->h_cta_times);
+            PHJ_CUDA(cudaMallocHost(&h->h_cta_times, cap * 8));
+            h->cap_cta_times = cap;
+        }
+    }
+    // ---- global table: always for NPJ; for radix it is allocated on first need ----
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING) {
+        uint64_t want = (uint64_t)std::ceil((double)std::max<size_t>(h->n[0], 1) / 2.8);
+        uint64_t buckets = 64;
+        while (buckets < want) buckets <<= 1;
+        if (buckets > h->gt_buckets) {
+            if (h->d_gt) cudaFree(h->d_gt);
+            h->d_gt = nullptr;
+            PHJ_CUDA(cudaMalloc(&h->d_gt, buckets * 32));
+        }
+        h->gt_buckets = buckets;
+    }
+    return PHJ_OK;
+}
+
+int ensure_gt_for_fallback(phj_handle* h) {
+    uint64_t want = (uint64_t)std::ceil((double)std::max<size_t>(h->n[0], 1) / 2.8);
+    uint64_t buckets = 64;
+    while (buckets < want) buckets <<= 1;
+    if (!h->d_gt || buckets > h->gt_buckets) {
+        if (h->d_gt) cudaFree(h->d_gt);
+        h->d_gt = nullptr;
+        PHJ_CUDA(cudaMalloc(&h->d_gt, buckets * 32));
+        h->gt_buckets = buckets;
+    }
+    return PHJ_OK;
+}
+
+uint32_t table_hash_shift(const phj_handle* h) {
+    // the table takes hash bits above the ones the partitioning consumed
+    return h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING ? (uint32_t)std::min(h->bits_total, 24) : 0u;
+}
+
+// ---- the joins ----------------------------------------------------------------------------------
+int run_scan(phj_handle* h, int ncounts_scalar, size_t ncounts_max) {
+    uint32_t chunks = (uint32_t)std::max<size_t>(1, (ncounts_max + kScanChunk - 1) / kScanChunk);
+    {
+        KernelScope ks(h, "scan_reduce");
+        scan_reduce<<<chunks, kScanTpb, 0, h->stream>>>(h->d_counts, h->d_scalars + ncounts_scalar,
+                                                        h->d_chunk_sums);
+    }
+    {
+        KernelScope ks(h, "scan_write");
+        scan_write<<<chunks, kScanTpb, 0, h->stream>>>(h->d_counts, h->d_scalars + ncounts_scalar,
+                                                       h->d_chunk_sums, h->d_cursors);
+    }
+    return PHJ_OK;
+}
+
+int run_gt(phj_handle* h, bool select, const ulonglong2* build, const ulonglong2* probe) {
+    const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
+    GtParams gp{};
+    gp.table = h->d_gt;
+    gp.bucket_mask = h->gt_buckets - 1;
+    gp.hash_shift = table_hash_shift(h);
+    gp.select = select ? 1 : 0;
+    gp.bounds_build = select ? h->d_bounds2[0] : nullptr;
+    gp.max_keys = h->join_max_keys;
+    gp.part_fn.pmask = h->pow2 ? h->P - 1 : ~0ull;
+    gp.part_fn.modulus = h->P;
+    gp.part_fn.shift = 0;
+    gp.part_fn.mask = ~0u;
+    gp.hp = hp;
+    gp.flags = h->d_scalars + kGtFlags;
+    gp.matches = h->d_matches;
+    const uint32_t grid = (uint32_t)h->sm_count * 8;
+    {
+        KernelScope ks(h, "gt_clear");
+        PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kGtFlags, 0, 4, h->stream));
+        gt_clear<<<grid, 256, 0, h->stream>>>(h->d_gt, h->gt_buckets * 4);
+    }
+    {
+        KernelScope ks(h, "gt_build");
+        gp.rel = build;
+        gp.n = h->n[0];
+        launch_gt(h, true, gp, grid);
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    {
+        KernelScope ks(h, "gt_probe");
+        gp.rel = probe;
+        gp.n = h->n[1];
+        launch_gt(h, false, gp, grid);
+    }
+    return PHJ_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+int join_no_partitioning(phj_handle* h, phj_result* out) {
+    // Deviation: the reference's table constructor throws for an empty build side
+    // (src/HashTables/LinearProbing.hpp:106-110); here an empty R simply joins to 0.
+    PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 8, h->stream));
+    int rc = run_gt(h, false, h->d_in[0], h->d_in[1]);
+    if (rc != PHJ_OK) return rc;
+    PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    out->matches = h->h_out[0];
+    out->partition_ns = 0;
+    out->build_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[2]) * 1e6);
+    out->probe_ns = (uint64_t)(ev_ms(h->ev[2], h->ev[3]) * 1e6);
+    out->join_ns = out->build_ns + out->probe_ns;
+    out->total_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[4]) * 1e6);
+    out->passes = 0;
+    out->partitions = 1;
+    // 16 B/tuple streamed + one 32-byte table sector per build insert and per probe
+    out->hbm_bytes_alg = 48ull * (h->n[0] + h->n[1]);
+    return PHJ_OK;
+}
+
+int join_radix(phj_handle* h, phj_result* out) {
+    const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
+    const bool two = h->b2 > 0;
+    PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
+
+    // ---- pass 1 ----
+    PassParams p1{};
+    for (int rel = 0; rel < 2; ++rel) {
+        p1.in[rel] = h->d_in[rel];
+        p1.out[rel] = h->d_buf_a[rel];
+        p1.bounds[rel] = two ? h->d_bounds1[rel] : h->d_bounds2[rel];
+    }
+    p1.segs = h->d_segs1;
+    p1.nsegs = h->d_scalars + kNsegs1;
+    p1.counts = h->d_counts;
+    p1.cursors = h->d_cursors;
+    p1.cursor_bias[0] = 0;
+    p1.cursor_bias[1] = h->n[0];
+    p1.bounds_stride = h->d1;
+    p1.ndigits = h->d1;
+    p1.hp = hp;
+    p1.df = digit_fn(h, 1);
+    if (h->nsegs1 > 0) {
+        {
+            KernelScope ks(h, "radix_histogram[1]");
+            PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
+        }
+        run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
+        {
+            KernelScope ks(h, "radix_scatter[1]");
+            PHJ_CUDA(launch_pass(h, true, h->b1, p1, h->nsegs1));
+        }
+    }
+    // ---- pass 2 ----
+    if (two) {
+        Plan2Params pl{};
+        FillEmptyParams fe{};
+        for (int rel = 0; rel < 2; ++rel) {
+            pl.bounds1[rel] = h->d_bounds1[rel];
+            pl.n[rel] = h->n[rel];
+            pl.target_segs[rel] = h->target_segs2[rel];
+            fe.bounds1[rel] = h->d_bounds1[rel];
+            fe.bounds2[rel] = h->d_bounds2[rel];
+            fe.n[rel] = h->n[rel];
+        }
+        pl.d1 = fe.d1 = h->d1;
+        pl.d2 = fe.d2 = h->d2;
+        pl.tile = kScatTile;
+        pl.segs = h->d_segs2;
+        pl.nsegs = h->d_scalars + kNsegs2;
+        pl.ncounts = h->d_scalars + kNcounts2;
+        pl.max_segs = h->max_segs2;
+        {
+            KernelScope ks(h, "plan_pass2");
+            plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
+            fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
+        }
+        PassParams p2{};
+        for (int rel = 0; rel < 2; ++rel) {
+            p2.in[rel] = h->d_buf_a[rel];
+            p2.out[rel] = h->d_buf_b[rel];
+            p2.bounds[rel] = h->d_bounds2[rel];
+        }
+        p2.segs = h->d_segs2;
+        p2.nsegs = h->d_scalars + kNsegs2;
+        p2.counts = h->d_counts;
+        p2.cursors = h->d_cursors;
+        p2.cursor_bias[0] = 0;
+        p2.cursor_bias[1] = h->n[0];
+        p2.bounds_stride = h->d2;
+        p2.ndigits = h->d2;
+        p2.hp = hp;
+        p2.df = digit_fn(h, 2);
+        {
+            KernelScope ks(h, "radix_histogram[2]");
+            PHJ_CUDA(launch_pass(h, false, h->b2, p2, h->max_segs2));
+        }
+        run_scan(h, kNcounts2, (size_t)h->max_segs2 * h->d2);
+        {
+            KernelScope ks(h, "radix_scatter[2]");
+            PHJ_CUDA(launch_pass(h, true, h->b2, p2, h->max_segs2));
+        }
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[1], h->stream));
+
+    // ---- build + probe per partition ----
+    const ulonglong2* part_build = two ? h->d_buf_b[0] : h->d_buf_a[0];
+    const ulonglong2* part_probe = two ? h->d_buf_b[1] : h->d_buf_a[1];
+    PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 8, h->stream));
+    PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kOversize, 0, 4, h->stream));
+    JoinParams jp{};
+    jp.build = part_build;
+    jp.probe = part_probe;
+    jp.bounds_build = h->d_bounds2[0];
+    jp.bounds_probe = h->d_bounds2[1];
+    jp.n_probe = h->n[1];
+    jp.npart = (uint32_t)h->nparts;
+    jp.slot_mask = h->join_slots - 1;
+    jp.max_keys = h->join_max_keys;
+    jp.hash_shift = table_hash_shift(h);
+    jp.hp = hp;
+    jp.matches = h->d_matches;
+    jp.cta_times = h->d_cta_times;
+    {
+        KernelScope ks(h, "join_partitions");
+        PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
+    }
+    {
+        KernelScope ks(h, "count_oversize");
+        count_oversize<<<(uint32_t)((h->nparts + 255) / 256), 256, 0, h->stream>>>(
+            h->d_bounds2[0], (uint32_t)h->nparts, h->join_max_keys, h->d_scalars + kOversize);
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 4, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_cta_times, h->d_cta_times, (size_t)h->join_grid * 16,
+                             cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+
+    const uint32_t oversize = (uint32_t)(h->h_out[1] & 0xffffffffu);
+    float extra_ms = 0;
+    if (oversize) {
+        // Build partitions too large for shared memory: join them through the global table.
+        int rc = ensure_gt_for_fallback(h);
+        if (rc != PHJ_OK) return rc;
+        PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
+        if ((rc = run_gt(h, true, part_build, part_probe)) != PHJ_OK) return rc;
+        PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
+        PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        PHJ_CUDA(cudaGetLastError());
+        extra_ms = ev_ms(h->ev[5], h->ev[4]);
+    }
+    out->matches = h->h_out[0];
+    out->partition_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[1]) * 1e6);
+    out->join_ns = (uint64_t)((ev_ms(h->ev[1], h->ev[3]) + extra_ms) * 1e6);
+    out->total_ns = (uint64_t)((ev_ms(h->ev[0], oversize ? h->ev[3] : h->ev[4]) + extra_ms) * 1e6);
+    // The reference reports build/probe of the worker with the largest build+probe
+    // (src/RadixCluster/HashJoin.hpp:67-87); a CTA is the worker here.
+    uint64_t best_b = 0, best_p = 0;
+    for (uint32_t i = 0; i < h->join_grid; ++i) {
+        uint64_t b = h->h_cta_times[2 * i], p = h->h_cta_times[2 * i + 1];
+        if (b + p > best_b + best_p) {
+            best_b = b;
+            best_p = p;
+        }
+    }
+    out->build_ns = best_b;
+    out->probe_ns = best_p;
+    out->passes = two ? 2 : 1;
+    out->partitions = h->P;
+    out->fallback_partitions = oversize;
+    // one histogram read + per pass (read + write) + one join read, 16 B each
+    out->hbm_bytes_alg = 16ull * (2 + 2 * out->passes) * (h->n[0] + h->n[1]);
+    h->joined_radix = true;
+    return PHJ_OK;
+}
+
+int validate_config(const phj_config* c) {
+    if (!c) return fail(PHJ_ERR_INVALID, "config is null");
+    if (c->algo != PHJ_ALGO_NO_PARTITIONING && c->algo != PHJ_ALGO_RADIX_PARTITIONING)
+        return fail(PHJ_ERR_INVALID, "Unrecognized join algorithm: %d.", c->algo);
+    if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
+        return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", c->hash);
+    if (c->algo == PHJ_ALGO_NO_PARTITIONING && (c->partitions != 0 || c->radix_bits[0] || c->radix_bits[1]))
+        // src/Arguments.hpp:12-17
+        return fail(PHJ_ERR_INVALID,
+                    "number of partitions can be specified only for RadixParitioning.");
+    return PHJ_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* phj_last_error(void) { return g_error.c_str(); }
+uint32_t phj_abi_version(void) { return PHJ_ABI_VERSION; }
+
+int phj_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int phj_get_device_info(int32_t device, phj_device_info* out) {
+    if (!out) return fail(PHJ_ERR_INVALID, "out is null");
+    cudaDeviceProp prop;
+    PHJ_CUDA(cudaGetDeviceProperties(&prop, device));
+    memset(out, 0, sizeof(*out));
+    snprintf(out->name, sizeof(out->name), "%s", prop.name);
+    out->sm_count = prop.multiProcessorCount;
+    out->cc_major = prop.major;
+    out->cc_minor = prop.minor;
+    out->global_mem_bytes = prop.totalGlobalMem;
+    out->l2_bytes = (uint64_t)prop.l2CacheSize;
+    out->smem_per_block_optin = prop.sharedMemPerBlockOptin;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device);
+    out->sm_clock_khz = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMemoryClockRate, device);
+    out->mem_clock_khz = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrGlobalMemoryBusWidth, device);
+    out->mem_bus_bits = v;
+    return PHJ_OK;
+}
+
+int phj_create(const phj_config* config, phj_handle** out) {
+    if (!out) return fail(PHJ_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int rc = validate_config(config);
+    if (rc != PHJ_OK) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PHJ_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (config->device < 0 || config->device >= ndev)
+        return fail(PHJ_ERR_INVALID, "device %d out of range [0, %d)", config->device, ndev);
+    PHJ_CUDA(cudaSetDevice(config->device));
+    cudaDeviceProp prop;
+    PHJ_CUDA(cudaGetDeviceProperties(&prop, config->device));
+    if (prop.major < 10)
+        return fail(PHJ_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    config->device, prop.major, prop.minor);
+    phj_handle* h = new phj_handle;
+    h->cfg = *config;
+    h->device = config->device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    const char* kt = getenv("PHJ_KERNEL_TIMES");
+    h->time_kernels = kt && kt[0] == '1';
+    auto cleanup = [&](int code) {
+        phj_destroy(h);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return cleanup(fail(PHJ_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto& ev : h->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return cleanup(fail(PHJ_ERR_CUDA, "cudaEventCreate failed"));
+    for (auto& k : h->ktimes) {
+        cudaEventCreate(&k.begin);
+        cudaEventCreate(&k.end);
+    }
+    if (cudaMalloc(&h->d_scalars, kNumScalars * 4) != cudaSuccess ||
+        cudaMalloc(&h->d_matches, 8) != cudaSuccess ||
+        cudaMallocHost(&h->h_out, 64) != cudaSuccess)
+        return cleanup(fail(PHJ_ERR_NOMEM, "allocation of engine scalars failed"));
+    cudaMemset(h->d_scalars, 0, kNumScalars * 4);
+    *out = h;
+    return PHJ_OK;
+}
+
+void phj_destroy(phj_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int rel = 0; rel < 2; ++rel) {
+        if (h->owns_in[rel] && h->d_in[rel]) cudaFree(h->d_in[rel]);
+        if (h->d_buf_a[rel]) cudaFree(h->d_buf_a[rel]);
+        if (h->d_buf_b[rel]) cudaFree(h->d_buf_b[rel]);
+        if (h->d_bounds1[rel]) cudaFree(h->d_bounds1[rel]);
+        if (h->d_bounds2[rel]) cudaFree(h->d_bounds2[rel]);
+    }
+    void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_cta_times) cudaFreeHost(h->h_cta_times);
+    for (auto& ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& k : h->ktimes) {
+        if (k.begin) cudaEventDestroy(k.begin);
+        if (k.end) cudaEventDestroy(k.end);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int set_relations(phj_handle* h, const void* build, size_t n_build, const void* probe,
+                         size_t n_probe, bool device_resident, uint64_t* h2d_ns) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if ((n_build && !build) || (n_probe && !probe))
+        return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
+    if (((uintptr_t)build | (uintptr_t)probe) & 15)
+        return fail(PHJ_ERR_INVALID, "relations must be 16-byte aligned (alignas(16) Tuple)");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    const void* src[2] = {build, probe};
+    const size_t nn[2] = {n_build, n_probe};
+    const bool replan = !h->have_data || nn[0] != h->n[0] || nn[1] != h->n[1];
+    for (int rel = 0; rel < 2; ++rel) {
+        if (device_resident) {
+            if (h->owns_in[rel] && h->d_in[rel]) cudaFree(h->d_in[rel]);
+            h->owns_in[rel] = false;
+            h->cap_in[rel] = 0;
+            h->d_in[rel] = reinterpret_cast<ulonglong2*>(const_cast<void*>(src[rel]));
+        } else {
+            if (!h->owns_in[rel]) {
+                h->d_in[rel] = nullptr;
+                h->cap_in[rel] = 0;
+            }
+            size_t want = std::max<size_t>(std::max<size_t>(nn[rel], 1),
+                                           rel == 0 ? h->cfg.reserve_build : h->cfg.reserve_probe);
+            if (nn[rel] > h->cap_in[rel] || !h->d_in[rel]) {
+                if (h->d_in[rel]) cudaFree(h->d_in[rel]);
+                h->d_in[rel] = nullptr;
+                PHJ_CUDA(cudaMalloc(&h->d_in[rel], want * 16));
+                h->cap_in[rel] = want;
+            }
+            h->owns_in[rel] = true;
+        }
+        h->n[rel] = nn[rel];
+    }
+    if (replan) {
+        h->have_data = false;
+        int rc = build_plan(h);
+        if (rc != PHJ_OK) return rc;
+    }
+    if (!device_resident) {
+        PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
+        for (int rel = 0; rel < 2; ++rel)
+            if (nn[rel])
+                PHJ_CUDA(cudaMemcpyAsync(h->d_in[rel], src[rel], nn[rel] * 16, cudaMemcpyHostToDevice,
+                                         h->stream));
+        PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        if (h2d_ns) *h2d_ns = (uint64_t)(ev_ms(h->ev[5], h->ev[0]) * 1e6);
+    }
+    h->have_data = true;
+    h->joined_radix = false;
+    return PHJ_OK;
+}
+
+int phj_upload(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
+               size_t n_probe) {
+    return set_relations(h, build, n_build, probe, n_probe, false, nullptr);
+}
+
+int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
+                    size_t n_probe) {
+    return set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr);
+}
+
+int phj_join(phj_handle* h, phj_result* out) {
+    if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    if (!h->have_data) return fail(PHJ_ERR_STATE, "phj_join called before phj_upload / phj_bind_device");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    memset(out, 0, sizeof(*out));
+    h->launches = 0;
+    h->n_ktimes = 0;
+    int rc = h->cfg.algo == PHJ_ALGO_NO_PARTITIONING ? join_no_partitioning(h, out) : join_radix(h, out);
+    out->kernel_launches = h->launches;
+    return rc;
+}
+
+int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
+                  size_t n_probe, phj_result* out) {
+    uint64_t h2d = 0;
+    int rc = set_relations(h, build, n_build, probe, n_probe, false, &h2d);
+    if (rc != PHJ_OK) return rc;
+    rc = phj_join(h, out);
+    if (rc == PHJ_OK) out->h2d_ns = h2d;
+    return rc;
+}
+
+int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* bounds) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
+    if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING || !h->joined_radix)
+        return fail(PHJ_ERR_STATE, "no partitioned relations: run a radix-partitioning phj_join first");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    const ulonglong2* src = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
+    if (out && h->n[which])
+        PHJ_CUDA(cudaMemcpy(out, src, h->n[which] * 16, cudaMemcpyDeviceToHost));
+    if (bounds) PHJ_CUDA(cudaMemcpy(bounds, h->d_bounds2[which], (h->P + 1) * 8, cudaMemcpyDeviceToHost));
+    return PHJ_OK;
+}
+
+int phj_kernel_times(phj_handle* h, const char** names, uint64_t* ns, uint32_t cap) {
+    if (!h) return 0;
+    uint32_t n = 0;
+    for (int i = 0; i < h->n_ktimes && n < cap; ++i) {
+        if (!h->ktimes[i].used) continue;
+        names[n] = h->ktimes[i].name;
+        ns[n] = (uint64_t)(ev_ms(h->ktimes[i].begin, h->ktimes[i].end) * 1e6);
+        ++n;
+    }
+    return (int)n;
+}
+
+uint64_t phj_hash_host(int32_t hash, uint64_t seed, int64_t key) {
+    return phj::hash_key_dyn(hash, (uint64_t)key, phj::make_hash_params(hash, seed));
+}
+
+int phj_hash_batch(int32_t hash, uint64_t seed, const int64_t* keys, size_t n, uint64_t* out,
+                   int32_t device) {
+    if (hash < PHJ_HASH_XXH3 || hash > PHJ_HASH_CITY)
+        return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", hash);
+    if (n == 0) return PHJ_OK;
+    if (!keys || !out) return fail(PHJ_ERR_INVALID, "keys/out is null");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PHJ_ERR_CUDA, "no CUDA device available; this engine has no CPU fallback");
+    }
+    PHJ_CUDA(cudaSetDevice(device));
+    int64_t* d_keys = nullptr;
+    uint64_t* d_out = nullptr;
+    PHJ_CUDA(cudaMalloc(&d_keys, n * 8));
+    if (cudaMalloc(&d_out, n * 8) != cudaSuccess) {
+        cudaFree(d_keys);
+        return fail(PHJ_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaMemcpy(d_keys, keys, n * 8, cudaMemcpyHostToDevice);
+    const phj::HashParams hp = phj::make_hash_params(hash, seed);
+    const uint32_t grid = (uint32_t)((n + 255) / 256);
+    switch (hash) {
+        case PHJ_HASH_MURMUR3: phj::hash_batch_kernel<phj::kMurmur3><<<grid, 256>>>(d_keys, n, hp, d_out); break;
+        case PHJ_HASH_CITY: phj::hash_batch_kernel<phj::kCity><<<grid, 256>>>(d_keys, n, hp, d_out); break;
+        default: phj::hash_batch_kernel<phj::kXXH3><<<grid, 256>>>(d_keys, n, hp, d_out); break;
+    }
+    cudaError_t e = cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_keys);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PHJ_ERR_CUDA, "hash_batch failed: %s", cudaGetErrorString(e));
+    return PHJ_OK;
+}
+
+int phj_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(PHJ_ERR_INVALID, "out is null");
+    PHJ_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return PHJ_OK;
+}
+
+int phj_host_free(void* p) {
+    if (p) PHJ_CUDA(cudaFreeHost(p));
+    return PHJ_OK;
+}
+
+}  // extern "C"

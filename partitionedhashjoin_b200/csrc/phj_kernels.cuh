@@ -1,0 +1,725 @@
+// phj_kernels.cuh -- sm_100a kernels of the hash-join hot path.
+//
+// Reference loops these kernels replace (file:line under /root/reference/):
+//   radix_histogram   scanTable                 src/RadixCluster/HashJoin.hpp:343-357
+//   scan_*            createPrefixSumTable      src/RadixCluster/HashJoin.hpp:363-390
+//                     + ComputePartitionsBoundaries                         :18-25
+//   radix_scatter     partitionTable            src/RadixCluster/HashJoin.hpp:394-412
+//   join_partitions   Join lambda               src/RadixCluster/HashJoin.hpp:258-323
+//                     (+ LinearProbingHashTable::Insert/Get, src/HashTables/LinearProbing.hpp:114-180)
+//   gt_build/gt_probe NoPartitioning Build/Probe src/NoPartitioning/HashJoin.hpp:76-126,128-187
+//
+// Vocabulary: a *segment* is what the reference calls a worker's batch: a contiguous slice of one
+// relation (inside one parent partition for pass 2) that one CTA histograms and later scatters
+// with private write cursors. `counts` is the reference's PrefixSumTable, laid out
+// [parent][digit][segment] so that ONE flat exclusive scan yields every cursor and, at segment 0
+// of each digit, the partition boundaries.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phj_hash.cuh"
+
+namespace phj {
+
+constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN marks a free table slot
+
+struct __align__(16) Segment {
+    uint64_t begin, end;  // tuple range inside the relation's input array
+    uint32_t cnt_index;   // counter index of (this segment, digit 0)
+    uint32_t cnt_stride;  // counter stride between digits = #segments of the parent partition
+    uint32_t rel;         // 0 build (R), 1 probe (S)
+    uint32_t parent_first;  // bit 31: first segment of its parent; bits 0..30: parent partition id
+};
+
+// How a 64-bit hash becomes this pass's digit. full = POW2 ? h & pmask : h % modulus is the
+// reference's partition id (src/Common/XXHasher.hpp:21); the pass takes bits [shift, shift+bits).
+struct DigitFn {
+    uint64_t pmask;
+    uint64_t modulus;
+    uint32_t shift;
+    uint32_t mask;
+};
+
+template <bool POW2>
+__device__ __forceinline__ uint32_t digit_of(uint64_t h, const DigitFn& f) {
+    uint64_t full = POW2 ? (h & f.pmask) : (h % f.modulus);
+    return (uint32_t)(full >> f.shift) & f.mask;
+}
+
+struct PassParams {
+    const ulonglong2* in[2];
+    ulonglong2* out[2];
+    const Segment* segs;
+    const uint32_t* nsegs;     // device-resident segment count (CTAs beyond it exit)
+    uint32_t* counts;          // histogram out (radix_histogram)
+    const uint64_t* cursors;   // exclusive scan of counts (radix_scatter)
+    uint64_t cursor_bias[2];   // flat scan spans R then S: S cursors are offset by |R|
+    uint64_t* bounds[2];       // partition boundaries of this pass's output, per relation
+    uint32_t bounds_stride;    // digits per parent in `bounds` indexing
+    uint32_t ndigits;          // digits this pass really has (<= the kernel's 1 << BITS)
+    HashParams hp;
+    DigitFn df;
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 ld_stream_v2(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(v.x), "=l"(v.y)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_v2(ulonglong2* p, const ulonglong2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// TMA 1-D bulk store shared::cta -> global (UBLKCP in SASS). 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// =================================================================================================
+// K1  radix_histogram: one CTA per segment; per-warp private digit counters in shared memory,
+// lanes of a warp that hit the same digit are merged with match.any so a Zipf heavy hitter costs
+// one update per warp instead of 32 serialised ones, and no shared-memory atomics are needed.
+// HBM: reads 16 B/tuple (the key's 32-byte sector is fetched whole either way).
+// =================================================================================================
+template <int BITS, int HASH, bool POW2, int TPB, int IPT>
+__global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
+    constexpr int D = 1 << BITS;
+    constexpr int NW = TPB / 32;
+    constexpr int T = TPB * IPT;
+    __shared__ uint32_t wc[NW][D + 1];  // [..][D] swallows the out-of-range lanes of a tail tile
+
+    if (blockIdx.x >= *p.nsegs) return;
+    const Segment seg = p.segs[blockIdx.x];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* wcw = wc[warp];
+
+    for (int i = lane; i <= D; i += 32) wcw[i] = 0;
+    __syncwarp();
+
+    for (uint64_t tile = seg.begin; tile < seg.end; tile += T) {
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+        uint64_t key[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            key[i] = idx < seg.end ? ld_stream_u64(reinterpret_cast<const uint64_t*>(in + idx)) : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            const uint32_t d = idx < seg.end ? digit_of<POW2>(hash_key<HASH>(key[i], p.hp), p.df) : D;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (lane == __ffs(peers) - 1) wcw[d] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < (int)p.ndigits; d += TPB) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sum += wc[w][d];
+        p.counts[seg.cnt_index + (uint64_t)d * seg.cnt_stride] = sum;
+    }
+}
+
+// =================================================================================================
+// K2  flat exclusive scan of the counters (uint32 counts -> uint64 cursors), two launches:
+// scan_reduce (per-chunk sums) and scan_write (every CTA re-scans the <= 1024 chunk sums with
+// warp shuffles for its carry-in, then scans its own chunk).
+// =================================================================================================
+constexpr int kScanTpb = 1024;
+constexpr int kScanIpt = 4;
+constexpr int kScanChunk = kScanTpb * kScanIpt;
+
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan over one value per thread (blockDim.x <= 1024). Returns the exclusive
+// prefix; *total receives the block sum. `sh` needs 33 uint64.
+__device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* sh, uint64_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint64_t incl = warp_incl_scan_u64(v, lane);
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = lane < nw ? sh[lane] : 0;
+        uint64_t wi = warp_incl_scan_u64(w, lane);
+        sh[lane] = wi - w;
+        if (lane == 31) sh[32] = wi;
+    }
+    __syncthreads();
+    uint64_t excl = incl - v + sh[warp];
+    if (total) *total = sh[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(kScanTpb) scan_reduce(const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ n_ptr,
+                                                        uint64_t* __restrict__ chunk_sums) {
+    __shared__ uint64_t sh[33];
+    const uint32_t n = *n_ptr;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk;
+    if (base >= n) return;
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanIpt; ++i) {
+        uint64_t idx = base + (uint64_t)i * kScanTpb + threadIdx.x;
+        if (idx < n) s += counts[idx];
+    }
+    uint64_t total;
+    block_excl_scan_u64(s, sh, &total);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanTpb) scan_write(const uint32_t* __restrict__ counts,
+                                                       const uint32_t* __restrict__ n_ptr,
+                                                       const uint64_t* __restrict__ chunk_sums,
+                                                       uint64_t* __restrict__ cursors) {
+    __shared__ uint64_t sh[33];
+    __shared__ uint64_t carry_sh;
+    const uint32_t n = *n_ptr;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk;
+    if (base >= n) return;
+    // carry-in = sum of the chunk sums before this CTA's chunk (<= 1024 chunks by construction)
+    uint64_t c = threadIdx.x < blockIdx.x ? chunk_sums[threadIdx.x] : 0;
+    uint64_t carry;
+    block_excl_scan_u64(c, sh, &carry);
+    if (threadIdx.x == 0) carry_sh = carry;
+    // each thread owns kScanIpt consecutive counters
+    const uint64_t first = base + (uint64_t)threadIdx.x * kScanIpt;
+    uint32_t v[kScanIpt];
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanIpt; ++i) {
+        v[i] = first + i < n ? counts[first + i] : 0;
+        s += v[i];
+    }
+    uint64_t excl = block_excl_scan_u64(s, sh, nullptr) + carry_sh;
+#pragma unroll
+    for (int i = 0; i < kScanIpt; ++i) {
+        if (first + i < n) cursors[first + i] = excl;
+        excl += v[i];
+    }
+}
+
+// =================================================================================================
+// K3  radix_scatter: one CTA per segment, tile by tile:
+//   load T tuples into registers (warp-striped, 512 B per warp request)
+//   rank   stable in-warp rank with match.any + per-warp digit counters (plain LDS/STS)
+//   scan   per-digit scan across warps + across digits -> tile-local slot of every tuple
+//   stage  tuples to their slot in shared memory (a counting sort of the tile)
+//   flush  every digit's run goes out as one contiguous piece at the segment's private cursor:
+//          TMA bulk store (cp.async.bulk.global.shared::cta, one per non-empty run) or
+//          consecutive threads writing consecutive 16-byte tuples with st.global.v4
+// Within a segment the order is preserved and segments are cut in input order, so the output
+// equals the reference's stable partitionTable order (src/RadixCluster/HashJoin.hpp:400-407).
+// HBM: reads 16 B/tuple, writes 16 B/tuple.
+// =================================================================================================
+template <int BITS, int TPB, int IPT>
+struct ScatterSmem {
+    static constexpr int D = 1 << BITS;
+    static constexpr int NW = TPB / 32;
+    static constexpr int T = TPB * IPT;
+    static constexpr size_t stage_bytes = (size_t)T * 16;
+    static constexpr size_t gcur_bytes = (size_t)D * 8;
+    static constexpr size_t gbase_bytes = (size_t)D * 8;
+    static constexpr size_t wc_bytes = (size_t)NW * (D + 1) * 4;
+    static constexpr size_t dbase_bytes = (size_t)(D + 4) * 4;
+    static constexpr size_t sdig_bytes = (size_t)T * 2;
+    static constexpr size_t total =
+        stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 33 * 8 + 64;
+};
+
+template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE>
+__global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
+    using L = ScatterSmem<BITS, TPB, IPT>;
+    constexpr int D = L::D, NW = L::NW, T = L::T;
+    static_assert(D <= TPB, "one thread per digit in the scan step");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ulonglong2* stage = reinterpret_cast<ulonglong2*>(smem_raw);
+    uint64_t* gcur = reinterpret_cast<uint64_t*>(smem_raw + L::stage_bytes);
+    uint64_t* gbase = gcur + D;
+    uint64_t* scan_sh = gbase + D;  // 33 entries
+    uint32_t* wc = reinterpret_cast<uint32_t*>(scan_sh + 33);
+    uint32_t* dbase = wc + NW * (D + 1);
+    uint16_t* sdig = reinterpret_cast<uint16_t*>(dbase + D + 4);
+
+    if (blockIdx.x >= *p.nsegs) return;
+    const Segment seg = p.segs[blockIdx.x];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    ulonglong2* __restrict__ out = p.out[seg.rel];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* wcw = wc + warp * (D + 1);
+    const uint32_t lt = lanemask_lt();
+
+    // private write cursors of this segment (the reference's PrefixSumTable row + boundaries)
+    if (tid < D) {
+        uint64_t c = 0;
+        if (tid < (int)p.ndigits) {
+            c = p.cursors[seg.cnt_index + (uint64_t)tid * seg.cnt_stride] - p.cursor_bias[seg.rel];
+            if (seg.parent_first >> 31)
+                p.bounds[seg.rel][(uint64_t)(seg.parent_first & 0x7fffffffu) * p.bounds_stride + tid] = c;
+        }
+        gcur[tid] = c;
+    }
+
+    ulonglong2 v[IPT];
+    auto load_tile = [&](uint64_t tile) {
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            if (idx < seg.end) v[i] = ld_stream_v2(in + idx);
+        }
+    };
+    if (seg.begin < seg.end) load_tile(seg.begin);
+
+    for (uint64_t tile = seg.begin; tile < seg.end; tile += T) {
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+        const uint32_t n_valid = (uint32_t)min((uint64_t)T, seg.end - tile);
+
+        for (int i = lane; i <= D; i += 32) wcw[i] = 0;
+        __syncwarp();
+
+        // ---- rank (stable within the warp's 32*IPT consecutive tuples) ----
+        uint32_t dr[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const bool valid = base + (uint64_t)i * 32 < seg.end;
+            const uint32_t d = valid ? digit_of<POW2>(hash_key<HASH>(v[i].x, p.hp), p.df) : D;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t prev = wcw[d];
+            __syncwarp();
+            if (lane == __ffs(peers) - 1) wcw[d] = prev + __popc(peers);
+            __syncwarp();
+            dr[i] = d | ((prev + __popc(peers & lt)) << 16);
+        }
+        __syncthreads();
+
+        // ---- per-digit scan across warps, then across digits ----
+        {
+            uint32_t tot = 0;
+            if (tid < D) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    uint32_t c = wc[w * (D + 1) + tid];
+                    wc[w * (D + 1) + tid] = tot;
+                    tot += c;
+                }
+            }
+            uint64_t excl = block_excl_scan_u64(tot, scan_sh, nullptr);
+            if (tid < D) {
+                dbase[tid] = (uint32_t)excl;
+                if (tid == D - 1) dbase[D] = n_valid;
+                gbase[tid] = gcur[tid] - excl;  // out index of tile slot j of this digit = gbase + j
+                gcur[tid] += tot;
+            }
+            if (TMA_STORE) bulk_wait_read0();  // previous tile's bulk stores have read `stage`
+        }
+        __syncthreads();
+
+        // ---- stage ----
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t d = dr[i] & 0xffffu;
+            if (d < D) {
+                const uint32_t pos = dbase[d] + wcw[d] + (dr[i] >> 16);
+                stage[pos] = v[i];
+                if (!TMA_STORE) sdig[pos] = (uint16_t)d;
+            }
+        }
+        // prefetch the next tile while this one is flushed
+        if (tile + T < seg.end) load_tile(tile + T);
+        if (TMA_STORE) fence_proxy_async_smem();
+        __syncthreads();
+
+        // ---- flush ----
+        if (TMA_STORE) {
+            if (tid < D) {
+                const uint32_t b = dbase[tid], e = dbase[tid + 1];
+                if (e > b) bulk_store_s2g(out + gbase[tid] + b, stage + b, (e - b) * 16u);
+                bulk_commit();
+            }
+        } else {
+            for (uint32_t j = tid; j < n_valid; j += TPB) {
+                const uint32_t d = sdig[j];
+                st_stream_v2(out + gbase[d] + j, stage[j]);
+            }
+        }
+        // The next iteration's first two barriers separate this flush from the next stage step.
+    }
+    if (TMA_STORE) bulk_wait_read0();
+}
+
+// =================================================================================================
+// plan_pass2: cut every pass-1 partition ("parent") of both relations into segments for pass 2.
+// Single CTA; runs on the device so the pipeline never waits for the host.
+// =================================================================================================
+struct Plan2Params {
+    const uint64_t* bounds1[2];  // D1 + 1 boundaries per relation (last = n)
+    uint64_t n[2];
+    uint32_t d1;          // parents per relation
+    uint32_t d2;          // digits of pass 2
+    uint32_t tile;        // tuples per tile of the pass-2 kernels
+    uint32_t target_segs[2];
+    Segment* segs;        // out
+    uint32_t* nsegs;      // out: total segments
+    uint32_t* ncounts;    // out: total counters = d2 * nsegs
+    uint32_t max_segs;
+};
+
+__global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
+    __shared__ uint64_t sh[33];
+    __shared__ uint32_t rel_base_sh;
+    uint32_t seg_base = 0;  // segments emitted by previous relations
+    for (int rel = 0; rel < 2; ++rel) {
+        const uint64_t n = p.n[rel];
+        // segment length: a whole number of tiles, about n / target_segs
+        uint64_t seg_len = (n + p.target_segs[rel] - 1) / (p.target_segs[rel] ? p.target_segs[rel] : 1);
+        seg_len = ((seg_len + p.tile - 1) / p.tile) * p.tile;
+        if (seg_len == 0) seg_len = p.tile;
+        uint64_t lo = 0, len = 0;
+        uint32_t ns = 0;
+        if (threadIdx.x < p.d1) {
+            lo = p.bounds1[rel][threadIdx.x];
+            const uint64_t hi = (threadIdx.x + 1 == p.d1) ? n : p.bounds1[rel][threadIdx.x + 1];
+            len = hi - lo;
+            ns = (uint32_t)((len + seg_len - 1) / seg_len);
+        }
+        uint64_t total;
+        const uint32_t first = (uint32_t)block_excl_scan_u64(ns, sh, &total);
+        if (threadIdx.x < p.d1) {
+            for (uint32_t s = 0; s < ns; ++s) {
+                const uint32_t gi = seg_base + first + s;
+                if (gi >= p.max_segs) break;
+                Segment sg;
+                sg.begin = lo + (uint64_t)s * seg_len;
+                sg.end = min(lo + len, sg.begin + seg_len);
+                sg.cnt_index = (seg_base + first) * p.d2 + s;
+                sg.cnt_stride = ns;
+                sg.rel = rel;
+                sg.parent_first = threadIdx.x | (s == 0 ? 0x80000000u : 0u);
+                p.segs[gi] = sg;
+            }
+        }
+        if (threadIdx.x == 0) rel_base_sh = seg_base + (uint32_t)total;
+        __syncthreads();
+        seg_base = rel_base_sh;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *p.nsegs = min(seg_base, p.max_segs);
+        *p.ncounts = min(seg_base, p.max_segs) * p.d2;
+    }
+}
+
+// Boundaries of parents that received no segment (empty parents) are never written by
+// radix_scatter: fill them from their parent's start. One thread per (rel, parent).
+struct FillEmptyParams {
+    const uint64_t* bounds1[2];
+    uint64_t* bounds2[2];
+    uint64_t n[2];
+    uint32_t d1, d2;
+};
+__global__ void fill_empty_parent_bounds(FillEmptyParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * p.d1) return;
+    const int rel = i / p.d1;
+    const uint32_t parent = i % p.d1;
+    const uint64_t lo = p.bounds1[rel][parent];
+    const uint64_t hi = (parent + 1 == p.d1) ? p.n[rel] : p.bounds1[rel][parent + 1];
+    if (hi == lo)
+        for (uint32_t d = 0; d < p.d2; ++d) p.bounds2[rel][(uint64_t)parent * p.d2 + d] = lo;
+}
+
+// =================================================================================================
+// K4+K5  join_partitions: the probe relation's partitioned array is cut into gridDim.x equal
+// slices; a CTA walks the partitions its slice overlaps, builds the partition's build-side keys
+// into a shared-memory open-addressing table (64-bit atomicCAS, duplicates collapse: the join
+// counts probe tuples with >= 1 match) and streams its share of the probe partition through it.
+// Equal slices make skew a non-issue: the partition holding a Zipf heavy hitter is simply probed
+// by many CTAs, each rebuilding the (L2-resident) build partition. Partitions whose build side
+// does not fit the table are left to gt_build/gt_probe and counted in *oversize.
+// HBM: reads 16 B per probe tuple + ~16 B per build tuple.
+// =================================================================================================
+struct JoinParams {
+    const ulonglong2* build;  // partitioned R
+    const ulonglong2* probe;  // partitioned S
+    const uint64_t* bounds_build;  // npart + 1
+    const uint64_t* bounds_probe;
+    uint64_t n_probe;
+    uint32_t npart;
+    uint32_t slot_mask;   // table slots - 1
+    uint32_t max_keys;    // largest build partition the table accepts
+    uint32_t hash_shift;  // table slot = (h >> hash_shift) & slot_mask
+    HashParams hp;
+    unsigned long long* matches;
+    uint64_t* cta_times;  // 2 per CTA: build ns, probe ns
+};
+
+template <int HASH, int TPB>
+__global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ uint32_t has_empty_key;
+    __shared__ unsigned long long block_count;
+    const uint32_t nslots = p.slot_mask + 1;
+    const int tid = threadIdx.x;
+
+    const uint64_t per = p.n_probe / gridDim.x, rem = p.n_probe % gridDim.x;
+    const uint64_t lo = per * blockIdx.x + min((uint64_t)blockIdx.x, rem);
+    const uint64_t hi = lo + per + (blockIdx.x < rem ? 1 : 0);
+    if (tid == 0) block_count = 0;
+    uint64_t build_ns = 0, probe_ns = 0;
+    uint32_t count = 0;
+
+    if (lo < hi) {
+        // last partition whose start is <= lo
+        uint32_t a = 0, b = p.npart;
+        while (b - a > 1) {
+            const uint32_t m = (a + b) >> 1;
+            if (p.bounds_probe[m] <= lo) a = m; else b = m;
+        }
+        for (uint32_t part = a; part < p.npart; ++part) {
+            const uint64_t ps0 = p.bounds_probe[part];
+            if (ps0 >= hi) break;
+            const uint64_t s0 = max(lo, ps0), s1 = min(hi, p.bounds_probe[part + 1]);
+            if (s0 >= s1) continue;
+            const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
+            if (r1 == r0) continue;              // src/RadixCluster/HashJoin.hpp:273-276
+            if (r1 - r0 > p.max_keys) continue;  // global-table path
+
+            const uint64_t t0 = globaltimer_ns();
+            __syncthreads();  // previous partition's probes are done with the table
+            for (uint32_t i = tid; i < nslots; i += TPB) table[i] = kEmptyKey;
+            if (tid == 0) has_empty_key = 0;
+            __syncthreads();
+            for (uint64_t i = r0 + tid; i < r1; i += TPB) {
+                const uint64_t key = __ldg(reinterpret_cast<const unsigned long long*>(p.build + i));
+                if (key == kEmptyKey) {
+                    has_empty_key = 1;
+                    continue;
+                }
+                uint32_t slot = (uint32_t)(hash_key<HASH>(key, p.hp) >> p.hash_shift) & p.slot_mask;
+                for (;;) {
+                    const unsigned long long old = atomicCAS(
+                        reinterpret_cast<unsigned long long*>(table + slot), kEmptyKey, key);
+                    if (old == kEmptyKey || old == key) break;
+                    slot = (slot + 1) & p.slot_mask;
+                }
+            }
+            __syncthreads();
+            const uint64_t t1 = globaltimer_ns();
+            const uint32_t sentinel_hit = has_empty_key;
+
+            constexpr int U = 4;
+            for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
+                uint64_t key[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t i = i0 + (uint64_t)u * TPB + tid;
+                    key[u] = i < s1 ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t i = i0 + (uint64_t)u * TPB + tid;
+                    if (i >= s1) continue;
+                    if (key[u] == kEmptyKey) {
+                        count += sentinel_hit;
+                        continue;
+                    }
+                    uint32_t slot = (uint32_t)(hash_key<HASH>(key[u], p.hp) >> p.hash_shift) & p.slot_mask;
+                    for (;;) {
+                        const uint64_t t = table[slot];
+                        if (t == key[u]) {
+                            ++count;
+                            break;
+                        }
+                        if (t == kEmptyKey) break;
+                        slot = (slot + 1) & p.slot_mask;
+                    }
+                }
+            }
+            const uint64_t t2 = globaltimer_ns();
+            build_ns += t1 - t0;
+            probe_ns += t2 - t1;
+        }
+    }
+    __syncthreads();
+    // block reduction of the match count
+    uint32_t c = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0 && c) atomicAdd(&block_count, (unsigned long long)c);
+    __syncthreads();
+    if (tid == 0) {
+        if (block_count) atomicAdd(p.matches, block_count);
+        p.cta_times[2 * blockIdx.x] = build_ns;
+        p.cta_times[2 * blockIdx.x + 1] = probe_ns;
+    }
+}
+
+// Counts the partitions join_partitions skipped (build side larger than the smem table).
+__global__ void count_oversize(const uint64_t* __restrict__ bounds_build, uint32_t npart,
+                               uint32_t max_keys, uint32_t* __restrict__ oversize) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npart && bounds_build[i + 1] - bounds_build[i] > max_keys) atomicAdd(oversize, 1u);
+}
+
+// =================================================================================================
+// K6/K7  global open-addressing table: the no-partitioning join, and the fallback for oversize
+// radix partitions. Buckets are 32-byte sectors of four 8-byte keys; a key hashes to a bucket,
+// takes the first free slot (atomicCAS) and overflows into the next bucket -- the GPU analogue of
+// the reference's 64-byte, 3-slot LinearProbing buckets (src/HashTables/LinearProbing.hpp:22-83,
+// 114-134). A probe reads one whole bucket with two 16-byte loads, so the common case costs one
+// DRAM sector; it stops at the first bucket that has a free slot (LinearProbing.hpp:172-174).
+// =================================================================================================
+struct GtParams {
+    const ulonglong2* rel;     // R for build, S for probe
+    uint64_t n;
+    uint64_t* table;           // nbuckets * 4 keys
+    uint64_t bucket_mask;      // nbuckets - 1
+    uint32_t hash_shift;
+    uint32_t select;           // 0: every tuple; 1: only tuples of oversize partitions
+    const uint64_t* bounds_build;  // select == 1: partition sizes of R
+    uint32_t max_keys;
+    DigitFn part_fn;           // select == 1: tuple -> partition id (shift 0, mask = all)
+    HashParams hp;
+    uint32_t* flags;           // [0]: build side contains kEmptyKey
+    unsigned long long* matches;
+};
+
+__global__ void gt_clear(uint64_t* __restrict__ table, uint64_t nkeys) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nkeys / 2; i += stride)
+        t2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
+}
+
+template <bool POW2>
+__device__ __forceinline__ bool gt_selected(const GtParams& p, uint64_t h) {
+    if (!p.select) return true;
+    const uint64_t part = POW2 ? (h & p.part_fn.pmask) : (h % p.part_fn.modulus);
+    return p.bounds_build[part + 1] - p.bounds_build[part] > p.max_keys;
+}
+
+template <int HASH, bool POW2>
+__global__ void __launch_bounds__(256) gt_build(GtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const uint64_t key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i));
+        const uint64_t h = hash_key<HASH>(key, p.hp);
+        if (!gt_selected<POW2>(p, h)) continue;
+        if (key == kEmptyKey) {
+            p.flags[0] = 1;
+            continue;
+        }
+        uint64_t bucket = (h >> p.hash_shift) & p.bucket_mask;
+        bool done = false;
+        while (!done) {
+            unsigned long long* b = reinterpret_cast<unsigned long long*>(p.table + bucket * 4);
+#pragma unroll
+            for (int s = 0; s < 4 && !done; ++s) {
+                unsigned long long cur = b[s];
+                if (cur == key) {
+                    done = true;
+                } else if (cur == kEmptyKey) {
+                    const unsigned long long old = atomicCAS(b + s, kEmptyKey, key);
+                    done = (old == kEmptyKey || old == key);
+                }
+            }
+            bucket = (bucket + 1) & p.bucket_mask;
+        }
+    }
+}
+
+template <int HASH, bool POW2>
+__global__ void __launch_bounds__(256) gt_probe(GtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t sentinel_hit = p.flags[0];
+    uint32_t count = 0;
+    constexpr int U = 4;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n; i0 += stride * U) {
+        uint64_t key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            key[u] = i < p.n ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + (uint64_t)u * stride >= p.n) continue;
+            const uint64_t h = hash_key<HASH>(key[u], p.hp);
+            if (!gt_selected<POW2>(p, h)) continue;
+            if (key[u] == kEmptyKey) {
+                count += sentinel_hit;
+                continue;
+            }
+            uint64_t bucket = (h >> p.hash_shift) & p.bucket_mask;
+            for (;;) {
+                const ulonglong2* b = reinterpret_cast<const ulonglong2*>(p.table + bucket * 4);
+                const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
+                if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
+                    ++count;
+                    break;
+                }
+                if (k23.y == kEmptyKey) break;  // slots fill in order: last free => bucket not full
+                bucket = (bucket + 1) & p.bucket_mask;
+            }
+        }
+    }
+    __shared__ unsigned long long block_count;
+    if (threadIdx.x == 0) block_count = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
+}
+
+// Test hook: raw hashes of a key array.
+template <int HASH>
+__global__ void hash_batch_kernel(const int64_t* __restrict__ keys, uint64_t n, HashParams hp,
+                                  uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hash_key<HASH>((uint64_t)keys[i], hp);
+}
+
+}  // namespace phj

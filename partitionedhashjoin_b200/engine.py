@@ -1,0 +1,295 @@
+"""Python host mirror of the reference's joiner interface, on top of the C ABI (include/phj.h).
+
+The C++ mirror (what a reference maintainer would use) lives in ``host/``; this module gives the
+tests and ``bench.py`` the same surface with the reference's names:
+
+* ``NoPartitioningHashJoiner(configuration).Run(tableA, tableB, timer)``
+  -- ``NoPartitioning::HashJoiner::Run`` (reference src/NoPartitioning/HashJoin.hpp:54-74)
+* ``RadixClusteringHashJoiner(configuration, hasher).Run(tableA, tableB, timer)``
+  -- ``RadixClustering::HashJoiner::Run`` (reference src/RadixCluster/HashJoin.hpp:190-241)
+* ``HashJoinTimer`` / ``NoOpHashJoinTimer`` -- ``Common::IHashJoinTimer`` (src/Common/Results.hpp:131-247)
+
+Everything that computes goes through ``libphj_b200.so``; nothing here falls back to numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (ALGO_NO_PARTITIONING, ALGO_RADIX_PARTITIONING, HASH_NAMES, TUPLE_DTYPE, PhjConfig,
+                   PhjDeviceInfo, PhjError, PhjResult, check, lib)
+
+
+# ---------------------------------------------------------------------------------------------
+# host data helpers
+# ---------------------------------------------------------------------------------------------
+def as_tuples(a) -> np.ndarray:
+    """View/convert to a C-contiguous array of TUPLE_DTYPE (16-byte {id, payload} records)."""
+    a = np.asarray(a)
+    if a.dtype != TUPLE_DTYPE:
+        if a.dtype.fields is None and a.ndim == 2 and a.shape[1] == 2:
+            a = np.ascontiguousarray(a, dtype="<i8").view(TUPLE_DTYPE).reshape(-1)
+        else:
+            raise TypeError(f"expected TUPLE_DTYPE or an (n, 2) int64 array, got {a.dtype} {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def make_tuples(ids, payloads=None) -> np.ndarray:
+    ids = np.asarray(ids, dtype=np.int64)
+    out = np.empty(ids.shape[0], dtype=TUPLE_DTYPE)
+    out["id"] = ids
+    out["payload"] = np.arange(ids.shape[0], dtype=np.int64) if payloads is None else payloads
+    return out
+
+
+class PinnedTuples:
+    """A relation in page-locked host memory (phj_host_alloc): what phj_join_host uploads from."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        self._ptr = C.c_void_p()
+        check(lib.phj_host_alloc(C.byref(self._ptr), max(self.n, 1) * 16))
+        buf = (C.c_char * (max(self.n, 1) * 16)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=TUPLE_DTYPE, count=self.n)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            lib.phj_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fill_sequential(out: np.ndarray, start: int = 1, threads: int = 0) -> np.ndarray:
+    """DataGenerator::Sequential::FillTable (reference src/DataGenerator/Sequential.cpp:6-40)."""
+    assert out.dtype == TUPLE_DTYPE and out.flags.c_contiguous
+    check(lib.phj_fill_sequential(out.ctypes.data, out.shape[0], start, threads))
+    return out
+
+
+def fill_zipf(out: np.ndarray, alpha: float, range_first: int, range_second: int, base_seed: int,
+              batches: int = 64, threads: int = 0) -> np.ndarray:
+    """DataGenerator::Zipf::FillTable with explicit seeding (reference src/DataGenerator/Zipf.cpp:58-108)."""
+    assert out.dtype == TUPLE_DTYPE and out.flags.c_contiguous
+    rc = lib.phj_fill_zipf(out.ctypes.data, out.shape[0], alpha, range_first, range_second, base_seed,
+                           batches, threads)
+    if rc != 0:
+        raise ValueError("phj_fill_zipf rejected its arguments (alpha < 0.01, empty range, 0 batches "
+                         "or a seed that is a multiple of 2^31-1)")
+    return out
+
+
+def hash_host(hash_id: int, seed: int, key: int) -> int:
+    return int(lib.phj_hash_host(hash_id, C.c_uint64(seed & (2**64 - 1)), key))
+
+
+def hash_batch(hash_id: int, seed: int, keys: np.ndarray, device: int = 0) -> np.ndarray:
+    """Raw 64-bit hashes computed ON THE DEVICE (test hook for the __device__ hashers)."""
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    out = np.empty(keys.shape[0], dtype=np.uint64)
+    check(lib.phj_hash_batch(hash_id, C.c_uint64(seed & (2**64 - 1)), keys.ctypes.data, keys.shape[0],
+                             out.ctypes.data, device))
+    return out
+
+
+def device_count() -> int:
+    return int(lib.phj_device_count())
+
+
+def device_info(device: int = 0) -> dict:
+    info = PhjDeviceInfo()
+    check(lib.phj_get_device_info(device, C.byref(info)))
+    d = {name: getattr(info, name) for name, _ in info._fields_}
+    d["name"] = info.name.decode()
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# thin handle wrapper
+# ---------------------------------------------------------------------------------------------
+class Engine:
+    """One phj_handle. ``algo``: 'no-partitioning' | 'radix-partitioning' (the CLI spellings,
+    reference src/Common/Configuration.cpp:4-12)."""
+
+    ALGOS = {"no-partitioning": ALGO_NO_PARTITIONING, "radix-partitioning": ALGO_RADIX_PARTITIONING}
+
+    def __init__(self, algo="radix-partitioning", partitions: int = 0, radix_bits=(0, 0), hash="xxh3",
+                 hash_seed: int = 0x9E3779B97F4A7C15, table_seed: int = 1, device: int = 0,
+                 flags: int = 0):
+        cfg = PhjConfig()
+        if isinstance(algo, str):
+            if algo not in self.ALGOS:
+                raise ValueError(f"Unrecognized join algorithm type: {algo}.")
+            algo = self.ALGOS[algo]
+        cfg.algo = algo
+        cfg.hash = HASH_NAMES[hash] if isinstance(hash, str) else hash
+        cfg.partitions = partitions
+        cfg.radix_bits[0], cfg.radix_bits[1] = radix_bits
+        cfg.hash_seed = hash_seed & (2**64 - 1)
+        cfg.table_seed = table_seed & (2**64 - 1)
+        cfg.device = device
+        cfg.flags = flags
+        self._h = C.c_void_p()
+        check(lib.phj_create(C.byref(cfg), C.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.phj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, build: np.ndarray, probe: np.ndarray):
+        build, probe = as_tuples(build), as_tuples(probe)
+        check(lib.phj_upload(self._h, build.ctypes.data, build.shape[0], probe.ctypes.data, probe.shape[0]))
+        self._n = (build.shape[0], probe.shape[0])
+
+    def bind_device(self, d_build: int, n_build: int, d_probe: int, n_probe: int, keepalive=None):
+        """Join relations already resident on the device (raw device pointers, e.g. tensor.data_ptr())."""
+        check(lib.phj_bind_device(self._h, C.c_void_p(d_build), n_build, C.c_void_p(d_probe), n_probe))
+        self._keep = [keepalive]
+        self._n = (n_build, n_probe)
+
+    def join(self) -> dict:
+        res = PhjResult()
+        check(lib.phj_join(self._h, C.byref(res)))
+        return res.as_dict()
+
+    def join_host(self, build: np.ndarray, probe: np.ndarray) -> dict:
+        build, probe = as_tuples(build), as_tuples(probe)
+        res = PhjResult()
+        check(lib.phj_join_host(self._h, build.ctypes.data, build.shape[0], probe.ctypes.data,
+                                probe.shape[0], C.byref(res)))
+        self._n = (build.shape[0], probe.shape[0])
+        return res.as_dict()
+
+    def read_partitions(self, which: int, partitions: int):
+        """(partitioned relation, partitions+1 boundaries) of the last radix join."""
+        n = self._n[which]
+        out = np.empty(n, dtype=TUPLE_DTYPE)
+        bounds = np.empty(partitions + 1, dtype=np.uint64)
+        check(lib.phj_read_partitions(self._h, which, out.ctypes.data, bounds.ctypes.data))
+        return out, bounds
+
+    def kernel_times(self) -> list:
+        names = (C.c_char_p * 32)()
+        ns = (C.c_uint64 * 32)()
+        k = lib.phj_kernel_times(self._h, names, ns, 32)
+        return [(names[i].decode(), int(ns[i])) for i in range(k)]
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's interface, by its own names
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class NoPartitioningConfiguration:
+    """NoPartitioning::Configuration (reference src/NoPartitioning/Configuration.hpp:6-8)."""
+    MinBatchSize: int = 10000  # CPU batching knob; accepted for source compatibility, unused
+
+
+@dataclasses.dataclass
+class RadixClusteringConfiguration:
+    """RadixClustering::Configuration (reference src/RadixCluster/Configuration.hpp:6-9)."""
+    MinBatchSize: int = 10000
+    NumberOfPartitions: int = 32
+
+
+@dataclasses.dataclass
+class Hasher:
+    """Stands in for a Common::IHasher instance: which function and which seed."""
+    name: str = "xxh3"
+    seed: int = 0x9E3779B97F4A7C15
+
+
+class HashJoinTimingResult:
+    """Common::HashJoinTimingResult (reference src/Common/Results.hpp:60-88); nanoseconds."""
+
+    def __init__(self, build=0, probe=0, partitioning=0, parameters=None):
+        self.build_ns, self.probe_ns, self.partitioning_ns = build, probe, partitioning
+        self.parameters = dict(parameters or {})
+
+
+class NoOpHashJoinTimer:
+    """Common::NoOpHashJoinTimer (reference src/Common/Results.hpp:151-165)."""
+
+    def SetBuildPhaseDuration(self, ns): pass
+    def SetProbePhaseDuration(self, ns): pass
+    def SetPartitionPhaseDuration(self, ns): pass
+    def GetResult(self): return HashJoinTimingResult()
+
+
+class HashJoinTimer(NoOpHashJoinTimer):
+    """Common::HashJoinTimer's set-duration interface (reference src/Common/Results.hpp:213-240).
+    The device path reports measured durations, so only the thread-safe Set*Duration half of
+    IHashJoinTimer is driven."""
+
+    def __init__(self, parameters=None):
+        self._r = HashJoinTimingResult(parameters=parameters)
+
+    def SetBuildPhaseDuration(self, ns): self._r.build_ns = int(ns)
+    def SetProbePhaseDuration(self, ns): self._r.probe_ns = int(ns)
+    def SetPartitionPhaseDuration(self, ns): self._r.partitioning_ns = int(ns)
+    def GetResult(self): return self._r
+
+
+class _JoinerBase:
+    def __init__(self, engine: Engine):
+        self._engine = engine
+        self.last_result: Optional[dict] = None
+
+    def Run(self, tableA, tableB, timer=None):
+        """tableA is the build relation, tableB the probe relation. Like the reference the returned
+        joined table is empty (count-only join, reference Readme.md:10); the count is in
+        ``self.last_result['matches']``."""
+        timer = timer or NoOpHashJoinTimer()
+        self._engine.upload(tableA, tableB)
+        res = self._engine.join()
+        self.last_result = res
+        timer.SetPartitionPhaseDuration(res["partition_ns"])
+        timer.SetBuildPhaseDuration(res["build_ns"])
+        timer.SetProbePhaseDuration(res["probe_ns"])
+        return np.empty(0, dtype=[("id", "<i8"), ("payloadA", "<i8"), ("payloadB", "<i8")])
+
+    def close(self):
+        self._engine.close()
+
+
+class NoPartitioningHashJoiner(_JoinerBase):
+    def __init__(self, configuration: Optional[NoPartitioningConfiguration] = None,
+                 hasher: Optional[Hasher] = None, device: int = 0):
+        hasher = hasher or Hasher()
+        super().__init__(Engine("no-partitioning", hash=hasher.name, hash_seed=hasher.seed, device=device))
+        self.configuration = configuration or NoPartitioningConfiguration()
+
+
+class RadixClusteringHashJoiner(_JoinerBase):
+    def __init__(self, configuration: Optional[RadixClusteringConfiguration] = None,
+                 hasher: Optional[Hasher] = None, device: int = 0, radix_bits=(0, 0), flags: int = 0):
+        configuration = configuration or RadixClusteringConfiguration()
+        hasher = hasher or Hasher()
+        if configuration.NumberOfPartitions < 0:
+            raise ValueError("NumberOfPartitions must be >= 0")
+        super().__init__(Engine("radix-partitioning", partitions=configuration.NumberOfPartitions,
+                                radix_bits=radix_bits, hash=hasher.name, hash_seed=hasher.seed,
+                                device=device, flags=flags))
+        self.configuration = configuration

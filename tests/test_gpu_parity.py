@@ -1,0 +1,226 @@
+"""GPU parity tests (run on the B200 with -m gpu): everything goes through the C ABI
+(libphj_b200.so) and is compared with the oracle (oracle/phj_oracle.c) on the same seeded inputs,
+with the golden vectors made by the unmodified reference, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+SEED_P = 0x9E3779B97F4A7C15
+HASHES = ["xxh3", "murmur3", "city"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(phj):
+    assert phj.device_count() > 0, "GPU tests need a CUDA device; there is no CPU fallback"
+    info = phj.device_info(0)
+    print("device:", info)
+    assert info["cc_major"] >= 10
+
+
+def cases_for(phj, name):
+    adv = _cases.adversarial_cases()
+    if name in adv:
+        return adv[name]
+    nr, ns, alpha, seed, batches = _cases.GENERATOR_CASES[name]
+    R = np.empty(nr, dtype=phj.TUPLE_DTYPE)
+    S = np.empty(ns, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1)
+    phj.fill_zipf(S, alpha, 1, nr, seed, batches)
+    return R, S
+
+
+def run(phj, R, S, algo, **kw):
+    with phj.Engine(algo, **kw) as e:
+        e.upload(R, S)
+        return e.join()
+
+
+# ---- K8: device hashers are bit-exact ------------------------------------------------------------
+@pytest.mark.parametrize("hash_id", [0, 1, 2])
+def test_device_hashers_bit_exact(phj, oracle, hash_id):
+    keys = np.concatenate([_cases.splitmix64(200000, 5).astype(np.int64),
+                           np.array([0, 1, 2, 3, -1, 2**63 - 1, -(2**63), 10_000_000, 123456789], dtype=np.int64)])
+    for seed in (0, 1, SEED_P, 2**64 - 1):
+        assert (phj.hash_batch(hash_id, seed, keys) == oracle.hash_batch(hash_id, seed, keys)).all()
+
+
+def test_device_xxh3_golden(phj):
+    keys = np.array([r["key"] for r in GOLDEN["xxh3"]], dtype=np.int64)
+    for seed in sorted({r["seed"] for r in GOLDEN["xxh3"]}):
+        sel = [i for i, r in enumerate(GOLDEN["xxh3"]) if r["seed"] == seed]
+        got = phj.hash_batch(0, seed, keys[sel])
+        assert got.tolist() == [GOLDEN["xxh3"][i]["hash"] for i in sel]
+
+
+# ---- counts: golden (reference) + oracle ----------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(GOLDEN["joins"]))
+def test_counts_match_reference_golden(phj, oracle, name):
+    R, S = cases_for(phj, name)
+    want = GOLDEN["joins"][name]["matches"]
+    assert oracle.count_by_sort(R, S) == want
+    assert run(phj, R, S, "no-partitioning")["matches"] == want
+    for P in (0, 1, 2, 3, 32, 64, 100, 1000, 2048, 4096, 65536):
+        res = run(phj, R, S, "radix-partitioning", partitions=P)
+        assert res["matches"] == want, (name, P, res)
+    for bits in ((6, 6), (8, 4), (3, 8), (8, 8), (5, 0), (1, 1)):
+        res = run(phj, R, S, "radix-partitioning", partitions=1 << sum(bits), radix_bits=bits)
+        assert res["matches"] == want, (name, bits, res)
+    res = run(phj, R, S, "radix-partitioning", partitions=4096, flags=phj.FLAG_NO_TMA_STORE)
+    assert res["matches"] == want
+
+
+@pytest.mark.parametrize("hash", HASHES)
+@pytest.mark.parametrize("name", ["dup_build_keys", "extreme_keys", "random64", "gen_small_105"])
+def test_counts_every_hasher(phj, name, hash):
+    R, S = cases_for(phj, name)
+    want = GOLDEN["joins"][name]["matches"]
+    for seed in (0, 1, SEED_P):
+        assert run(phj, R, S, "no-partitioning", hash=hash, hash_seed=seed)["matches"] == want
+        assert run(phj, R, S, "radix-partitioning", partitions=256, hash=hash, hash_seed=seed)["matches"] == want
+        assert run(phj, R, S, "radix-partitioning", partitions=77, hash=hash, hash_seed=seed)["matches"] == want
+
+
+def test_empty_relations(phj):
+    R, S = _cases.sequential(100), _cases.tuples(np.arange(50, 150))
+    empty = _cases.tuples(np.empty(0, dtype=np.int64))
+    for algo, kw in (("no-partitioning", {}), ("radix-partitioning", {"partitions": 64}),
+                     ("radix-partitioning", {"partitions": 4096})):
+        assert run(phj, R, empty, algo, **kw)["matches"] == 0
+        assert run(phj, empty, S, algo, **kw)["matches"] == 0  # deviation: the reference NPJ throws here
+        assert run(phj, empty, empty, algo, **kw)["matches"] == 0
+        assert run(phj, R, S, algo, **kw)["matches"] == 50
+
+
+def test_reuse_handle_and_reupload(phj, oracle):
+    """One handle, several relations of different sizes, repeated joins."""
+    with phj.Engine("radix-partitioning", partitions=512) as e:
+        for n_r, n_s, seed in ((5000, 40000, 1), (70000, 10000, 2), (123, 456789, 3), (5000, 40000, 4)):
+            R = _cases.tuples(_cases.splitmix64(n_r, seed).astype(np.int64) % 9000)
+            S = _cases.tuples(_cases.splitmix64(n_s, seed + 100).astype(np.int64) % 12000)
+            want = oracle.count_by_sort(R, S)
+            e.upload(R, S)
+            assert e.join()["matches"] == want
+            assert e.join()["matches"] == want
+            assert e.join_host(R, S)["matches"] == want
+
+
+# ---- intermediate state: the partitioned relations equal the reference algorithm's ---------------
+@pytest.mark.parametrize("hash_id,hash", list(enumerate(HASHES)))
+@pytest.mark.parametrize("P,bits", [(64, (0, 0)), (4096, (6, 6)), (2048, (0, 0)), (256, (8, 0)), (256, (4, 4)),
+                                    (100, (0, 0)), (1000, (0, 0)), (65536, (8, 8)), (1, (0, 0))])
+def test_partition_layout_equals_oracle(phj, oracle, P, bits, hash_id, hash):
+    """partitionedTable + PartitionsInfo (src/RadixCluster/HashJoin.hpp:16-33,195-198,394-412):
+    partition p = Hash(id, P) at [bounds[p], bounds[p+1]), input order kept -- bit-identical."""
+    R = _cases.tuples(_cases.splitmix64(30011, 9).astype(np.int64) % 5003)
+    S = _cases.tuples(_cases.splitmix64(250007, 10).astype(np.int64) % 7001)
+    with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P) as e:
+        e.upload(R, S)
+        res = e.join()
+        assert res["matches"] == oracle.count_by_sort(R, S)
+        for which, rel in ((0, R), (1, S)):
+            got, gb = e.read_partitions(which, P)
+            want, wb = oracle.radix_partition(rel, P, hash_id, SEED_P, workers=1)
+            assert gb[:-1].tolist() == wb[:, 0].tolist() and int(gb[-1]) == rel.shape[0]
+            assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+
+
+def test_partition_layout_skewed_generator_data(phj, oracle):
+    nr, ns = 100000, 1500000
+    R = np.empty(nr, dtype=phj.TUPLE_DTYPE)
+    S = np.empty(ns, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1)
+    phj.fill_zipf(S, 1.25, 1, nr, 4711, 16)
+    for flags in (0, phj.FLAG_NO_TMA_STORE):
+        with phj.Engine("radix-partitioning", partitions=4096, hash_seed=SEED_P, flags=flags) as e:
+            e.upload(R, S)
+            assert e.join()["matches"] == ns
+            got, gb = e.read_partitions(1, 4096)
+            want, wb = oracle.radix_partition(S, 4096, 0, SEED_P, workers=1)
+            assert gb[:-1].tolist() == wb[:, 0].tolist()
+            assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+
+
+def test_oversize_partitions_use_the_global_table(phj, oracle):
+    """|R|/P far above the shared-memory table: those partitions go through gt_build/gt_probe."""
+    R = _cases.tuples(_cases.splitmix64(400000, 1).astype(np.int64) % 1000003)
+    S = _cases.tuples(_cases.splitmix64(900000, 2).astype(np.int64) % 1000003)
+    want = oracle.count_by_sort(R, S)
+    res = run(phj, R, S, "radix-partitioning", partitions=8)
+    assert res["matches"] == want and res["fallback_partitions"] == 8
+    # one giant partition next to small ones: 90 % of R shares... nothing; use a skewed build side
+    hot = np.concatenate([np.arange(1, 300001), _cases.splitmix64(50000, 3).astype(np.int64)])
+    R2 = _cases.tuples(hot)
+    res = run(phj, R2, S, "radix-partitioning", partitions=32)
+    assert res["matches"] == oracle.count_by_sort(R2, S) and res["fallback_partitions"] > 0
+
+
+# ---- full size (BASELINE.json configs): size-independent properties ------------------------------
+FULL = [(10_000_000, 200_000_000)]
+
+
+@pytest.fixture(scope="module")
+def full_relations(phj):
+    nr, ns = FULL[0]
+    R = np.empty(nr, dtype=phj.TUPLE_DTYPE)
+    S = np.empty(ns, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1)
+    phj.fill_zipf(S, 1.05, 1, nr, 12345, 64)
+    return R, S
+
+
+def test_full_size_counts(phj, full_relations):
+    """10 M x 200 M (configs[0]/[1]): generator data joins to |S| (every probe key lies in
+    [1, |R|]); NPJ == radix for every fan-out/hasher; shrinking R to its first
+    half must give exactly the number of probe keys <= |R|/2 (counted independently with numpy)."""
+    R, S = full_relations
+    ns = S.shape[0]
+    half = R.shape[0] // 2
+    want_half = int((S["id"] <= half).sum())
+    with phj.Engine("no-partitioning") as e:
+        e.upload(R, S)
+        assert e.join()["matches"] == ns
+        e.upload(R[:half], S)
+        assert e.join()["matches"] == want_half
+    for kw in ({"partitions": 0}, {"partitions": 2048}, {"partitions": 4096, "hash": "murmur3"},
+               {"partitions": 4096, "hash": "city"}, {"partitions": 1024}, {"partitions": 32},
+               {"partitions": 8192, "radix_bits": (7, 6)}):
+        with phj.Engine("radix-partitioning", **kw) as e:
+            e.upload(R, S)
+            res = e.join()
+            assert res["matches"] == ns, (kw, res)
+            e.upload(R[:half], S)
+            assert e.join()["matches"] == want_half, kw
+
+
+def test_full_size_partition_properties(phj, oracle, full_relations):
+    """At full size the partitioned probe relation is a permutation of S (checksums), every
+    partition holds only its own hash class, and order inside partitions is input order."""
+    R, S = full_relations
+    P = 4096
+    with phj.Engine("radix-partitioning", partitions=P, hash_seed=SEED_P) as e:
+        e.upload(R, S)
+        assert e.join()["matches"] == S.shape[0]
+        got, bounds = e.read_partitions(1, P)
+    assert int(bounds[0]) == 0 and int(bounds[-1]) == S.shape[0] and (np.diff(bounds.astype(np.int64)) >= 0).all()
+    # permutation: payload is the input index, so the sorted payloads are 0..n-1 and ids follow
+    assert int(got["payload"].sum(dtype=np.uint64)) == int(S["payload"].sum(dtype=np.uint64))
+    assert int((got["id"].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).sum(dtype=np.uint64)) == \
+        int((S["id"].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).sum(dtype=np.uint64))
+    assert (S["id"][got["payload"]] == got["id"]).all()
+    # hash class + stability on a sample of partitions (the hot one included)
+    sizes = np.diff(bounds.astype(np.int64))
+    for p in [0, 1, P // 2, P - 1, int(sizes.argmax()), int(sizes.argmin())]:
+        a, b = int(bounds[p]), int(bounds[p + 1])
+        part = oracle.hash_batch(0, SEED_P, got["id"][a:b]) % np.uint64(P)
+        assert (part == p).all()
+        assert (np.diff(got["payload"][a:b]) > 0).all()
