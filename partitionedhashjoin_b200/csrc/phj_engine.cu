@@ -135,6 +135,7 @@ struct phj_handle {
     KernelTime ktimes[kMaxKernelTimes] = {};
     int n_ktimes = 0;
     bool time_kernels = false;
+    bool debug_sync = false;  // PHJ_DEBUG_SYNC=1: synchronise and check after every launch
     bool joined_radix = false;
     uint32_t launches = 0;
 };
@@ -165,7 +166,8 @@ int dev_reserve(T** p, size_t* cap, size_t want) {
 struct KernelScope {
     phj_handle* h;
     int idx;
-    KernelScope(phj_handle* h_, const char* name) : h(h_), idx(-1) {
+    const char* name_;
+    KernelScope(phj_handle* h_, const char* name) : h(h_), idx(-1), name_(name) {
         ++h->launches;
         if (h->time_kernels && h->n_ktimes < kMaxKernelTimes) {
             idx = h->n_ktimes++;
@@ -176,6 +178,13 @@ struct KernelScope {
     }
     ~KernelScope() {
         if (idx >= 0) cudaEventRecord(h->ktimes[idx].end, h->stream);
+        if (h->debug_sync) {
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess)
+                fprintf(stderr, "[phj debug] kernel %s (launch #%u) failed: %s\n", name_, h->launches,
+                        cudaGetErrorString(e));
+        }
     }
 };
 
@@ -658,6 +667,8 @@ int join_radix(phj_handle* h, phj_result* out) {
     jp.bounds_build = h->d_bounds2[0];
     jp.bounds_probe = h->d_bounds2[1];
     jp.n_probe = h->n[1];
+    jp.slice_len = h->n[1] / h->join_grid;
+    jp.slice_rem = h->n[1] % h->join_grid;
     jp.npart = (uint32_t)h->nparts;
     jp.slot_mask = h->join_slots - 1;
     jp.max_keys = h->join_max_keys;
@@ -675,6 +686,20 @@ int join_radix(phj_handle* h, phj_result* out) {
             h->d_bounds2[0], (uint32_t)h->nparts, h->join_max_keys, h->d_scalars + kOversize);
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    if (const char* rj = getenv("PHJ_DEBUG_REJOIN")) {
+        // debugging aid: run only the join kernel again on the already partitioned relations
+        PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        fprintf(stderr, "[phj debug] first join: %llu\n", (unsigned long long)h->h_out[0]);
+        for (int i = 0; i < atoi(rj); ++i) {
+            PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 16, h->stream));
+            PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
+            PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 16, cudaMemcpyDeviceToHost, h->stream));
+            PHJ_CUDA(cudaStreamSynchronize(h->stream));
+            fprintf(stderr, "[phj debug] rejoin %d: %llu probed %llu\n", i, (unsigned long long)h->h_out[0],
+                    (unsigned long long)h->h_out[1]);
+        }
+    }
     PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 4, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_cta_times, h->d_cta_times, (size_t)h->join_grid * 16,
@@ -759,7 +784,7 @@ int phj_get_device_info(int32_t device, phj_device_info* out) {
     cudaDeviceProp prop;
     PHJ_CUDA(cudaGetDeviceProperties(&prop, device));
     memset(out, 0, sizeof(*out));
-    snprintf(out->name, sizeof(out->name), "%s", prop.name);
+    snprintf(out->name, sizeof(out->name), "%.127s", prop.name);
     out->sm_count = prop.multiProcessorCount;
     out->cc_major = prop.major;
     out->cc_minor = prop.minor;
@@ -803,6 +828,8 @@ int phj_create(const phj_config* config, phj_handle** out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     const char* kt = getenv("PHJ_KERNEL_TIMES");
     h->time_kernels = kt && kt[0] == '1';
+    const char* ds = getenv("PHJ_DEBUG_SYNC");
+    h->debug_sync = ds && ds[0] == '1';
     auto cleanup = [&](int code) {
         phj_destroy(h);
         return code;
@@ -816,7 +843,7 @@ int phj_create(const phj_config* config, phj_handle** out) {
         cudaEventCreate(&k.end);
     }
     if (cudaMalloc(&h->d_scalars, kNumScalars * 4) != cudaSuccess ||
-        cudaMalloc(&h->d_matches, 8) != cudaSuccess ||
+        cudaMalloc(&h->d_matches, 16) != cudaSuccess ||
         cudaMallocHost(&h->h_out, 64) != cudaSuccess)
         return cleanup(fail(PHJ_ERR_NOMEM, "allocation of engine scalars failed"));
     cudaMemset(h->d_scalars, 0, kNumScalars * 4);

@@ -89,6 +89,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Block barrier preceded by an explicit warp reconvergence. Measured on B200 (CUDA 12.9): after a
+// region with per-lane loops (hash-table probing), ptxas may keep loop state in uniform registers
+// and reach `bar.sync` without WARPSYNC; lanes of one warp then passed the barrier at different
+// times and join_partitions lost matches. bar.warp.sync cannot be elided by the compiler.
+__device__ __forceinline__ void cta_sync() {
+    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+    __syncthreads();
+}
 // TMA 1-D bulk store shared::cta -> global (UBLKCP in SASS). 16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
@@ -98,6 +106,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// Full completion: the bulk stores' global writes are done (not merely their smem reads). A CTA must
+// execute this before it exits -- measured on B200: with only the .read wait the next kernel on the
+// stream could still observe the old contents of the destination.
+__device__ __forceinline__ void bulk_wait_all0() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
             __syncwarp();
         }
     }
-    __syncthreads();
+    cta_sync();
     for (int d = threadIdx.x; d < (int)p.ndigits; d += TPB) {
         uint32_t sum = 0;
 #pragma unroll
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
             __syncwarp();
             dr[i] = d | ((prev + __popc(peers & lt)) << 16);
         }
-        __syncthreads();
+        cta_sync();
 
         // ---- per-digit scan across warps, then across digits ----
         {
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
             }
             if (TMA_STORE) bulk_wait_read0();  // previous tile's bulk stores have read `stage`
         }
-        __syncthreads();
+        cta_sync();
 
         // ---- stage ----
 #pragma unroll
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
         // prefetch the next tile while this one is flushed
         if (tile + T < seg.end) load_tile(tile + T);
         if (TMA_STORE) fence_proxy_async_smem();
-        __syncthreads();
+        cta_sync();
 
         // ---- flush ----
         if (TMA_STORE) {
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
         }
         // The next iteration's first two barriers separate this flush from the next stage step.
     }
-    if (TMA_STORE) bulk_wait_read0();
+    if (TMA_STORE) bulk_wait_all0();
 }
 
 // =================================================================================================
@@ -484,6 +498,7 @@ struct JoinParams {
     const uint64_t* bounds_build;  // npart + 1
     const uint64_t* bounds_probe;
     uint64_t n_probe;
+    uint64_t slice_len, slice_rem;  // n_probe / gridDim.x and n_probe % gridDim.x
     uint32_t npart;
     uint32_t slot_mask;   // table slots - 1
     uint32_t max_keys;    // largest build partition the table accepts
@@ -502,9 +517,9 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
     const uint32_t nslots = p.slot_mask + 1;
     const int tid = threadIdx.x;
 
-    const uint64_t per = p.n_probe / gridDim.x, rem = p.n_probe % gridDim.x;
-    const uint64_t lo = per * blockIdx.x + min((uint64_t)blockIdx.x, rem);
-    const uint64_t hi = lo + per + (blockIdx.x < rem ? 1 : 0);
+    // Slice of the partitioned probe relation owned by this CTA (the host did the division).
+    const uint64_t lo = p.slice_len * blockIdx.x + min((uint64_t)blockIdx.x, p.slice_rem);
+    const uint64_t hi = lo + p.slice_len + (blockIdx.x < p.slice_rem ? 1 : 0);
     if (tid == 0) block_count = 0;
     uint64_t build_ns = 0, probe_ns = 0;
     uint32_t count = 0;
@@ -526,53 +541,71 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             if (r1 - r0 > p.max_keys) continue;  // global-table path
 
             const uint64_t t0 = globaltimer_ns();
-            __syncthreads();  // previous partition's probes are done with the table
+            cta_sync();  // previous partition's probes are done with the table
             for (uint32_t i = tid; i < nslots; i += TPB) table[i] = kEmptyKey;
             if (tid == 0) has_empty_key = 0;
-            __syncthreads();
-            for (uint64_t i = r0 + tid; i < r1; i += TPB) {
-                const uint64_t key = __ldg(reinterpret_cast<const unsigned long long*>(p.build + i));
-                if (key == kEmptyKey) {
-                    has_empty_key = 1;
-                    continue;
+            cta_sync();
+            // Warp-converged insertion: every lane of a warp runs the same number of loop trips
+            // (vote on `pending`), so no per-lane loop ever splits the warp (see cta_sync()).
+            for (uint64_t i0 = r0; i0 < r1; i0 += TPB) {
+                const uint64_t i = i0 + tid;
+                uint64_t key = 0;
+                bool pending = i < r1;
+                if (pending) {
+                    key = __ldg(reinterpret_cast<const unsigned long long*>(p.build + i));
+                    if (key == kEmptyKey) {
+                        has_empty_key = 1;
+                        pending = false;
+                    }
                 }
                 uint32_t slot = (uint32_t)(hash_key<HASH>(key, p.hp) >> p.hash_shift) & p.slot_mask;
-                for (;;) {
-                    const unsigned long long old = atomicCAS(
-                        reinterpret_cast<unsigned long long*>(table + slot), kEmptyKey, key);
-                    if (old == kEmptyKey || old == key) break;
-                    slot = (slot + 1) & p.slot_mask;
+                while (__any_sync(0xffffffffu, pending)) {
+                    if (pending) {
+                        const unsigned long long old = atomicCAS(
+                            reinterpret_cast<unsigned long long*>(table + slot), kEmptyKey, key);
+                        if (old == kEmptyKey || old == key) pending = false;
+                        else slot = (slot + 1) & p.slot_mask;
+                    }
                 }
             }
-            __syncthreads();
+            cta_sync();
             const uint64_t t1 = globaltimer_ns();
             const uint32_t sentinel_hit = has_empty_key;
 
             constexpr int U = 4;
             for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
                 uint64_t key[U];
+                uint32_t slot[U];
+                bool pending[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint64_t i = i0 + (uint64_t)u * TPB + tid;
-                    key[u] = i < s1 ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
+                    pending[u] = i < s1;
+                    key[u] = pending[u] ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const uint64_t i = i0 + (uint64_t)u * TPB + tid;
-                    if (i >= s1) continue;
-                    if (key[u] == kEmptyKey) {
+                    if (pending[u] && key[u] == kEmptyKey) {
                         count += sentinel_hit;
-                        continue;
+                        pending[u] = false;
                     }
-                    uint32_t slot = (uint32_t)(hash_key<HASH>(key[u], p.hp) >> p.hash_shift) & p.slot_mask;
-                    for (;;) {
-                        const uint64_t t = table[slot];
-                        if (t == key[u]) {
-                            ++count;
-                            break;
+                    slot[u] = (uint32_t)(hash_key<HASH>(key[u], p.hp) >> p.hash_shift) & p.slot_mask;
+                }
+                // warp-converged linear probing, U independent probes in flight per lane
+                while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pending[u]) {
+                            const uint64_t t = table[slot[u]];
+                            if (t == key[u]) {
+                                ++count;
+                                pending[u] = false;
+                            } else if (t == kEmptyKey) {
+                                pending[u] = false;
+                            } else {
+                                slot[u] = (slot[u] + 1) & p.slot_mask;
+                            }
                         }
-                        if (t == kEmptyKey) break;
-                        slot = (slot + 1) & p.slot_mask;
                     }
                 }
             }
@@ -581,13 +614,13 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             probe_ns += t2 - t1;
         }
     }
-    __syncthreads();
+    cta_sync();
     // block reduction of the match count
     uint32_t c = count;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((tid & 31) == 0 && c) atomicAdd(&block_count, (unsigned long long)c);
-    __syncthreads();
+    cta_sync();
     if (tid == 0) {
         if (block_count) atomicAdd(p.matches, block_count);
         p.cta_times[2 * blockIdx.x] = build_ns;
@@ -642,29 +675,31 @@ __device__ __forceinline__ bool gt_selected(const GtParams& p, uint64_t h) {
 template <int HASH, bool POW2>
 __global__ void __launch_bounds__(256) gt_build(GtParams p) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        const uint64_t key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i));
+    // uniform trip count per warp; per-lane work is predicated (warp-converged loops, see cta_sync())
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        bool pending = i < p.n;
+        const uint64_t key = pending ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
         const uint64_t h = hash_key<HASH>(key, p.hp);
-        if (!gt_selected<POW2>(p, h)) continue;
-        if (key == kEmptyKey) {
+        if (pending && !gt_selected<POW2>(p, h)) pending = false;
+        if (pending && key == kEmptyKey) {
             p.flags[0] = 1;
-            continue;
+            pending = false;
         }
         uint64_t bucket = (h >> p.hash_shift) & p.bucket_mask;
-        bool done = false;
-        while (!done) {
-            unsigned long long* b = reinterpret_cast<unsigned long long*>(p.table + bucket * 4);
-#pragma unroll
-            for (int s = 0; s < 4 && !done; ++s) {
-                unsigned long long cur = b[s];
-                if (cur == key) {
-                    done = true;
-                } else if (cur == kEmptyKey) {
-                    const unsigned long long old = atomicCAS(b + s, kEmptyKey, key);
-                    done = (old == kEmptyKey || old == key);
+        uint32_t s = 0;  // slot inside the bucket
+        while (__any_sync(0xffffffffu, pending)) {
+            if (pending) {
+                unsigned long long* slot = reinterpret_cast<unsigned long long*>(p.table + bucket * 4 + s);
+                unsigned long long cur = *slot;
+                if (cur == kEmptyKey) cur = atomicCAS(slot, kEmptyKey, key);
+                if (cur == kEmptyKey || cur == key) {
+                    pending = false;
+                } else if (++s == 4) {
+                    s = 0;
+                    bucket = (bucket + 1) & p.bucket_mask;
                 }
             }
-            bucket = (bucket + 1) & p.bucket_mask;
         }
     }
 }
@@ -675,42 +710,50 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
     const uint32_t sentinel_hit = p.flags[0];
     uint32_t count = 0;
     constexpr int U = 4;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < p.n; i0 += stride * U) {
-        uint64_t key[U];
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += stride * U) {
+        uint64_t key[U], bucket[U];
+        bool pending[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint64_t i = i0 + (uint64_t)u * stride;
-            key[u] = i < p.n ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
+            const uint64_t i = base + (uint64_t)u * stride + threadIdx.x;
+            pending[u] = i < p.n;
+            key[u] = pending[u] ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (i0 + (uint64_t)u * stride >= p.n) continue;
             const uint64_t h = hash_key<HASH>(key[u], p.hp);
-            if (!gt_selected<POW2>(p, h)) continue;
-            if (key[u] == kEmptyKey) {
+            if (pending[u] && !gt_selected<POW2>(p, h)) pending[u] = false;
+            if (pending[u] && key[u] == kEmptyKey) {
                 count += sentinel_hit;
-                continue;
+                pending[u] = false;
             }
-            uint64_t bucket = (h >> p.hash_shift) & p.bucket_mask;
-            for (;;) {
-                const ulonglong2* b = reinterpret_cast<const ulonglong2*>(p.table + bucket * 4);
-                const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
-                if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
-                    ++count;
-                    break;
+            bucket[u] = (h >> p.hash_shift) & p.bucket_mask;
+        }
+        while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (pending[u]) {
+                    const ulonglong2* b = reinterpret_cast<const ulonglong2*>(p.table + bucket[u] * 4);
+                    const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
+                    if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
+                        ++count;
+                        pending[u] = false;
+                    } else if (k23.y == kEmptyKey) {
+                        pending[u] = false;  // slots fill in order: last one free => bucket not full
+                    } else {
+                        bucket[u] = (bucket[u] + 1) & p.bucket_mask;
+                    }
                 }
-                if (k23.y == kEmptyKey) break;  // slots fill in order: last free => bucket not full
-                bucket = (bucket + 1) & p.bucket_mask;
             }
         }
     }
     __shared__ unsigned long long block_count;
     if (threadIdx.x == 0) block_count = 0;
-    __syncthreads();
+    cta_sync();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
     if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
-    __syncthreads();
+    cta_sync();
     if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
 }
 
