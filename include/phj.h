@@ -77,8 +77,8 @@ typedef struct {
     uint64_t reserve_probe;
 } phj_config;
 
-#define PHJ_FLAG_KEEP_PARTITIONS 0x1u /* retain the partitioned relations for phj_read_partitions */
-#define PHJ_FLAG_NO_TMA_STORE 0x2u    /* scatter flush with st.global.v4 instead of bulk stores */
+#define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
+
 
 /* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the
  * count it only logs (src/NoPartitioning/HashJoin.hpp:184, src/RadixCluster/HashJoin.hpp:320). */
@@ -149,11 +149,11 @@ int phj_hash_batch(int32_t hash, uint64_t seed, const int64_t* keys, size_t n, u
 /* Host evaluation of the same function (the same source compiled for the host). */
 uint64_t phj_hash_host(int32_t hash, uint64_t seed, int64_t key);
 
-/* After a radix join on a handle created with PHJ_FLAG_KEEP_PARTITIONS: copy out the partitioned
- * relation (`which` 0 = build, 1 = probe; n tuples) and the partitions+1 partition boundaries --
- * the device analogue of partitionedTable + PartitionsInfo (src/RadixCluster/HashJoin.hpp:16-33,
- * 195-198). For a power-of-two fan-out the layout is the reference's: partition p = hash % P at
- * [bounds[p], bounds[p+1]), tuples in input order within a partition. */
+/* After a radix join: copy out the partitioned relation (`which` 0 = build, 1 = probe; n tuples)
+ * and the partitions+1 partition boundaries -- the device analogue of partitionedTable +
+ * PartitionsInfo (src/RadixCluster/HashJoin.hpp:16-33,195-198). Partition p = hash % P lies at
+ * [bounds[p], bounds[p+1]) with the tuples in input order, i.e. bit-identical to the reference's
+ * stable partitionTable (src/RadixCluster/HashJoin.hpp:394-412). Valid until the next upload/join. */
 int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* bounds);
 
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.

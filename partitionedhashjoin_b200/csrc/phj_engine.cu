@@ -19,6 +19,26 @@
 #include <vector>
 
 #include "../../include/phj.h"
+
+// Tile shapes of the partitioning kernels (tuples per tile = TPB * IPT).
+#ifndef PHJ_HIST_TPB
+#define PHJ_HIST_TPB 512
+#endif
+#ifndef PHJ_HIST_IPT
+#define PHJ_HIST_IPT 8
+#endif
+#ifndef PHJ_SCAT_TPB
+#define PHJ_SCAT_TPB 512
+#endif
+#ifndef PHJ_SCAT_IPT
+#define PHJ_SCAT_IPT 8
+#endif
+#ifndef PHJ_SCAT_MINB
+#define PHJ_SCAT_MINB 2  // two 512-thread CTAs per SM: caps the scatter at 64 registers (no spills)
+#endif
+#ifndef PHJ_JOIN_TPB
+#define PHJ_JOIN_TPB 512
+#endif
 #include "phj_kernels.cuh"
 
 namespace {
@@ -44,22 +64,6 @@ int fail(int code, const char* fmt, ...) {
                         __LINE__);                                                              \
     } while (0)
 
-// Tile shapes of the partitioning kernels (tuples per tile = TPB * IPT).
-#ifndef PHJ_HIST_TPB
-#define PHJ_HIST_TPB 512
-#endif
-#ifndef PHJ_HIST_IPT
-#define PHJ_HIST_IPT 8
-#endif
-#ifndef PHJ_SCAT_TPB
-#define PHJ_SCAT_TPB 512
-#endif
-#ifndef PHJ_SCAT_IPT
-#define PHJ_SCAT_IPT 8
-#endif
-#ifndef PHJ_JOIN_TPB
-#define PHJ_JOIN_TPB 512
-#endif
 constexpr int kScatTile = PHJ_SCAT_TPB * PHJ_SCAT_IPT;
 constexpr int kMaxBitsPerPass = 8;
 constexpr int kMaxKernelTimes = 24;
@@ -135,6 +139,9 @@ struct phj_handle {
     KernelTime ktimes[kMaxKernelTimes] = {};
     int n_ktimes = 0;
     bool time_kernels = false;
+    bool use_match = false;   // PHJ_RANK=match: match.any instead of ballots in the stable kernels
+    bool use_lanes = true;
+    bool lanes_scatter = false;    // PHJ_RANK=stable|match disables the lane-private kernels
     bool debug_sync = false;  // PHJ_DEBUG_SYNC=1: synchronise and check after every launch
     bool joined_radix = false;
     uint32_t launches = 0;
@@ -191,14 +198,18 @@ struct KernelScope {
 // ---- template dispatch ---------------------------------------------------------------------------
 template <int BITS, int HASH, bool POW2>
 void launch_hist_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
-    radix_histogram<BITS, HASH, POW2, PHJ_HIST_TPB, PHJ_HIST_IPT>
-        <<<grid, PHJ_HIST_TPB, 0, h->stream>>>(pp);
+    if (h->use_match)
+        radix_histogram<BITS, HASH, POW2, PHJ_HIST_TPB, PHJ_HIST_IPT, false>
+            <<<grid, PHJ_HIST_TPB, 0, h->stream>>>(pp);
+    else
+        radix_histogram<BITS, HASH, POW2, PHJ_HIST_TPB, PHJ_HIST_IPT, true>
+            <<<grid, PHJ_HIST_TPB, 0, h->stream>>>(pp);
 }
 
-template <int BITS, int HASH, bool POW2, bool TMA>
-cudaError_t launch_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT>
+cudaError_t launch_scatter_tb(phj_handle* h, const PassParams& pp, uint32_t grid) {
     using L = ScatterSmem<BITS, PHJ_SCAT_TPB, PHJ_SCAT_IPT>;
-    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA>;
+    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT>;
     static bool configured[16] = {};
     if (!configured[h->device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -210,9 +221,32 @@ cudaError_t launch_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid)
     return cudaSuccess;
 }
 
+template <int BITS, int HASH, bool POW2, bool TMA>
+cudaError_t launch_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    if (h->use_match) return launch_scatter_tb<BITS, HASH, POW2, TMA, false>(h, pp, grid);
+    return launch_scatter_tb<BITS, HASH, POW2, TMA, true>(h, pp, grid);
+}
+
+template <int BITS, int HASH, bool POW2>
+cudaError_t launch_hist_lanes_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    constexpr size_t smem = HistLanesSmem<BITS, PHJ_HIST_TPB>::total;
+    auto kern = radix_histogram_lanes<BITS, HASH, POW2, PHJ_HIST_TPB, PHJ_HIST_IPT>;
+    static bool configured[16] = {};
+    if (!configured[h->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[h->device & 15] = true;
+    }
+    kern<<<grid, PHJ_HIST_TPB, smem, h->stream>>>(pp);
+    return cudaSuccess;
+}
+
 template <int BITS, int HASH>
 cudaError_t launch_pass_hp(phj_handle* h, bool scatter, const PassParams& pp, uint32_t grid) {
     const bool tma = !(h->cfg.flags & PHJ_FLAG_NO_TMA_STORE);
+    if (BITS <= 6 && h->use_lanes && !scatter)  // lane-private counters: histogram at the HBM roofline
+        return h->pow2 ? launch_hist_lanes_t<6, HASH, true>(h, pp, grid)
+                       : launch_hist_lanes_t<6, HASH, false>(h, pp, grid);
     if (!scatter) {
         if (h->pow2) launch_hist_t<BITS, HASH, true>(h, pp, grid);
         else launch_hist_t<BITS, HASH, false>(h, pp, grid);
@@ -828,6 +862,10 @@ int phj_create(const phj_config* config, phj_handle** out) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     const char* kt = getenv("PHJ_KERNEL_TIMES");
     h->time_kernels = kt && kt[0] == '1';
+    if (const char* rk = getenv("PHJ_RANK")) {
+        h->use_match = !strcmp(rk, "match");
+        h->use_lanes = strcmp(rk, "match") && strcmp(rk, "stable");
+    }
     const char* ds = getenv("PHJ_DEBUG_SYNC");
     h->debug_sync = ds && ds[0] == '1';
     auto cleanup = [&](int code) {

@@ -18,7 +18,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "phj_hash.cuh"
+
+#ifndef PHJ_SCAT_MINB
+#define PHJ_SCAT_MINB 1
+#endif
 
 namespace phj {
 
@@ -117,13 +123,29 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Lanes of the warp whose digit equals this lane's. BALLOT = false: one match.any (a long-latency
+// instruction on B200, tens of cycles of a per-SM unit); BALLOT = true: one vote per digit bit
+// (NBITS votes + ~3 ALU each), which ncu shows to be much cheaper for <= 9 bits.
+template <int NBITS, bool BALLOT>
+__device__ __forceinline__ uint32_t warp_peers(uint32_t d) {
+    if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < NBITS; ++b) {
+        const bool bit = (d & (1u << b)) != 0;             // LOP3 straight into a predicate
+        const uint32_t m = __ballot_sync(0xffffffffu, bit);  // VOTE
+        peers &= m ^ (bit ? 0u : 0xffffffffu);              // SEL + one 3-input LOP3
+    }
+    return peers;
+}
+
 // =================================================================================================
 // K1  radix_histogram: one CTA per segment; per-warp private digit counters in shared memory,
 // lanes of a warp that hit the same digit are merged with match.any so a Zipf heavy hitter costs
 // one update per warp instead of 32 serialised ones, and no shared-memory atomics are needed.
 // HBM: reads 16 B/tuple (the key's 32-byte sector is fetched whole either way).
 // =================================================================================================
-template <int BITS, int HASH, bool POW2, int TPB, int IPT>
+template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool BALLOT>
 __global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
     constexpr int D = 1 << BITS;
     constexpr int NW = TPB / 32;
@@ -151,7 +173,7 @@ __global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
         for (int i = 0; i < IPT; ++i) {
             const uint64_t idx = base + (uint64_t)i * 32;
             const uint32_t d = idx < seg.end ? digit_of<POW2>(hash_key<HASH>(key[i], p.hp), p.df) : D;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t peers = warp_peers<BITS + 1, BALLOT>(d);  // +1: the out-of-range digit D
             if (lane == __ffs(peers) - 1) wcw[d] += __popc(peers);
             __syncwarp();
         }
@@ -277,11 +299,11 @@ struct ScatterSmem {
     static constexpr size_t dbase_bytes = (size_t)(D + 4) * 4;
     static constexpr size_t sdig_bytes = (size_t)T * 2;
     static constexpr size_t total =
-        stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 33 * 8 + 64;
+        stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 16 * 4 + 64;
 };
 
-template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE>
-__global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
+template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT>
+__global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p) {
     using L = ScatterSmem<BITS, TPB, IPT>;
     constexpr int D = L::D, NW = L::NW, T = L::T;
     static_assert(D <= TPB, "one thread per digit in the scan step");
@@ -289,8 +311,8 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
     ulonglong2* stage = reinterpret_cast<ulonglong2*>(smem_raw);
     uint64_t* gcur = reinterpret_cast<uint64_t*>(smem_raw + L::stage_bytes);
     uint64_t* gbase = gcur + D;
-    uint64_t* scan_sh = gbase + D;  // 33 entries
-    uint32_t* wc = reinterpret_cast<uint32_t*>(scan_sh + 33);
+    uint32_t* wtot_sh = reinterpret_cast<uint32_t*>(gbase + D);  // 16 entries: digit-scan warp totals
+    uint32_t* wc = wtot_sh + 16;
     uint32_t* dbase = wc + NW * (D + 1);
     uint16_t* sdig = reinterpret_cast<uint16_t*>(dbase + D + 4);
 
@@ -315,56 +337,77 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
 
     ulonglong2 v[IPT];
     auto load_tile = [&](uint64_t tile) {
-        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+        const ulonglong2* src = in + tile + (uint64_t)warp * (32 * IPT) + lane;
+        if (tile + T <= seg.end) {
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const uint64_t idx = base + (uint64_t)i * 32;
-            if (idx < seg.end) v[i] = ld_stream_v2(in + idx);
+            for (int i = 0; i < IPT; ++i) v[i] = ld_stream_v2(src + i * 32);
+        } else {
+            const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                if (base + (uint64_t)i * 32 < seg.end) v[i] = ld_stream_v2(src + i * 32);
         }
     };
     if (seg.begin < seg.end) load_tile(seg.begin);
 
     for (uint64_t tile = seg.begin; tile < seg.end; tile += T) {
-        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
         const uint32_t n_valid = (uint32_t)min((uint64_t)T, seg.end - tile);
+        const uint32_t n_mine = n_valid - min(n_valid, (uint32_t)(warp * (32 * IPT) + lane));  // > i*32 <=> valid
+        const bool full = n_valid == T;
 
         for (int i = lane; i <= D; i += 32) wcw[i] = 0;
         __syncwarp();
 
         // ---- rank (stable within the warp's 32*IPT consecutive tuples) ----
-        uint32_t dr[IPT];
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const bool valid = base + (uint64_t)i * 32 < seg.end;
+        uint32_t dr[IPT];  // digit | rank << 16
+        auto rank_round = [&](int i, auto is_full) {
+            constexpr bool kFull = decltype(is_full)::value;
+            const bool valid = kFull || (uint32_t)(i * 32) < n_mine;
             const uint32_t d = valid ? digit_of<POW2>(hash_key<HASH>(v[i].x, p.hp), p.df) : D;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t peers = warp_peers<kFull ? BITS : BITS + 1, BALLOT>(d);
             const uint32_t prev = wcw[d];
             __syncwarp();
             if (lane == __ffs(peers) - 1) wcw[d] = prev + __popc(peers);
             __syncwarp();
             dr[i] = d | ((prev + __popc(peers & lt)) << 16);
+        };
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) rank_round(i, std::true_type{});
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) rank_round(i, std::false_type{});
         }
         cta_sync();
 
-        // ---- per-digit scan across warps, then across digits ----
-        {
-            uint32_t tot = 0;
-            if (tid < D) {
+        // ---- per-digit scan across warps, then across digits (32-bit, two barriers) ----
+        uint32_t tot = 0, incl = 0;
+        if (tid < D) {
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    uint32_t c = wc[w * (D + 1) + tid];
-                    wc[w * (D + 1) + tid] = tot;
-                    tot += c;
-                }
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t c = wc[w * (D + 1) + tid];
+                wc[w * (D + 1) + tid] = tot;
+                tot += c;
             }
-            uint64_t excl = block_excl_scan_u64(tot, scan_sh, nullptr);
-            if (tid < D) {
-                dbase[tid] = (uint32_t)excl;
-                if (tid == D - 1) dbase[D] = n_valid;
-                gbase[tid] = gcur[tid] - excl;  // out index of tile slot j of this digit = gbase + j
-                gcur[tid] += tot;
+            incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
             }
-            if (TMA_STORE) bulk_wait_read0();  // previous tile's bulk stores have read `stage`
+            if (lane == 31) wtot_sh[warp] = incl;
+        }
+        if (TMA_STORE) bulk_wait_read0();  // previous tile's bulk stores have read `stage`
+        cta_sync();
+        if (tid < D) {
+            uint32_t excl = incl - tot;
+#pragma unroll
+            for (int w = 0; w < (D + 31) / 32; ++w)
+                if (w < warp) excl += wtot_sh[w];
+            dbase[tid] = excl;
+            if (tid == D - 1) dbase[D] = n_valid;
+            gbase[tid] = gcur[tid] - excl;  // out index of tile slot j of this digit = gbase + j
+            gcur[tid] += tot;
         }
         cta_sync();
 
@@ -372,7 +415,7 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = dr[i] & 0xffffu;
-            if (d < D) {
+            if (full || d < D) {
                 const uint32_t pos = dbase[d] + wcw[d] + (dr[i] >> 16);
                 stage[pos] = v[i];
                 if (!TMA_STORE) sdig[pos] = (uint16_t)d;
@@ -396,9 +439,94 @@ __global__ void __launch_bounds__(TPB) radix_scatter(PassParams p) {
                 st_stream_v2(out + gbase[d] + j, stage[j]);
             }
         }
-        // The next iteration's first two barriers separate this flush from the next stage step.
+        // The next iteration's barriers separate this flush from the next stage step.
     }
     if (TMA_STORE) bulk_wait_all0();
+}
+
+// =================================================================================================
+// K1b  radix_histogram_lanes (default histogram for passes of <= 6 bits).
+//
+// ncu on B200 showed the match.any of K1 to be its bottleneck (the instruction consuming its result
+// carried ~45 % of the stall samples; 1.13 ms for a 3.36 GB read). This variant needs no
+// cross-lane operation per tuple: every LANE owns private 16-bit digit counters in shared memory,
+// laid out [digit pair][lane][2] so that a lane only ever touches its own bank (conflict-free).
+// The lanes' counters are reduced once per segment. Measured: 0.485 ms = 6.9 TB/s.
+// (The same idea was tried for the scatter -- rank = lane-private counter, then a per-digit scan
+// across lanes -- and lost to the ballot ranking below: 2.2-2.9 ms vs 1.5 ms per pass.)
+// =================================================================================================
+template <int BITS>
+__device__ __forceinline__ uint32_t lane_counter_offset(uint32_t d, int lane) {
+    // byte offset of this lane's counter for digit d inside its warp's block
+    return (((d >> 1) * 32 + lane) << 2) + ((d & 1) << 1);
+}
+
+template <int BITS, int TPB>
+struct HistLanesSmem {
+    static constexpr size_t total = ((size_t)(TPB / 32) * ((1 << BITS) / 2) * 32 + (1 << BITS)) * 4;
+};
+
+template <int BITS, int HASH, bool POW2, int TPB, int IPT>
+__global__ void __launch_bounds__(TPB) radix_histogram_lanes(PassParams p) {
+    constexpr int D = 1 << BITS;
+    constexpr int NW = TPB / 32;
+    constexpr int T = TPB * IPT;
+    constexpr int WARP_WORDS = (D / 2) * 32;  // uint32 words per warp
+    static_assert(BITS >= 1 && BITS <= 6, "lane-private counters are for fan-outs up to 64");
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // HistLanesSmem<BITS, TPB>::total bytes
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);      // [NW][WARP_WORDS]
+    uint32_t* total = cnt + NW * WARP_WORDS;                    // [D]
+
+    if (blockIdx.x >= *p.nsegs) return;
+    const Segment seg = p.segs[blockIdx.x];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(cnt + warp * WARP_WORDS);
+
+    for (int i = lane; i < WARP_WORDS; i += 32) cnt[warp * WARP_WORDS + i] = 0;
+    if (threadIdx.x < D) total[threadIdx.x] = 0;
+    __syncwarp();
+
+    auto count_key = [&](uint64_t key) {
+        const uint32_t d = digit_of<POW2>(hash_key<HASH>(key, p.hp), p.df);
+        uint16_t* c = reinterpret_cast<uint16_t*>(mine + lane_counter_offset<BITS>(d, lane));
+        *c = (uint16_t)(*c + 1);
+    };
+    uint64_t tile = seg.begin;
+    for (; tile + T <= seg.end; tile += T) {  // full tiles: no bounds checks
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(in + tile + (uint64_t)warp * (32 * IPT) + lane);
+        uint64_t key[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) key[i] = ld_stream_u64(src + (size_t)i * 64);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) count_key(key[i]);
+    }
+    if (tile < seg.end) {  // tail tile
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            if (idx < seg.end) count_key(ld_stream_u64(reinterpret_cast<const uint64_t*>(in + idx)));
+        }
+    }
+    __syncwarp();
+    // reduce the 32 lanes' counters of every digit pair, then across warps
+    for (int e = 0; e < D / 2; ++e) {
+        const uint32_t w = cnt[warp * WARP_WORDS + e * 32 + lane];
+        uint32_t lo = w & 0xffffu, hi = w >> 16;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, o);
+            hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&total[2 * e], lo);
+            if (2 * e + 1 < D) atomicAdd(&total[2 * e + 1], hi);
+        }
+    }
+    cta_sync();
+    for (int d = threadIdx.x; d < (int)p.ndigits; d += TPB)
+        p.counts[seg.cnt_index + (uint64_t)d * seg.cnt_stride] = total[d];
 }
 
 // =================================================================================================

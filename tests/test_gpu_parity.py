@@ -75,8 +75,9 @@ def test_counts_match_reference_golden(phj, oracle, name):
     for bits in ((6, 6), (8, 4), (3, 8), (8, 8), (5, 0), (1, 1)):
         res = run(phj, R, S, "radix-partitioning", partitions=1 << sum(bits), radix_bits=bits)
         assert res["matches"] == want, (name, bits, res)
-    res = run(phj, R, S, "radix-partitioning", partitions=4096, flags=phj.FLAG_NO_TMA_STORE)
-    assert res["matches"] == want
+    for flags in (phj.FLAG_NO_TMA_STORE,):
+        res = run(phj, R, S, "radix-partitioning", partitions=4096, flags=flags)
+        assert res["matches"] == want, (name, flags, res)
 
 
 @pytest.mark.parametrize("hash", HASHES)
@@ -115,23 +116,37 @@ def test_reuse_handle_and_reupload(phj, oracle):
 
 
 # ---- intermediate state: the partitioned relations equal the reference algorithm's ---------------
+def assert_same_partitioning(got, gb, want, wb, n, exact_order):
+    """Boundaries identical; partition contents identical -- in input order when `exact_order`,
+    else as multisets (the payload is the input index, so sorting by it inside each partition
+    restores input order)."""
+    assert gb[:-1].tolist() == wb[:, 0].tolist() and int(gb[-1]) == n
+    if not exact_order:
+        part_of = np.repeat(np.arange(wb.shape[0]), (wb[:, 1] - wb[:, 0]).astype(np.int64))
+        order = np.lexsort((got["payload"], part_of))
+        got = got[order]
+    assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+
+
 @pytest.mark.parametrize("hash_id,hash", list(enumerate(HASHES)))
 @pytest.mark.parametrize("P,bits", [(64, (0, 0)), (4096, (6, 6)), (2048, (0, 0)), (256, (8, 0)), (256, (4, 4)),
-                                    (100, (0, 0)), (1000, (0, 0)), (65536, (8, 8)), (1, (0, 0))])
+                                    (100, (0, 0)), (1000, (0, 0)), (65536, (8, 8)), (1, (0, 0)), (8192, (7, 6))])
 def test_partition_layout_equals_oracle(phj, oracle, P, bits, hash_id, hash):
     """partitionedTable + PartitionsInfo (src/RadixCluster/HashJoin.hpp:16-33,195-198,394-412):
-    partition p = Hash(id, P) at [bounds[p], bounds[p+1]), input order kept -- bit-identical."""
+    partition p = Hash(id, P) at [bounds[p], bounds[p+1]), input order kept: the partitioned
+    relations are bit-identical to the reference algorithm's output."""
     R = _cases.tuples(_cases.splitmix64(30011, 9).astype(np.int64) % 5003)
     S = _cases.tuples(_cases.splitmix64(250007, 10).astype(np.int64) % 7001)
-    with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P) as e:
-        e.upload(R, S)
-        res = e.join()
-        assert res["matches"] == oracle.count_by_sort(R, S)
-        for which, rel in ((0, R), (1, S)):
-            got, gb = e.read_partitions(which, P)
-            want, wb = oracle.radix_partition(rel, P, hash_id, SEED_P, workers=1)
-            assert gb[:-1].tolist() == wb[:, 0].tolist() and int(gb[-1]) == rel.shape[0]
-            assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+    want_count = oracle.count_by_sort(R, S)
+    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True)):
+        with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P,
+                        flags=flags) as e:
+            e.upload(R, S)
+            assert e.join()["matches"] == want_count
+            for which, rel in ((0, R), (1, S)):
+                got, gb = e.read_partitions(which, P)
+                want, wb = oracle.radix_partition(rel, P, hash_id, SEED_P, workers=1)
+                assert_same_partitioning(got, gb, want, wb, rel.shape[0], exact)
 
 
 def test_partition_layout_skewed_generator_data(phj, oracle):
@@ -140,14 +155,17 @@ def test_partition_layout_skewed_generator_data(phj, oracle):
     S = np.empty(ns, dtype=phj.TUPLE_DTYPE)
     phj.fill_sequential(R, 1)
     phj.fill_zipf(S, 1.25, 1, nr, 4711, 16)
-    for flags in (0, phj.FLAG_NO_TMA_STORE):
+    want, wb = oracle.radix_partition(S, 4096, 0, SEED_P, workers=1)
+    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True)):
         with phj.Engine("radix-partitioning", partitions=4096, hash_seed=SEED_P, flags=flags) as e:
             e.upload(R, S)
             assert e.join()["matches"] == ns
             got, gb = e.read_partitions(1, 4096)
-            want, wb = oracle.radix_partition(S, 4096, 0, SEED_P, workers=1)
-            assert gb[:-1].tolist() == wb[:, 0].tolist()
-            assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+            assert_same_partitioning(got, gb, want, wb, ns, exact)
+            if not exact:  # deterministic: a second run gives the very same bytes
+                assert e.join()["matches"] == ns
+                again, _ = e.read_partitions(1, 4096)
+                assert (again["id"] == got["id"]).all() and (again["payload"] == got["payload"]).all()
 
 
 def test_oversize_partitions_use_the_global_table(phj, oracle):
@@ -211,6 +229,10 @@ def test_full_size_partition_properties(phj, oracle, full_relations):
         e.upload(R, S)
         assert e.join()["matches"] == S.shape[0]
         got, bounds = e.read_partitions(1, P)
+    check_full_size_partitioning(oracle, S, got, bounds, P, stable=True)
+
+
+def check_full_size_partitioning(oracle, S, got, bounds, P, stable):
     assert int(bounds[0]) == 0 and int(bounds[-1]) == S.shape[0] and (np.diff(bounds.astype(np.int64)) >= 0).all()
     # permutation: payload is the input index, so the sorted payloads are 0..n-1 and ids follow
     assert int(got["payload"].sum(dtype=np.uint64)) == int(S["payload"].sum(dtype=np.uint64))
@@ -223,4 +245,5 @@ def test_full_size_partition_properties(phj, oracle, full_relations):
         a, b = int(bounds[p]), int(bounds[p + 1])
         part = oracle.hash_batch(0, SEED_P, got["id"][a:b]) % np.uint64(P)
         assert (part == p).all()
-        assert (np.diff(got["payload"][a:b]) > 0).all()
+        if stable:
+            assert (np.diff(got["payload"][a:b]) > 0).all()
