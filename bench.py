@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- join throughput (|R|+|S|) tuples/s of the radix-partitioned hash join on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one complete join (partition R and S, build + probe every partition, match count back
+on the host) of the workload BASELINE.json's metric is quoted on: configs[1], the 10 M x 200 M
+radix join with two partitioning passes and XXH3 ("uniform" keys = the reference generator at its
+minimum skew 0.01; --skew selects configs[2]/[3]). Prints ONE JSON line:
+
+  value      tuples/s with both relations already resident in HBM (CUDA events, max over ranks)
+  e2e        the same join through the C ABI's host entry point (phj_join_host): pinned host
+             relations are copied to the device inside the timed region, the count is read back
+  roofline   radix_scatter (the dominant kernel): algorithmic bytes per launch / its mean duration,
+             taken from CUDA events recorded around every launch of the timed steps
+  cpu_baseline  the UNMODIFIED reference's radix join (oracle/_ref) on this box's host cores
+
+--impl reference times that CPU implementation instead (rank 0 only).
+Only the reference / cpu_baseline legs touch oracle/; the GPU arm uses the product library alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BUILD, N_PROBE = 10_000_000, 200_000_000
+BASE_SEED, BATCHES = 12345, 64
+METRIC = "join throughput (|R|+|S|) tuples/sec"
+UNIT = "tuples/s"
+# ncu (profiles/r01_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum of one
+# radix_scatter launch at this workload
+SCATTER_DRAM_TRAFFIC_BYTES = 6.669e9
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+            time.sleep(0.25)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(phj, n_build, n_probe, skew, rank=0, pinned=True):
+    """Reference generator output (Sequential build side, Zipf probe side over [1, |R|])."""
+    if pinned:
+        Rp, Sp = phj.PinnedTuples(n_build), phj.PinnedTuples(n_probe)
+        R, S = Rp.array, Sp.array
+    else:
+        Rp = Sp = None
+        R, S = np.empty(n_build, dtype=phj.TUPLE_DTYPE), np.empty(n_probe, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1)
+    phj.fill_zipf(S, skew, 1, n_build, BASE_SEED + 1000 * rank, BATCHES)
+    return R, S, (Rp, Sp)
+
+
+def dist_setup(n_gpus):
+    """torch.distributed only for N > 1 (barrier + max over ranks + count all-reduce)."""
+    if n_gpus <= 1:
+        return None, 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if world != n_gpus:
+        raise SystemExit(f"--gpus {n_gpus} needs torchrun with {n_gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist, rank, world, local
+
+
+def reference_arm(args, rank):
+    """--impl reference: the unmodified reference radix join (oracle/_ref) on the host cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    ref = _oracle.Reference()  # nothing of the product is imported on this arm
+    # bounded sample: the whole build side and a prefix of the probe side, sized so that
+    # steps + warmup joins stay within ~2 minutes (and within the reference's per-join leak)
+    total = args.steps + args.warmup
+    n_probe = int(min(N_PROBE, max(10_000_000, N_PROBE * 6 // max(total, 1))))
+    n_probe -= n_probe % 1000
+    # inputs from the reference's own generators (Sequential + seeded Zipf batches)
+    R = ref.fill_sequential(N_BUILD, 1, threads=0)
+    S = ref.fill_zipf(n_probe, args.skew, 1, N_BUILD, BASE_SEED, BATCHES, threads=0)
+    workers = ref.default_workers()
+    times, matches = [], None
+    for i in range(total):
+        res = ref.join(R, S, 1, partitions=args.ref_partitions, threads=0, seeded=False)
+        matches = res["matches"]
+        if i >= args.warmup:
+            times.append((res["partition_ns"] + res["build_ns"] + res["probe_ns"]) / 1e9)
+    assert matches == n_probe, (matches, n_probe)
+    per_step = sum(times) / len(times)
+    value = (N_BUILD + n_probe) / per_step
+    sample = (f"reference RadixClustering::HashJoiner P={args.ref_partitions}, {N_BUILD} x {n_probe} "
+              f"(probe prefix of the 200 M workload), phase sum partition+build+probe, {workers} workers")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args, n_probe=n_probe),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "matches": matches,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_probe=N_PROBE, n_build=N_BUILD):
+    return {"workload": f"radix-cluster hash join {n_build // 10**6}M x {n_probe // 10**6}M, 2-pass radix "
+                        f"partitioning ({args.partitions} partitions), {args.hash}, Zipf skew {args.skew}"
+                        f"{' (uniform)' if args.skew <= 0.01 else ''}, count-only",
+            "primary": n_build, "secondary": n_probe, "skew": args.skew, "partitions": args.partitions,
+            "hash": args.hash, "tuple_bytes": 16, "l2_flush": "inputs (3.36 GB per GPU) are larger than L2"}
+
+
+def cpu_baseline_leg(args, R, S):
+    """The reference's own CPU radix join, timed on this box (rank 0, N = 1)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _oracle
+        ref = _oracle.Reference()
+    except Exception as e:  # the checker is optional for the GPU arm
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    workers = ref.default_workers()
+    t0 = time.time()
+    res = ref.join(R, S, 1, partitions=args.ref_partitions, threads=0, seeded=False)
+    wall = time.time() - t0
+    assert res["matches"] == S.shape[0], res
+    phase = (res["partition_ns"] + res["build_ns"] + res["probe_ns"]) / 1e9
+    return {"value": (R.shape[0] + S.shape[0]) / phase, "unit": UNIT, "cores": workers, "kind": "reference",
+            "sample": f"full workload, 1 run of the reference RadixClustering::HashJoiner P={args.ref_partitions} "
+                      f"({workers} workers): phases {res['partition_ns'] / 1e6:.0f}/{res['build_ns'] / 1e6:.0f}/"
+                      f"{res['probe_ns'] / 1e6:.0f} ms, wall incl. copies and allocation {wall:.1f} s",
+            "matches": res["matches"]}
+
+
+def gpu_arm(args):
+    dist, rank, world, local = dist_setup(args.gpus)
+    os.environ["PHJ_KERNEL_TIMES"] = "1"  # CUDA events around every kernel launch (roofline.achieved)
+    import partitionedhashjoin_b200 as phj
+    if phj.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+
+    if world > 1:
+        from partitionedhashjoin_b200 import multigpu
+        return multigpu.bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSampler,
+                              METRIC, UNIT, measured_hbm_peak)
+
+    R, S, keep = make_inputs(phj, N_BUILD, N_PROBE, args.skew)
+    n_tuples = R.shape[0] + S.shape[0]
+    eng = phj.Engine("radix-partitioning", partitions=args.partitions, hash=args.hash, device=local)
+    eng.upload(R, S)
+    for _ in range(args.warmup):
+        res = eng.join()
+    assert res["matches"] == S.shape[0], res
+
+    # ---- timed region: K joins, inputs resident in HBM ----
+    import ctypes as C
+    launches, kernel_ns = 0, {}
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        device_ns = 0
+        for _ in range(args.steps):
+            res = eng.join()  # synchronous: returns with the count on the host
+            device_ns += res["total_ns"]
+            launches += res["kernel_launches"]
+            for name, ns in eng.kernel_times():
+                kernel_ns.setdefault(name, []).append(ns)
+        wall = time.perf_counter() - t0
+    assert res["matches"] == S.shape[0], res
+    ms_per_step = device_ns / args.steps / 1e6
+    value = n_tuples / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_hbm_peak()
+    scat = [ns for name, v in kernel_ns.items() if name.startswith("radix_scatter") for ns in v]
+    scat_ms = sum(scat) / len(scat) / 1e6
+    alg_bytes = 32.0 * n_tuples  # every tuple is read once and written once: 16 B + 16 B
+    achieved = alg_bytes / (scat_ms / 1e3) / 1e9
+    per_kernel = {name: round(sum(v) / len(v) / 1e3, 1) for name, v in kernel_ns.items()}
+    kernel_share = sum(scat) / max(1, sum(sum(v) for v in kernel_ns.values()))
+
+    # ---- e2e: host relations in, count out, through phj_join_host ----
+    e2e_steps = max(3, min(args.steps, 8))
+    eng.join_host(R, S)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r2 = eng.join_host(R, S)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert r2["matches"] == S.shape[0]
+
+    # ---- the other configurations of BASELINE.json, a few steps each (informational) ----
+    others = {}
+    if not args.quick:
+        def few(engine, n=3):
+            engine.upload(R, S)
+            engine.join()
+            best = min(engine.join()["total_ns"] for _ in range(n))
+            return round(n_tuples / (best / 1e9) / 1e9, 2)
+        for h in ("xxh3", "murmur3", "city"):
+            if h != args.hash:
+                with phj.Engine("radix-partitioning", partitions=args.partitions, hash=h, device=local) as e2:
+                    others[f"radix_{h}_Gtuples_s"] = few(e2)
+        with phj.Engine("no-partitioning", device=local) as e2:
+            others["no_partitioning_Gtuples_s"] = few(e2)
+        for skew in (1.05, 1.25):
+            if abs(skew - args.skew) > 1e-9:
+                phj.fill_zipf(S, skew, 1, N_BUILD, BASE_SEED, BATCHES)
+                with phj.Engine("radix-partitioning", partitions=args.partitions, hash=args.hash, device=local) as e2:
+                    others[f"radix_zipf{skew}_Gtuples_s"] = few(e2)
+                with phj.Engine("no-partitioning", device=local) as e2:
+                    others[f"no_partitioning_zipf{skew}_Gtuples_s"] = few(e2)
+        phj.fill_zipf(S, args.skew, 1, N_BUILD, BASE_SEED, BATCHES)
+
+    cpu = cpu_baseline_leg(args, R, S) if not args.no_cpu_baseline else None
+    eng.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": n_tuples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]),
+                "d2h_bytes_per_step": int(r2["d2h_bytes"]),
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "radix_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": SCATTER_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scat_ms,
+                     "launches_per_step": len(scat) // args.steps, "share_of_step": kernel_share,
+                     "join_bytes_alg_96B_per_tuple_frac": 96.0 * n_tuples / (ms_per_step / 1e3) / 1e9 / peak},
+        "cpu_baseline": cpu, "clocks": clocks.summary(), "kernel_us": per_kernel,
+        "wall_ms_per_step": wall / args.steps * 1e3, "matches": res["matches"], "other_configs": others,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skew", type=float, default=0.01)
+    ap.add_argument("--hash", default="xxh3", choices=["xxh3", "murmur3", "city"])
+    ap.add_argument("--partitions", type=int, default=4096)
+    ap.add_argument("--ref-partitions", type=int, default=2048)
+    ap.add_argument("--quick", action="store_true", help="skip the informational extra configurations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", 0))
+        reference_arm(args, rank)
+        return
+    gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

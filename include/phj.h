@@ -98,6 +98,8 @@ typedef struct {
     uint64_t partitions; /* fan-out actually used */
     uint64_t fallback_partitions; /* partitions whose build side exceeded the shared-memory table
                                      and went through the global table instead */
+    uint64_t h2d_bytes; /* bytes copied host -> device by this call (phj_join_host), else 0 */
+    uint64_t d2h_bytes; /* bytes copied device -> host by this call (count, per-CTA phase times) */
 } phj_result;
 
 typedef struct phj_handle phj_handle;

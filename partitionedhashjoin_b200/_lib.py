@@ -55,6 +55,8 @@ class PhjResult(C.Structure):
         ("passes", C.c_uint32),
         ("partitions", C.c_uint64),
         ("fallback_partitions", C.c_uint64),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
     ]
 
     def as_dict(self):

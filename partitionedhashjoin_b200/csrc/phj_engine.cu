@@ -274,21 +274,15 @@ cudaError_t launch_pass(phj_handle* h, bool scatter, int bits, const PassParams&
     return launch_pass_b<8>(h, scatter, pp, grid);
 }
 
-template <int HASH>
-cudaError_t launch_join_t(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
-    auto kern = join_partitions<HASH, PHJ_JOIN_TPB>;
+cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
+    auto kern = join_partitions<PHJ_JOIN_TPB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     kern<<<grid, PHJ_JOIN_TPB, smem, h->stream>>>(jp);
     return cudaSuccess;
-}
-
-cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
-    switch (h->cfg.hash) {
-        case PHJ_HASH_MURMUR3: return launch_join_t<kMurmur3>(h, jp, grid, smem);
-        case PHJ_HASH_CITY: return launch_join_t<kCity>(h, jp, grid, smem);
-        default: return launch_join_t<kXXH3>(h, jp, grid, smem);
-    }
 }
 
 template <int HASH>
@@ -471,8 +465,12 @@ int build_plan(phj_handle* h) {
             }
         }
         // ---- join geometry ----
+        // Table of 32-byte buckets in shared memory: aim for a load factor of ~0.3 (nearly every
+        // probe ends in its home bucket) while the table stays <= 64 KB (3 CTAs per SM); beyond that
+        // accept ~0.6, and beyond 128 KB the partition goes through the global table.
         uint64_t mean = std::max<uint64_t>(1, h->n[0] / std::max<uint64_t>(1, h->P));
         uint32_t slots = 1024;
+        while (slots < 8192 && (double)slots < 3.2 * (double)mean) slots <<= 1;
         while (slots < 16384 && (double)slots < 1.6 * (double)mean) slots <<= 1;
         h->join_slots = slots;
         h->join_max_keys = slots / 4 * 3;
@@ -600,6 +598,7 @@ int join_no_partitioning(phj_handle* h, phj_result* out) {
     out->total_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[4]) * 1e6);
     out->passes = 0;
     out->partitions = 1;
+    out->d2h_bytes = 8;
     // 16 B/tuple streamed + one 32-byte table sector per build insert and per probe
     out->hbm_bytes_alg = 48ull * (h->n[0] + h->n[1]);
     return PHJ_OK;
@@ -704,10 +703,11 @@ int join_radix(phj_handle* h, phj_result* out) {
     jp.slice_len = h->n[1] / h->join_grid;
     jp.slice_rem = h->n[1] % h->join_grid;
     jp.npart = (uint32_t)h->nparts;
-    jp.slot_mask = h->join_slots - 1;
+    jp.bucket_mask = h->join_slots / 4 - 1;
+    jp.bucket_shift = 64 - ilog2_ceil(h->join_slots / 4);
     jp.max_keys = h->join_max_keys;
-    jp.hash_shift = table_hash_shift(h);
-    jp.hp = hp;
+    jp.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;  // odd
+    if (h->cfg.table_seed == 0) jp.table_mul = 0xBF58476D1CE4E5B9ULL;
     jp.matches = h->d_matches;
     jp.cta_times = h->d_cta_times;
     {
@@ -775,6 +775,7 @@ int join_radix(phj_handle* h, phj_result* out) {
     out->passes = two ? 2 : 1;
     out->partitions = h->P;
     out->fallback_partitions = oversize;
+    out->d2h_bytes = 8 + 4 + (uint64_t)h->join_grid * 16 + (oversize ? 8 : 0);
     // one histogram read + per pass (read + write) + one join read, 16 B each
     out->hbm_bytes_alg = 16ull * (2 + 2 * out->passes) * (h->n[0] + h->n[1]);
     h->joined_radix = true;
@@ -998,7 +999,10 @@ int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const p
     int rc = set_relations(h, build, n_build, probe, n_probe, false, &h2d);
     if (rc != PHJ_OK) return rc;
     rc = phj_join(h, out);
-    if (rc == PHJ_OK) out->h2d_ns = h2d;
+    if (rc == PHJ_OK) {
+        out->h2d_ns = h2d;
+        out->h2d_bytes = 16ull * (n_build + n_probe);
+    }
     return rc;
 }
 

@@ -613,8 +613,9 @@ __global__ void fill_empty_parent_bounds(FillEmptyParams p) {
 // =================================================================================================
 // K4+K5  join_partitions: the probe relation's partitioned array is cut into gridDim.x equal
 // slices; a CTA walks the partitions its slice overlaps, builds the partition's build-side keys
-// into a shared-memory open-addressing table (64-bit atomicCAS, duplicates collapse: the join
-// counts probe tuples with >= 1 match) and streams its share of the probe partition through it.
+// into a shared-memory table of 32-byte buckets (four keys; 64-bit atomicCAS on the first free
+// slot, overflow into the next bucket; duplicates collapse: the join counts probe tuples with
+// >= 1 match) and streams its share of the probe partition through it, one bucket read per step.
 // Equal slices make skew a non-issue: the partition holding a Zipf heavy hitter is simply probed
 // by many CTAs, each rebuilding the (L2-resident) build partition. Partitions whose build side
 // does not fit the table are left to gt_build/gt_probe and counted in *oversize.
@@ -628,21 +629,29 @@ struct JoinParams {
     uint64_t n_probe;
     uint64_t slice_len, slice_rem;  // n_probe / gridDim.x and n_probe % gridDim.x
     uint32_t npart;
-    uint32_t slot_mask;   // table slots - 1
-    uint32_t max_keys;    // largest build partition the table accepts
-    uint32_t hash_shift;  // table slot = (h >> hash_shift) & slot_mask
-    HashParams hp;
+    uint32_t bucket_mask;   // table buckets - 1 (a bucket = four 8-byte keys = one 32-byte line)
+    uint32_t bucket_shift;  // bucket = table_hash(key) >> bucket_shift
+    uint32_t max_keys;      // largest build partition the table accepts
+    uint64_t table_mul;     // odd multiplier of the table hash (derived from the table seed)
     unsigned long long* matches;
     uint64_t* cta_times;  // 2 per CTA: build ns, probe ns
 };
 
-template <int HASH, int TPB>
+// Hash of a key inside one partition's table. All keys of a partition share the partitioning hash's
+// low bits, so the table uses an independent multiplicative (Fibonacci-style) hash: 5 instructions
+// instead of a second 22-instruction XXH3. Like the reference's second XXHasher instance
+// (src/main.cpp:215-217) it only influences speed, never the count.
+__device__ __forceinline__ uint32_t table_bucket(uint64_t key, uint64_t mul, uint32_t shift) {
+    return (uint32_t)(((key ^ (key >> 29)) * mul) >> shift);
+}
+
+template <int TPB>
 __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ uint32_t has_empty_key;
     __shared__ unsigned long long block_count;
-    const uint32_t nslots = p.slot_mask + 1;
+    const uint32_t nslots = (p.bucket_mask + 1) * 4;
     const int tid = threadIdx.x;
 
     // Slice of the partitioned probe relation owned by this CTA (the host did the division).
@@ -670,11 +679,15 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
 
             const uint64_t t0 = globaltimer_ns();
             cta_sync();  // previous partition's probes are done with the table
-            for (uint32_t i = tid; i < nslots; i += TPB) table[i] = kEmptyKey;
+            {
+                ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+                for (uint32_t i = tid; i < nslots / 2; i += TPB) t2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
+            }
             if (tid == 0) has_empty_key = 0;
             cta_sync();
-            // Warp-converged insertion: every lane of a warp runs the same number of loop trips
-            // (vote on `pending`), so no per-lane loop ever splits the warp (see cta_sync()).
+            // ---- build: first free slot of the home bucket, overflowing into the next bucket.
+            // Warp-converged: every lane runs the same number of loop trips (vote on `pending`),
+            // so no per-lane loop ever splits the warp (see cta_sync()).
             for (uint64_t i0 = r0; i0 < r1; i0 += TPB) {
                 const uint64_t i = i0 + tid;
                 uint64_t key = 0;
@@ -686,13 +699,14 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                         pending = false;
                     }
                 }
-                uint32_t slot = (uint32_t)(hash_key<HASH>(key, p.hp) >> p.hash_shift) & p.slot_mask;
+                uint32_t slot = (table_bucket(key, p.table_mul, p.bucket_shift) & p.bucket_mask) * 4;
                 while (__any_sync(0xffffffffu, pending)) {
                     if (pending) {
-                        const unsigned long long old = atomicCAS(
-                            reinterpret_cast<unsigned long long*>(table + slot), kEmptyKey, key);
-                        if (old == kEmptyKey || old == key) pending = false;
-                        else slot = (slot + 1) & p.slot_mask;
+                        unsigned long long cur = table[slot];
+                        if (cur == kEmptyKey)
+                            cur = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), kEmptyKey, key);
+                        if (cur == kEmptyKey || cur == key) pending = false;  // duplicates collapse
+                        else slot = (slot + 1) & (nslots - 1);
                     }
                 }
             }
@@ -700,10 +714,12 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             const uint64_t t1 = globaltimer_ns();
             const uint32_t sentinel_hit = has_empty_key;
 
+            // ---- probe: one 32-byte bucket (two LDS.128) per step; a bucket with a free last slot
+            // ends the search (slots fill in order, LinearProbing.hpp:172-174 analogue) ----
             constexpr int U = 4;
             for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
                 uint64_t key[U];
-                uint32_t slot[U];
+                uint32_t bucket[U];
                 bool pending[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -717,24 +733,22 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                         count += sentinel_hit;
                         pending[u] = false;
                     }
-                    slot[u] = (uint32_t)(hash_key<HASH>(key[u], p.hp) >> p.hash_shift) & p.slot_mask;
+                    bucket[u] = table_bucket(key[u], p.table_mul, p.bucket_shift) & p.bucket_mask;
                 }
-                // warp-converged linear probing, U independent probes in flight per lane
-                while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+                bool any = pending[0] | pending[1] | pending[2] | pending[3];
+                while (__any_sync(0xffffffffu, any)) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (pending[u]) {
-                            const uint64_t t = table[slot[u]];
-                            if (t == key[u]) {
-                                ++count;
-                                pending[u] = false;
-                            } else if (t == kEmptyKey) {
-                                pending[u] = false;
-                            } else {
-                                slot[u] = (slot[u] + 1) & p.slot_mask;
-                            }
+                            const ulonglong2* bk = reinterpret_cast<const ulonglong2*>(table + bucket[u] * 4);
+                            const ulonglong2 k01 = bk[0], k23 = bk[1];
+                            const bool hit = (k01.x == key[u]) | (k01.y == key[u]) | (k23.x == key[u]) | (k23.y == key[u]);
+                            count += hit;
+                            pending[u] = !hit && k23.y != kEmptyKey;
+                            bucket[u] = (bucket[u] + 1) & p.bucket_mask;
                         }
                     }
+                    any = pending[0] | pending[1] | pending[2] | pending[3];
                 }
             }
             const uint64_t t2 = globaltimer_ns();
