@@ -1,0 +1,135 @@
+// GPU joiners with the reference's joiner interface.
+//
+// Drop-in counterparts of NoPartitioning::HashJoiner (reference src/NoPartitioning/HashJoin.hpp:14-41)
+// and RadixClustering::HashJoiner (reference src/RadixCluster/HashJoin.hpp:91-135): same
+// Run(tableA /*build*/, tableB /*probe*/, timer) signature and return type, and like the reference
+// the returned joined table is empty -- the join is count-only (reference Readme.md:10). What the
+// reference constructs them from (thread pool, hash-table factory, hasher objects) has no meaning
+// on a GPU; they are constructed from the algorithm's Configuration plus a GpuConfiguration (hash
+// function, seeds, device) and talk to the device only through the C ABI of include/phj.h.
+//
+// Extras the reference lacks: GetLastResult() exposes the match count (the reference only logs
+// "Joined N tuples", src/NoPartitioning/HashJoin.hpp:184) and the device-side figures.
+#pragma once
+#include <chrono>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "../../../include/phj.h"
+#include "../Common/Configuration.hpp"
+#include "../Common/Results.hpp"
+#include "../Common/Table.hpp"
+
+namespace Gpu {
+
+// Errors surface like the reference's: an exception out of Run (it rethrows task exceptions,
+// src/RadixCluster/HashJoin.hpp:218-222), carrying phj_last_error().
+class JoinError : public std::runtime_error {
+   public:
+    JoinError(int status, const std::string& what) : std::runtime_error(what), m_status(status) {}
+    int Status() const { return m_status; }
+
+   private:
+    int m_status;
+};
+
+namespace internal {
+class Engine {
+   public:
+    Engine(int algo, uint64_t partitions, const Common::GpuConfiguration& gpu) {
+        phj_config cfg{};
+        cfg.algo = algo;
+        cfg.hash = static_cast<int32_t>(gpu.Hash);
+        cfg.partitions = partitions;
+        cfg.radix_bits[0] = gpu.RadixBits[0];
+        cfg.radix_bits[1] = gpu.RadixBits[1];
+        cfg.hash_seed = gpu.Seed;
+        cfg.table_seed = gpu.TableSeed;
+        cfg.device = gpu.Device;
+        cfg.flags = gpu.NoTmaStore ? PHJ_FLAG_NO_TMA_STORE : 0;
+        Check(phj_create(&cfg, &m_handle));
+    }
+    ~Engine() { phj_destroy(m_handle); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    phj_result Join(const Common::Table<Common::Tuple>& build, const Common::Table<Common::Tuple>& probe,
+                    int repeat) {
+        static_assert(sizeof(Common::Tuple) == sizeof(phj_tuple) && alignof(Common::Tuple) == 16, "layout");
+        Check(phj_upload(m_handle, reinterpret_cast<const phj_tuple*>(build.Data()), build.GetSize(),
+                         reinterpret_cast<const phj_tuple*>(probe.Data()), probe.GetSize()));
+        phj_result best{};
+        for (int i = 0; i < (repeat < 1 ? 1 : repeat); ++i) {
+            phj_result r{};
+            Check(phj_join(m_handle, &r));
+            if (i == 0 || r.total_ns < best.total_ns) best = r;
+        }
+        return best;
+    }
+
+   private:
+    static void Check(int status) {
+        if (status != PHJ_OK) throw JoinError(status, phj_last_error());
+    }
+    phj_handle* m_handle = nullptr;
+};
+
+inline std::shared_ptr<Common::Table<Common::JoinedTuple>> Report(const phj_result& r,
+                                                                   std::shared_ptr<Common::IHashJoinTimer> timer) {
+    using ns = std::chrono::nanoseconds;
+    timer->SetPartitionPhaseDuration(ns(static_cast<long long>(r.partition_ns)));
+    timer->SetBuildPhaseDuration(ns(static_cast<long long>(r.build_ns)));
+    timer->SetProbePhaseDuration(ns(static_cast<long long>(r.probe_ns)));
+    return std::make_shared<Common::Table<Common::JoinedTuple>>(Common::generate_uuid());
+}
+}  // namespace internal
+
+namespace NoPartitioning {
+class HashJoiner {
+   public:
+    HashJoiner(::NoPartitioning::Configuration configuration, const Common::GpuConfiguration& gpu = {})
+        : m_configuration(configuration), m_gpu(gpu), m_engine(PHJ_ALGO_NO_PARTITIONING, 0, gpu) {}
+
+    // tableA is the build relation, tableB the probe relation
+    std::shared_ptr<Common::Table<Common::JoinedTuple>> Run(
+        std::shared_ptr<Common::Table<Common::Tuple>> tableA, std::shared_ptr<Common::Table<Common::Tuple>> tableB,
+        std::shared_ptr<Common::IHashJoinTimer> timer = std::make_shared<Common::NoOpHashJoinTimer>()) {
+        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat);
+        return internal::Report(m_last, timer);
+    }
+    const phj_result& GetLastResult() const { return m_last; }
+
+   private:
+    ::NoPartitioning::Configuration m_configuration;
+    Common::GpuConfiguration m_gpu;
+    internal::Engine m_engine;
+    phj_result m_last{};
+};
+}  // namespace NoPartitioning
+
+namespace RadixClustering {
+class HashJoiner {
+   public:
+    HashJoiner(::RadixClustering::Configuration configuration, const Common::GpuConfiguration& gpu = {})
+        : m_configuration(configuration),
+          m_gpu(gpu),
+          m_engine(PHJ_ALGO_RADIX_PARTITIONING, configuration.NumberOfPartitions, gpu) {}
+
+    std::shared_ptr<Common::Table<Common::JoinedTuple>> Run(
+        std::shared_ptr<Common::Table<Common::Tuple>> tableA, std::shared_ptr<Common::Table<Common::Tuple>> tableB,
+        std::shared_ptr<Common::IHashJoinTimer> timer = std::make_shared<Common::NoOpHashJoinTimer>()) {
+        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat);
+        return internal::Report(m_last, timer);
+    }
+    const phj_result& GetLastResult() const { return m_last; }
+
+   private:
+    ::RadixClustering::Configuration m_configuration;
+    Common::GpuConfiguration m_gpu;
+    internal::Engine m_engine;
+    phj_result m_last{};
+};
+}  // namespace RadixClustering
+
+}  // namespace Gpu

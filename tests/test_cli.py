@@ -1,0 +1,91 @@
+"""The C++ host mirror (partitionedhashjoin_b200/host): CLI surface and JSON rendering match the
+reference's (src/main.cpp:141-208, src/Arguments.hpp:7-19, src/Common/Results.hpp:262-279)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "partitionedhashjoin_b200", "host")
+PHJOIN = os.path.join(HOST, "phjoin")
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def phjoin():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "partitionedhashjoin_b200", "csrc")], check=True, capture_output=True)
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    return PHJOIN
+
+
+def run(phjoin, *args, cwd=None):
+    return subprocess.run([phjoin, *args], capture_output=True, text=True, cwd=cwd)
+
+
+def test_help_lists_reference_flags(phjoin):
+    r = run(phjoin, "--help")
+    assert r.returncode == 0
+    for flag in ("--primary", "--secondary", "--skew", "--log", "--join", "--format", "--unit", "--output",
+                 "--filename", "--partitions", "=10000000", "=200000000", "=1.05", "=hashjoin.txt"):
+        assert flag in r.stdout
+    assert run(phjoin, "-h").returncode == 0
+
+
+@pytest.mark.parametrize("args,message", [
+    ((), "the option '--join' is required but missing"),
+    (("--join", "hash-join"), "Unrecognized join algorithm type: hash-join."),
+    (("--join", "no-partitioning", "-p", "32"), "number of partitions can be specified only for RadixParitioning."),
+    (("--join", "radix-partitioning", "--unit", "minutes"), "Unrecognized time unit: minutes"),
+    (("--join", "radix-partitioning", "--format", "xml"), "Unrecognized results format: xml."),
+    (("--join", "radix-partitioning", "--output", "stdout"), "Unrecognized output type: stdout."),
+    (("--join", "radix-partitioning", "--filename", ""), "empty configuration filename specified."),
+    (("--join", "radix-partitioning", "--log", "verbose"), "Unrecognized logger level: verbose."),
+    (("--join", "radix-partitioning", "--primary", "ten"), "option '--primary' is invalid"),
+    (("--join", "radix-partitioning", "--bogus", "1"), "unrecognised option '--bogus'"),
+    (("--join", "radix-partitioning", "--hash", "sha1"), "Unrecognized hash function: sha1."),
+])
+def test_argument_errors_exit_1_with_option_table(phjoin, args, message):
+    """Any parse/validation error: message, option table, exit(1) (reference src/main.cpp:199-205)."""
+    r = run(phjoin, *args)
+    assert r.returncode == 1
+    assert message in r.stdout and "Allowed options" in r.stdout
+
+
+def test_json_rendering_matches_reference(tmp_path):
+    """Common::JSONResultsFormatter output == what the reference's formatter (boost ptree) writes."""
+    g = GOLDEN["json"]
+    src = tmp_path / "fmt.cpp"
+    params = "".join(f'  p.SetParameter("{k}", "{v}");\n' for k, v in g["parameters"].items())
+    src.write_text(
+        f'#include "{HOST}/Common/Results.hpp"\n#include <iostream>\n'
+        "int main(int, char** argv) {\n  Common::Parameters p;\n" + params +
+        f'  Common::HashJoinTimingResult r(std::chrono::nanoseconds({g["build_ns"]}LL), '
+        f'std::chrono::nanoseconds({g["probe_ns"]}LL), std::chrono::nanoseconds({g["partition_ns"]}LL), p);\n'
+        "  Common::ResultsFormatConfiguration c; c.TimeUnit = argv[1];\n"
+        "  Common::JSONResultsFormatter f(c); f.Format(std::cout, r); return 0; }\n")
+    exe = tmp_path / "fmt"
+    subprocess.run(["g++", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    for unit in ("ms", "us"):
+        out = subprocess.run([str(exe), unit], capture_output=True, text=True, check=True).stdout
+        assert out == g[unit]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("join,extra,typ", [("no-partitioning", [], "NoPartitioning"),
+                                             ("radix-partitioning", ["-p", "64"], "RadixParitioning"),
+                                             ("radix-partitioning", ["--partitions=4096", "--hash", "city", "--repeat", "2"], "RadixParitioning")])
+def test_cli_end_to_end(phjoin, tmp_path, join, extra, typ):
+    out = tmp_path / "result.txt"
+    r = run(phjoin, "--join", join, "--primary", "200000", "--secondary", "3000000", "--skew", "1.25", "-u", "us",
+            "-f", str(out), *extra)
+    assert r.returncode == 0, r.stderr
+    assert "Joined 3000000 tuples." in r.stderr  # generator data: every probe key lies in [1, |R|]
+    d = json.load(open(out))
+    assert d["id"] == "hashjointimingresult"
+    assert d["parameters"]["Type"] == typ and d["parameters"]["PrimaryRelationSize"] == "200000"
+    assert d["parameters"]["Skew"] == "1.250000"
+    assert (d["parameters"].get("NumberOfPartitions") is not None) == (join == "radix-partitioning")
+    assert list(d["results"]) == ["partition", "build", "probe"]
+    assert int(d["results"]["probe"]) > 0 and int(d["results"]["build"]) > 0
+    assert (int(d["results"]["partition"]) > 0) == (join == "radix-partitioning")
