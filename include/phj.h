@@ -39,7 +39,17 @@ typedef struct {
 } phj_joined_tuple;
 
 /* Common::JoinAlgorithmType (src/Common/Configuration.hpp:12-15). */
-enum { PHJ_ALGO_NO_PARTITIONING = 0, PHJ_ALGO_RADIX_PARTITIONING = 1 };
+enum {
+    PHJ_ALGO_NO_PARTITIONING = 0,
+    PHJ_ALGO_RADIX_PARTITIONING = 1,
+    /* Multi-GPU exchange step (no counterpart in the single-process reference): phj_join only
+     * splits the uploaded relations by owner rank, owner = (hash >> shard_shift) % partitions with
+     * `partitions` = number of ranks (a power of two <= 64); the pieces are then exchanged
+     * (NCCL all-to-all) and every rank runs an ordinary RADIX_PARTITIONING join on what it
+     * received. shard_shift must be >= log2 of that local join's fan-out so the two use disjoint
+     * hash bits. */
+    PHJ_ALGO_SHARD_SPLIT = 2
+};
 
 /* Hasher behind Common::IHasher (src/Common/IHasher.hpp:6-11). The reference ships only XXH3
  * (src/Common/XXHasher.hpp:19-22); MURMUR3 and CITY are extensions named by the north star:
@@ -75,6 +85,8 @@ typedef struct {
     uint32_t flags;      /* PHJ_FLAG_* */
     uint64_t reserve_build; /* optional capacity hints (tuples); 0 = size on first upload */
     uint64_t reserve_probe;
+    uint32_t shard_shift;   /* PHJ_ALGO_SHARD_SPLIT: first hash bit of the owner-rank digit */
+    uint32_t reserved;      /* must be 0 */
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
@@ -157,6 +169,12 @@ uint64_t phj_hash_host(int32_t hash, uint64_t seed, int64_t key);
  * [bounds[p], bounds[p+1]) with the tuples in input order, i.e. bit-identical to the reference's
  * stable partitionTable (src/RadixCluster/HashJoin.hpp:394-412). Valid until the next upload/join. */
 int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* bounds);
+
+/* Device-resident view of the same: *d_data is the partitioned relation (n tuples), *d_bounds its
+ * partitions+1 boundaries (uint64). Owned by the handle; valid until the next upload/join. Used by
+ * the multi-GPU path to hand the SHARD_SPLIT output to the all-to-all without a host round trip. */
+int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, const uint64_t** d_bounds,
+                          size_t* n);
 
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
  * names[i] points to a static string. */

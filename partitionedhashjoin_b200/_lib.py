@@ -19,6 +19,7 @@ assert TUPLE_DTYPE.itemsize == 16
 
 ALGO_NO_PARTITIONING = 0
 ALGO_RADIX_PARTITIONING = 1
+ALGO_SHARD_SPLIT = 2
 HASH_XXH3, HASH_MURMUR3, HASH_CITY = 0, 1, 2
 HASH_NAMES = {"xxh3": HASH_XXH3, "xxhash": HASH_XXH3, "murmur3": HASH_MURMUR3, "city": HASH_CITY}
 FLAG_NO_TMA_STORE = 0x2
@@ -38,6 +39,8 @@ class PhjConfig(C.Structure):
         ("flags", C.c_uint32),
         ("reserve_build", C.c_uint64),
         ("reserve_probe", C.c_uint64),
+        ("shard_shift", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -92,6 +95,8 @@ SIGNATURES = {
     "phj_hash_batch": (C.c_int, [C.c_int32, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),
     "phj_hash_host": (C.c_uint64, [C.c_int32, C.c_uint64, C.c_int64]),
     "phj_read_partitions": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "phj_device_partitions": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_size_t)]),
     "phj_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
     "phj_get_device_info": (C.c_int, [C.c_int32, C.POINTER(PhjDeviceInfo)]),
     "phj_device_count": (C.c_int, []),

@@ -325,7 +325,10 @@ int plan_radix(phj_handle* h) {
         return fail(PHJ_ERR_INVALID, "partitions=%llu exceeds the supported fan-out of %llu",
                     (unsigned long long)P, 1ull << (2 * kMaxBitsPerPass));
     int b1 = (int)c.radix_bits[0], b2 = (int)c.radix_bits[1];
-    if (b1 == 0 && b2 == 0) {
+    if (c.algo == PHJ_ALGO_SHARD_SPLIT) {
+        b1 = h->bits_total;
+        b2 = 0;
+    } else if (b1 == 0 && b2 == 0) {
         if (h->bits_total <= 7) {
             b1 = h->bits_total;
             b2 = 0;
@@ -352,6 +355,12 @@ DigitFn digit_fn(const phj_handle* h, int pass) {
     DigitFn f;
     f.pmask = h->pow2 ? h->P - 1 : ~0ull;
     f.modulus = h->P;
+    if (h->cfg.algo == PHJ_ALGO_SHARD_SPLIT) {  // owner rank = hash bits [shard_shift, +log2 ranks)
+        f.pmask = ~0ull;
+        f.shift = h->cfg.shard_shift;
+        f.mask = (uint32_t)(h->P - 1);
+        return f;
+    }
     if (pass == 1) {
         f.shift = (uint32_t)h->b2;
         f.mask = (1u << std::max(h->b1, 1)) - 1;  // b1 == 0 only when P == 1 (digit always 0)
@@ -515,7 +524,7 @@ int ensure_gt_for_fallback(phj_handle* h) {
 
 uint32_t table_hash_shift(const phj_handle* h) {
     // the table takes hash bits above the ones the partitioning consumed
-    return h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING ? (uint32_t)std::min(h->bits_total, 24) : 0u;
+    return h->cfg.algo != PHJ_ALGO_NO_PARTITIONING ? (uint32_t)std::min(h->bits_total, 24) : 0u;
 }
 
 // ---- the joins ----------------------------------------------------------------------------------
@@ -688,6 +697,17 @@ int join_radix(phj_handle* h, phj_result* out) {
         }
     }
     PHJ_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    if (h->cfg.algo == PHJ_ALGO_SHARD_SPLIT) {
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        PHJ_CUDA(cudaGetLastError());
+        out->partition_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[1]) * 1e6);
+        out->total_ns = out->partition_ns;
+        out->passes = 1;
+        out->partitions = h->P;
+        out->hbm_bytes_alg = 16ull * 3 * (h->n[0] + h->n[1]);  // histogram read + scatter read/write
+        h->joined_radix = true;
+        return PHJ_OK;
+    }
 
     // ---- build + probe per partition ----
     const ulonglong2* part_build = two ? h->d_buf_b[0] : h->d_buf_a[0];
@@ -784,8 +804,15 @@ int join_radix(phj_handle* h, phj_result* out) {
 
 int validate_config(const phj_config* c) {
     if (!c) return fail(PHJ_ERR_INVALID, "config is null");
-    if (c->algo != PHJ_ALGO_NO_PARTITIONING && c->algo != PHJ_ALGO_RADIX_PARTITIONING)
+    if (c->algo != PHJ_ALGO_NO_PARTITIONING && c->algo != PHJ_ALGO_RADIX_PARTITIONING &&
+        c->algo != PHJ_ALGO_SHARD_SPLIT)
         return fail(PHJ_ERR_INVALID, "Unrecognized join algorithm: %d.", c->algo);
+    if (c->algo == PHJ_ALGO_SHARD_SPLIT) {
+        const uint64_t w = c->partitions;
+        if (w == 0 || w > 64 || (w & (w - 1)) || c->shard_shift > 58 || c->radix_bits[0] || c->radix_bits[1])
+            return fail(PHJ_ERR_INVALID, "shard split needs partitions = number of ranks (a power of two <= 64), "
+                                         "shard_shift <= 58 and no radix_bits");
+    }
     if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
         return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", c->hash);
     if (c->algo == PHJ_ALGO_NO_PARTITIONING && (c->partitions != 0 || c->radix_bits[0] || c->radix_bits[1]))
@@ -1009,13 +1036,25 @@ int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const p
 int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* bounds) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
-    if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING || !h->joined_radix)
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING || !h->joined_radix)
         return fail(PHJ_ERR_STATE, "no partitioned relations: run a radix-partitioning phj_join first");
     PHJ_CUDA(cudaSetDevice(h->device));
     const ulonglong2* src = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
     if (out && h->n[which])
         PHJ_CUDA(cudaMemcpy(out, src, h->n[which] * 16, cudaMemcpyDeviceToHost));
     if (bounds) PHJ_CUDA(cudaMemcpy(bounds, h->d_bounds2[which], (h->P + 1) * 8, cudaMemcpyDeviceToHost));
+    return PHJ_OK;
+}
+
+int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, const uint64_t** d_bounds,
+                          size_t* n) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING || !h->joined_radix)
+        return fail(PHJ_ERR_STATE, "no partitioned relations: run a radix-partitioning phj_join first");
+    if (d_data) *d_data = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
+    if (d_bounds) *d_bounds = h->d_bounds2[which];
+    if (n) *n = h->n[which];
     return PHJ_OK;
 }
 

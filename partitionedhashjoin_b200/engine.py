@@ -120,11 +120,12 @@ class Engine:
     """One phj_handle. ``algo``: 'no-partitioning' | 'radix-partitioning' (the CLI spellings,
     reference src/Common/Configuration.cpp:4-12)."""
 
-    ALGOS = {"no-partitioning": ALGO_NO_PARTITIONING, "radix-partitioning": ALGO_RADIX_PARTITIONING}
+    ALGOS = {"no-partitioning": ALGO_NO_PARTITIONING, "radix-partitioning": ALGO_RADIX_PARTITIONING,
+             "shard-split": _lib.ALGO_SHARD_SPLIT}
 
     def __init__(self, algo="radix-partitioning", partitions: int = 0, radix_bits=(0, 0), hash="xxh3",
                  hash_seed: int = 0x9E3779B97F4A7C15, table_seed: int = 1, device: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, shard_shift: int = 0):
         cfg = PhjConfig()
         if isinstance(algo, str):
             if algo not in self.ALGOS:
@@ -138,6 +139,7 @@ class Engine:
         cfg.table_seed = table_seed & (2**64 - 1)
         cfg.device = device
         cfg.flags = flags
+        cfg.shard_shift = shard_shift
         self._h = C.c_void_p()
         check(lib.phj_create(C.byref(cfg), C.byref(self._h)))
         self._keep = []
@@ -190,6 +192,18 @@ class Engine:
         bounds = np.empty(partitions + 1, dtype=np.uint64)
         check(lib.phj_read_partitions(self._h, which, out.ctypes.data, bounds.ctypes.data))
         return out, bounds
+
+    def read_bounds(self, which: int, partitions: int) -> np.ndarray:
+        """Only the partitions+1 boundaries of the last radix join / shard split."""
+        bounds = np.empty(partitions + 1, dtype=np.uint64)
+        check(lib.phj_read_partitions(self._h, which, None, bounds.ctypes.data))
+        return bounds
+
+    def device_partitions(self, which: int):
+        """(device pointer of the partitioned relation, device pointer of its boundaries, n)."""
+        d_data, d_bounds, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(lib.phj_device_partitions(self._h, which, C.byref(d_data), C.byref(d_bounds), C.byref(n)))
+        return d_data.value or 0, d_bounds.value or 0, int(n.value)
 
     def kernel_times(self) -> list:
         names = (C.c_char_p * 32)()

@@ -1,0 +1,79 @@
+"""The multi-rank host logic of the sharded join (partitionedhashjoin_b200/multigpu.py) over gloo on
+the CPU: split sizes, the size + data all-to-all, the local joins and the count all-reduce, with
+the oracle standing in for the device (tests/_dist_worker.py). The same orchestration class runs on
+NCCL with GpuBackend in bench.py --gpus N and in the gpu-marked test below."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def torchrun(world, script, *args, timeout=300):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), script, *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.parametrize("world,case", [(2, "random"), (2, "skewed"), (2, "tiny"), (4, "random"), (1, "random")])
+def test_sharded_join_over_gloo(world, case):
+    r = torchrun(world, os.path.join(HERE, "_dist_worker.py"), case)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
+
+
+def test_world_must_be_power_of_two():
+    from partitionedhashjoin_b200 import multigpu
+    with pytest.raises(ValueError):
+        multigpu.ShardedRadixJoin(None, 0, 3, backend=None)
+
+
+@pytest.mark.gpu
+def test_sharded_join_single_gpu_backend(phj, oracle):
+    """GpuBackend with one rank: shard split (1 owner) -> zero-copy bind -> local radix join."""
+    import numpy as np
+
+    import _cases
+    from partitionedhashjoin_b200 import multigpu
+    R = _cases.tuples(_cases.splitmix64(60000, 5).astype(np.int64) % 50021)
+    S = _cases.tuples(_cases.splitmix64(900000, 6).astype(np.int64) % 70001)
+    job = multigpu.ShardedRadixJoin(None, 0, 1, multigpu.GpuBackend(1, 0, partitions_local=256))
+    job.upload(R, S)
+    assert job.join()["matches"] == oracle.count_by_sort(R, S)
+    job.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shard_split_kernel_matches_oracle(phj, oracle, world):
+    """PHJ_ALGO_SHARD_SPLIT on the device: piece r holds exactly the tuples whose owner digit is r,
+    in input order (what every rank sends to rank r)."""
+    import numpy as np
+
+    import _cases
+    from partitionedhashjoin_b200 import multigpu
+    seed = 0x9E3779B97F4A7C15
+    R = _cases.tuples(_cases.splitmix64(50000, 15).astype(np.int64))
+    S = _cases.tuples(_cases.splitmix64(700001, 16).astype(np.int64) % 12345)
+    with phj.Engine("shard-split", partitions=world, hash_seed=seed, shard_shift=multigpu.SHARD_SHIFT) as e:
+        e.upload(R, S)
+        res = e.join()
+        assert res["matches"] == 0 and res["passes"] == 1
+        for which, rel in ((0, R), (1, S)):
+            got, bounds = e.read_partitions(which, world)
+            owner = ((oracle.hash_batch(0, seed, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT)) & np.uint64(world - 1)).astype(np.int64)
+            want = rel[np.argsort(owner, kind="stable")]
+            assert np.diff(bounds.astype(np.int64)).tolist() == np.bincount(owner, minlength=world).tolist()
+            assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
