@@ -39,6 +39,9 @@
 #ifndef PHJ_JOIN_TPB
 #define PHJ_JOIN_TPB 512
 #endif
+#ifndef PHJ_JOIN_BUCKET
+#define PHJ_JOIN_BUCKET 2  // keys per shared-memory bucket (2: one LDS.128 per probe step)
+#endif
 #include "phj_kernels.cuh"
 
 namespace {
@@ -275,7 +278,7 @@ cudaError_t launch_pass(phj_handle* h, bool scatter, int bits, const PassParams&
 }
 
 cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
-    auto kern = join_partitions<PHJ_JOIN_TPB>;
+    auto kern = join_partitions<PHJ_JOIN_TPB, PHJ_JOIN_BUCKET>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -556,6 +559,15 @@ int run_gt(phj_handle* h, bool select, const ulonglong2* build, const ulonglong2
     gp.part_fn.modulus = h->P;
     gp.part_fn.shift = 0;
     gp.part_fn.mask = ~0u;
+    if (select && h->pow2 && h->bits_total > 0) {
+        // partition-local table regions (at most 1024 of them, never smaller than 1024 buckets)
+        uint32_t rb = (uint32_t)std::min(h->bits_total, 10);
+        const uint32_t bucket_bits = (uint32_t)ilog2_ceil(h->gt_buckets);
+        if (bucket_bits < rb + 10) rb = bucket_bits > 10 ? bucket_bits - 10 : 0;
+        gp.region_bits = rb;
+        gp.region_shift = (uint32_t)h->bits_total - rb;
+        gp.local_mask = (h->gt_buckets >> rb) - 1;
+    }
     gp.hp = hp;
     gp.flags = h->d_scalars + kGtFlags;
     gp.matches = h->d_matches;
@@ -723,8 +735,8 @@ int join_radix(phj_handle* h, phj_result* out) {
     jp.slice_len = h->n[1] / h->join_grid;
     jp.slice_rem = h->n[1] % h->join_grid;
     jp.npart = (uint32_t)h->nparts;
-    jp.bucket_mask = h->join_slots / 4 - 1;
-    jp.bucket_shift = 64 - ilog2_ceil(h->join_slots / 4);
+    jp.bucket_mask = h->join_slots / PHJ_JOIN_BUCKET - 1;
+    jp.bucket_shift = 64 - ilog2_ceil(h->join_slots / PHJ_JOIN_BUCKET);
     jp.max_keys = h->join_max_keys;
     jp.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;  // odd
     if (h->cfg.table_seed == 0) jp.table_mul = 0xBF58476D1CE4E5B9ULL;

@@ -629,7 +629,7 @@ struct JoinParams {
     uint64_t n_probe;
     uint64_t slice_len, slice_rem;  // n_probe / gridDim.x and n_probe % gridDim.x
     uint32_t npart;
-    uint32_t bucket_mask;   // table buckets - 1 (a bucket = four 8-byte keys = one 32-byte line)
+    uint32_t bucket_mask;   // table buckets - 1 (a bucket = BK 8-byte keys, read with 16-byte loads)
     uint32_t bucket_shift;  // bucket = table_hash(key) >> bucket_shift
     uint32_t max_keys;      // largest build partition the table accepts
     uint64_t table_mul;     // odd multiplier of the table hash (derived from the table seed)
@@ -645,13 +645,13 @@ __device__ __forceinline__ uint32_t table_bucket(uint64_t key, uint64_t mul, uin
     return (uint32_t)(((key ^ (key >> 29)) * mul) >> shift);
 }
 
-template <int TPB>
+template <int TPB, int BK>
 __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* table = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ uint32_t has_empty_key;
     __shared__ unsigned long long block_count;
-    const uint32_t nslots = (p.bucket_mask + 1) * 4;
+    const uint32_t nslots = (p.bucket_mask + 1) * BK;
     const int tid = threadIdx.x;
 
     // Slice of the partitioned probe relation owned by this CTA (the host did the division).
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                         pending = false;
                     }
                 }
-                uint32_t slot = (table_bucket(key, p.table_mul, p.bucket_shift) & p.bucket_mask) * 4;
+                uint32_t slot = (table_bucket(key, p.table_mul, p.bucket_shift) & p.bucket_mask) * BK;
                 while (__any_sync(0xffffffffu, pending)) {
                     if (pending) {
                         unsigned long long cur = table[slot];
@@ -714,9 +714,27 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             const uint64_t t1 = globaltimer_ns();
             const uint32_t sentinel_hit = has_empty_key;
 
-            // ---- probe: one 32-byte bucket (two LDS.128) per step; a bucket with a free last slot
-            // ends the search (slots fill in order, LinearProbing.hpp:172-174 analogue) ----
+            // ---- probe: one bucket (BK keys) per step; a bucket whose last slot is free ends the
+            // search (slots fill in order, LinearProbing.hpp:172-174 analogue). The first step is
+            // peeled: at the table's load factor nearly every search ends there, and the converged
+            // loop only runs for the few that overflow.
             constexpr int U = 4;
+            auto probe_step = [&](uint64_t key, uint32_t& bucket, bool& pending) {
+                bool hit, full;
+                if (BK == 2) {
+                    const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(table + bucket * 2);
+                    hit = (k.x == key) | (k.y == key);
+                    full = k.y != kEmptyKey;
+                } else {
+                    const ulonglong2* bk = reinterpret_cast<const ulonglong2*>(table + bucket * 4);
+                    const ulonglong2 k01 = bk[0], k23 = bk[1];
+                    hit = (k01.x == key) | (k01.y == key) | (k23.x == key) | (k23.y == key);
+                    full = k23.y != kEmptyKey;
+                }
+                count += hit;
+                pending = !hit && full;
+                bucket = (bucket + 1) & p.bucket_mask;
+            };
             for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
                 uint64_t key[U];
                 uint32_t bucket[U];
@@ -735,19 +753,14 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                     }
                     bucket[u] = table_bucket(key[u], p.table_mul, p.bucket_shift) & p.bucket_mask;
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (pending[u]) probe_step(key[u], bucket[u], pending[u]);
                 bool any = pending[0] | pending[1] | pending[2] | pending[3];
                 while (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (pending[u]) {
-                            const ulonglong2* bk = reinterpret_cast<const ulonglong2*>(table + bucket[u] * 4);
-                            const ulonglong2 k01 = bk[0], k23 = bk[1];
-                            const bool hit = (k01.x == key[u]) | (k01.y == key[u]) | (k23.x == key[u]) | (k23.y == key[u]);
-                            count += hit;
-                            pending[u] = !hit && k23.y != kEmptyKey;
-                            bucket[u] = (bucket[u] + 1) & p.bucket_mask;
-                        }
-                    }
+                    for (int u = 0; u < U; ++u)
+                        if (pending[u]) probe_step(key[u], bucket[u], pending[u]);
                     any = pending[0] | pending[1] | pending[2] | pending[3];
                 }
             }
@@ -795,6 +808,11 @@ struct GtParams {
     const uint64_t* bounds_build;  // select == 1: partition sizes of R
     uint32_t max_keys;
     DigitFn part_fn;           // select == 1: tuple -> partition id (shift 0, mask = all)
+    uint32_t region_bits;      // select == 1: the table is cut into 2^region_bits regions, one per
+                               // group of partitions, so a partition's keys share a small, L2-sized
+                               // piece of the table and the partition-ordered probe stays in L2
+    uint32_t region_shift;     // region = partition >> region_shift
+    uint64_t local_mask;       // buckets per region - 1
     HashParams hp;
     uint32_t* flags;           // [0]: build side contains kEmptyKey
     unsigned long long* matches;
@@ -805,6 +823,14 @@ __global__ void gt_clear(uint64_t* __restrict__ table, uint64_t nkeys) {
     ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nkeys / 2; i += stride)
         t2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
+}
+
+template <bool POW2>
+__device__ __forceinline__ uint64_t gt_bucket(const GtParams& p, uint64_t h) {
+    const uint64_t local = h >> p.hash_shift;
+    if (!p.select || p.region_bits == 0) return local & p.bucket_mask;
+    const uint64_t part = POW2 ? (h & p.part_fn.pmask) : (h % p.part_fn.modulus);
+    return (((part >> p.region_shift) & ((1ull << p.region_bits) - 1)) * (p.local_mask + 1)) | (local & p.local_mask);
 }
 
 template <bool POW2>
@@ -828,7 +854,7 @@ __global__ void __launch_bounds__(256) gt_build(GtParams p) {
             p.flags[0] = 1;
             pending = false;
         }
-        uint64_t bucket = (h >> p.hash_shift) & p.bucket_mask;
+        uint64_t bucket = gt_bucket<POW2>(p, h);
         uint32_t s = 0;  // slot inside the bucket
         while (__any_sync(0xffffffffu, pending)) {
             if (pending) {
@@ -869,7 +895,7 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
                 count += sentinel_hit;
                 pending[u] = false;
             }
-            bucket[u] = (h >> p.hash_shift) & p.bucket_mask;
+            bucket[u] = gt_bucket<POW2>(p, h);
         }
         while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
 #pragma unroll
