@@ -90,6 +90,9 @@ typedef struct {
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
+#define PHJ_FLAG_FUSE_HIST2 0x4u   /* experimental: the pass-1 scatter also accumulates the pass-2
+                                      histogram (saves one read of both relations, costs shared
+                                      memory; slower on B200 as measured) */
 
 
 /* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the

@@ -23,6 +23,7 @@ ALGO_SHARD_SPLIT = 2
 HASH_XXH3, HASH_MURMUR3, HASH_CITY = 0, 1, 2
 HASH_NAMES = {"xxh3": HASH_XXH3, "xxhash": HASH_XXH3, "murmur3": HASH_MURMUR3, "city": HASH_CITY}
 FLAG_NO_TMA_STORE = 0x2
+FLAG_FUSE_HIST2 = 0x4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

@@ -114,6 +114,11 @@ struct phj_handle {
     uint32_t d1 = 0, d2 = 0;  // digits actually used per pass
     uint64_t nparts = 0;      // d1 * d2 (>= P)
     uint32_t nsegs1 = 0, max_segs2 = 0, target_segs2[2] = {0, 0};
+    uint32_t nseg1_rel[2] = {0, 0}, cnt_base1_rel[2] = {0, 0};
+    uint64_t seg_len[2] = {0, 0};   // tuples per segment (both passes)
+    phj::Parent2* d_parents2[2] = {nullptr, nullptr};
+    size_t cap_parents2 = 0;
+    bool fuse2 = false;             // pass-2 histogram accumulated by the pass-1 scatter
     phj::Segment* d_segs1 = nullptr;
     phj::Segment* d_segs2 = nullptr;
     size_t cap_segs1 = 0, cap_segs2 = 0;
@@ -209,19 +214,27 @@ void launch_hist_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
             <<<grid, PHJ_HIST_TPB, 0, h->stream>>>(pp);
 }
 
-template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT>
-cudaError_t launch_scatter_tb(phj_handle* h, const PassParams& pp, uint32_t grid) {
+template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT, bool FUSE2>
+cudaError_t launch_scatter_tbf(phj_handle* h, const PassParams& pp, uint32_t grid) {
     using L = ScatterSmem<BITS, PHJ_SCAT_TPB, PHJ_SCAT_IPT>;
-    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT>;
+    size_t smem = L::total + (FUSE2 ? L::fuse2_bytes : 0);
+    if (const char* x = getenv("PHJ_SCAT_EXTRA_SMEM")) smem += (size_t)atoi(x);  // experiment: L1 sensitivity
+    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT, FUSE2>;
     static bool configured[16] = {};
     if (!configured[h->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)L::total);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[h->device & 15] = true;
     }
-    kern<<<grid, PHJ_SCAT_TPB, L::total, h->stream>>>(pp);
+    kern<<<grid, PHJ_SCAT_TPB, smem, h->stream>>>(pp);
     return cudaSuccess;
+}
+
+template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT>
+cudaError_t launch_scatter_tb(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    if (BITS == 6 && pp.counts2 != nullptr)  // fused pass-2 histogram (6-bit passes only)
+        return launch_scatter_tbf<6, HASH, POW2, TMA, BALLOT, true>(h, pp, grid);
+    return launch_scatter_tbf<BITS, HASH, POW2, TMA, BALLOT, false>(h, pp, grid);
 }
 
 template <int BITS, int HASH, bool POW2, bool TMA>
@@ -280,9 +293,6 @@ cudaError_t launch_pass(phj_handle* h, bool scatter, int bits, const PassParams&
 cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size_t smem) {
     auto kern = join_partitions<PHJ_JOIN_TPB, PHJ_JOIN_BUCKET>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     kern<<<grid, PHJ_JOIN_TPB, smem, h->stream>>>(jp);
     return cudaSuccess;
@@ -400,6 +410,9 @@ int build_plan(phj_handle* h) {
             uint64_t len = nseg[rel] ? (h->n[rel] + nseg[rel] - 1) / nseg[rel] : 0;
             len = ((len + kScatTile - 1) / kScatTile) * kScatTile;
             nseg[rel] = len ? (uint32_t)((h->n[rel] + len - 1) / len) : 0;
+            h->seg_len[rel] = len ? len : kScatTile;
+            h->nseg1_rel[rel] = nseg[rel];
+            h->cnt_base1_rel[rel] = cnt_base;
             for (uint32_t s = 0; s < nseg[rel]; ++s) {
                 Segment sg;
                 sg.begin = (uint64_t)s * len;
@@ -420,10 +433,21 @@ int build_plan(phj_handle* h) {
                                      cudaMemcpyHostToDevice, h->stream));
         // ---- pass 2 capacity ----
         size_t ncounts_max = ncounts1;
+        h->fuse2 = false;
         if (h->b2 > 0) {
             for (int rel = 0; rel < 2; ++rel)
-                h->target_segs2[rel] = std::max<uint32_t>(1, segments_for(h, h->n[rel], kScatTile));
+                h->target_segs2[rel] = std::max<uint32_t>(1, nseg[rel]);
             h->max_segs2 = h->target_segs2[0] + h->target_segs2[1] + 2 * h->d1;
+            // Opt-in: measured slower than the separate histogram read on B200 (the extra 33 KB of
+            // shared memory shrinks L1, which bounds the loads in flight).
+            h->fuse2 = h->b1 <= 6 && h->b2 <= 6 && (h->cfg.flags & PHJ_FLAG_FUSE_HIST2);
+            if (h->d1 > h->cap_parents2 || !h->d_parents2[0]) {
+                for (int rel = 0; rel < 2; ++rel) {
+                    if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
+                    PHJ_CUDA(cudaMalloc(&h->d_parents2[rel], (size_t)h->d1 * sizeof(Parent2)));
+                }
+                h->cap_parents2 = h->d1;
+            }
             if ((rc = dev_reserve(&h->d_segs2, &h->cap_segs2, h->max_segs2)) != PHJ_OK) return rc;
             ncounts_max = std::max<size_t>(ncounts_max, (size_t)h->max_segs2 * h->d2);
         }
@@ -647,29 +671,29 @@ int join_radix(phj_handle* h, phj_result* out) {
     p1.ndigits = h->d1;
     p1.hp = hp;
     p1.df = digit_fn(h, 1);
-    if (h->nsegs1 > 0) {
-        {
-            KernelScope ks(h, "radix_histogram[1]");
-            PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
-        }
-        run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
-        {
-            KernelScope ks(h, "radix_scatter[1]");
-            PHJ_CUDA(launch_pass(h, true, h->b1, p1, h->nsegs1));
-        }
-    }
-    // ---- pass 2 ----
+    // pass-2 bookkeeping (needed before scatter 1 when the pass-2 histogram is fused into it)
+    Plan2Params pl{};
+    FillEmptyParams fe{};
+    PassParams p2{};
     if (two) {
-        Plan2Params pl{};
-        FillEmptyParams fe{};
         for (int rel = 0; rel < 2; ++rel) {
             pl.bounds1[rel] = h->d_bounds1[rel];
+            pl.parents2[rel] = h->d_parents2[rel];
+            pl.cnt_base1[rel] = h->cnt_base1_rel[rel];
+            pl.nseg1[rel] = h->nseg1_rel[rel];
+            pl.seg_len[rel] = h->seg_len[rel];
             pl.n[rel] = h->n[rel];
             pl.target_segs[rel] = h->target_segs2[rel];
             fe.bounds1[rel] = h->d_bounds1[rel];
             fe.bounds2[rel] = h->d_bounds2[rel];
             fe.n[rel] = h->n[rel];
+            p2.in[rel] = h->d_buf_a[rel];
+            p2.out[rel] = h->d_buf_b[rel];
+            p2.bounds[rel] = h->d_bounds2[rel];
         }
+        pl.cursors = h->d_cursors;
+        pl.bias[0] = 0;
+        pl.bias[1] = h->n[0];
         pl.d1 = fe.d1 = h->d1;
         pl.d2 = fe.d2 = h->d2;
         pl.tile = kScatTile;
@@ -677,17 +701,6 @@ int join_radix(phj_handle* h, phj_result* out) {
         pl.nsegs = h->d_scalars + kNsegs2;
         pl.ncounts = h->d_scalars + kNcounts2;
         pl.max_segs = h->max_segs2;
-        {
-            KernelScope ks(h, "plan_pass2");
-            plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
-            fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
-        }
-        PassParams p2{};
-        for (int rel = 0; rel < 2; ++rel) {
-            p2.in[rel] = h->d_buf_a[rel];
-            p2.out[rel] = h->d_buf_b[rel];
-            p2.bounds[rel] = h->d_bounds2[rel];
-        }
         p2.segs = h->d_segs2;
         p2.nsegs = h->d_scalars + kNsegs2;
         p2.counts = h->d_counts;
@@ -698,7 +711,44 @@ int join_radix(phj_handle* h, phj_result* out) {
         p2.ndigits = h->d2;
         p2.hp = hp;
         p2.df = digit_fn(h, 2);
+    }
+    auto run_plan2 = [&]() {
+        KernelScope ks(h, "plan_pass2");
+        plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
+        fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
+    };
+    const bool fuse2 = two && h->fuse2;
+    if (h->nsegs1 > 0) {
         {
+            KernelScope ks(h, "radix_histogram[1]");
+            PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
+        }
+        run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
+        if (fuse2) {
+            // the scanned cursors already hold the pass-1 boundaries: plan pass 2 now, and let the
+            // pass-1 scatter count every tuple into its pass-2 segment (no second histogram read)
+            run_plan2();
+            PHJ_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->max_segs2 * h->d2 * sizeof(uint32_t), h->stream));
+            for (int rel = 0; rel < 2; ++rel) {
+                p1.parents2[rel] = h->d_parents2[rel];
+                p1.seg_len2[rel] = h->seg_len[rel];
+            }
+            p1.counts2 = h->d_counts;
+            p1.df2 = digit_fn(h, 2);
+            p1.d2 = h->d2;
+        }
+        {
+            KernelScope ks(h, "radix_scatter[1]");
+            PHJ_CUDA(launch_pass(h, true, h->b1, p1, h->nsegs1));
+        }
+    } else if (fuse2) {
+        run_plan2();
+        PHJ_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->max_segs2 * h->d2 * sizeof(uint32_t), h->stream));
+    }
+    // ---- pass 2 ----
+    if (two) {
+        if (!fuse2) {
+            run_plan2();
             KernelScope ks(h, "radix_histogram[2]");
             PHJ_CUDA(launch_pass(h, false, h->b2, p2, h->max_segs2));
         }
@@ -939,6 +989,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_buf_b[rel]) cudaFree(h->d_buf_b[rel]);
         if (h->d_bounds1[rel]) cudaFree(h->d_bounds1[rel]);
         if (h->d_bounds2[rel]) cudaFree(h->d_bounds2[rel]);
+        if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
                     h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt};

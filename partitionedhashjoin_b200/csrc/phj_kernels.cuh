@@ -29,6 +29,7 @@
 namespace phj {
 
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN marks a free table slot
+constexpr uint32_t kFuse2MaxD2 = 64;  // fused pass-2 histogram: pass 2 of at most 6 bits (with a 6-bit pass 1)
 
 struct __align__(16) Segment {
     uint64_t begin, end;  // tuple range inside the relation's input array
@@ -66,6 +67,21 @@ struct PassParams {
     uint32_t ndigits;          // digits this pass really has (<= the kernel's 1 << BITS)
     HashParams hp;
     DigitFn df;
+    // Fused pass-2 histogram (radix_scatter<..., FUSE2 = true>, pass 1 only): while a tile is
+    // staged, every tuple also counts into the pass-2 counter of the pass-2 segment its OUTPUT
+    // position falls into, so pass 2 needs no histogram read of its own.
+    const struct Parent2* parents2[2];  // per relation, one entry per pass-1 partition
+    uint32_t* counts2;                  // pass-2 counters (zeroed before the launch)
+    uint64_t seg_len2[2];               // pass-2 segment length per relation
+    DigitFn df2;                        // pass-2 digit of the same hash
+    uint32_t d2;                        // pass-2 digits
+};
+
+// Where pass-1 partition `parent` of a relation sits in pass 2's bookkeeping.
+struct __align__(16) Parent2 {
+    uint64_t lo;        // start of the partition in the pass-1 output (= its boundary)
+    uint32_t cnt_base;  // index of counter (digit 0, segment 0) of this parent
+    uint32_t nseg;      // pass-2 segments of this parent (= counter stride between digits)
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------
@@ -299,10 +315,12 @@ struct ScatterSmem {
     static constexpr size_t dbase_bytes = (size_t)(D + 4) * 4;
     static constexpr size_t sdig_bytes = (size_t)T * 2;
     static constexpr size_t total =
-        stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 16 * 4 + 64;
+        (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 16 * 4 + 64 + 15) / 16 * 16;
+    // extra shared memory of the fused pass-2 histogram: counters + split positions + counter indices
+    static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 4 + (size_t)D * 8 + (size_t)D * 8;
 };
 
-template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT>
+template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT, bool FUSE2>
 __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p) {
     using L = ScatterSmem<BITS, TPB, IPT>;
     constexpr int D = L::D, NW = L::NW, T = L::T;
@@ -315,6 +333,11 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
     uint32_t* wc = wtot_sh + 16;
     uint32_t* dbase = wc + NW * (D + 1);
     uint16_t* sdig = reinterpret_cast<uint16_t*>(dbase + D + 4);
+    // FUSE2: [2][D][d2] pass-2 counters of this segment + per-digit split position / first segment
+    uint32_t* h2 = reinterpret_cast<uint32_t*>(smem_raw + L::total);
+    uint64_t* split_pos = reinterpret_cast<uint64_t*>(h2 + 2 * D * kFuse2MaxD2);
+    uint32_t* h2_first = reinterpret_cast<uint32_t*>(split_pos + D);  // counter index of (digit 0, first seg)
+    uint32_t* h2_stride = h2_first + D;
 
     if (blockIdx.x >= *p.nsegs) return;
     const Segment seg = p.segs[blockIdx.x];
@@ -333,6 +356,20 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
                 p.bounds[seg.rel][(uint64_t)(seg.parent_first & 0x7fffffffu) * p.bounds_stride + tid] = c;
         }
         gcur[tid] = c;
+        if (FUSE2) {
+            // Which pass-2 segment of parent `tid` this CTA's output run starts in, and where the
+            // next one begins. The run is at most one pass-1 segment long (<= seg_len2), so it
+            // touches at most two pass-2 segments: slot 0 and slot 1.
+            Parent2 par{0, 0, 1};
+            if (tid < (int)p.ndigits) par = p.parents2[seg.rel][tid];
+            const uint64_t first = (c - par.lo) / p.seg_len2[seg.rel];
+            split_pos[tid] = par.lo + (first + 1) * p.seg_len2[seg.rel];
+            h2_first[tid] = par.cnt_base + (uint32_t)first;
+            h2_stride[tid] = par.nseg;
+        }
+    }
+    if (FUSE2) {
+        for (int i = tid; i < 2 * D * (int)kFuse2MaxD2; i += TPB) h2[i] = 0;
     }
 
     ulonglong2 v[IPT];
@@ -359,17 +396,19 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
         __syncwarp();
 
         // ---- rank (stable within the warp's 32*IPT consecutive tuples) ----
-        uint32_t dr[IPT];  // digit | rank << 16
+        uint32_t dr[IPT];  // digit (9 bits) | pass-2 digit << 9 (FUSE2, 7 bits) | rank << 16
         auto rank_round = [&](int i, auto is_full) {
             constexpr bool kFull = decltype(is_full)::value;
             const bool valid = kFull || (uint32_t)(i * 32) < n_mine;
-            const uint32_t d = valid ? digit_of<POW2>(hash_key<HASH>(v[i].x, p.hp), p.df) : D;
+            const uint64_t h = hash_key<HASH>(v[i].x, p.hp);
+            const uint32_t d = valid ? digit_of<POW2>(h, p.df) : D;
             const uint32_t peers = warp_peers<kFull ? BITS : BITS + 1, BALLOT>(d);
             const uint32_t prev = wcw[d];
             __syncwarp();
             if (lane == __ffs(peers) - 1) wcw[d] = prev + __popc(peers);
             __syncwarp();
             dr[i] = d | ((prev + __popc(peers & lt)) << 16);
+            if (FUSE2) dr[i] |= digit_of<POW2>(h, p.df2) << 9;
         };
         if (full) {
 #pragma unroll
@@ -414,11 +453,15 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
         // ---- stage ----
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
-            const uint32_t d = dr[i] & 0xffffu;
+            const uint32_t d = dr[i] & 0x1ffu;
             if (full || d < D) {
                 const uint32_t pos = dbase[d] + wcw[d] + (dr[i] >> 16);
                 stage[pos] = v[i];
                 if (!TMA_STORE) sdig[pos] = (uint16_t)d;
+                if (FUSE2) {
+                    const uint32_t slot = gbase[d] + pos >= split_pos[d];
+                    atomicAdd(&h2[(slot * D + d) * kFuse2MaxD2 + ((dr[i] >> 9) & 0x7fu)], 1u);
+                }
             }
         }
         // prefetch the next tile while this one is flushed
@@ -440,6 +483,17 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
             }
         }
         // The next iteration's barriers separate this flush from the next stage step.
+    }
+    if (FUSE2) {
+        // flush this segment's pass-2 counts (<= 2 * D * d2 non-zero entries)
+        cta_sync();
+        for (uint32_t i = tid; i < 2u * D * kFuse2MaxD2; i += TPB) {
+            const uint32_t c = h2[i];
+            if (c) {
+                const uint32_t d2 = i % kFuse2MaxD2, d = (i / kFuse2MaxD2) % D, slot = i / (kFuse2MaxD2 * D);
+                atomicAdd(&p.counts2[h2_first[d] + d2 * h2_stride[d] + slot], c);
+            }
+        }
     }
     if (TMA_STORE) bulk_wait_all0();
 }
@@ -534,7 +588,14 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes(PassParams p) {
 // Single CTA; runs on the device so the pipeline never waits for the host.
 // =================================================================================================
 struct Plan2Params {
-    const uint64_t* bounds1[2];  // D1 + 1 boundaries per relation (last = n)
+    // pass-1 boundaries come straight from the scanned cursors: boundary(rel, d) =
+    // cursors[cnt_base1[rel] + d * nseg1[rel]] - bias[rel]; they are also written to bounds1.
+    const uint64_t* cursors;
+    uint32_t cnt_base1[2], nseg1[2];
+    uint64_t bias[2];
+    uint64_t* bounds1[2];  // out: D1 + 1 boundaries per relation (last = n, preset by the host)
+    Parent2* parents2[2];  // out
+    uint64_t seg_len[2];   // pass-2 segment length (host-chosen, a multiple of the tile)
     uint64_t n[2];
     uint32_t d1;          // parents per relation
     uint32_t d2;          // digits of pass 2
@@ -552,21 +613,28 @@ __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
     uint32_t seg_base = 0;  // segments emitted by previous relations
     for (int rel = 0; rel < 2; ++rel) {
         const uint64_t n = p.n[rel];
-        // segment length: a whole number of tiles, about n / target_segs
-        uint64_t seg_len = (n + p.target_segs[rel] - 1) / (p.target_segs[rel] ? p.target_segs[rel] : 1);
-        seg_len = ((seg_len + p.tile - 1) / p.tile) * p.tile;
-        if (seg_len == 0) seg_len = p.tile;
+        const uint64_t seg_len = p.seg_len[rel];
         uint64_t lo = 0, len = 0;
         uint32_t ns = 0;
         if (threadIdx.x < p.d1) {
-            lo = p.bounds1[rel][threadIdx.x];
-            const uint64_t hi = (threadIdx.x + 1 == p.d1) ? n : p.bounds1[rel][threadIdx.x + 1];
+            auto boundary = [&](uint32_t d) -> uint64_t {
+                if (d >= p.d1 || p.nseg1[rel] == 0) return d >= p.d1 ? n : 0;
+                return p.cursors[p.cnt_base1[rel] + (uint64_t)d * p.nseg1[rel]] - p.bias[rel];
+            };
+            lo = boundary(threadIdx.x);
+            const uint64_t hi = boundary(threadIdx.x + 1);
             len = hi - lo;
             ns = (uint32_t)((len + seg_len - 1) / seg_len);
+            p.bounds1[rel][threadIdx.x] = lo;
         }
         uint64_t total;
         const uint32_t first = (uint32_t)block_excl_scan_u64(ns, sh, &total);
         if (threadIdx.x < p.d1) {
+            Parent2 par;
+            par.lo = lo;
+            par.cnt_base = (seg_base + first) * p.d2;
+            par.nseg = ns;
+            p.parents2[rel][threadIdx.x] = par;
             for (uint32_t s = 0; s < ns; ++s) {
                 const uint32_t gi = seg_base + first + s;
                 if (gi >= p.max_segs) break;
