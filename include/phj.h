@@ -179,6 +179,24 @@ int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* 
 int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, const uint64_t** d_bounds,
                           size_t* n);
 
+/* ---- multi-GPU exchange fused into the split (handles created with PHJ_ALGO_SHARD_SPLIT) ------
+ * phj_shard_count: histogram + scan of the uploaded relations by owner rank; counts[rel * ranks +
+ * owner] tuples go to `owner`. phj_shard_scatter: the scatter of the same split, with owner d's
+ * piece of relation `rel` written straight to dst[rel][d] + off[rel][d] tuples -- typically a
+ * peer GPU's receive buffer mapped with phj_shared_open, i.e. the partition shuffle happens as
+ * NVLink stores from the scatter kernel (TMA bulk stores) instead of a separate all-to-all.
+ * Call order per join: phj_shard_count, exchange counts, phj_shard_scatter, barrier across ranks. */
+int phj_shard_count(phj_handle* h, uint64_t* counts);
+int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off_build,
+                      void* const* dst_probe, const uint64_t* off_probe, phj_result* out);
+
+/* Device memory that other processes on the node can map (CUDA IPC): the receive buffers of the
+ * fused shuffle. `ipc_handle` is 64 opaque bytes to hand to the peers (any transport). */
+int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* ipc_handle);
+int phj_shared_open(int32_t device, const unsigned char* ipc_handle, void** d_ptr);
+int phj_shared_close(int32_t device, void* d_ptr);
+int phj_shared_free(int32_t device, void* d_ptr);
+
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
  * names[i] points to a static string. */
 int phj_kernel_times(phj_handle* h, const char** names, uint64_t* ns, uint32_t cap);

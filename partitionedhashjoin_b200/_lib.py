@@ -98,6 +98,12 @@ SIGNATURES = {
     "phj_read_partitions": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "phj_device_partitions": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_size_t)]),
+    "phj_shard_count": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phj_shard_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PhjResult)]),
+    "phj_shared_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),
+    "phj_shared_free": (C.c_int, [C.c_int32, C.c_void_p]),
     "phj_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
     "phj_get_device_info": (C.c_int, [C.c_int32, C.POINTER(PhjDeviceInfo)]),
     "phj_device_count": (C.c_int, []),

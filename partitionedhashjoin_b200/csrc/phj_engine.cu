@@ -119,6 +119,9 @@ struct phj_handle {
     phj::Parent2* d_parents2[2] = {nullptr, nullptr};
     size_t cap_parents2 = 0;
     bool fuse2 = false;             // pass-2 histogram accumulated by the pass-1 scatter
+    ulonglong2** d_outd[2] = {nullptr, nullptr};  // shard split: per-owner destination bases
+    bool shard_counted = false;
+    uint64_t shard_bounds[2][65] = {};
     phj::Segment* d_segs1 = nullptr;
     phj::Segment* d_segs2 = nullptr;
     size_t cap_segs1 = 0, cap_segs2 = 0;
@@ -992,7 +995,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1118,6 +1121,144 @@ int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, con
     if (d_data) *d_data = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
     if (d_bounds) *d_bounds = h->d_bounds2[which];
     if (n) *n = h->n[which];
+    return PHJ_OK;
+}
+
+// ---- fused multi-GPU shuffle -----------------------------------------------------------------
+static void fill_pass1_params(phj_handle* h, PassParams& p1) {
+    const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
+    for (int rel = 0; rel < 2; ++rel) {
+        p1.in[rel] = h->d_in[rel];
+        p1.out[rel] = h->d_buf_a[rel];
+        p1.bounds[rel] = h->d_bounds2[rel];
+    }
+    p1.segs = h->d_segs1;
+    p1.nsegs = h->d_scalars + kNsegs1;
+    p1.counts = h->d_counts;
+    p1.cursors = h->d_cursors;
+    p1.cursor_bias[0] = 0;
+    p1.cursor_bias[1] = h->n[0];
+    p1.bounds_stride = h->d1;
+    p1.ndigits = h->d1;
+    p1.hp = hp;
+    p1.df = digit_fn(h, 1);
+}
+
+int phj_shard_count(phj_handle* h, uint64_t* counts) {
+    if (!h || !counts) return fail(PHJ_ERR_INVALID, "handle or counts is null");
+    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
+    if (!h->have_data) return fail(PHJ_ERR_STATE, "phj_shard_count called before phj_upload / phj_bind_device");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    h->launches = 0;
+    h->n_ktimes = 0;
+    PassParams p1{};
+    fill_pass1_params(h, p1);
+    PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    if (h->nsegs1 > 0) {
+        {
+            KernelScope ks(h, "radix_histogram[split]");
+            PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
+        }
+        run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
+        BoundsParams bp{};
+        bp.cursors = h->d_cursors;
+        for (int rel = 0; rel < 2; ++rel) {
+            bp.bounds[rel] = h->d_bounds2[rel];
+            bp.cnt_base[rel] = h->cnt_base1_rel[rel];
+            bp.nseg[rel] = h->nseg1_rel[rel];
+        }
+        bp.bias[1] = h->n[0];
+        bp.ndigits = h->d1;
+        KernelScope ks(h, "bounds_from_cursors");
+        bounds_from_cursors<<<1, 2 * 64, 0, h->stream>>>(bp);
+    }
+    const uint32_t w = h->d1;
+    for (int rel = 0; rel < 2; ++rel)
+        PHJ_CUDA(cudaMemcpyAsync(h->shard_bounds[rel], h->d_bounds2[rel], (w + 1) * 8, cudaMemcpyDeviceToHost,
+                                 h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    for (int rel = 0; rel < 2; ++rel)
+        for (uint32_t d = 0; d < w; ++d) counts[rel * w + d] = h->shard_bounds[rel][d + 1] - h->shard_bounds[rel][d];
+    h->shard_counted = true;
+    return PHJ_OK;
+}
+
+int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off_build,
+                      void* const* dst_probe, const uint64_t* off_probe, phj_result* out) {
+    if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
+    if (!h->shard_counted) return fail(PHJ_ERR_STATE, "phj_shard_scatter needs a preceding phj_shard_count");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    memset(out, 0, sizeof(*out));
+    const uint32_t w = h->d1;
+    void* const* dst[2] = {dst_build, dst_probe};
+    const uint64_t* off[2] = {off_build, off_probe};
+    PassParams p1{};
+    fill_pass1_params(h, p1);
+    ulonglong2* host_ptrs[2][64];
+    for (int rel = 0; rel < 2; ++rel) {
+        if (!dst[rel]) continue;  // this relation stays local (split into buf_a)
+        if (!h->d_outd[rel]) PHJ_CUDA(cudaMalloc(&h->d_outd[rel], 64 * sizeof(void*)));
+        for (uint32_t d = 0; d < w; ++d)  // run d starts at cursor == bounds[d]: rebase it to off[d]
+            host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) -
+                                h->shard_bounds[rel][d];
+        PHJ_CUDA(cudaMemcpyAsync(h->d_outd[rel], host_ptrs[rel], w * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
+        p1.outd[rel] = h->d_outd[rel];
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    if (h->nsegs1 > 0) {
+        KernelScope ks(h, "radix_scatter[split]");
+        PHJ_CUDA(launch_pass(h, true, h->b1, p1, h->nsegs1));
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    out->partition_ns = (uint64_t)((ev_ms(h->ev[1], h->ev[3])) * 1e6);
+    out->total_ns = out->partition_ns;
+    out->passes = 1;
+    out->partitions = h->P;
+    out->kernel_launches = h->launches;
+    out->hbm_bytes_alg = 16ull * 2 * (h->n[0] + h->n[1]);
+    h->shard_counted = false;
+    h->joined_radix = true;
+    return PHJ_OK;
+}
+
+int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* ipc_handle) {
+    if (!d_ptr || !ipc_handle) return fail(PHJ_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    PHJ_CUDA(cudaSetDevice(device));
+    PHJ_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return fail(PHJ_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &hd, 64);
+    return PHJ_OK;
+}
+
+int phj_shared_open(int32_t device, const unsigned char* ipc_handle, void** d_ptr) {
+    if (!d_ptr || !ipc_handle) return fail(PHJ_ERR_INVALID, "null argument");
+    PHJ_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, 64);
+    PHJ_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return PHJ_OK;
+}
+
+int phj_shared_close(int32_t device, void* d_ptr) {
+    PHJ_CUDA(cudaSetDevice(device));
+    if (d_ptr) PHJ_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return PHJ_OK;
+}
+
+int phj_shared_free(int32_t device, void* d_ptr) {
+    PHJ_CUDA(cudaSetDevice(device));
+    if (d_ptr) PHJ_CUDA(cudaFree(d_ptr));
     return PHJ_OK;
 }
 

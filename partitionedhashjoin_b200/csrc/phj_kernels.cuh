@@ -62,6 +62,8 @@ struct PassParams {
     uint32_t* counts;          // histogram out (radix_histogram)
     const uint64_t* cursors;   // exclusive scan of counts (radix_scatter)
     uint64_t cursor_bias[2];   // flat scan spans R then S: S cursors are offset by |R|
+    ulonglong2* const* outd[2];  // optional (shard split): per-digit output base, device array of
+                               // ndigits pointers per relation; digit d's run goes to outd[d] + cursor
     uint64_t* bounds[2];       // partition boundaries of this pass's output, per relation
     uint32_t bounds_stride;    // digits per parent in `bounds` indexing
     uint32_t ndigits;          // digits this pass really has (<= the kernel's 1 << BITS)
@@ -473,13 +475,17 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
         if (TMA_STORE) {
             if (tid < D) {
                 const uint32_t b = dbase[tid], e = dbase[tid + 1];
-                if (e > b) bulk_store_s2g(out + gbase[tid] + b, stage + b, (e - b) * 16u);
+                if (e > b) {
+                    ulonglong2* od = p.outd[seg.rel] ? p.outd[seg.rel][tid] : out;  // maybe a peer GPU
+                    bulk_store_s2g(od + gbase[tid] + b, stage + b, (e - b) * 16u);
+                }
                 bulk_commit();
             }
         } else {
             for (uint32_t j = tid; j < n_valid; j += TPB) {
                 const uint32_t d = sdig[j];
-                st_stream_v2(out + gbase[d] + j, stage[j]);
+                ulonglong2* od = p.outd[seg.rel] ? p.outd[seg.rel][d] : out;
+                st_stream_v2(od + gbase[d] + j, stage[j]);
             }
         }
         // The next iteration's barriers separate this flush from the next stage step.
@@ -991,6 +997,23 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
     if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
     cta_sync();
     if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
+}
+
+// Partition boundaries straight from the scanned cursors (single-pass plans that need them before
+// the scatter runs): bounds[rel][d] = cursors[cnt_base[rel] + d * nseg[rel]] - bias[rel].
+struct BoundsParams {
+    const uint64_t* cursors;
+    uint64_t* bounds[2];
+    uint32_t cnt_base[2], nseg[2];
+    uint64_t bias[2];
+    uint32_t ndigits;
+};
+__global__ void bounds_from_cursors(BoundsParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * p.ndigits) return;
+    const int rel = i / p.ndigits;
+    const uint32_t d = i % p.ndigits;
+    if (p.nseg[rel]) p.bounds[rel][d] = p.cursors[p.cnt_base[rel] + (uint64_t)d * p.nseg[rel]] - p.bias[rel];
 }
 
 // Test hook: raw hashes of a key array.

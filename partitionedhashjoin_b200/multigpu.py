@@ -145,6 +145,185 @@ class ShardedRadixJoin:
         self.backend.close()
 
 
+class FusedGpuBackend(GpuBackend):
+    """The partition shuffle as NVLink stores: every rank's receive window is mapped by its peers
+    (CUDA IPC, phj_shared_*), and the split scatter's TMA bulk stores write each owner's piece
+    straight into that owner's window (phj_shard_scatter). No separate all-to-all of tuples."""
+
+    def __init__(self, world, device, **kw):
+        super().__init__(world, device, **kw)
+        from . import _lib
+        self._C, self._lib, self._check = __import__("ctypes"), _lib.lib, _lib.check
+        self.win = [None, None]                                # own windows: device pointers
+        self.peer = [[None] * world, [None] * world]           # mapped windows of every rank
+        self.rank = None
+
+    # -- windows ---------------------------------------------------------------------------
+    def win_alloc(self, which, rows):
+        C = self._C
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._check(self._lib.phj_shared_alloc(self.device, max(rows, 1) * 16, C.byref(ptr), handle))
+        self.win[which] = ptr.value
+        return bytes(handle)
+
+    def win_free(self, which):
+        if self.win[which]:
+            self._check(self._lib.phj_shared_free(self.device, self._C.c_void_p(self.win[which])))
+            self.win[which] = None
+
+    def peer_open(self, which, src, handle, own):
+        C = self._C
+        if own:
+            self.peer[which][src] = self.win[which]
+            return
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.phj_shared_open(self.device, buf, C.byref(ptr)))
+        self.peer[which][src] = ptr.value
+
+    def peer_close(self, which, src, own):
+        p = self.peer[which][src]
+        if p and not own:
+            self._check(self._lib.phj_shared_close(self.device, self._C.c_void_p(p)))
+        self.peer[which][src] = None
+
+    # -- the split, in two halves ------------------------------------------------------------
+    def count(self):
+        C = self._C
+        counts = np.zeros((2, self.world), dtype=np.uint64)
+        self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
+        return counts.astype(np.int64)
+
+    def scatter(self, offsets):
+        """offsets[rel][owner]: first row of this rank's piece inside the owner's window."""
+        from ._lib import PhjResult
+        C = self._C
+        arrs = []
+        for which in (0, 1):
+            ptrs = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer[which]])
+            offs = np.ascontiguousarray(offsets[which], dtype=np.uint64)
+            arrs += [ptrs, offs]
+        res = PhjResult()
+        self._check(self._lib.phj_shard_scatter(self.split_engine._h, arrs[0], arrs[1].ctypes.data, arrs[2],
+                                                arrs[3].ctypes.data, C.byref(res)))
+        self.launches += res.kernel_launches
+        return int(res.total_ns)
+
+    def local_join_window(self, rows_R, rows_S):
+        self.local_engine.bind_device(self.win[0] if rows_R else 0, rows_R, self.win[1] if rows_S else 0, rows_S)
+        res = self.local_engine.join()
+        self.launches += res["kernel_launches"]
+        return res["matches"], res
+
+    def close(self):
+        super().close()
+
+
+class FusedShardedRadixJoin:
+    """One rank of the sharded join with the shuffle fused into the split scatter.
+
+      count     histogram + scan of the shard by owner rank             (phj_shard_count)
+      sizes     all-gather of the world x 2 x world piece sizes: every rank knows where its piece
+                starts inside every owner's window, and how big every window must be
+      windows   (re)allocated and re-mapped collectively only when a window is too small
+      scatter   the split scatter writes owner d's piece into d's window over NVLink
+      barrier   all pieces have landed
+      local     ordinary radix join on the window; all-reduce of the count
+    """
+
+    GROW = 1.125
+
+    def __init__(self, dist, rank, world, backend):
+        if world & (world - 1):
+            raise ValueError("the number of ranks must be a power of two")
+        self.dist, self.rank, self.world, self.backend = dist, rank, world, backend
+        self.caps = np.zeros((2, world), dtype=np.int64)  # rows of every rank's windows (same on all ranks)
+        self.last = {}
+
+    def upload(self, R_shard, S_shard):
+        self.backend.upload(R_shard, S_shard)
+
+    def _gather_counts(self, counts):
+        if self.world == 1:
+            return counts.reshape(1, 2, 1)
+        be = self.backend
+        mine = be.int_tensor(counts.reshape(-1))
+        everyone = be.int_tensor(np.zeros(self.world * 2 * self.world))
+        self.dist.all_gather_into_tensor(everyone, mine)
+        return everyone.cpu().numpy().reshape(self.world, 2, self.world)  # [source][rel][owner]
+
+    def _ensure_windows(self, need):
+        """need[rel][owner] rows. Every rank sees the same `need` and `caps`, so all of them take the
+        same decision without further communication."""
+        grow = need > self.caps
+        if not grow.any():
+            return False
+        be, world, rank = self.backend, self.world, self.rank
+        for which in (0, 1):
+            for r in range(world):
+                if grow[which][r]:
+                    be.peer_close(which, r, own=(r == rank))
+        if world > 1:
+            self.dist.barrier()  # nobody maps a window that is about to be freed
+        new_caps = np.where(grow, (need * self.GROW).astype(np.int64) + 4096, self.caps)
+        handles = [None, None]
+        for which in (0, 1):
+            if grow[which][rank]:
+                be.win_free(which)
+                handles[which] = be.win_alloc(which, int(new_caps[which][rank]))
+        if world > 1:
+            everyone = [None] * world
+            self.dist.all_gather_object(everyone, handles)
+        else:
+            everyone = [handles]
+        for which in (0, 1):
+            for r in range(world):
+                if grow[which][r]:
+                    be.peer_open(which, r, everyone[r][which], own=(r == rank))
+        self.caps = new_caps
+        return True
+
+    def join(self) -> dict:
+        be, world, rank = self.backend, self.world, self.rank
+        t0 = time.perf_counter()
+        counts = be.count()                                   # [rel][owner]
+        t1 = time.perf_counter()
+        M = self._gather_counts(counts)                       # [source][rel][owner]
+        need = M.sum(axis=0)                                  # rows arriving at every owner
+        regrown = self._ensure_windows(need)
+        offsets = M[:rank].sum(axis=0)                        # rows of lower ranks come first
+        t2 = time.perf_counter()
+        scatter_ns = be.scatter(offsets)
+        if world > 1:
+            self.dist.barrier()                               # every rank's stores are complete
+        t3 = time.perf_counter()
+        rows = [int(need[0][rank]), int(need[1][rank])]
+        local_matches, res = be.local_join_window(rows[0], rows[1])
+        t4 = time.perf_counter()
+        total = be.count_tensor(local_matches)
+        if world > 1:
+            self.dist.all_reduce(total)
+        matches = int(total.item())
+        t5 = time.perf_counter()
+        self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
+                     "exchange_s": t3 - t1, "sizes_s": t2 - t1, "scatter_s": t3 - t2, "local_s": t4 - t3,
+                     "reduce_s": t5 - t4, "total_s": t5 - t0, "recv_rows": rows, "regrown": regrown,
+                     "send_bytes_remote": int(16 * (counts.sum() - counts[:, rank].sum())) if world > 1 else 0,
+                     "local_result": res, "split_device_ns": scatter_ns, "scatter_device_ns": scatter_ns}
+        return self.last
+
+    def close(self):
+        be, world, rank = self.backend, self.world, self.rank
+        for which in (0, 1):
+            for r in range(world):
+                be.peer_close(which, r, own=(r == rank))
+        if world > 1:
+            self.dist.barrier()
+        for which in (0, 1):
+            be.win_free(which)
+        be.close()
+
+
 def shard_inputs(phj, rank, world, n_build, n_probe, skew, base_seed, batches):
     """Weak-scaling shards: R = keys 1..world*n_build cut by rank, S = Zipf over the whole key range."""
     Rp, Sp = phj.PinnedTuples(n_build), phj.PinnedTuples(n_probe)
@@ -163,8 +342,13 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     import partitionedhashjoin_b200 as phj
     n_build, n_probe = 10_000_000, 200_000_000
     Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
-    backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
-    job = ShardedRadixJoin(dist, rank, world, backend)
+    fused = getattr(args, "shuffle", "fused") == "fused"
+    if fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
+        backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
+        job = FusedShardedRadixJoin(dist, rank, world, backend)
+    else:      # split locally, then one NCCL all-to-all per relation
+        backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
+        job = ShardedRadixJoin(dist, rank, world, backend)
     job.upload(Rp.array, Sp.array)
     for _ in range(args.warmup):
         res = job.join()
@@ -213,7 +397,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         lr = res["local_result"]
         cfg = workload_config(args)
         cfg["workload"] = (f"radix join sharded over {world} B200: {world} x (10M x 200M) row shards = "
-                           f"{world * 10}M x {world * 200}M, NCCL all-to-all partition shuffle, then local "
+                           f"{world * 10}M x {world * 200}M, partition shuffle "
+                           f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}, then local "
                            f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
         cfg["parallelism"] = f"partition-sharded x{world}"
         exch_bytes = res["send_bytes_remote"]
@@ -235,6 +420,6 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             "clocks": clocks.summary(), "matches": res["matches"], "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
-    backend.close()
+    job.close()
     dist.barrier()
     dist.destroy_process_group()

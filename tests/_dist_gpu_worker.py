@@ -1,0 +1,74 @@
+"""Worker of the gpu-marked multi-rank tests: one rank per GPU over NCCL, the product backends
+(multigpu.GpuBackend / FusedGpuBackend) on the device, the oracle only as the checker.
+TEST INFRASTRUCTURE."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import _cases  # noqa: E402
+import _oracle  # noqa: E402
+from partitionedhashjoin_b200 import multigpu  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1]  # fused | nccl
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    oracle = _oracle.Oracle()
+    # same global relations on every rank; each rank uploads its row range
+    keys_r = _cases.splitmix64(400_000, 21).astype(np.int64) % 300_007
+    keys_s = np.where(_cases.splitmix64(3_000_000, 22) % np.uint64(10) < 3, 4242,
+                      _cases.splitmix64(3_000_000, 23) % np.uint64(450_001)).astype(np.int64)
+    R, S = _cases.tuples(keys_r), _cases.tuples(keys_s)
+    want = oracle.count_by_sort(R, S)
+
+    def shard(rel, scale=1):
+        per = rel.shape[0] // world
+        lo, hi = rank * per, (rel.shape[0] if rank == world - 1 else (rank + 1) * per)
+        return rel[lo:hi]
+
+    if mode == "fused":
+        job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(world, local, partitions_local=256))
+    else:
+        job = multigpu.ShardedRadixJoin(dist, rank, world, multigpu.GpuBackend(world, local, partitions_local=256))
+    job.upload(shard(R), shard(S))
+    res = job.join()
+    assert res["matches"] == want, (res["matches"], want)
+    res = job.join()
+    assert res["matches"] == want, (res["matches"], want)
+    if mode == "fused":
+        assert not res["regrown"]
+        # what landed in this rank's window is exactly the tuples it owns, pieces in source-rank order
+        # with input order inside a piece (stable split)
+        be = job.backend
+        for which, rel in ((0, R), (1, S)):
+            rows = res["recv_rows"][which]
+            got = torch.as_tensor(multigpu._CudaView(be.win[which], rows), device=f"cuda:{local}").cpu().numpy() \
+                if rows else np.empty((0, 2), np.int64)
+            owner = ((oracle.hash_batch(0, 0x9E3779B97F4A7C15, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT))
+                     & np.uint64(world - 1)).astype(np.int64)
+            expect = rel[owner == rank]  # global input order == source-rank order, then input order
+            assert got.shape[0] == expect.shape[0], (got.shape, expect.shape)
+            assert (got[:, 0] == expect["id"]).all() and (got[:, 1] == expect["payload"]).all()
+        # bigger shards: windows regrow collectively
+        job.upload(shard(R), np.concatenate([shard(S)] * 2))
+        res = job.join()
+        assert res["matches"] == 2 * want and res["regrown"]
+    if rank == 0:
+        print(json.dumps({"mode": mode, "world": world, "matches": res["matches"], "want": want}))
+    job.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

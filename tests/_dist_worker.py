@@ -57,8 +57,71 @@ class OracleBackend:
         pass
 
 
+class OracleFusedBackend(OracleBackend):
+    """CPU stand-in for multigpu.FusedGpuBackend: the receive windows are POSIX shared memory that
+    the peers map by name (the role CUDA IPC plays on the device) and write their pieces into."""
+
+    def __init__(self, world, oracle):
+        super().__init__(world, oracle)
+        self.win, self.peer = [None, None], [[None] * world, [None] * world]
+        self.allocs = 0
+
+    def win_alloc(self, which, rows):
+        from multiprocessing import shared_memory
+        shm = shared_memory.SharedMemory(create=True, size=max(rows, 1) * 16)
+        self.win[which] = shm
+        self.allocs += 1
+        return shm.name.encode()
+
+    def win_free(self, which):
+        if self.win[which] is not None:
+            self.win[which].close()
+            self.win[which].unlink()
+            self.win[which] = None
+
+    def peer_open(self, which, src, handle, own):
+        from multiprocessing import shared_memory
+        self.peer[which][src] = self.win[which] if own else shared_memory.SharedMemory(name=handle.decode())
+
+    def peer_close(self, which, src, own):
+        if self.peer[which][src] is not None and not own:
+            self.peer[which][src].close()
+        self.peer[which][src] = None
+
+    def count(self):
+        self.pieces = []
+        counts = []
+        for rel in self.rel:
+            owner = ((self.oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT))
+                     & np.uint64(self.world - 1)).astype(np.int64)
+            self.pieces.append([rel[owner == d] for d in range(self.world)])
+            counts.append(np.bincount(owner, minlength=self.world))
+        return np.stack(counts).astype(np.int64)
+
+    def scatter(self, offsets):
+        for which in (0, 1):
+            for d in range(self.world):
+                piece = self.pieces[which][d]
+                if piece.shape[0]:
+                    win = np.ndarray((self.peer[which][d].size // 16,), dtype=_cases.TUPLE, buffer=self.peer[which][d].buf)
+                    o = int(offsets[which][d])
+                    win[o:o + piece.shape[0]] = piece
+                    del win
+        return 0
+
+    def local_join_window(self, rows_R, rows_S):
+        got = []
+        for which, rows in ((0, rows_R), (1, rows_S)):
+            win = np.ndarray((rows,), dtype=_cases.TUPLE, buffer=self.win[which].buf) if rows else np.empty(0, _cases.TUPLE)
+            got.append(win.copy())
+            del win
+        self.received = tuple(got)
+        return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
+
+
 def main():
     case = sys.argv[1]
+    fused = len(sys.argv) > 2 and sys.argv[2] == "fused"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     oracle = _oracle.Oracle()
@@ -85,8 +148,12 @@ def main():
             hi = n
         return rel[lo:hi]
 
-    backend = OracleBackend(world, oracle)
-    job = multigpu.ShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
+    if fused:
+        backend = OracleFusedBackend(world, oracle)
+        job = multigpu.FusedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
+    else:
+        backend = OracleBackend(world, oracle)
+        job = multigpu.ShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
     job.upload(shard(R), shard(S))
     res = job.join()
     # every received tuple belongs to this rank, and nothing was lost or duplicated
@@ -102,8 +169,18 @@ def main():
     assert res["matches"] == want, (res["matches"], want)
     res2 = job.join()  # the job is reusable
     assert res2["matches"] == want
+    if fused:
+        assert res["regrown"] and not res2["regrown"] and backend.allocs <= 2  # windows are kept
+        # a bigger probe shard: the windows grow collectively, the count follows
+        job.upload(shard(R), np.concatenate([shard(S)] * 3))
+        res3 = job.join()
+        assert res3["matches"] == 3 * want
+        job.upload(shard(R), shard(S))
+        assert job.join()["matches"] == want
     if rank == 0:
-        print(json.dumps({"case": case, "world": world, "matches": res["matches"], "want": want}))
+        print(json.dumps({"case": case, "world": world, "matches": res["matches"], "want": want, "fused": fused}))
+    if fused:
+        job.close()
     if world > 1:
         dist.barrier()
     dist.destroy_process_group()

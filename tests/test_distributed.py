@@ -34,6 +34,16 @@ def test_sharded_join_over_gloo(world, case):
     assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
 
 
+@pytest.mark.parametrize("world,case", [(2, "random"), (2, "skewed"), (2, "tiny"), (4, "random"), (1, "random")])
+def test_fused_shuffle_over_gloo(world, case):
+    """FusedShardedRadixJoin: sizes all-gather -> window offsets -> every rank writes its pieces into
+    the owners' windows (shared memory stands in for the CUDA-IPC-mapped NVLink windows)."""
+    r = torchrun(world, os.path.join(HERE, "_dist_worker.py"), case, "fused")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == world and line["fused"] and line["matches"] == line["want"] and line["want"] > 0
+
+
 def test_world_must_be_power_of_two():
     from partitionedhashjoin_b200 import multigpu
     with pytest.raises(ValueError):
@@ -77,3 +87,34 @@ def test_shard_split_kernel_matches_oracle(phj, oracle, world):
             want = rel[np.argsort(owner, kind="stable")]
             assert np.diff(bounds.astype(np.int64)).tolist() == np.bincount(owner, minlength=world).tolist()
             assert (got["id"] == want["id"]).all() and (got["payload"] == want["payload"]).all()
+
+
+@pytest.mark.gpu
+def test_fused_shuffle_single_gpu(phj, oracle):
+    """FusedGpuBackend with one rank: phj_shard_count + phj_shard_scatter into the rank's own
+    shared window (phj_shared_alloc), then the local join bound to the window."""
+    import numpy as np
+
+    import _cases
+    from partitionedhashjoin_b200 import multigpu
+    R = _cases.tuples(_cases.splitmix64(60000, 5).astype(np.int64) % 50021)
+    S = _cases.tuples(_cases.splitmix64(900000, 6).astype(np.int64) % 70001)
+    job = multigpu.FusedShardedRadixJoin(None, 0, 1, multigpu.FusedGpuBackend(1, 0, partitions_local=256))
+    job.upload(R, S)
+    want = oracle.count_by_sort(R, S)
+    assert job.join()["matches"] == want
+    assert job.join()["matches"] == want
+    job.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,mode", [(2, "fused"), (2, "nccl"), (4, "fused"), (8, "fused")])
+def test_sharded_join_on_gpus(phj, world, mode):
+    """One rank per GPU over NCCL: the fused NVLink-store shuffle (and the all-to-all variant)
+    against the oracle's count; skipped when the box has fewer GPUs."""
+    if phj.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = torchrun(world, os.path.join(HERE, "_dist_gpu_worker.py"), mode, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
