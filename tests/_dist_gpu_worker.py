@@ -45,6 +45,7 @@ def main():
     assert res["matches"] == want, (res["matches"], want)
     res = job.join()
     assert res["matches"] == want, (res["matches"], want)
+    first = res["matches"]
     if mode == "fused":
         assert not res["regrown"]
         # what landed in this rank's window is exactly the tuples it owns, pieces in source-rank order
@@ -64,7 +65,7 @@ def main():
         res = job.join()
         assert res["matches"] == 2 * want and res["regrown"]
     if rank == 0:
-        print(json.dumps({"mode": mode, "world": world, "matches": res["matches"], "want": want}))
+        print(json.dumps({"mode": mode, "world": world, "matches": first, "want": want}))
     job.close()
     dist.barrier()
     dist.destroy_process_group()
