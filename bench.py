@@ -304,8 +304,10 @@ def main():
     ap.add_argument("--hash", default="xxh3", choices=["xxh3", "murmur3", "city"])
     ap.add_argument("--partitions", type=int, default=4096)
     ap.add_argument("--ref-partitions", type=int, default=2048)
-    ap.add_argument("--shuffle", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: partition shuffle fused into the split scatter (peer stores) or NCCL all-to-all")
+    ap.add_argument("--shuffle", default="pass1", choices=["pass1", "fused", "nccl"],
+                    help="N > 1: pass1 = the split scatter writes (owner : pass-1 digit) pieces into the owners' "
+                         "windows over NVLink and the local join starts at pass 2; fused = same stores, split by "
+                         "owner only; nccl = local split + NCCL all-to-all")
     ap.add_argument("--quick", action="store_true", help="skip the informational extra configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -43,11 +43,12 @@ enum {
     PHJ_ALGO_NO_PARTITIONING = 0,
     PHJ_ALGO_RADIX_PARTITIONING = 1,
     /* Multi-GPU exchange step (no counterpart in the single-process reference): phj_join only
-     * splits the uploaded relations by owner rank, owner = (hash >> shard_shift) % partitions with
-     * `partitions` = number of ranks (a power of two <= 64); the pieces are then exchanged
-     * (NCCL all-to-all) and every rank runs an ordinary RADIX_PARTITIONING join on what it
-     * received. shard_shift must be >= log2 of that local join's fan-out so the two use disjoint
-     * hash bits. */
+     * splits the uploaded relations by the digit (hash >> shard_shift) % partitions, `partitions`
+     * a power of two <= 256. Either partitions = number of ranks (digit = owner rank; shard_shift
+     * beyond the local join's hash bits) and every rank then runs an ordinary RADIX_PARTITIONING
+     * join on what it received; or partitions = ranks x local pass-1 digits with shard_shift =
+     * the local join's radix_bits[1] (digit = owner rank : local pass-1 digit), in which case what
+     * a rank receives is already pass-1 partitioned (phj_bind_device_partitioned). */
     PHJ_ALGO_SHARD_SPLIT = 2
 };
 
@@ -146,6 +147,15 @@ int phj_upload(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_
  * reads them in place and never writes them). */
 int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
                     size_t n_probe);
+
+/* Same, for device-resident relations that are ALREADY partitioned by the pass-1 digit of this
+ * handle's plan (partition id = hash % partitions, pass-1 digit = its top radix_bits[0] bits):
+ * parent d lies at [bounds[d], bounds[d + 1]), nparents + 1 host boundaries per relation. The join
+ * then starts at pass 2 (or, for a one-pass plan, at build + probe). This is how the multi-GPU path
+ * makes the NVLink shuffle double as pass 1 (the split digit is owner rank x pass-1 digit). */
+int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
+                                size_t n_probe, const uint64_t* bounds_build, const uint64_t* bounds_probe,
+                                uint32_t nparents);
 
 /* ---- the join ---------------------------------------------------------------------------------
  * Stands in for HashJoiner::Run(tableA, tableB, timer) (src/NoPartitioning/HashJoin.hpp:54-74,

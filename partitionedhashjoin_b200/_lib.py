@@ -90,6 +90,8 @@ SIGNATURES = {
     "phj_abi_version": (C.c_uint32, []),
     "phj_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "phj_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "phj_bind_device_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                              C.c_void_p, C.c_void_p, C.c_uint32]),
     "phj_join": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
     "phj_join_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                 C.POINTER(PhjResult)]),

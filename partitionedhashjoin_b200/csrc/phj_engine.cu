@@ -70,6 +70,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kScatTile = PHJ_SCAT_TPB * PHJ_SCAT_IPT;
 constexpr int kMaxBitsPerPass = 8;
 constexpr int kMaxKernelTimes = 24;
+constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
 
 enum Scalar : int {  // device-resident uint32 scalars
     kNsegs1 = 0,
@@ -121,7 +122,11 @@ struct phj_handle {
     bool fuse2 = false;             // pass-2 histogram accumulated by the pass-1 scatter
     ulonglong2** d_outd[2] = {nullptr, nullptr};  // shard split: per-owner destination bases
     bool shard_counted = false;
-    uint64_t shard_bounds[2][65] = {};
+    uint64_t shard_bounds[2][kMaxSplitDigits + 1] = {};
+    // relations bound already partitioned by the pass-1 digit (phj_bind_device_partitioned)
+    bool prepart = false;
+    uint64_t* d_pre_bounds = nullptr;  // [2][d1 + 1]
+    size_t cap_pre_bounds = 0;
     phj::Segment* d_segs1 = nullptr;
     phj::Segment* d_segs2 = nullptr;
     size_t cap_segs1 = 0, cap_segs2 = 0;
@@ -260,9 +265,27 @@ cudaError_t launch_hist_lanes_t(phj_handle* h, const PassParams& pp, uint32_t gr
     return cudaSuccess;
 }
 
+template <int BITS, int HASH, bool POW2>
+cudaError_t launch_hist_lanes8_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    constexpr int kTpb = 256;  // 8 warps x 8 KB of byte counters: three CTAs per SM at 256 digits
+    constexpr size_t smem = HistLanes8Smem<BITS, kTpb>::total;
+    auto kern = radix_histogram_lanes8<BITS, HASH, POW2, kTpb, PHJ_HIST_IPT>;
+    static bool configured[16] = {};
+    if (!configured[h->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[h->device & 15] = true;
+    }
+    kern<<<grid, kTpb, smem, h->stream>>>(pp);
+    return cudaSuccess;
+}
+
 template <int BITS, int HASH>
 cudaError_t launch_pass_hp(phj_handle* h, bool scatter, const PassParams& pp, uint32_t grid) {
     const bool tma = !(h->cfg.flags & PHJ_FLAG_NO_TMA_STORE);
+    if (BITS > 6 && h->use_lanes && !scatter)  // byte-wide lane-private counters for 128 / 256 digits
+        return h->pow2 ? launch_hist_lanes8_t<8, HASH, true>(h, pp, grid)
+                       : launch_hist_lanes8_t<8, HASH, false>(h, pp, grid);
     if (BITS <= 6 && h->use_lanes && !scatter)  // lane-private counters: histogram at the HBM roofline
         return h->pow2 ? launch_hist_lanes_t<6, HASH, true>(h, pp, grid)
                        : launch_hist_lanes_t<6, HASH, false>(h, pp, grid);
@@ -720,8 +743,24 @@ int join_radix(phj_handle* h, phj_result* out) {
         plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
         fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
     };
-    const bool fuse2 = two && h->fuse2;
-    if (h->nsegs1 > 0) {
+    const bool fuse2 = two && h->fuse2 && !h->prepart;
+    if (h->prepart) {
+        // The relations arrived partitioned by the pass-1 digit (the multi-GPU shuffle was pass 1):
+        // their boundaries stand in for the scanned pass-1 cursors, pass 2 reads them in place.
+        if (two) {
+            pl.cursors = h->d_pre_bounds;
+            for (int rel = 0; rel < 2; ++rel) {
+                pl.cnt_base1[rel] = rel * (h->d1 + 1);
+                pl.nseg1[rel] = 1;
+                pl.bias[rel] = 0;
+                p2.in[rel] = h->d_in[rel];
+            }
+        } else {
+            for (int rel = 0; rel < 2; ++rel)
+                PHJ_CUDA(cudaMemcpyAsync(h->d_bounds2[rel], h->d_pre_bounds + rel * (h->d1 + 1), (h->d1 + 1) * 8,
+                                         cudaMemcpyDeviceToDevice, h->stream));
+        }
+    } else if (h->nsegs1 > 0) {
         {
             KernelScope ks(h, "radix_histogram[1]");
             PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
@@ -775,8 +814,8 @@ int join_radix(phj_handle* h, phj_result* out) {
     }
 
     // ---- build + probe per partition ----
-    const ulonglong2* part_build = two ? h->d_buf_b[0] : h->d_buf_a[0];
-    const ulonglong2* part_probe = two ? h->d_buf_b[1] : h->d_buf_a[1];
+    const ulonglong2* part_build = two ? h->d_buf_b[0] : h->prepart ? h->d_in[0] : h->d_buf_a[0];
+    const ulonglong2* part_probe = two ? h->d_buf_b[1] : h->prepart ? h->d_in[1] : h->d_buf_a[1];
     PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 8, h->stream));
     PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kOversize, 0, 4, h->stream));
     JoinParams jp{};
@@ -857,7 +896,7 @@ int join_radix(phj_handle* h, phj_result* out) {
     }
     out->build_ns = best_b;
     out->probe_ns = best_p;
-    out->passes = two ? 2 : 1;
+    out->passes = (two ? 2 : 1) - (h->prepart ? 1 : 0);
     out->partitions = h->P;
     out->fallback_partitions = oversize;
     out->d2h_bytes = 8 + 4 + (uint64_t)h->join_grid * 16 + (oversize ? 8 : 0);
@@ -874,9 +913,10 @@ int validate_config(const phj_config* c) {
         return fail(PHJ_ERR_INVALID, "Unrecognized join algorithm: %d.", c->algo);
     if (c->algo == PHJ_ALGO_SHARD_SPLIT) {
         const uint64_t w = c->partitions;
-        if (w == 0 || w > 64 || (w & (w - 1)) || c->shard_shift > 58 || c->radix_bits[0] || c->radix_bits[1])
-            return fail(PHJ_ERR_INVALID, "shard split needs partitions = number of ranks (a power of two <= 64), "
-                                         "shard_shift <= 58 and no radix_bits");
+        if (w == 0 || w > kMaxSplitDigits || (w & (w - 1)) || c->shard_shift > 56 || c->radix_bits[0] ||
+            c->radix_bits[1])
+            return fail(PHJ_ERR_INVALID, "shard split needs partitions = ranks x local pass-1 digits (a power of "
+                                         "two <= 256), shard_shift <= 56 and no radix_bits");
     }
     if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
         return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", c->hash);
@@ -995,7 +1035,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1]};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1061,6 +1101,7 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
     }
     h->have_data = true;
     h->joined_radix = false;
+    h->prepart = false;
     return PHJ_OK;
 }
 
@@ -1072,6 +1113,38 @@ int phj_upload(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_
 int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
                     size_t n_probe) {
     return set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr);
+}
+
+int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
+                                size_t n_probe, const uint64_t* bounds_build, const uint64_t* bounds_probe,
+                                uint32_t nparents) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING)
+        return fail(PHJ_ERR_STATE, "pre-partitioned relations need a radix-partitioning handle");
+    if (!bounds_build || !bounds_probe) return fail(PHJ_ERR_INVALID, "partition boundaries are null");
+    const uint64_t* hb[2] = {bounds_build, bounds_probe};
+    const size_t nn[2] = {n_build, n_probe};
+    for (int rel = 0; rel < 2; ++rel) {
+        if (hb[rel][0] != 0 || hb[rel][nparents] != nn[rel])
+            return fail(PHJ_ERR_INVALID, "boundaries must start at 0 and end at the relation size");
+        for (uint32_t d = 0; d < nparents; ++d)
+            if (hb[rel][d] > hb[rel][d + 1]) return fail(PHJ_ERR_INVALID, "boundaries must not decrease");
+    }
+    int rc = set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr);
+    if (rc != PHJ_OK) return rc;
+    if (!h->pow2 || nparents != h->d1) {
+        h->have_data = false;
+        return fail(PHJ_ERR_INVALID, "relations are partitioned %u ways but this handle's pass 1 has %u digits "
+                                     "(partitions and radix_bits must be powers of two that match the split)",
+                    nparents, h->d1);
+    }
+    if ((rc = dev_reserve(&h->d_pre_bounds, &h->cap_pre_bounds, 2 * ((size_t)h->d1 + 1))) != PHJ_OK) return rc;
+    for (int rel = 0; rel < 2; ++rel)
+        PHJ_CUDA(cudaMemcpyAsync(h->d_pre_bounds + rel * (h->d1 + 1), hb[rel], (h->d1 + 1) * 8,
+                                 cudaMemcpyHostToDevice, h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    h->prepart = true;
+    return PHJ_OK;
 }
 
 int phj_join(phj_handle* h, phj_result* out) {
@@ -1105,7 +1178,7 @@ int phj_read_partitions(phj_handle* h, int32_t which, phj_tuple* out, uint64_t* 
     if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING || !h->joined_radix)
         return fail(PHJ_ERR_STATE, "no partitioned relations: run a radix-partitioning phj_join first");
     PHJ_CUDA(cudaSetDevice(h->device));
-    const ulonglong2* src = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
+    const ulonglong2* src = h->b2 > 0 ? h->d_buf_b[which] : h->prepart ? h->d_in[which] : h->d_buf_a[which];
     if (out && h->n[which])
         PHJ_CUDA(cudaMemcpy(out, src, h->n[which] * 16, cudaMemcpyDeviceToHost));
     if (bounds) PHJ_CUDA(cudaMemcpy(bounds, h->d_bounds2[which], (h->P + 1) * 8, cudaMemcpyDeviceToHost));
@@ -1118,7 +1191,7 @@ int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, con
     if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
     if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING || !h->joined_radix)
         return fail(PHJ_ERR_STATE, "no partitioned relations: run a radix-partitioning phj_join first");
-    if (d_data) *d_data = h->b2 > 0 ? h->d_buf_b[which] : h->d_buf_a[which];
+    if (d_data) *d_data = h->b2 > 0 ? h->d_buf_b[which] : h->prepart ? h->d_in[which] : h->d_buf_a[which];
     if (d_bounds) *d_bounds = h->d_bounds2[which];
     if (n) *n = h->n[which];
     return PHJ_OK;
@@ -1170,7 +1243,7 @@ int phj_shard_count(phj_handle* h, uint64_t* counts) {
         bp.bias[1] = h->n[0];
         bp.ndigits = h->d1;
         KernelScope ks(h, "bounds_from_cursors");
-        bounds_from_cursors<<<1, 2 * 64, 0, h->stream>>>(bp);
+        bounds_from_cursors<<<2, kMaxSplitDigits, 0, h->stream>>>(bp);
     }
     const uint32_t w = h->d1;
     for (int rel = 0; rel < 2; ++rel)
@@ -1196,10 +1269,10 @@ int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off
     const uint64_t* off[2] = {off_build, off_probe};
     PassParams p1{};
     fill_pass1_params(h, p1);
-    ulonglong2* host_ptrs[2][64];
+    ulonglong2* host_ptrs[2][kMaxSplitDigits];
     for (int rel = 0; rel < 2; ++rel) {
         if (!dst[rel]) continue;  // this relation stays local (split into buf_a)
-        if (!h->d_outd[rel]) PHJ_CUDA(cudaMalloc(&h->d_outd[rel], 64 * sizeof(void*)));
+        if (!h->d_outd[rel]) PHJ_CUDA(cudaMalloc(&h->d_outd[rel], kMaxSplitDigits * sizeof(void*)));
         for (uint32_t d = 0; d < w; ++d)  // run d starts at cursor == bounds[d]: rebase it to off[d]
             host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) -
                                 h->shard_bounds[rel][d];

@@ -590,6 +590,93 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes(PassParams p) {
 }
 
 // =================================================================================================
+// K1c  radix_histogram_lanes8: the lane-private idea for fan-outs of 128 / 256 (the multi-GPU split
+// whose digit is owner rank x local pass-1 digit). Counters are 8 bits wide -- [digit / 4][lane]
+// words, one byte per digit, a lane still only touches its own bank -- so a warp's block is
+// D * 32 bytes (8 KB for 256 digits). A lane adds at most IPT per tile; every FLUSH_TILES tiles
+// (IPT * FLUSH_TILES <= 255) the warp folds its bytes into the CTA's 32-bit totals and clears them.
+// =================================================================================================
+template <int BITS, int TPB>
+struct HistLanes8Smem {
+    static constexpr size_t total = ((size_t)(TPB / 32) * ((1 << BITS) / 4) * 32 + (1 << BITS)) * 4;
+};
+
+template <int BITS, int HASH, bool POW2, int TPB, int IPT>
+__global__ void __launch_bounds__(TPB) radix_histogram_lanes8(PassParams p) {
+    constexpr int D = 1 << BITS;
+    constexpr int NW = TPB / 32;
+    constexpr int T = TPB * IPT;
+    constexpr int WARP_WORDS = (D / 4) * 32;
+    constexpr int FLUSH_TILES = 255 / IPT;
+    static_assert(BITS >= 2 && BITS <= 8, "byte counters: fan-outs up to 256");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);  // [NW][WARP_WORDS]
+    uint32_t* total = cnt + NW * WARP_WORDS;                // [D]
+
+    if (blockIdx.x >= *p.nsegs) return;
+    const Segment seg = p.segs[blockIdx.x];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* mine_w = cnt + warp * WARP_WORDS;
+    unsigned char* mine = reinterpret_cast<unsigned char*>(mine_w);
+
+    for (int i = lane; i < WARP_WORDS; i += 32) mine_w[i] = 0;
+    for (int i = threadIdx.x; i < D; i += TPB) total[i] = 0;
+    cta_sync();
+
+    auto count_key = [&](uint64_t key) {
+        const uint32_t d = digit_of<POW2>(hash_key<HASH>(key, p.hp), p.df);
+        unsigned char* c = mine + ((((d >> 2) * 32 + lane) << 2) | (d & 3));
+        *c = (unsigned char)(*c + 1);
+    };
+    auto flush = [&]() {
+        __syncwarp();
+        for (int e = 0; e < D / 4; ++e) {
+            const uint32_t w = mine_w[e * 32 + lane];
+            mine_w[e * 32 + lane] = 0;
+            uint32_t even = w & 0x00ff00ffu, odd = (w >> 8) & 0x00ff00ffu;  // two 16-bit sums each
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                even += __shfl_xor_sync(0xffffffffu, even, o);
+                odd += __shfl_xor_sync(0xffffffffu, odd, o);
+            }
+            if (lane < 4) {
+                const uint32_t v = lane == 0 ? (even & 0xffffu) : lane == 1 ? (odd & 0xffffu)
+                                 : lane == 2 ? (even >> 16) : (odd >> 16);
+                if (v) atomicAdd(&total[4 * e + lane], v);
+            }
+        }
+        __syncwarp();
+    };
+    uint64_t tile = seg.begin;
+    int since_flush = 0;
+    for (; tile + T <= seg.end; tile += T) {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(in + tile + (uint64_t)warp * (32 * IPT) + lane);
+        uint64_t key[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) key[i] = ld_stream_u64(src + (size_t)i * 64);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) count_key(key[i]);
+        if (++since_flush == FLUSH_TILES) {
+            flush();
+            since_flush = 0;
+        }
+    }
+    if (tile < seg.end) {
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            if (idx < seg.end) count_key(ld_stream_u64(reinterpret_cast<const uint64_t*>(in + idx)));
+        }
+    }
+    flush();
+    cta_sync();
+    for (int d = threadIdx.x; d < (int)p.ndigits; d += TPB)
+        p.counts[seg.cnt_index + (uint64_t)d * seg.cnt_stride] = total[d];
+}
+
+// =================================================================================================
 // plan_pass2: cut every pass-1 partition ("parent") of both relations into segments for pass 2.
 // Single CTA; runs on the device so the pipeline never waits for the host.
 // =================================================================================================

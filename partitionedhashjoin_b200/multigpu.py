@@ -145,18 +145,52 @@ class ShardedRadixJoin:
         self.backend.close()
 
 
+def split_plan(world, partitions_local, pass1_in_shuffle=True):
+    """(b1, b2) of the local radix join and the number of split digits. With pass1_in_shuffle the
+    split digit is owner rank x local pass-1 digit (<= 256 digits in all), so what a rank receives
+    is already pass-1 partitioned; otherwise the split is by owner rank only (b1 = b2 = 0 here)."""
+    bits = int(partitions_local).bit_length() - 1
+    if not pass1_in_shuffle or partitions_local < 4 or (1 << bits) != partitions_local:
+        return 0, 0, world
+    b1 = min((bits + 1) // 2, 8 - (world.bit_length() - 1))
+    b2 = bits - b1
+    if b1 < 1 or b2 > 8:
+        return 0, 0, world
+    return b1, b2, world << b1
+
+
 class FusedGpuBackend(GpuBackend):
     """The partition shuffle as NVLink stores: every rank's receive window is mapped by its peers
-    (CUDA IPC, phj_shared_*), and the split scatter's TMA bulk stores write each owner's piece
-    straight into that owner's window (phj_shard_scatter). No separate all-to-all of tuples."""
+    (CUDA IPC, phj_shared_*), and the split scatter's TMA bulk stores write each piece straight
+    into its owner's window (phj_shard_scatter). No separate all-to-all of tuples, and -- with
+    pass1_in_shuffle -- no local pass 1 either: the split digit is (owner rank : local pass-1
+    digit), the window is laid out digit-major, and the local join starts at pass 2."""
 
-    def __init__(self, world, device, **kw):
-        super().__init__(world, device, **kw)
-        from . import _lib
-        self._C, self._lib, self._check = __import__("ctypes"), _lib.lib, _lib.check
+    def __init__(self, world, device, partitions_local=4096, hash="xxh3", hash_seed=0x9E3779B97F4A7C15,
+                 pass1_in_shuffle=True):
+        import ctypes
+        import torch
+
+        from . import _lib, engine
+        self.torch, self.world, self.device = torch, world, device
+        self.b1, self.b2, self.ndig = split_plan(world, partitions_local, pass1_in_shuffle)
+        self.d1 = self.ndig // world
+        if self.b1:
+            self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
+                                              device=device, shard_shift=self.b2)
+            self.local_engine = engine.Engine("radix-partitioning", partitions=partitions_local,
+                                              radix_bits=(self.b1, self.b2), hash=hash, hash_seed=hash_seed,
+                                              device=device)
+        else:
+            self.split_engine = engine.Engine("shard-split", partitions=world, hash=hash, hash_seed=hash_seed,
+                                              device=device, shard_shift=SHARD_SHIFT)
+            self.local_engine = engine.Engine("radix-partitioning", partitions=partitions_local, hash=hash,
+                                              hash_seed=hash_seed, device=device)
+        self._recv = [None, None]
+        self.launches = 0
+        self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
         self.win = [None, None]                                # own windows: device pointers
         self.peer = [[None] * world, [None] * world]           # mapped windows of every rank
-        self.rank = None
 
     # -- windows ---------------------------------------------------------------------------
     def win_alloc(self, which, rows):
@@ -189,18 +223,18 @@ class FusedGpuBackend(GpuBackend):
 
     # -- the split, in two halves ------------------------------------------------------------
     def count(self):
-        C = self._C
-        counts = np.zeros((2, self.world), dtype=np.uint64)
+        """Tuples of this rank's shard per split digit: counts[rel][digit]."""
+        counts = np.zeros((2, self.ndig), dtype=np.uint64)
         self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
         return counts.astype(np.int64)
 
     def scatter(self, offsets):
-        """offsets[rel][owner]: first row of this rank's piece inside the owner's window."""
+        """offsets[rel][digit]: first row of this rank's piece of `digit` inside its owner's window."""
         from ._lib import PhjResult
         C = self._C
         arrs = []
         for which in (0, 1):
-            ptrs = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer[which]])
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[which][d // self.d1]) for d in range(self.ndig)])
             offs = np.ascontiguousarray(offsets[which], dtype=np.uint64)
             arrs += [ptrs, offs]
         res = PhjResult()
@@ -209,26 +243,31 @@ class FusedGpuBackend(GpuBackend):
         self.launches += res.kernel_launches
         return int(res.total_ns)
 
-    def local_join_window(self, rows_R, rows_S):
-        self.local_engine.bind_device(self.win[0] if rows_R else 0, rows_R, self.win[1] if rows_S else 0, rows_S)
+    def local_join_window(self, rows, bounds):
+        """rows[rel] tuples have landed in this rank's windows; bounds[rel] are the d1 + 1 boundaries
+        of the local pass-1 digits inside them."""
+        ptr = [self.win[w] if rows[w] else 0 for w in (0, 1)]
+        if self.b1:
+            self.local_engine.bind_device_partitioned(ptr[0], rows[0], ptr[1], rows[1], bounds[0], bounds[1])
+        else:
+            self.local_engine.bind_device(ptr[0], rows[0], ptr[1], rows[1])
         res = self.local_engine.join()
         self.launches += res["kernel_launches"]
         return res["matches"], res
-
-    def close(self):
-        super().close()
 
 
 class FusedShardedRadixJoin:
     """One rank of the sharded join with the shuffle fused into the split scatter.
 
-      count     histogram + scan of the shard by owner rank             (phj_shard_count)
-      sizes     all-gather of the world x 2 x world piece sizes: every rank knows where its piece
-                starts inside every owner's window, and how big every window must be
+      count     histogram + scan of the shard by split digit = (owner rank : local pass-1 digit)
+                                                                          (phj_shard_count)
+      sizes     all-gather of the world x 2 x digits piece sizes: every rank knows where each of its
+                pieces starts inside its owner's window (digit-major, then source rank: the stable
+                order of the reference's partitionTable), and how big every window must be
       windows   (re)allocated and re-mapped collectively only when a window is too small
-      scatter   the split scatter writes owner d's piece into d's window over NVLink
+      scatter   the split scatter writes every piece into its owner's window over NVLink
       barrier   all pieces have landed
-      local     ordinary radix join on the window; all-reduce of the count
+      local     radix join on the window, starting at pass 2; all-reduce of the count
     """
 
     GROW = 1.125
@@ -245,12 +284,12 @@ class FusedShardedRadixJoin:
 
     def _gather_counts(self, counts):
         if self.world == 1:
-            return counts.reshape(1, 2, 1)
+            return counts[None]
         be = self.backend
         mine = be.int_tensor(counts.reshape(-1))
-        everyone = be.int_tensor(np.zeros(self.world * 2 * self.world))
+        everyone = be.int_tensor(np.zeros(self.world * counts.size))
         self.dist.all_gather_into_tensor(everyone, mine)
-        return everyone.cpu().numpy().reshape(self.world, 2, self.world)  # [source][rel][owner]
+        return everyone.cpu().numpy().reshape(self.world, 2, -1)  # [source][rel][digit]
 
     def _ensure_windows(self, need):
         """need[rel][owner] rows. Every rank sees the same `need` and `caps`, so all of them take the
@@ -283,33 +322,48 @@ class FusedShardedRadixJoin:
         self.caps = new_caps
         return True
 
+    @staticmethod
+    def layout(M, world, rank):
+        """From M[source][rel][digit] (digit = owner : local digit): rows arriving at every owner,
+        this rank's write offsets per digit, and the local-digit boundaries of this rank's windows."""
+        ndig = M.shape[2]
+        d1 = ndig // world
+        tot = M.sum(axis=0).reshape(2, world, d1)              # [rel][owner][local digit]
+        need = tot.sum(axis=2)                                 # [rel][owner]
+        base = np.cumsum(tot, axis=2) - tot                    # start of a digit inside its owner's window
+        offsets = base.reshape(2, ndig) + M[:rank].sum(axis=0)  # lower ranks' pieces come first
+        bounds = np.concatenate([base[:, rank, :], need[:, rank:rank + 1]], axis=1)  # [rel][d1 + 1]
+        return need, offsets, bounds
+
     def join(self) -> dict:
         be, world, rank = self.backend, self.world, self.rank
         t0 = time.perf_counter()
-        counts = be.count()                                   # [rel][owner]
+        counts = be.count()                                   # [rel][digit]
         t1 = time.perf_counter()
-        M = self._gather_counts(counts)                       # [source][rel][owner]
-        need = M.sum(axis=0)                                  # rows arriving at every owner
+        M = self._gather_counts(counts)                       # [source][rel][digit]
+        need, offsets, bounds = self.layout(M, world, rank)
         regrown = self._ensure_windows(need)
-        offsets = M[:rank].sum(axis=0)                        # rows of lower ranks come first
         t2 = time.perf_counter()
         scatter_ns = be.scatter(offsets)
         if world > 1:
             self.dist.barrier()                               # every rank's stores are complete
         t3 = time.perf_counter()
         rows = [int(need[0][rank]), int(need[1][rank])]
-        local_matches, res = be.local_join_window(rows[0], rows[1])
+        local_matches, res = be.local_join_window(rows, bounds)
         t4 = time.perf_counter()
         total = be.count_tensor(local_matches)
         if world > 1:
             self.dist.all_reduce(total)
         matches = int(total.item())
         t5 = time.perf_counter()
+        d1 = counts.shape[1] // world
+        mine = counts[:, rank * d1:(rank + 1) * d1].sum()
         self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
                      "exchange_s": t3 - t1, "sizes_s": t2 - t1, "scatter_s": t3 - t2, "local_s": t4 - t3,
                      "reduce_s": t5 - t4, "total_s": t5 - t0, "recv_rows": rows, "regrown": regrown,
-                     "send_bytes_remote": int(16 * (counts.sum() - counts[:, rank].sum())) if world > 1 else 0,
-                     "local_result": res, "split_device_ns": scatter_ns, "scatter_device_ns": scatter_ns}
+                     "send_bytes_remote": int(16 * (counts.sum() - mine)) if world > 1 else 0,
+                     "local_result": res, "split_device_ns": scatter_ns, "scatter_device_ns": scatter_ns,
+                     "bounds": bounds}
         return self.last
 
     def close(self):
@@ -342,9 +396,10 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     import partitionedhashjoin_b200 as phj
     n_build, n_probe = 10_000_000, 200_000_000
     Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
-    fused = getattr(args, "shuffle", "fused") == "fused"
+    fused = getattr(args, "shuffle", "pass1") in ("fused", "pass1")
     if fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
-        backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
+        backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
+                                  pass1_in_shuffle=getattr(args, "shuffle", "pass1") == "pass1")
         job = FusedShardedRadixJoin(dist, rank, world, backend)
     else:      # split locally, then one NCCL all-to-all per relation
         backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
@@ -398,7 +453,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         cfg = workload_config(args)
         cfg["workload"] = (f"radix join sharded over {world} B200: {world} x (10M x 200M) row shards = "
                            f"{world * 10}M x {world * 200}M, partition shuffle "
-                           f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}, then local "
+                           f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
+                           f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}, then local "
                            f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
         cfg["parallelism"] = f"partition-sharded x{world}"
         exch_bytes = res["send_bytes_remote"]

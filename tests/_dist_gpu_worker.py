@@ -18,7 +18,7 @@ from partitionedhashjoin_b200 import multigpu  # noqa: E402
 
 
 def main():
-    mode = sys.argv[1]  # fused | nccl
+    mode = sys.argv[1]  # pass1 | fused | nccl
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -36,8 +36,10 @@ def main():
         lo, hi = rank * per, (rel.shape[0] if rank == world - 1 else (rank + 1) * per)
         return rel[lo:hi]
 
-    if mode == "fused":
-        job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(world, local, partitions_local=256))
+    fused = mode in ("pass1", "fused")
+    if fused:
+        job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(
+            world, local, partitions_local=256, pass1_in_shuffle=(mode == "pass1")))
     else:
         job = multigpu.ShardedRadixJoin(dist, rank, world, multigpu.GpuBackend(world, local, partitions_local=256))
     job.upload(shard(R), shard(S))
@@ -46,7 +48,7 @@ def main():
     res = job.join()
     assert res["matches"] == want, (res["matches"], want)
     first = res["matches"]
-    if mode == "fused":
+    if fused:
         assert not res["regrown"]
         # what landed in this rank's window is exactly the tuples it owns, pieces in source-rank order
         # with input order inside a piece (stable split)
@@ -55,9 +57,13 @@ def main():
             rows = res["recv_rows"][which]
             got = torch.as_tensor(multigpu._CudaView(be.win[which], rows), device=f"cuda:{local}").cpu().numpy() \
                 if rows else np.empty((0, 2), np.int64)
-            owner = ((oracle.hash_batch(0, 0x9E3779B97F4A7C15, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT))
-                     & np.uint64(world - 1)).astype(np.int64)
-            expect = rel[owner == rank]  # global input order == source-rank order, then input order
+            shift = be.b2 if be.b1 else multigpu.SHARD_SHIFT
+            digit = ((oracle.hash_batch(0, 0x9E3779B97F4A7C15, rel["id"]) >> np.uint64(shift))
+                     & np.uint64(be.ndig - 1)).astype(np.int64)
+            mine = digit // be.d1 == rank
+            # digit-major, then global input order (= source-rank order, then input order): a stable sort
+            expect = rel[mine][np.argsort(digit[mine], kind="stable")]
+            assert np.diff(res["bounds"][which]).tolist() == np.bincount(digit[mine] % be.d1, minlength=be.d1).tolist()
             assert got.shape[0] == expect.shape[0], (got.shape, expect.shape)
             assert (got[:, 0] == expect["id"]).all() and (got[:, 1] == expect["payload"]).all()
         # bigger shards: windows regrow collectively

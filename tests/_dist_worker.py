@@ -61,10 +61,17 @@ class OracleFusedBackend(OracleBackend):
     """CPU stand-in for multigpu.FusedGpuBackend: the receive windows are POSIX shared memory that
     the peers map by name (the role CUDA IPC plays on the device) and write their pieces into."""
 
-    def __init__(self, world, oracle):
+    def __init__(self, world, oracle, partitions_local, pass1_in_shuffle):
         super().__init__(world, oracle)
         self.win, self.peer = [None, None], [[None] * world, [None] * world]
         self.allocs = 0
+        self.b1, self.b2, self.ndig = multigpu.split_plan(world, partitions_local, pass1_in_shuffle)
+        self.d1 = self.ndig // world
+
+    def digit(self, ids):
+        h = self.oracle.hash_batch(0, SEED, ids)
+        shift = self.b2 if self.b1 else multigpu.SHARD_SHIFT
+        return ((h >> np.uint64(shift)) & np.uint64(self.ndig - 1)).astype(np.int64)
 
     def win_alloc(self, which, rows):
         from multiprocessing import shared_memory
@@ -92,36 +99,44 @@ class OracleFusedBackend(OracleBackend):
         self.pieces = []
         counts = []
         for rel in self.rel:
-            owner = ((self.oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT))
-                     & np.uint64(self.world - 1)).astype(np.int64)
-            self.pieces.append([rel[owner == d] for d in range(self.world)])
-            counts.append(np.bincount(owner, minlength=self.world))
+            dig = self.digit(rel["id"])
+            self.pieces.append([rel[dig == d] for d in range(self.ndig)])
+            counts.append(np.bincount(dig, minlength=self.ndig))
         return np.stack(counts).astype(np.int64)
 
     def scatter(self, offsets):
         for which in (0, 1):
-            for d in range(self.world):
+            for d in range(self.ndig):
                 piece = self.pieces[which][d]
                 if piece.shape[0]:
-                    win = np.ndarray((self.peer[which][d].size // 16,), dtype=_cases.TUPLE, buffer=self.peer[which][d].buf)
+                    shm = self.peer[which][d // self.d1]
+                    win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
                     o = int(offsets[which][d])
                     win[o:o + piece.shape[0]] = piece
                     del win
         return 0
 
-    def local_join_window(self, rows_R, rows_S):
+    def local_join_window(self, rows, bounds):
         got = []
-        for which, rows in ((0, rows_R), (1, rows_S)):
-            win = np.ndarray((rows,), dtype=_cases.TUPLE, buffer=self.win[which].buf) if rows else np.empty(0, _cases.TUPLE)
+        for which in (0, 1):
+            n = rows[which]
+            win = np.ndarray((n,), dtype=_cases.TUPLE, buffer=self.win[which].buf) if n else np.empty(0, _cases.TUPLE)
             got.append(win.copy())
             del win
+            # the window is partitioned by the local pass-1 digit exactly as `bounds` says
+            b = np.asarray(bounds[which])
+            assert b.shape[0] == self.d1 + 1 and b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+            if n:
+                local = self.digit(got[which]["id"]) & (self.d1 - 1)
+                assert (local == np.repeat(np.arange(self.d1), np.diff(b))).all()
         self.received = tuple(got)
         return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
 
 
 def main():
     case = sys.argv[1]
-    fused = len(sys.argv) > 2 and sys.argv[2] == "fused"
+    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1")
+    pass1 = fused and sys.argv[2] == "pass1"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     oracle = _oracle.Oracle()
@@ -149,7 +164,8 @@ def main():
         return rel[lo:hi]
 
     if fused:
-        backend = OracleFusedBackend(world, oracle)
+        backend = OracleFusedBackend(world, oracle, 256, pass1)
+        assert (backend.b1 > 0) == pass1
         job = multigpu.FusedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
     else:
         backend = OracleBackend(world, oracle)
@@ -160,7 +176,10 @@ def main():
     got_R, got_S = backend.received
     for rel in (got_R, got_S):
         if rel.shape[0]:
-            owner = (oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT)) & np.uint64(world - 1)
+            if fused:
+                owner = backend.digit(rel["id"]) // backend.d1
+            else:
+                owner = (oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT)) & np.uint64(world - 1)
             assert (owner == rank).all()
     rows = torch.tensor([got_R.shape[0], got_S.shape[0]], dtype=torch.int64)
     if world > 1:

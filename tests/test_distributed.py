@@ -34,11 +34,13 @@ def test_sharded_join_over_gloo(world, case):
     assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
 
 
-@pytest.mark.parametrize("world,case", [(2, "random"), (2, "skewed"), (2, "tiny"), (4, "random"), (1, "random")])
-def test_fused_shuffle_over_gloo(world, case):
+@pytest.mark.parametrize("world,case,mode", [(2, "random", "pass1"), (2, "skewed", "pass1"), (2, "tiny", "pass1"),
+                                             (4, "random", "pass1"), (1, "random", "pass1"), (2, "random", "fused")])
+def test_fused_shuffle_over_gloo(world, case, mode):
     """FusedShardedRadixJoin: sizes all-gather -> window offsets -> every rank writes its pieces into
-    the owners' windows (shared memory stands in for the CUDA-IPC-mapped NVLink windows)."""
-    r = torchrun(world, os.path.join(HERE, "_dist_worker.py"), case, "fused")
+    the owners' windows (shared memory stands in for the CUDA-IPC-mapped NVLink windows). pass1:
+    the split digit is (owner : local pass-1 digit) and the window arrives pass-1 partitioned."""
+    r = torchrun(world, os.path.join(HERE, "_dist_worker.py"), case, mode)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["world"] == world and line["fused"] and line["matches"] == line["want"] and line["want"] > 0
@@ -99,16 +101,18 @@ def test_fused_shuffle_single_gpu(phj, oracle):
     from partitionedhashjoin_b200 import multigpu
     R = _cases.tuples(_cases.splitmix64(60000, 5).astype(np.int64) % 50021)
     S = _cases.tuples(_cases.splitmix64(900000, 6).astype(np.int64) % 70001)
-    job = multigpu.FusedShardedRadixJoin(None, 0, 1, multigpu.FusedGpuBackend(1, 0, partitions_local=256))
-    job.upload(R, S)
     want = oracle.count_by_sort(R, S)
-    assert job.join()["matches"] == want
-    assert job.join()["matches"] == want
-    job.close()
+    for pass1, parts in ((True, 256), (True, 4096), (True, 16), (False, 256)):
+        job = multigpu.FusedShardedRadixJoin(None, 0, 1, multigpu.FusedGpuBackend(1, 0, partitions_local=parts,
+                                                                                  pass1_in_shuffle=pass1))
+        job.upload(R, S)
+        assert job.join()["matches"] == want
+        assert job.join()["matches"] == want
+        job.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,mode", [(2, "fused"), (2, "nccl"), (4, "fused"), (8, "fused")])
+@pytest.mark.parametrize("world,mode", [(2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"), (8, "pass1")])
 def test_sharded_join_on_gpus(phj, world, mode):
     """One rank per GPU over NCCL: the fused NVLink-store shuffle (and the all-to-all variant)
     against the oracle's count; skipped when the box has fewer GPUs."""

@@ -149,6 +149,42 @@ def test_partition_layout_equals_oracle(phj, oracle, P, bits, hash_id, hash):
                 assert_same_partitioning(got, gb, want, wb, rel.shape[0], exact)
 
 
+@pytest.mark.parametrize("P,bits", [(256, (4, 4)), (4096, (6, 6)), (4096, (5, 7)), (1 << 14, (8, 6)), (64, (6, 0))])
+def test_prepartitioned_bind_equals_plain_join(phj, oracle, P, bits):
+    """phj_bind_device_partitioned: a SHARD_SPLIT by the plan's pass-1 digit (what the multi-GPU
+    shuffle delivers) followed by a join that starts at pass 2 gives the same count AND bit-identical
+    final partitions as the ordinary two-pass join -- i.e. as the reference's partitionTable."""
+    R = _cases.tuples(_cases.splitmix64(120_000, 31).astype(np.int64) % 90_001)
+    S = _cases.tuples(np.where(_cases.splitmix64(1_500_000, 32) % np.uint64(10) < 2, 77,
+                               _cases.splitmix64(1_500_000, 33) % np.uint64(130_003)).astype(np.int64))
+    b1, b2 = bits
+    with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash_seed=SEED_P) as plain, \
+            phj.Engine("shard-split", partitions=1 << b1, shard_shift=b2, hash_seed=SEED_P) as split, \
+            phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash_seed=SEED_P) as pre:
+        plain.upload(R, S)
+        want = plain.join()
+        assert want["matches"] == oracle.count_by_sort(R, S)
+        split.upload(R, S)
+        split.join()
+        ptr, n, bnd = [], [], []
+        for which in (0, 1):
+            p_, _, n_ = split.device_partitions(which)
+            ptr.append(p_), n.append(n_), bnd.append(split.read_bounds(which, 1 << b1))
+        pre.bind_device_partitioned(ptr[0], n[0], ptr[1], n[1], bnd[0], bnd[1])
+        for _ in range(2):  # reusable
+            got = pre.join()
+            assert got["matches"] == want["matches"]
+            assert got["passes"] == want["passes"] - 1
+        for which in (0, 1):
+            a, ab = plain.read_partitions(which, P)
+            b, bb = pre.read_partitions(which, P)
+            assert (ab == bb).all()
+            assert (a["id"] == b["id"]).all() and (a["payload"] == b["payload"]).all()
+        # a plan whose pass 1 has a different fan-out is rejected
+        with pytest.raises(phj.PhjError):
+            pre.bind_device_partitioned(ptr[0], n[0], ptr[1], n[1], bnd[0][:-1], bnd[1][:-1])
+
+
 def test_partition_layout_skewed_generator_data(phj, oracle):
     nr, ns = 100000, 1500000
     R = np.empty(nr, dtype=phj.TUPLE_DTYPE)
