@@ -86,11 +86,14 @@ typedef struct {
     uint32_t flags;      /* PHJ_FLAG_* */
     uint64_t reserve_build; /* optional capacity hints (tuples); 0 = size on first upload */
     uint64_t reserve_probe;
-    uint32_t shard_shift;   /* PHJ_ALGO_SHARD_SPLIT: first hash bit of the owner-rank digit */
-    uint32_t reserved;      /* must be 0 */
+    uint32_t shard_shift;   /* PHJ_ALGO_SHARD_SPLIT: first hash bit of the split digit */
+    uint32_t split_ctas;    /* PHJ_ALGO_SHARD_SPLIT: cap on the CTAs of the split scatter (0 = one per
+                               segment); an NVLink-bound split leaves the other SMs to a local join */
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
+#define PHJ_FLAG_SPLIT_REMOTE_ONLY 0x8u /* SHARD_SPLIT handle used only through phj_shard_scatter with
+                                           both destinations given: no local output buffers */
 #define PHJ_FLAG_FUSE_HIST2 0x4u   /* experimental: the pass-1 scatter also accumulates the pass-2
                                       histogram (saves one read of both relations, costs shared
                                       memory; slower on B200 as measured) */
@@ -206,6 +209,11 @@ int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* 
 int phj_shared_open(int32_t device, const unsigned char* ipc_handle, void** d_ptr);
 int phj_shared_close(int32_t device, void* d_ptr);
 int phj_shared_free(int32_t device, void* d_ptr);
+
+/* Plain synchronous copies between host memory and memory from phj_shared_alloc (input arenas of
+ * the multi-GPU path, test read-back of the windows). */
+int phj_memcpy_h2d(int32_t device, void* d_dst, const void* h_src, size_t bytes);
+int phj_memcpy_d2h(int32_t device, void* h_dst, const void* d_src, size_t bytes);
 
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
  * names[i] points to a static string. */

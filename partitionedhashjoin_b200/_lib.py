@@ -24,6 +24,7 @@ HASH_XXH3, HASH_MURMUR3, HASH_CITY = 0, 1, 2
 HASH_NAMES = {"xxh3": HASH_XXH3, "xxhash": HASH_XXH3, "murmur3": HASH_MURMUR3, "city": HASH_CITY}
 FLAG_NO_TMA_STORE = 0x2
 FLAG_FUSE_HIST2 = 0x4
+FLAG_SPLIT_REMOTE_ONLY = 0x8
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 
@@ -41,7 +42,7 @@ class PhjConfig(C.Structure):
         ("reserve_build", C.c_uint64),
         ("reserve_probe", C.c_uint64),
         ("shard_shift", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("split_ctas", C.c_uint32),
     ]
 
 
@@ -106,6 +107,8 @@ SIGNATURES = {
     "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),
     "phj_shared_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "phj_memcpy_h2d": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "phj_memcpy_d2h": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "phj_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
     "phj_get_device_info": (C.c_int, [C.c_int32, C.POINTER(PhjDeviceInfo)]),
     "phj_device_count": (C.c_int, []),

@@ -514,16 +514,15 @@ int build_plan(phj_handle* h) {
         PHJ_CUDA(cudaMemcpyAsync(h->d_scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
         PHJ_CUDA(cudaStreamSynchronize(h->stream));
 
-        // ---- partition buffers ----
+        // ---- partition buffers: sized here, allocated by ensure_buffers() for the passes a join
+        // really runs (a pre-partitioned join needs no pass-1 output, a remote split none at all) ----
         for (int rel = 0; rel < 2; ++rel) {
-            if (h->n[rel] > h->cap_buf[rel] || !h->d_buf_a[rel]) {
+            if (h->n[rel] > h->cap_buf[rel]) {
                 if (h->d_buf_a[rel]) cudaFree(h->d_buf_a[rel]);
                 if (h->d_buf_b[rel]) cudaFree(h->d_buf_b[rel]);
                 h->d_buf_a[rel] = h->d_buf_b[rel] = nullptr;
-                size_t want = std::max<size_t>(h->n[rel], 1);
-                PHJ_CUDA(cudaMalloc(&h->d_buf_a[rel], want * 16));
-                PHJ_CUDA(cudaMalloc(&h->d_buf_b[rel], want * 16));
-                h->cap_buf[rel] = want;
+                h->cap_buf[rel] = std::max<size_t>(std::max<size_t>(h->n[rel], 1),
+                                                   rel == 0 ? h->cfg.reserve_build : h->cfg.reserve_probe);
             }
         }
         // ---- join geometry ----
@@ -558,6 +557,17 @@ int build_plan(phj_handle* h) {
             PHJ_CUDA(cudaMalloc(&h->d_gt, buckets * 32));
         }
         h->gt_buckets = buckets;
+    }
+    return PHJ_OK;
+}
+
+// Pass-1 / pass-2 output buffers, allocated on first need (phj_upload / phj_bind_* call this for
+// the plan at hand, so phj_join itself allocates nothing).
+int ensure_buffers(phj_handle* h, bool need_a, bool need_b) {
+    for (int rel = 0; rel < 2; ++rel) {
+        const size_t want = std::max<size_t>(h->cap_buf[rel], 1);
+        if (need_a && !h->d_buf_a[rel]) PHJ_CUDA(cudaMalloc(&h->d_buf_a[rel], want * 16));
+        if (need_b && !h->d_buf_b[rel]) PHJ_CUDA(cudaMalloc(&h->d_buf_b[rel], want * 16));
     }
     return PHJ_OK;
 }
@@ -678,6 +688,10 @@ int join_no_partitioning(phj_handle* h, phj_result* out) {
 int join_radix(phj_handle* h, phj_result* out) {
     const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
     const bool two = h->b2 > 0;
+    {
+        int rc = ensure_buffers(h, !h->prepart, two);  // no-op unless the plan changed since the bind
+        if (rc != PHJ_OK) return rc;
+    }
     PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
 
     // ---- pass 1 ----
@@ -1005,7 +1019,11 @@ int phj_create(const phj_config* config, phj_handle** out) {
         phj_destroy(h);
         return code;
     };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // the multi-GPU split runs beside local joins: its CTAs go first whenever an SM slot frees up
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking,
+                                     config->algo == PHJ_ALGO_SHARD_SPLIT ? prio_hi : prio_lo) != cudaSuccess)
         return cleanup(fail(PHJ_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto& ev : h->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return cleanup(fail(PHJ_ERR_CUDA, "cudaEventCreate failed"));
@@ -1051,7 +1069,7 @@ void phj_destroy(phj_handle* h) {
 }
 
 static int set_relations(phj_handle* h, const void* build, size_t n_build, const void* probe,
-                         size_t n_probe, bool device_resident, uint64_t* h2d_ns) {
+                         size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool defer_buffers = false) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     if ((n_build && !build) || (n_probe && !probe))
         return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
@@ -1102,6 +1120,11 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
     h->have_data = true;
     h->joined_radix = false;
     h->prepart = false;
+    if (!defer_buffers && h->cfg.algo != PHJ_ALGO_NO_PARTITIONING &&
+        !(h->cfg.algo == PHJ_ALGO_SHARD_SPLIT && (h->cfg.flags & PHJ_FLAG_SPLIT_REMOTE_ONLY))) {
+        int rc = ensure_buffers(h, true, h->b2 > 0);
+        if (rc != PHJ_OK) return rc;
+    }
     return PHJ_OK;
 }
 
@@ -1130,8 +1153,9 @@ int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_bui
         for (uint32_t d = 0; d < nparents; ++d)
             if (hb[rel][d] > hb[rel][d + 1]) return fail(PHJ_ERR_INVALID, "boundaries must not decrease");
     }
-    int rc = set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr);
+    int rc = set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr, true);
     if (rc != PHJ_OK) return rc;
+    if ((rc = ensure_buffers(h, false, h->b2 > 0)) != PHJ_OK) return rc;
     if (!h->pow2 || nparents != h->d1) {
         h->have_data = false;
         return fail(PHJ_ERR_INVALID, "relations are partitioned %u ways but this handle's pass 1 has %u digits "
@@ -1279,10 +1303,20 @@ int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off
         PHJ_CUDA(cudaMemcpyAsync(h->d_outd[rel], host_ptrs[rel], w * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
         p1.outd[rel] = h->d_outd[rel];
     }
+    if (!dst_build || !dst_probe) {
+        int rc = ensure_buffers(h, true, false);
+        if (rc != PHJ_OK) return rc;
+        fill_pass1_params(h, p1);
+        for (int rel = 0; rel < 2; ++rel)
+            if (dst[rel]) p1.outd[rel] = h->d_outd[rel];
+    }
     PHJ_CUDA(cudaEventRecord(h->ev[1], h->stream));
     if (h->nsegs1 > 0) {
+        // split_ctas caps the grid: an NVLink-bound split needs a fraction of the SMs, the rest stay
+        // free for the local join of the previous chunk running on another stream
+        const uint32_t grid = h->cfg.split_ctas ? std::min<uint32_t>(h->nsegs1, h->cfg.split_ctas) : h->nsegs1;
         KernelScope ks(h, "radix_scatter[split]");
-        PHJ_CUDA(launch_pass(h, true, h->b1, p1, h->nsegs1));
+        PHJ_CUDA(launch_pass(h, true, h->b1, p1, grid));
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
@@ -1332,6 +1366,20 @@ int phj_shared_close(int32_t device, void* d_ptr) {
 int phj_shared_free(int32_t device, void* d_ptr) {
     PHJ_CUDA(cudaSetDevice(device));
     if (d_ptr) PHJ_CUDA(cudaFree(d_ptr));
+    return PHJ_OK;
+}
+
+int phj_memcpy_h2d(int32_t device, void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes && (!d_dst || !h_src)) return fail(PHJ_ERR_INVALID, "null argument");
+    PHJ_CUDA(cudaSetDevice(device));
+    if (bytes) PHJ_CUDA(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return PHJ_OK;
+}
+
+int phj_memcpy_d2h(int32_t device, void* h_dst, const void* d_src, size_t bytes) {
+    if (bytes && (!h_dst || !d_src)) return fail(PHJ_ERR_INVALID, "null argument");
+    PHJ_CUDA(cudaSetDevice(device));
+    if (bytes) PHJ_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return PHJ_OK;
 }
 

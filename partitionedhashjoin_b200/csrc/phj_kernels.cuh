@@ -341,13 +341,18 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
     uint32_t* h2_first = reinterpret_cast<uint32_t*>(split_pos + D);  // counter index of (digit 0, first seg)
     uint32_t* h2_stride = h2_first + D;
 
-    if (blockIdx.x >= *p.nsegs) return;
-    const Segment seg = p.segs[blockIdx.x];
-    const ulonglong2* __restrict__ in = p.in[seg.rel];
-    ulonglong2* __restrict__ out = p.out[seg.rel];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* wcw = wc + warp * (D + 1);
     const uint32_t lt = lanemask_lt();
+    const uint32_t nsegs = *p.nsegs;
+
+    // One CTA per segment by default; a smaller grid (the multi-GPU split, which leaves SMs to the
+    // local join running beside it) makes every CTA walk several segments.
+    for (uint32_t si = blockIdx.x; si < nsegs; si += gridDim.x) {
+    if (si != blockIdx.x) cta_sync();  // the previous segment's last tile is staged and flushed
+    const Segment seg = p.segs[si];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    ulonglong2* __restrict__ out = p.out[seg.rel];
 
     // private write cursors of this segment (the reference's PrefixSumTable row + boundaries)
     if (tid < D) {
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
             }
         }
     }
+    }  // segments of this CTA
     if (TMA_STORE) bulk_wait_all0();
 }
 

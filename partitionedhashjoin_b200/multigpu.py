@@ -189,8 +189,8 @@ class FusedGpuBackend(GpuBackend):
         self._recv = [None, None]
         self.launches = 0
         self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
-        self.win = [None, None]                                # own windows: device pointers
-        self.peer = [[None] * world, [None] * world]           # mapped windows of every rank
+        self.win = [None] * 3                                  # own windows: device pointers
+        self.peer = [[None] * world for _ in range(3)]         # mapped windows of every rank
 
     # -- windows ---------------------------------------------------------------------------
     def win_alloc(self, which, rows):
@@ -276,7 +276,7 @@ class FusedShardedRadixJoin:
         if world & (world - 1):
             raise ValueError("the number of ranks must be a power of two")
         self.dist, self.rank, self.world, self.backend = dist, rank, world, backend
-        self.caps = np.zeros((2, world), dtype=np.int64)  # rows of every rank's windows (same on all ranks)
+        self.caps = np.zeros((3, world), dtype=np.int64)  # rows of every rank's windows (same on all ranks)
         self.last = {}
 
     def upload(self, R_shard, S_shard):
@@ -292,34 +292,33 @@ class FusedShardedRadixJoin:
         return everyone.cpu().numpy().reshape(self.world, 2, -1)  # [source][rel][digit]
 
     def _ensure_windows(self, need):
-        """need[rel][owner] rows. Every rank sees the same `need` and `caps`, so all of them take the
-        same decision without further communication."""
-        grow = need > self.caps
-        if not grow.any():
+        """need: {window id: rows arriving at every owner}. Every rank sees the same `need` and `caps`,
+        so all of them take the same decision without further communication."""
+        grow = {w: np.asarray(n) > self.caps[w] for w, n in need.items()}
+        if not any(g.any() for g in grow.values()):
             return False
         be, world, rank = self.backend, self.world, self.rank
-        for which in (0, 1):
+        for w, g in grow.items():
             for r in range(world):
-                if grow[which][r]:
-                    be.peer_close(which, r, own=(r == rank))
+                if g[r]:
+                    be.peer_close(w, r, own=(r == rank))
         if world > 1:
             self.dist.barrier()  # nobody maps a window that is about to be freed
-        new_caps = np.where(grow, (need * self.GROW).astype(np.int64) + 4096, self.caps)
-        handles = [None, None]
-        for which in (0, 1):
-            if grow[which][rank]:
-                be.win_free(which)
-                handles[which] = be.win_alloc(which, int(new_caps[which][rank]))
+        handles = {}
+        for w, g in grow.items():
+            self.caps[w] = np.where(g, (np.asarray(need[w]) * self.GROW).astype(np.int64) + 4096, self.caps[w])
+            if g[rank]:
+                be.win_free(w)
+                handles[w] = be.win_alloc(w, int(self.caps[w][rank]))
         if world > 1:
             everyone = [None] * world
             self.dist.all_gather_object(everyone, handles)
         else:
             everyone = [handles]
-        for which in (0, 1):
+        for w, g in grow.items():
             for r in range(world):
-                if grow[which][r]:
-                    be.peer_open(which, r, everyone[r][which], own=(r == rank))
-        self.caps = new_caps
+                if g[r]:
+                    be.peer_open(w, r, everyone[r][w], own=(r == rank))
         return True
 
     @staticmethod
@@ -342,7 +341,7 @@ class FusedShardedRadixJoin:
         t1 = time.perf_counter()
         M = self._gather_counts(counts)                       # [source][rel][digit]
         need, offsets, bounds = self.layout(M, world, rank)
-        regrown = self._ensure_windows(need)
+        regrown = self._ensure_windows({0: need[0], 1: need[1]})
         t2 = time.perf_counter()
         scatter_ns = be.scatter(offsets)
         if world > 1:
@@ -368,14 +367,194 @@ class FusedShardedRadixJoin:
 
     def close(self):
         be, world, rank = self.backend, self.world, self.rank
-        for which in (0, 1):
+        for w in range(3):
             for r in range(world):
-                be.peer_close(which, r, own=(r == rank))
+                be.peer_close(w, r, own=(r == rank))
         if world > 1:
             self.dist.barrier()
-        for which in (0, 1):
-            be.win_free(which)
+        for w in range(3):
+            be.win_free(w)
         be.close()
+
+
+class PipelinedGpuBackend(FusedGpuBackend):
+    """FusedGpuBackend with the probe shard cut into row chunks, so that the NVLink shuffle of chunk
+    c + 1 (a split scatter capped to `split_ctas` CTAs on a high-priority stream) overlaps the local
+    pass 2 + join of chunk c (the match count is additive over a partition of S). Windows: 0 = build
+    side (filled with chunk 0), 1 / 2 = probe chunks, double-buffered."""
+
+    def __init__(self, world, device, partitions_local=4096, hash="xxh3", hash_seed=0x9E3779B97F4A7C15,
+                 chunks=4, split_ctas=0):
+        import ctypes
+        import torch
+
+        from . import _lib, engine
+        self.torch, self.world, self.device, self.chunks = torch, world, device, chunks
+        self.b1, self.b2, self.ndig = split_plan(world, partitions_local, True)
+        if not self.b1:
+            raise ValueError("the pipelined shuffle needs a power-of-two local fan-out >= 4 (two-level digit)")
+        self.d1 = self.ndig // world
+        self.splits = [engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
+                                     device=device, shard_shift=self.b2, flags=_lib.FLAG_SPLIT_REMOTE_ONLY,
+                                     split_ctas=split_ctas) for _ in range(chunks)]
+        self.locals = [engine.Engine("radix-partitioning", partitions=partitions_local, radix_bits=(self.b1, self.b2),
+                                     hash=hash, hash_seed=hash_seed, device=device) for _ in range(2)]
+        self.launches = 0
+        self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
+        self.win = [None] * 3
+        self.peer = [[None] * world for _ in range(3)]
+        self.arena = [None, None]   # device copies of this rank's shards
+        self.arena_cap = [0, 0]
+        self.n = [0, 0]
+
+    def thread_init(self):
+        self.torch.cuda.set_device(self.device)
+
+    def upload(self, R, S):
+        from .engine import as_tuples
+        C = self._C
+        rels = [as_tuples(R), as_tuples(S)]
+        for which, rel in enumerate(rels):
+            n = rel.shape[0]
+            if n > self.arena_cap[which] or not self.arena[which]:
+                if self.arena[which]:
+                    self._check(self._lib.phj_shared_free(self.device, C.c_void_p(self.arena[which])))
+                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                self._check(self._lib.phj_shared_alloc(self.device, max(n, 1) * 16, C.byref(ptr), handle))
+                self.arena[which], self.arena_cap[which] = ptr.value, max(n, 1)
+            self._check(self._lib.phj_memcpy_h2d(self.device, C.c_void_p(self.arena[which]), rel.ctypes.data, n * 16))
+            self.n[which] = n
+        # chunk c of the probe shard = rows [lo[c], lo[c + 1]); the build shard travels with chunk 0
+        per = -(-self.n[1] // self.chunks)
+        per = -(-per // 4096) * 4096
+        self.lo = [min(c * per, self.n[1]) for c in range(self.chunks + 1)]
+        for c, eng in enumerate(self.splits):
+            n_s = self.lo[c + 1] - self.lo[c]
+            eng.bind_device(self.arena[0] if c == 0 and self.n[0] else 0, self.n[0] if c == 0 else 0,
+                            self.arena[1] + self.lo[c] * 16 if n_s else 0, n_s)
+
+    def count(self, c):
+        counts = np.zeros((2, self.ndig), dtype=np.uint64)
+        self._check(self._lib.phj_shard_count(self.splits[c]._h, counts.ctypes.data))
+        return counts.astype(np.int64)
+
+    def scatter(self, c, offsets):
+        from ._lib import PhjResult
+        C = self._C
+        arrs = []
+        for which, w in ((0, 0), (1, 1 + c % 2)):
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][d // self.d1]) for d in range(self.ndig)])
+            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
+        res = PhjResult()
+        self._check(self._lib.phj_shard_scatter(self.splits[c]._h, arrs[0], arrs[1].ctypes.data, arrs[2],
+                                                arrs[3].ctypes.data, C.byref(res)))
+        self.launches += res.kernel_launches
+        return int(res.total_ns)
+
+    def local_join(self, c, rows, bounds):
+        w = 1 + c % 2
+        eng = self.locals[c % 2]
+        eng.bind_device_partitioned(self.win[0] if rows[0] else 0, rows[0], self.win[w] if rows[1] else 0, rows[1],
+                                    bounds[0], bounds[1])
+        res = eng.join()
+        self.launches += res["kernel_launches"]
+        return res["matches"], res
+
+    def close(self):
+        for e in self.splits + self.locals:
+            e.close()
+        for which in (0, 1):
+            if self.arena[which]:
+                self._lib.phj_shared_free(self.device, self._C.c_void_p(self.arena[which]))
+                self.arena[which] = None
+
+
+class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
+    """The fused shuffle, software-pipelined over row chunks of the probe shard: a producer thread
+    runs count -> sizes all-gather -> NVLink scatter -> barrier for chunk c + 1 while the caller's
+    thread runs the local pass 2 + join of chunk c. The two legs use different resources (NVLink vs
+    HBM), so the join costs about max(shuffle, local) instead of their sum."""
+
+    def join(self) -> dict:
+        import queue
+        import threading
+        be, world, rank, K = self.backend, self.world, self.rank, self.backend.chunks
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
+        ready = queue.Queue()
+        abort = threading.Event()
+        stats = {"count_s": 0.0, "sizes_s": 0.0, "scatter_s": 0.0, "scatter_device_ns": 0, "regrown": False,
+                 "send_bytes_remote": 0}
+
+        def producer():
+            try:
+                if hasattr(be, "thread_init"):
+                    be.thread_init()
+                build = None
+                for c in range(K):
+                    while not free[c % 2].acquire(timeout=0.05):
+                        if abort.is_set():
+                            return
+                    t0 = time.perf_counter()
+                    counts = be.count(c)
+                    t1 = time.perf_counter()
+                    M = self._gather_counts(counts)
+                    need, offsets, bounds = self.layout(M, world, rank)
+                    want = {1 + c % 2: need[1]}
+                    if c == 0:
+                        want[0] = need[0]
+                        build = (int(need[0][rank]), bounds[0])
+                    stats["regrown"] |= self._ensure_windows(want)
+                    t2 = time.perf_counter()
+                    stats["scatter_device_ns"] += be.scatter(c, offsets)
+                    if world > 1:
+                        self.dist.barrier()
+                    t3 = time.perf_counter()
+                    stats["count_s"] += t1 - t0
+                    stats["sizes_s"] += t2 - t1
+                    stats["scatter_s"] += t3 - t2
+                    d1 = counts.shape[1] // world
+                    stats["send_bytes_remote"] += int(16 * (counts.sum() - counts[:, rank * d1:(rank + 1) * d1].sum()))
+                    ready.put((c, [build[0], int(need[1][rank])], [build[1], bounds[1]]))
+            except BaseException as e:  # hand the failure to the consumer
+                ready.put(e)
+
+        t0 = time.perf_counter()
+        th = threading.Thread(target=producer, name="phj-shuffle", daemon=True)
+        th.start()
+        local_matches, local_s, wait_s, res, recv_rows = 0, 0.0, 0.0, None, [0, 0]
+        try:
+            for _ in range(K):
+                tw = time.perf_counter()
+                item = ready.get()
+                if isinstance(item, BaseException):
+                    raise item
+                c, rows, bounds = item
+                tj = time.perf_counter()
+                m, res = be.local_join(c, rows, bounds)
+                local_matches += m
+                free[c % 2].release()
+                local_s += time.perf_counter() - tj
+                wait_s += tj - tw
+                recv_rows = [rows[0], recv_rows[1] + rows[1]]
+        except BaseException:
+            abort.set()
+            raise
+        finally:
+            th.join(timeout=60)
+        t4 = time.perf_counter()
+        total = be.count_tensor(local_matches)
+        if world > 1:
+            self.dist.all_reduce(total)
+        matches = int(total.item())
+        t5 = time.perf_counter()
+        self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": stats["count_s"],
+                     "exchange_s": stats["sizes_s"] + stats["scatter_s"], "sizes_s": stats["sizes_s"],
+                     "scatter_s": stats["scatter_s"], "local_s": local_s, "wait_s": wait_s, "reduce_s": t5 - t4,
+                     "total_s": t5 - t0, "recv_rows": recv_rows, "regrown": stats["regrown"],
+                     "send_bytes_remote": stats["send_bytes_remote"] if world > 1 else 0, "local_result": res,
+                     "split_device_ns": stats["scatter_device_ns"], "scatter_device_ns": stats["scatter_device_ns"],
+                     "chunks": K}
+        return self.last
 
 
 def shard_inputs(phj, rank, world, n_build, n_probe, skew, base_seed, batches):
@@ -396,10 +575,15 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     import partitionedhashjoin_b200 as phj
     n_build, n_probe = 10_000_000, 200_000_000
     Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
-    fused = getattr(args, "shuffle", "pass1") in ("fused", "pass1")
-    if fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
+    mode = getattr(args, "shuffle", "pipelined")
+    fused = mode in ("fused", "pass1", "pipelined")
+    if mode == "pipelined":  # chunked: the NVLink shuffle of chunk c + 1 overlaps the local join of chunk c
+        backend = PipelinedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
+                                      chunks=args.chunks, split_ctas=args.split_ctas)
+        job = PipelinedShardedRadixJoin(dist, rank, world, backend)
+    elif fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
         backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
-                                  pass1_in_shuffle=getattr(args, "shuffle", "pass1") == "pass1")
+                                  pass1_in_shuffle=(mode == "pass1"))
         job = FusedShardedRadixJoin(dist, rank, world, backend)
     else:      # split locally, then one NCCL all-to-all per relation
         backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
@@ -454,7 +638,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         cfg["workload"] = (f"radix join sharded over {world} B200: {world} x (10M x 200M) row shards = "
                            f"{world * 10}M x {world * 200}M, partition shuffle "
                            f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
-                           f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}, then local "
+                           f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}"
+                           f"{f', pipelined over {args.chunks} probe chunks' if mode == 'pipelined' else ''}, then local "
                            f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
         cfg["parallelism"] = f"partition-sharded x{world}"
         exch_bytes = res["send_bytes_remote"]

@@ -18,7 +18,7 @@ from partitionedhashjoin_b200 import multigpu  # noqa: E402
 
 
 def main():
-    mode = sys.argv[1]  # pass1 | fused | nccl
+    mode = sys.argv[1]  # pipelined | pass1 | fused | nccl
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -37,7 +37,10 @@ def main():
         return rel[lo:hi]
 
     fused = mode in ("pass1", "fused")
-    if fused:
+    if mode == "pipelined":
+        job = multigpu.PipelinedShardedRadixJoin(dist, rank, world, multigpu.PipelinedGpuBackend(
+            world, local, partitions_local=256, chunks=3, split_ctas=64))
+    elif fused:
         job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(
             world, local, partitions_local=256, pass1_in_shuffle=(mode == "pass1")))
     else:
@@ -70,6 +73,13 @@ def main():
         job.upload(shard(R), np.concatenate([shard(S)] * 2))
         res = job.join()
         assert res["matches"] == 2 * want and res["regrown"]
+    if mode == "pipelined":
+        assert not res["regrown"] and res["chunks"] == 3
+        job.upload(shard(R), np.concatenate([shard(S)] * 2))
+        res = job.join()
+        assert res["matches"] == 2 * want and res["regrown"]
+        res = job.join()
+        assert res["matches"] == 2 * want and not res["regrown"]
     if rank == 0:
         print(json.dumps({"mode": mode, "world": world, "matches": first, "want": want}))
     job.close()

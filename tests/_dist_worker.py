@@ -63,7 +63,7 @@ class OracleFusedBackend(OracleBackend):
 
     def __init__(self, world, oracle, partitions_local, pass1_in_shuffle):
         super().__init__(world, oracle)
-        self.win, self.peer = [None, None], [[None] * world, [None] * world]
+        self.win, self.peer = [None] * 3, [[None] * world for _ in range(3)]
         self.allocs = 0
         self.b1, self.b2, self.ndig = multigpu.split_plan(world, partitions_local, pass1_in_shuffle)
         self.d1 = self.ndig // world
@@ -116,11 +116,12 @@ class OracleFusedBackend(OracleBackend):
                     del win
         return 0
 
-    def local_join_window(self, rows, bounds):
+    def local_join_window(self, rows, bounds, windows=(0, 1)):
         got = []
         for which in (0, 1):
             n = rows[which]
-            win = np.ndarray((n,), dtype=_cases.TUPLE, buffer=self.win[which].buf) if n else np.empty(0, _cases.TUPLE)
+            shm = self.win[windows[which]]
+            win = np.ndarray((n,), dtype=_cases.TUPLE, buffer=shm.buf) if n else np.empty(0, _cases.TUPLE)
             got.append(win.copy())
             del win
             # the window is partitioned by the local pass-1 digit exactly as `bounds` says
@@ -133,10 +134,53 @@ class OracleFusedBackend(OracleBackend):
         return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
 
 
+class OraclePipelinedBackend(OracleFusedBackend):
+    """CPU stand-in for multigpu.PipelinedGpuBackend: the probe shard travels in row chunks through
+    two alternating windows, the build shard with chunk 0 into window 0."""
+
+    def __init__(self, world, oracle, partitions_local, chunks):
+        super().__init__(world, oracle, partitions_local, True)
+        self.chunks = chunks
+        self.joined = []
+
+    def upload(self, R, S):
+        super().upload(R, S)
+        n = self.rel[1].shape[0]
+        per = -(-n // self.chunks) if n else 0
+        self.lo = [min(c * per, n) for c in range(self.chunks + 1)]
+
+    def count(self, c):
+        rels = [self.rel[0] if c == 0 else self.rel[0][:0], self.rel[1][self.lo[c]:self.lo[c + 1]]]
+        self.pieces, counts = [], []
+        for rel in rels:
+            dig = self.digit(rel["id"]) if rel.shape[0] else np.empty(0, np.int64)
+            self.pieces.append([rel[dig == d] for d in range(self.ndig)])
+            counts.append(np.bincount(dig, minlength=self.ndig))
+        return np.stack(counts).astype(np.int64)
+
+    def scatter(self, c, offsets):
+        for which, w in ((0, 0), (1, 1 + c % 2)):
+            for d in range(self.ndig):
+                piece = self.pieces[which][d]
+                if piece.shape[0]:
+                    shm = self.peer[w][d // self.d1]
+                    win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
+                    o = int(offsets[which][d])
+                    win[o:o + piece.shape[0]] = piece
+                    del win
+        return 0
+
+    def local_join(self, c, rows, bounds):
+        m, res = self.local_join_window(rows, bounds, windows=(0, 1 + c % 2))
+        self.joined.append(self.received)
+        return m, res
+
+
 def main():
     case = sys.argv[1]
-    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1")
-    pass1 = fused and sys.argv[2] == "pass1"
+    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1", "pipelined")
+    pass1 = fused and sys.argv[2] in ("pass1", "pipelined")
+    pipelined = fused and sys.argv[2] == "pipelined"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     oracle = _oracle.Oracle()
@@ -163,7 +207,10 @@ def main():
             hi = n
         return rel[lo:hi]
 
-    if fused:
+    if pipelined:
+        backend = OraclePipelinedBackend(world, oracle, 256, chunks=3)
+        job = multigpu.PipelinedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
+    elif fused:
         backend = OracleFusedBackend(world, oracle, 256, pass1)
         assert (backend.b1 > 0) == pass1
         job = multigpu.FusedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
@@ -173,7 +220,12 @@ def main():
     job.upload(shard(R), shard(S))
     res = job.join()
     # every received tuple belongs to this rank, and nothing was lost or duplicated
-    got_R, got_S = backend.received
+    if pipelined:
+        got_R = backend.joined[0][0]
+        got_S = np.concatenate([j[1] for j in backend.joined])
+        backend.joined = []
+    else:
+        got_R, got_S = backend.received
     for rel in (got_R, got_S):
         if rel.shape[0]:
             if fused:
@@ -189,7 +241,7 @@ def main():
     res2 = job.join()  # the job is reusable
     assert res2["matches"] == want
     if fused:
-        assert res["regrown"] and not res2["regrown"] and backend.allocs <= 2  # windows are kept
+        assert res["regrown"] and not res2["regrown"] and backend.allocs <= 3  # windows are kept
         # a bigger probe shard: the windows grow collectively, the count follows
         job.upload(shard(R), np.concatenate([shard(S)] * 3))
         res3 = job.join()
