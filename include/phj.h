@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PHJ_ABI_VERSION 1
+#define PHJ_ABI_VERSION 2
 
 /* Common::Tuple (src/Common/Table.hpp:20-25): alignas(16) {int64 id; int64 payload}. */
 typedef struct {
@@ -89,6 +89,10 @@ typedef struct {
     uint32_t shard_shift;   /* PHJ_ALGO_SHARD_SPLIT: first hash bit of the split digit */
     uint32_t split_ctas;    /* PHJ_ALGO_SHARD_SPLIT: cap on the CTAs of the split scatter (0 = one per
                                segment); an NVLink-bound split leaves the other SMs to a local join */
+    uint32_t split_chunks;  /* PHJ_ALGO_SHARD_SPLIT: the probe relation is split in this many row chunks
+                               (1..16, 0 = 1) that phj_shard_scatter sends one at a time; the build
+                               relation travels with chunk 0 */
+    uint32_t reserved;      /* must be 0 */
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
@@ -193,14 +197,17 @@ int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, con
                           size_t* n);
 
 /* ---- multi-GPU exchange fused into the split (handles created with PHJ_ALGO_SHARD_SPLIT) ------
- * phj_shard_count: histogram + scan of the uploaded relations by owner rank; counts[rel * ranks +
- * owner] tuples go to `owner`. phj_shard_scatter: the scatter of the same split, with owner d's
- * piece of relation `rel` written straight to dst[rel][d] + off[rel][d] tuples -- typically a
- * peer GPU's receive buffer mapped with phj_shared_open, i.e. the partition shuffle happens as
- * NVLink stores from the scatter kernel (TMA bulk stores) instead of a separate all-to-all.
- * Call order per join: phj_shard_count, exchange counts, phj_shard_scatter, barrier across ranks. */
+ * phj_shard_count: histogram + scan of the uploaded relations by split digit, once for all row
+ * chunks: counts[(chunk * 2 + rel) * digits + digit] tuples of `chunk` carry `digit` (digits =
+ * config.partitions, chunks = max(1, config.split_chunks)). phj_shard_scatter: the scatter of ONE
+ * chunk, digit d's piece of relation `rel` written straight to dst[rel][d] + off[rel][d] tuples --
+ * typically a peer GPU's receive window mapped with phj_shared_open, i.e. the partition shuffle
+ * happens as NVLink stores from the scatter kernel (TMA bulk stores) instead of a separate
+ * all-to-all. A null dst keeps that relation local (split into the handle's own buffer, chunk
+ * count 1 only). Call order per join: phj_shard_count, exchange the counts, then per chunk:
+ * phj_shard_scatter + a barrier across ranks. */
 int phj_shard_count(phj_handle* h, uint64_t* counts);
-int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off_build,
+int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
                       void* const* dst_probe, const uint64_t* off_probe, phj_result* out);
 
 /* Device memory that other processes on the node can map (CUDA IPC): the receive buffers of the

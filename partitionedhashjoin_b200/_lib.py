@@ -43,6 +43,8 @@ class PhjConfig(C.Structure):
         ("reserve_probe", C.c_uint64),
         ("shard_shift", C.c_uint32),
         ("split_ctas", C.c_uint32),
+        ("split_chunks", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -102,7 +104,8 @@ SIGNATURES = {
     "phj_device_partitions": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_size_t)]),
     "phj_shard_count": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "phj_shard_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PhjResult)]),
+    "phj_shard_scatter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(PhjResult)]),
     "phj_shared_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),

@@ -71,6 +71,7 @@ constexpr int kScatTile = PHJ_SCAT_TPB * PHJ_SCAT_IPT;
 constexpr int kMaxBitsPerPass = 8;
 constexpr int kMaxKernelTimes = 24;
 constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
+constexpr int kMaxSplitChunks = 16;
 
 enum Scalar : int {  // device-resident uint32 scalars
     kNsegs1 = 0,
@@ -122,7 +123,12 @@ struct phj_handle {
     bool fuse2 = false;             // pass-2 histogram accumulated by the pass-1 scatter
     ulonglong2** d_outd[2] = {nullptr, nullptr};  // shard split: per-owner destination bases
     bool shard_counted = false;
-    uint64_t shard_bounds[2][kMaxSplitDigits + 1] = {};
+    uint32_t nchunks = 1;                         // row chunks of the probe relation
+    uint32_t chunk_first_seg[2][kMaxSplitChunks + 1] = {};  // per relation, in its own segment numbering
+    uint64_t* d_shard_starts = nullptr;           // [rel][digit][chunk + 1] (split_starts kernel)
+    uint64_t* h_shard_starts = nullptr;           // pinned copy
+    size_t plan_n[2] = {0, 0};                    // relation sizes the current plan has room for
+    size_t segs_n[2] = {0, 0};                    // relation sizes the pass-1 segment table covers
     // relations bound already partitioned by the pass-1 digit (phj_bind_device_partitioned)
     bool prepart = false;
     uint64_t* d_pre_bounds = nullptr;  // [2][d1 + 1]
@@ -419,22 +425,39 @@ uint32_t segments_for(const phj_handle* h, size_t n, int tile) {
     return (uint32_t)std::max<uint64_t>(1, std::min(target, by_len));
 }
 
+// The last boundary of every relation (= n) is never written by a kernel.
+int upload_tail_bounds(phj_handle* h) {
+    for (int rel = 0; rel < 2; ++rel) {
+        h->h_out[4 + rel] = h->n[rel];  // pinned staging
+        PHJ_CUDA(cudaMemcpyAsync(h->d_bounds1[rel] + h->d1, h->h_out + 4 + rel, 8, cudaMemcpyHostToDevice, h->stream));
+        PHJ_CUDA(cudaMemcpyAsync(h->d_bounds2[rel] + h->nparts, h->h_out + 4 + rel, 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    return PHJ_OK;
+}
+
 int build_plan(phj_handle* h) {
     int rc;
     if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING) {
         h->P = 1;
         h->pow2 = true;
         h->nparts = 1;
+        for (int rel = 0; rel < 2; ++rel) h->plan_n[rel] = h->segs_n[rel] = h->n[rel];
     } else {
         if ((rc = plan_radix(h)) != PHJ_OK) return rc;
         // ---- pass 1 segments (host-built: sizes are known) ----
         std::vector<Segment> segs;
         uint32_t nseg[2];
         uint32_t cnt_base = 0;
+        uint32_t nseg_plan[2];
         for (int rel = 0; rel < 2; ++rel) {
-            nseg[rel] = segments_for(h, h->n[rel], kScatTile);
-            uint64_t len = nseg[rel] ? (h->n[rel] + nseg[rel] - 1) / nseg[rel] : 0;
+            // sized for max(n, reserve): a later bind of fewer pre-partitioned tuples keeps the plan
+            const size_t pn = std::max<size_t>(h->n[rel], rel == 0 ? h->cfg.reserve_build : h->cfg.reserve_probe);
+            h->plan_n[rel] = pn;
+            nseg_plan[rel] = segments_for(h, pn, kScatTile);
+            uint64_t len = nseg_plan[rel] ? (pn + nseg_plan[rel] - 1) / nseg_plan[rel] : 0;
             len = ((len + kScatTile - 1) / kScatTile) * kScatTile;
+            nseg_plan[rel] = len ? (uint32_t)((pn + len - 1) / len) : 0;
             nseg[rel] = len ? (uint32_t)((h->n[rel] + len - 1) / len) : 0;
             h->seg_len[rel] = len ? len : kScatTile;
             h->nseg1_rel[rel] = nseg[rel];
@@ -453,6 +476,14 @@ int build_plan(phj_handle* h) {
         }
         h->nsegs1 = (uint32_t)segs.size();
         uint32_t ncounts1 = cnt_base;
+        // row chunks of the multi-GPU split: whole segments; the build relation goes with chunk 0
+        h->nchunks = h->cfg.algo == PHJ_ALGO_SHARD_SPLIT ? std::max<uint32_t>(1, h->cfg.split_chunks) : 1;
+        for (uint32_t c = 0; c <= h->nchunks; ++c) {
+            h->chunk_first_seg[0][c] = c == 0 ? 0 : nseg[0];
+            h->chunk_first_seg[1][c] = (uint32_t)((uint64_t)nseg[1] * c / h->nchunks);
+        }
+        h->segs_n[0] = h->n[0];
+        h->segs_n[1] = h->n[1];
         if ((rc = dev_reserve(&h->d_segs1, &h->cap_segs1, segs.size())) != PHJ_OK) return rc;
         if (!segs.empty())
             PHJ_CUDA(cudaMemcpyAsync(h->d_segs1, segs.data(), segs.size() * sizeof(Segment),
@@ -462,7 +493,7 @@ int build_plan(phj_handle* h) {
         h->fuse2 = false;
         if (h->b2 > 0) {
             for (int rel = 0; rel < 2; ++rel)
-                h->target_segs2[rel] = std::max<uint32_t>(1, nseg[rel]);
+                h->target_segs2[rel] = std::max<uint32_t>(1, nseg_plan[rel]);
             h->max_segs2 = h->target_segs2[0] + h->target_segs2[1] + 2 * h->d1;
             // Opt-in: measured slower than the separate histogram read on B200 (the extra 33 KB of
             // shared memory shrinks L1, which bounds the loads in flight).
@@ -503,11 +534,8 @@ int build_plan(phj_handle* h) {
             // boundary (= n) is never written by a kernel.
             PHJ_CUDA(cudaMemsetAsync(h->d_bounds1[rel], 0, nb1 * 8, h->stream));
             PHJ_CUDA(cudaMemsetAsync(h->d_bounds2[rel], 0, nb2 * 8, h->stream));
-            uint64_t nn = h->n[rel];
-            PHJ_CUDA(cudaMemcpyAsync(h->d_bounds1[rel] + h->d1, &nn, 8, cudaMemcpyHostToDevice, h->stream));
-            PHJ_CUDA(cudaMemcpyAsync(h->d_bounds2[rel] + h->nparts, &nn, 8, cudaMemcpyHostToDevice, h->stream));
-            PHJ_CUDA(cudaStreamSynchronize(h->stream));
         }
+        if ((rc = upload_tail_bounds(h)) != PHJ_OK) return rc;
         uint32_t sc[kNumScalars] = {};
         sc[kNsegs1] = h->nsegs1;
         sc[kNcounts1] = ncounts1;
@@ -529,7 +557,7 @@ int build_plan(phj_handle* h) {
         // Table of 32-byte buckets in shared memory: aim for a load factor of ~0.3 (nearly every
         // probe ends in its home bucket) while the table stays <= 64 KB (3 CTAs per SM); beyond that
         // accept ~0.6, and beyond 128 KB the partition goes through the global table.
-        uint64_t mean = std::max<uint64_t>(1, h->n[0] / std::max<uint64_t>(1, h->P));
+        uint64_t mean = std::max<uint64_t>(1, h->plan_n[0] / std::max<uint64_t>(1, h->P));
         uint32_t slots = 1024;
         while (slots < 8192 && (double)slots < 3.2 * (double)mean) slots <<= 1;
         while (slots < 16384 && (double)slots < 1.6 * (double)mean) slots <<= 1;
@@ -931,6 +959,8 @@ int validate_config(const phj_config* c) {
             c->radix_bits[1])
             return fail(PHJ_ERR_INVALID, "shard split needs partitions = ranks x local pass-1 digits (a power of "
                                          "two <= 256), shard_shift <= 56 and no radix_bits");
+        if (c->split_chunks > (uint32_t)kMaxSplitChunks)
+            return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
     }
     if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
         return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", c->hash);
@@ -1053,11 +1083,12 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_cta_times) cudaFreeHost(h->h_cta_times);
+    if (h->h_shard_starts) cudaFreeHost(h->h_shard_starts);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& k : h->ktimes) {
@@ -1069,7 +1100,7 @@ void phj_destroy(phj_handle* h) {
 }
 
 static int set_relations(phj_handle* h, const void* build, size_t n_build, const void* probe,
-                         size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool defer_buffers = false) {
+                         size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool prepartitioned = false) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     if ((n_build && !build) || (n_probe && !probe))
         return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
@@ -1078,7 +1109,11 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
     PHJ_CUDA(cudaSetDevice(h->device));
     const void* src[2] = {build, probe};
     const size_t nn[2] = {n_build, n_probe};
-    const bool replan = !h->have_data || nn[0] != h->n[0] || nn[1] != h->n[1];
+    // A pre-partitioned bind (shrink_ok) keeps a plan that has room; everything else needs the pass-1
+    // segment table to cover exactly these sizes.
+    const bool replan = !h->have_data || nn[0] > h->plan_n[0] || nn[1] > h->plan_n[1] ||
+                        (!prepartitioned && (nn[0] != h->segs_n[0] || nn[1] != h->segs_n[1]));
+    const bool resized = nn[0] != h->n[0] || nn[1] != h->n[1];
     for (int rel = 0; rel < 2; ++rel) {
         if (device_resident) {
             if (h->owns_in[rel] && h->d_in[rel]) cudaFree(h->d_in[rel]);
@@ -1106,6 +1141,9 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
         h->have_data = false;
         int rc = build_plan(h);
         if (rc != PHJ_OK) return rc;
+    } else if (resized && h->cfg.algo != PHJ_ALGO_NO_PARTITIONING) {
+        int rc = upload_tail_bounds(h);
+        if (rc != PHJ_OK) return rc;
     }
     if (!device_resident) {
         PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
@@ -1120,7 +1158,7 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
     h->have_data = true;
     h->joined_radix = false;
     h->prepart = false;
-    if (!defer_buffers && h->cfg.algo != PHJ_ALGO_NO_PARTITIONING &&
+    if (!prepartitioned && h->cfg.algo != PHJ_ALGO_NO_PARTITIONING &&
         !(h->cfg.algo == PHJ_ALGO_SHARD_SPLIT && (h->cfg.flags & PHJ_FLAG_SPLIT_REMOTE_ONLY))) {
         int rc = ensure_buffers(h, true, h->b2 > 0);
         if (rc != PHJ_OK) return rc;
@@ -1248,73 +1286,95 @@ int phj_shard_count(phj_handle* h, uint64_t* counts) {
     PHJ_CUDA(cudaSetDevice(h->device));
     h->launches = 0;
     h->n_ktimes = 0;
+    const uint32_t w = h->d1, K = h->nchunks;
+    const size_t nstarts = (size_t)2 * w * (K + 1);
+    if (!h->d_shard_starts) {
+        const size_t cap = (size_t)2 * kMaxSplitDigits * (kMaxSplitChunks + 1);
+        PHJ_CUDA(cudaMalloc(&h->d_shard_starts, cap * 8));
+        PHJ_CUDA(cudaMallocHost(&h->h_shard_starts, cap * 8));
+    }
     PassParams p1{};
     fill_pass1_params(h, p1);
     PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (h->nsegs1 > 0) {
-        {
-            KernelScope ks(h, "radix_histogram[split]");
-            PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
-        }
-        run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
-        BoundsParams bp{};
-        bp.cursors = h->d_cursors;
-        for (int rel = 0; rel < 2; ++rel) {
-            bp.bounds[rel] = h->d_bounds2[rel];
-            bp.cnt_base[rel] = h->cnt_base1_rel[rel];
-            bp.nseg[rel] = h->nseg1_rel[rel];
-        }
-        bp.bias[1] = h->n[0];
-        bp.ndigits = h->d1;
-        KernelScope ks(h, "bounds_from_cursors");
-        bounds_from_cursors<<<2, kMaxSplitDigits, 0, h->stream>>>(bp);
+        KernelScope ks(h, "radix_histogram[split]");
+        PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
     }
-    const uint32_t w = h->d1;
-    for (int rel = 0; rel < 2; ++rel)
-        PHJ_CUDA(cudaMemcpyAsync(h->shard_bounds[rel], h->d_bounds2[rel], (w + 1) * 8, cudaMemcpyDeviceToHost,
-                                 h->stream));
+    if (h->nsegs1 > 0) run_scan(h, kNcounts1, (size_t)h->nsegs1 * h->d1);
+    SplitStartsParams sp{};
+    sp.cursors = h->d_cursors;
+    sp.starts = h->d_shard_starts;
+    for (int rel = 0; rel < 2; ++rel) {
+        sp.cnt_base[rel] = h->cnt_base1_rel[rel];
+        sp.nseg[rel] = h->nseg1_rel[rel];
+        sp.n[rel] = h->n[rel];
+        for (uint32_t c = 0; c <= K; ++c) sp.first_seg[rel][c] = h->chunk_first_seg[rel][c];
+    }
+    sp.bias[1] = h->n[0];
+    sp.ndigits = w;
+    sp.nchunks = K;
+    {
+        KernelScope ks(h, "split_starts");
+        split_starts<<<(uint32_t)((nstarts + 255) / 256), 256, 0, h->stream>>>(sp);
+    }
+    PHJ_CUDA(cudaMemcpyAsync(h->h_shard_starts, h->d_shard_starts, nstarts * 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
-    for (int rel = 0; rel < 2; ++rel)
-        for (uint32_t d = 0; d < w; ++d) counts[rel * w + d] = h->shard_bounds[rel][d + 1] - h->shard_bounds[rel][d];
+    for (uint32_t c = 0; c < K; ++c)
+        for (int rel = 0; rel < 2; ++rel)
+            for (uint32_t d = 0; d < w; ++d) {
+                const uint64_t* st = h->h_shard_starts + ((size_t)rel * w + d) * (K + 1);
+                counts[((size_t)c * 2 + rel) * w + d] = st[c + 1] - st[c];
+            }
     h->shard_counted = true;
     return PHJ_OK;
 }
 
-int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off_build,
+int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
                       void* const* dst_probe, const uint64_t* off_probe, phj_result* out) {
     if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
     if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
     if (!h->shard_counted) return fail(PHJ_ERR_STATE, "phj_shard_scatter needs a preceding phj_shard_count");
+    if (chunk >= h->nchunks) return fail(PHJ_ERR_INVALID, "chunk %u out of range [0, %u)", chunk, h->nchunks);
+    if ((!dst_build || !dst_probe) && h->nchunks > 1)
+        return fail(PHJ_ERR_INVALID, "a chunked split needs destinations for both relations");
     PHJ_CUDA(cudaSetDevice(h->device));
     memset(out, 0, sizeof(*out));
-    const uint32_t w = h->d1;
+    const uint32_t w = h->d1, K = h->nchunks;
     void* const* dst[2] = {dst_build, dst_probe};
     const uint64_t* off[2] = {off_build, off_probe};
+    if (!dst_build || !dst_probe) {
+        int rc = ensure_buffers(h, true, false);
+        if (rc != PHJ_OK) return rc;
+    }
     PassParams p1{};
     fill_pass1_params(h, p1);
     ulonglong2* host_ptrs[2][kMaxSplitDigits];
     for (int rel = 0; rel < 2; ++rel) {
         if (!dst[rel]) continue;  // this relation stays local (split into buf_a)
         if (!h->d_outd[rel]) PHJ_CUDA(cudaMalloc(&h->d_outd[rel], kMaxSplitDigits * sizeof(void*)));
-        for (uint32_t d = 0; d < w; ++d)  // run d starts at cursor == bounds[d]: rebase it to off[d]
-            host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) -
-                                h->shard_bounds[rel][d];
+        for (uint32_t d = 0; d < w; ++d) {
+            // this chunk's run of digit d starts at cursor == starts[rel][d][chunk]: rebase it to off[d]
+            const uint64_t start = h->h_shard_starts[((size_t)rel * w + d) * (K + 1) + chunk];
+            host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) - start;
+        }
         PHJ_CUDA(cudaMemcpyAsync(h->d_outd[rel], host_ptrs[rel], w * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
         p1.outd[rel] = h->d_outd[rel];
     }
-    if (!dst_build || !dst_probe) {
-        int rc = ensure_buffers(h, true, false);
-        if (rc != PHJ_OK) return rc;
-        fill_pass1_params(h, p1);
-        for (int rel = 0; rel < 2; ++rel)
-            if (dst[rel]) p1.outd[rel] = h->d_outd[rel];
+    // segments of this chunk: the build relation's (chunk 0 only) are followed by the probe relation's
+    const uint32_t nseg0 = h->nseg1_rel[0];
+    const uint32_t first = chunk == 0 ? 0 : nseg0 + h->chunk_first_seg[1][chunk];
+    const uint32_t last = nseg0 + h->chunk_first_seg[1][chunk + 1];
+    const uint32_t count = last - first;
+    if (K > 1) {
+        p1.seg_first = first;
+        p1.seg_count = count;
     }
     PHJ_CUDA(cudaEventRecord(h->ev[1], h->stream));
-    if (h->nsegs1 > 0) {
+    if (count > 0) {
         // split_ctas caps the grid: an NVLink-bound split needs a fraction of the SMs, the rest stay
         // free for the local join of the previous chunk running on another stream
-        const uint32_t grid = h->cfg.split_ctas ? std::min<uint32_t>(h->nsegs1, h->cfg.split_ctas) : h->nsegs1;
+        const uint32_t grid = h->cfg.split_ctas ? std::min<uint32_t>(count, h->cfg.split_ctas) : count;
         KernelScope ks(h, "radix_scatter[split]");
         PHJ_CUDA(launch_pass(h, true, h->b1, p1, grid));
     }
@@ -1326,9 +1386,10 @@ int phj_shard_scatter(phj_handle* h, void* const* dst_build, const uint64_t* off
     out->passes = 1;
     out->partitions = h->P;
     out->kernel_launches = h->launches;
-    out->hbm_bytes_alg = 16ull * 2 * (h->n[0] + h->n[1]);
-    h->shard_counted = false;
-    h->joined_radix = true;
+    out->hbm_bytes_alg = 16ull * 2 * (h->n[0] + h->n[1]) / K;
+    h->launches = 0;
+    if (chunk + 1 == K) h->shard_counted = false;
+    h->joined_radix = K == 1 && (!dst_build || !dst_probe);
     return PHJ_OK;
 }
 

@@ -59,6 +59,8 @@ struct PassParams {
     ulonglong2* out[2];
     const Segment* segs;
     const uint32_t* nsegs;     // device-resident segment count (CTAs beyond it exit)
+    uint32_t seg_first, seg_count;  // seg_count != 0: only segments [seg_first, seg_first + seg_count)
+                               // (one row chunk of the multi-GPU split); else all *nsegs of them
     uint32_t* counts;          // histogram out (radix_histogram)
     const uint64_t* cursors;   // exclusive scan of counts (radix_scatter)
     uint64_t cursor_bias[2];   // flat scan spans R then S: S cursors are offset by |R|
@@ -344,13 +346,13 @@ __global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* wcw = wc + warp * (D + 1);
     const uint32_t lt = lanemask_lt();
-    const uint32_t nsegs = *p.nsegs;
+    const uint32_t nsegs = p.seg_count ? p.seg_count : *p.nsegs;
 
     // One CTA per segment by default; a smaller grid (the multi-GPU split, which leaves SMs to the
     // local join running beside it) makes every CTA walk several segments.
     for (uint32_t si = blockIdx.x; si < nsegs; si += gridDim.x) {
     if (si != blockIdx.x) cta_sync();  // the previous segment's last tile is staged and flushed
-    const Segment seg = p.segs[si];
+    const Segment seg = p.segs[p.seg_first + si];
     const ulonglong2* __restrict__ in = p.in[seg.rel];
     ulonglong2* __restrict__ out = p.out[seg.rel];
 
@@ -1107,6 +1109,33 @@ __global__ void bounds_from_cursors(BoundsParams p) {
     const int rel = i / p.ndigits;
     const uint32_t d = i % p.ndigits;
     if (p.nseg[rel]) p.bounds[rel][d] = p.cursors[p.cnt_base[rel] + (uint64_t)d * p.nseg[rel]] - p.bias[rel];
+}
+
+// Multi-GPU split in K row chunks: where chunk c's tuples of digit d start in the (virtual) split
+// output, starts[(rel * ndigits + d) * (K + 1) + c]; entry K is the end of the digit. Chunk c of a
+// relation is the segment range [first_seg[rel][c], first_seg[rel][c + 1]).
+struct SplitStartsParams {
+    const uint64_t* cursors;
+    uint64_t* starts;
+    uint32_t cnt_base[2], nseg[2];
+    uint64_t bias[2], n[2];
+    uint32_t ndigits, nchunks;
+    uint32_t first_seg[2][17];  // up to 16 chunks
+};
+__global__ void split_starts(SplitStartsParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per_rel = p.ndigits * (p.nchunks + 1);
+    if (i >= 2 * per_rel) return;
+    const int rel = i / per_rel;
+    const uint32_t d = (i % per_rel) / (p.nchunks + 1), c = i % (p.nchunks + 1);
+    uint64_t v = 0;
+    if (p.nseg[rel]) {
+        const uint32_t s = c < p.nchunks ? p.first_seg[rel][c] : p.nseg[rel];
+        if (s < p.nseg[rel]) v = p.cursors[p.cnt_base[rel] + (uint64_t)d * p.nseg[rel] + s] - p.bias[rel];
+        else if (d + 1 < p.ndigits) v = p.cursors[p.cnt_base[rel] + (uint64_t)(d + 1) * p.nseg[rel]] - p.bias[rel];
+        else v = p.n[rel];
+    }
+    p.starts[i] = v;
 }
 
 // Test hook: raw hashes of a key array.

@@ -125,7 +125,8 @@ class Engine:
 
     def __init__(self, algo="radix-partitioning", partitions: int = 0, radix_bits=(0, 0), hash="xxh3",
                  hash_seed: int = 0x9E3779B97F4A7C15, table_seed: int = 1, device: int = 0,
-                 flags: int = 0, shard_shift: int = 0, split_ctas: int = 0, reserve=(0, 0)):
+                 flags: int = 0, shard_shift: int = 0, split_ctas: int = 0, reserve=(0, 0),
+                 split_chunks: int = 0):
         cfg = PhjConfig()
         if isinstance(algo, str):
             if algo not in self.ALGOS:
@@ -141,6 +142,7 @@ class Engine:
         cfg.flags = flags
         cfg.shard_shift = shard_shift
         cfg.split_ctas = split_ctas
+        cfg.split_chunks = split_chunks
         cfg.reserve_build, cfg.reserve_probe = reserve
         self._h = C.c_void_p()
         check(lib.phj_create(C.byref(cfg), C.byref(self._h)))

@@ -238,7 +238,7 @@ class FusedGpuBackend(GpuBackend):
             offs = np.ascontiguousarray(offsets[which], dtype=np.uint64)
             arrs += [ptrs, offs]
         res = PhjResult()
-        self._check(self._lib.phj_shard_scatter(self.split_engine._h, arrs[0], arrs[1].ctypes.data, arrs[2],
+        self._check(self._lib.phj_shard_scatter(self.split_engine._h, 0, arrs[0], arrs[1].ctypes.data, arrs[2],
                                                 arrs[3].ctypes.data, C.byref(res)))
         self.launches += res.kernel_launches
         return int(res.total_ns)
@@ -380,8 +380,9 @@ class FusedShardedRadixJoin:
 class PipelinedGpuBackend(FusedGpuBackend):
     """FusedGpuBackend with the probe shard cut into row chunks, so that the NVLink shuffle of chunk
     c + 1 (a split scatter capped to `split_ctas` CTAs on a high-priority stream) overlaps the local
-    pass 2 + join of chunk c (the match count is additive over a partition of S). Windows: 0 = build
-    side (filled with chunk 0), 1 / 2 = probe chunks, double-buffered."""
+    pass 2 + join of chunk c (the match count is additive over a partition of S). One histogram
+    pass counts all chunks at once. Windows: 0 = build side (travels with chunk 0), 1 / 2 = probe
+    chunks, double-buffered."""
 
     def __init__(self, world, device, partitions_local=4096, hash="xxh3", hash_seed=0x9E3779B97F4A7C15,
                  chunks=4, split_ctas=0):
@@ -394,48 +395,36 @@ class PipelinedGpuBackend(FusedGpuBackend):
         if not self.b1:
             raise ValueError("the pipelined shuffle needs a power-of-two local fan-out >= 4 (two-level digit)")
         self.d1 = self.ndig // world
-        self.splits = [engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
-                                     device=device, shard_shift=self.b2, flags=_lib.FLAG_SPLIT_REMOTE_ONLY,
-                                     split_ctas=split_ctas) for _ in range(chunks)]
-        self.locals = [engine.Engine("radix-partitioning", partitions=partitions_local, radix_bits=(self.b1, self.b2),
-                                     hash=hash, hash_seed=hash_seed, device=device) for _ in range(2)]
+        self._mk_local = lambda reserve: engine.Engine(
+            "radix-partitioning", partitions=partitions_local, radix_bits=(self.b1, self.b2), hash=hash,
+            hash_seed=hash_seed, device=device, reserve=reserve)
+        self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
+                                          device=device, shard_shift=self.b2, flags=_lib.FLAG_SPLIT_REMOTE_ONLY,
+                                          split_ctas=split_ctas, split_chunks=chunks)
+        self.locals = [None, None]
+        self.local_reserve = (0, 0)
         self.launches = 0
         self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
         self.win = [None] * 3
         self.peer = [[None] * world for _ in range(3)]
-        self.arena = [None, None]   # device copies of this rank's shards
-        self.arena_cap = [0, 0]
-        self.n = [0, 0]
 
     def thread_init(self):
         self.torch.cuda.set_device(self.device)
 
-    def upload(self, R, S):
-        from .engine import as_tuples
-        C = self._C
-        rels = [as_tuples(R), as_tuples(S)]
-        for which, rel in enumerate(rels):
-            n = rel.shape[0]
-            if n > self.arena_cap[which] or not self.arena[which]:
-                if self.arena[which]:
-                    self._check(self._lib.phj_shared_free(self.device, C.c_void_p(self.arena[which])))
-                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
-                self._check(self._lib.phj_shared_alloc(self.device, max(n, 1) * 16, C.byref(ptr), handle))
-                self.arena[which], self.arena_cap[which] = ptr.value, max(n, 1)
-            self._check(self._lib.phj_memcpy_h2d(self.device, C.c_void_p(self.arena[which]), rel.ctypes.data, n * 16))
-            self.n[which] = n
-        # chunk c of the probe shard = rows [lo[c], lo[c + 1]); the build shard travels with chunk 0
-        per = -(-self.n[1] // self.chunks)
-        per = -(-per // 4096) * 4096
-        self.lo = [min(c * per, self.n[1]) for c in range(self.chunks + 1)]
-        for c, eng in enumerate(self.splits):
-            n_s = self.lo[c + 1] - self.lo[c]
-            eng.bind_device(self.arena[0] if c == 0 and self.n[0] else 0, self.n[0] if c == 0 else 0,
-                            self.arena[1] + self.lo[c] * 16 if n_s else 0, n_s)
+    def reserve_local(self, rows_build, rows_probe):
+        """Window capacities changed: the local joins plan for that many tuples, so that every chunk
+        (they differ by a few tuples) re-binds without re-planning."""
+        if (rows_build, rows_probe) != self.local_reserve:
+            for e in self.locals:
+                if e is not None:
+                    e.close()
+            self.locals = [self._mk_local((rows_build, rows_probe)) for _ in range(2)]
+            self.local_reserve = (rows_build, rows_probe)
 
-    def count(self, c):
-        counts = np.zeros((2, self.ndig), dtype=np.uint64)
-        self._check(self._lib.phj_shard_count(self.splits[c]._h, counts.ctypes.data))
+    def count(self):
+        """counts[chunk][rel][digit] of this rank's shard, one histogram pass for all chunks."""
+        counts = np.zeros((self.chunks, 2, self.ndig), dtype=np.uint64)
+        self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
         return counts.astype(np.int64)
 
     def scatter(self, c, offsets):
@@ -446,7 +435,7 @@ class PipelinedGpuBackend(FusedGpuBackend):
             ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][d // self.d1]) for d in range(self.ndig)])
             arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
         res = PhjResult()
-        self._check(self._lib.phj_shard_scatter(self.splits[c]._h, arrs[0], arrs[1].ctypes.data, arrs[2],
+        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
                                                 arrs[3].ctypes.data, C.byref(res)))
         self.launches += res.kernel_launches
         return int(res.total_ns)
@@ -461,67 +450,64 @@ class PipelinedGpuBackend(FusedGpuBackend):
         return res["matches"], res
 
     def close(self):
-        for e in self.splits + self.locals:
-            e.close()
-        for which in (0, 1):
-            if self.arena[which]:
-                self._lib.phj_shared_free(self.device, self._C.c_void_p(self.arena[which]))
-                self.arena[which] = None
+        for e in [self.split_engine] + self.locals:
+            if e is not None:
+                e.close()
 
 
 class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
-    """The fused shuffle, software-pipelined over row chunks of the probe shard: a producer thread
-    runs count -> sizes all-gather -> NVLink scatter -> barrier for chunk c + 1 while the caller's
-    thread runs the local pass 2 + join of chunk c. The two legs use different resources (NVLink vs
-    HBM), so the join costs about max(shuffle, local) instead of their sum."""
+    """The fused shuffle, software-pipelined over row chunks of the probe shard: after ONE count +
+    sizes all-gather for all chunks, a producer thread runs NVLink scatter -> barrier for chunk
+    c + 1 while the caller's thread runs the local pass 2 + join of chunk c. The two legs use
+    different resources (NVLink vs HBM), so the join costs about max(shuffle, local), not the sum."""
 
     def join(self) -> dict:
         import queue
         import threading
         be, world, rank, K = self.backend, self.world, self.rank, self.backend.chunks
+        t0 = time.perf_counter()
+        counts = be.count()                                    # [chunk][rel][digit]
+        t1 = time.perf_counter()
+        M = self._gather_counts(counts)                        # [source][chunk * 2 + rel][digit]
+        M = M.reshape(world, K, 2, -1)
+        plans = [self.layout(M[:, c], world, rank) for c in range(K)]   # (need, offsets, bounds) per chunk
+        want = {0: plans[0][0][0]}
+        for slot in (0, 1):
+            needs = [plans[c][0][1] for c in range(slot, K, 2)]
+            if needs:
+                want[1 + slot] = np.max(needs, axis=0)
+        regrown = self._ensure_windows(want)
+        if hasattr(be, "reserve_local"):
+            be.reserve_local(int(self.caps[0][rank]), int(max(self.caps[1][rank], self.caps[2][rank])))
+        build_rows, build_bounds = int(plans[0][0][0][rank]), plans[0][2][0]
+        t2 = time.perf_counter()
+
         free = [threading.Semaphore(1), threading.Semaphore(1)]
         ready = queue.Queue()
         abort = threading.Event()
-        stats = {"count_s": 0.0, "sizes_s": 0.0, "scatter_s": 0.0, "scatter_device_ns": 0, "regrown": False,
-                 "send_bytes_remote": 0}
+        stats = {"scatter_s": 0.0, "scatter_device_ns": 0}
 
         def producer():
             try:
                 if hasattr(be, "thread_init"):
                     be.thread_init()
-                build = None
                 for c in range(K):
                     while not free[c % 2].acquire(timeout=0.05):
                         if abort.is_set():
                             return
-                    t0 = time.perf_counter()
-                    counts = be.count(c)
-                    t1 = time.perf_counter()
-                    M = self._gather_counts(counts)
-                    need, offsets, bounds = self.layout(M, world, rank)
-                    want = {1 + c % 2: need[1]}
-                    if c == 0:
-                        want[0] = need[0]
-                        build = (int(need[0][rank]), bounds[0])
-                    stats["regrown"] |= self._ensure_windows(want)
-                    t2 = time.perf_counter()
+                    ts = time.perf_counter()
+                    need, offsets, bounds = plans[c]
                     stats["scatter_device_ns"] += be.scatter(c, offsets)
                     if world > 1:
-                        self.dist.barrier()
-                    t3 = time.perf_counter()
-                    stats["count_s"] += t1 - t0
-                    stats["sizes_s"] += t2 - t1
-                    stats["scatter_s"] += t3 - t2
-                    d1 = counts.shape[1] // world
-                    stats["send_bytes_remote"] += int(16 * (counts.sum() - counts[:, rank * d1:(rank + 1) * d1].sum()))
-                    ready.put((c, [build[0], int(need[1][rank])], [build[1], bounds[1]]))
+                        self.dist.barrier()                    # every rank's stores of chunk c have landed
+                    stats["scatter_s"] += time.perf_counter() - ts
+                    ready.put((c, [build_rows, int(need[1][rank])], [build_bounds, bounds[1]]))
             except BaseException as e:  # hand the failure to the consumer
                 ready.put(e)
 
-        t0 = time.perf_counter()
         th = threading.Thread(target=producer, name="phj-shuffle", daemon=True)
         th.start()
-        local_matches, local_s, wait_s, res, recv_rows = 0, 0.0, 0.0, None, [0, 0]
+        local_matches, local_s, wait_s, res, recv_rows = 0, 0.0, 0.0, None, [build_rows, 0]
         try:
             for _ in range(K):
                 tw = time.perf_counter()
@@ -535,7 +521,7 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
                 free[c % 2].release()
                 local_s += time.perf_counter() - tj
                 wait_s += tj - tw
-                recv_rows = [rows[0], recv_rows[1] + rows[1]]
+                recv_rows[1] += rows[1]
         except BaseException:
             abort.set()
             raise
@@ -547,11 +533,13 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
             self.dist.all_reduce(total)
         matches = int(total.item())
         t5 = time.perf_counter()
-        self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": stats["count_s"],
-                     "exchange_s": stats["sizes_s"] + stats["scatter_s"], "sizes_s": stats["sizes_s"],
+        d1 = counts.shape[2] // world
+        mine = counts[:, :, rank * d1:(rank + 1) * d1].sum()
+        self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
+                     "exchange_s": (t2 - t1) + stats["scatter_s"], "sizes_s": t2 - t1,
                      "scatter_s": stats["scatter_s"], "local_s": local_s, "wait_s": wait_s, "reduce_s": t5 - t4,
-                     "total_s": t5 - t0, "recv_rows": recv_rows, "regrown": stats["regrown"],
-                     "send_bytes_remote": stats["send_bytes_remote"] if world > 1 else 0, "local_result": res,
+                     "pipeline_s": t4 - t2, "total_s": t5 - t0, "recv_rows": recv_rows, "regrown": regrown,
+                     "send_bytes_remote": int(16 * (counts.sum() - mine)) if world > 1 else 0, "local_result": res,
                      "split_device_ns": stats["scatter_device_ns"], "scatter_device_ns": stats["scatter_device_ns"],
                      "chunks": K}
         return self.last

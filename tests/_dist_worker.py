@@ -149,19 +149,23 @@ class OraclePipelinedBackend(OracleFusedBackend):
         per = -(-n // self.chunks) if n else 0
         self.lo = [min(c * per, n) for c in range(self.chunks + 1)]
 
-    def count(self, c):
-        rels = [self.rel[0] if c == 0 else self.rel[0][:0], self.rel[1][self.lo[c]:self.lo[c + 1]]]
-        self.pieces, counts = [], []
-        for rel in rels:
-            dig = self.digit(rel["id"]) if rel.shape[0] else np.empty(0, np.int64)
-            self.pieces.append([rel[dig == d] for d in range(self.ndig)])
-            counts.append(np.bincount(dig, minlength=self.ndig))
+    def count(self):
+        self.chunk_pieces, counts = [], []
+        for c in range(self.chunks):
+            rels = [self.rel[0] if c == 0 else self.rel[0][:0], self.rel[1][self.lo[c]:self.lo[c + 1]]]
+            pieces, cc = [], []
+            for rel in rels:
+                dig = self.digit(rel["id"]) if rel.shape[0] else np.empty(0, np.int64)
+                pieces.append([rel[dig == d] for d in range(self.ndig)])
+                cc.append(np.bincount(dig, minlength=self.ndig))
+            self.chunk_pieces.append(pieces)
+            counts.append(np.stack(cc))
         return np.stack(counts).astype(np.int64)
 
     def scatter(self, c, offsets):
         for which, w in ((0, 0), (1, 1 + c % 2)):
             for d in range(self.ndig):
-                piece = self.pieces[which][d]
+                piece = self.chunk_pieces[c][which][d]
                 if piece.shape[0]:
                     shm = self.peer[w][d // self.d1]
                     win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
