@@ -403,6 +403,7 @@ class PipelinedGpuBackend(FusedGpuBackend):
                                           split_ctas=split_ctas, split_chunks=chunks)
         self.locals = [None, None]
         self.local_reserve = (0, 0)
+        self.trace = None   # set to [] to record per-call host times and per-kernel device times
         self.launches = 0
         self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
         self.win = [None] * 3
@@ -435,18 +436,25 @@ class PipelinedGpuBackend(FusedGpuBackend):
             ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][d // self.d1]) for d in range(self.ndig)])
             arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
         res = PhjResult()
+        t0 = time.perf_counter()
         self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
                                                 arrs[3].ctypes.data, C.byref(res)))
         self.launches += res.kernel_launches
+        if self.trace is not None:
+            self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
         return int(res.total_ns)
 
     def local_join(self, c, rows, bounds):
         w = 1 + c % 2
         eng = self.locals[c % 2]
+        t0 = time.perf_counter()
         eng.bind_device_partitioned(self.win[0] if rows[0] else 0, rows[0], self.win[w] if rows[1] else 0, rows[1],
                                     bounds[0], bounds[1])
+        t1 = time.perf_counter()
         res = eng.join()
         self.launches += res["kernel_launches"]
+        if self.trace is not None:
+            self.trace.append(("local", c, t0, t1, time.perf_counter(), eng.kernel_times()))
         return res["matches"], res
 
     def close(self):
@@ -563,7 +571,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     import partitionedhashjoin_b200 as phj
     n_build, n_probe = 10_000_000, 200_000_000
     Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
-    mode = getattr(args, "shuffle", "pipelined")
+    mode = getattr(args, "shuffle", "pass1")
     fused = mode in ("fused", "pass1", "pipelined")
     if mode == "pipelined":  # chunked: the NVLink shuffle of chunk c + 1 overlaps the local join of chunk c
         backend = PipelinedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,

@@ -115,8 +115,8 @@ def test_fused_shuffle_single_gpu(phj, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pipelined"),
-                                        (8, "pipelined")])
+@pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"),
+                                        (8, "pass1"), (8, "pipelined")])
 def test_sharded_join_on_gpus(phj, world, mode):
     """One rank per GPU over NCCL: the fused NVLink-store shuffle (and the all-to-all variant)
     against the oracle's count; skipped when the box has fewer GPUs."""
