@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libphj_b200.so")
+# PHJ_LIB selects another build of the same library (kernel-shape variants, tools/tune_shapes.py)
+LIB_PATH = os.environ.get("PHJ_LIB") or os.path.join(PKG_DIR, "libphj_b200.so")
 
 #: numpy view of ``phj_tuple`` == reference ``Common::Tuple`` (src/Common/Table.hpp:20-25)
 TUPLE_DTYPE = np.dtype([("id", "<i8"), ("payload", "<i8")], align=True)

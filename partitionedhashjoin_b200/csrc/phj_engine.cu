@@ -316,6 +316,36 @@ cudaError_t launch_pass_b(phj_handle* h, bool scatter, const PassParams& pp, uin
     }
 }
 
+// The multi-GPU split scatter: tiles of 8192 tuples (1024 threads, one CTA per SM). It is bound by
+// NVLink, not by HBM, and NVLink efficiency grows with the length of the per-digit runs a tile
+// yields (measured at 2 GPUs, 128 digits: exchange 3.95 / 3.32 / 3.02 ms for 2048 / 4096 / 8192).
+template <int BITS, int HASH>
+cudaError_t launch_split_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
+    constexpr int kTpb = 1024, kIpt = 8;
+    using L = ScatterSmem<BITS, kTpb, kIpt>;
+    auto kern = radix_scatter<BITS, HASH, true, kTpb, kIpt, true, true, false, 1>;
+    static bool configured[16] = {};
+    if (!configured[h->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+        if (e != cudaSuccess) return e;
+        configured[h->device & 15] = true;
+    }
+    kern<<<grid, kTpb, L::total, h->stream>>>(pp);
+    return cudaSuccess;
+}
+
+cudaError_t launch_split_scatter(phj_handle* h, int bits, const PassParams& pp, uint32_t grid) {
+    const bool wide = bits > 6;
+    switch (h->cfg.hash) {
+        case PHJ_HASH_MURMUR3:
+            return wide ? launch_split_scatter_t<8, kMurmur3>(h, pp, grid) : launch_split_scatter_t<6, kMurmur3>(h, pp, grid);
+        case PHJ_HASH_CITY:
+            return wide ? launch_split_scatter_t<8, kCity>(h, pp, grid) : launch_split_scatter_t<6, kCity>(h, pp, grid);
+        default:
+            return wide ? launch_split_scatter_t<8, kXXH3>(h, pp, grid) : launch_split_scatter_t<6, kXXH3>(h, pp, grid);
+    }
+}
+
 // A pass with `bits` digit bits runs on the smallest instantiated shape that holds them.
 cudaError_t launch_pass(phj_handle* h, bool scatter, int bits, const PassParams& pp, uint32_t grid) {
     if (bits <= 6) return launch_pass_b<6>(h, scatter, pp, grid);
@@ -1376,7 +1406,11 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
         // free for the local join of the previous chunk running on another stream
         const uint32_t grid = h->cfg.split_ctas ? std::min<uint32_t>(count, h->cfg.split_ctas) : count;
         KernelScope ks(h, "radix_scatter[split]");
-        PHJ_CUDA(launch_pass(h, true, h->b1, p1, grid));
+        // remote destinations: the wide-tile kernel; a purely local split keeps the HBM-tuned shape
+        if (dst_build && dst_probe && !(h->cfg.flags & PHJ_FLAG_NO_TMA_STORE))
+            PHJ_CUDA(launch_split_scatter(h, h->b1, p1, grid));
+        else
+            PHJ_CUDA(launch_pass(h, true, h->b1, p1, grid));
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));

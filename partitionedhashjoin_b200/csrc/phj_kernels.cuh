@@ -324,8 +324,9 @@ struct ScatterSmem {
     static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 4 + (size_t)D * 8 + (size_t)D * 8;
 };
 
-template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT, bool FUSE2>
-__global__ void __launch_bounds__(TPB, PHJ_SCAT_MINB) radix_scatter(PassParams p) {
+template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT, bool FUSE2,
+          int MINB = PHJ_SCAT_MINB>
+__global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     using L = ScatterSmem<BITS, TPB, IPT>;
     constexpr int D = L::D, NW = L::NW, T = L::T;
     static_assert(D <= TPB, "one thread per digit in the scan step");

@@ -18,6 +18,7 @@ orchestration over gloo with a CPU stand-in (tests/test_distributed.py).
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -177,7 +178,8 @@ class FusedGpuBackend(GpuBackend):
         self.d1 = self.ndig // world
         if self.b1:
             self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
-                                              device=device, shard_shift=self.b2)
+                                              device=device, shard_shift=self.b2,
+                                              flags=int(os.environ.get("PHJ_SPLIT_FLAGS", "0"), 0))
             self.local_engine = engine.Engine("radix-partitioning", partitions=partitions_local,
                                               radix_bits=(self.b1, self.b2), hash=hash, hash_seed=hash_seed,
                                               device=device)
