@@ -123,6 +123,8 @@ typedef struct {
                                      and went through the global table instead */
     uint64_t h2d_bytes; /* bytes copied host -> device by this call (phj_join_host), else 0 */
     uint64_t d2h_bytes; /* bytes copied device -> host by this call (count, per-CTA phase times) */
+    uint64_t joined_tuples;  /* phj_join_materialize: rows of the joined table, else 0 */
+    uint64_t materialize_ns; /* phj_join_materialize: device time of the count + write kernels */
 } phj_result;
 
 typedef struct phj_handle phj_handle;
@@ -169,6 +171,19 @@ int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_bui
  * src/RadixCluster/HashJoin.hpp:190-241) on the relations given to phj_upload / phj_bind_device.
  * Synchronous; may be called repeatedly (the inputs stay resident). Not re-entrant per handle. */
 int phj_join(phj_handle* h, phj_result* out);
+
+/* The join WITH its result: fills the Table<JoinedTuple> that both reference Run()s return empty
+ * (src/NoPartitioning/HashJoin.hpp:186, src/RadixCluster/HashJoin.hpp:226-227) -- one
+ * phj_joined_tuple {id, payloadA (build), payloadB (probe)} per (probe tuple, equal-key build
+ * tuple), i.e. LinearProbingHashTable::GetAll semantics (src/HashTables/LinearProbing.hpp:183-200).
+ * Radix-partitioning handles only. out->matches is the count-only figure as in phj_join,
+ * out->joined_tuples the number of rows; the rows live in a device buffer owned by the handle
+ * (grown on demand inside this call), in no particular order, valid until the next call on the
+ * handle. phj_read_joined copies rows [first, first + count) to the host; phj_device_joined
+ * exposes the device buffer. */
+int phj_join_materialize(phj_handle* h, phj_result* out);
+int phj_read_joined(phj_handle* h, phj_joined_tuple* out, uint64_t first, uint64_t count);
+int phj_device_joined(phj_handle* h, const void** d_joined, uint64_t* rows);
 
 /* Upload + join in one call, the end-to-end path (host buffers in, count out). */
 int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,

@@ -382,6 +382,46 @@ int phjo_join_no_partitioning(const phjo_tuple* R, size_t nR, const phjo_tuple* 
     return 0;
 }
 
+/* The joined table both Run()s declare but leave empty (src/NoPartitioning/HashJoin.hpp:186,
+ * src/RadixCluster/HashJoin.hpp:226-227): Table<JoinedTuple>{id, payloadA, payloadB}
+ * (src/Common/Table.hpp:27-33), filled the way the probe loop would with GetAll
+ * (src/HashTables/LinearProbing.hpp:183-200): one row per (probe tuple, equal-key build tuple).
+ * The reference itself never executes this loop, so this is the definition the CUDA path is held
+ * to, not a restatement of executed reference code. Rows are emitted in probe order; rows of one
+ * probe tuple follow the table's bucket order. Returns the number of joined rows (even beyond cap). */
+uint64_t phjo_join_materialize(const phjo_tuple* R, size_t nR, const phjo_tuple* S, size_t nS,
+                               int table_kind, int hash_id, uint64_t seed_table, phjo_joined* out,
+                               uint64_t cap) {
+    if (nR == 0) return 0;
+    phjo_table* table = phjo_table_new(table_kind, 0, hash_id, seed_table, nR);
+    if (!table) return 0;
+    for (size_t i = 0; i != nR; ++i)
+        if (phjo_table_insert(table, R[i].id, &R[i])) {
+            phjo_table_free(table);
+            return UINT64_MAX;
+        }
+    size_t scratch_cap = 64;
+    const phjo_tuple** scratch = (const phjo_tuple**)malloc(scratch_cap * sizeof(*scratch));
+    uint64_t n = 0;
+    for (size_t i = 0; i != nS; ++i) {
+        size_t k = phjo_table_get_all(table, S[i].id, scratch, scratch_cap);
+        if (k > scratch_cap) {
+            scratch_cap = k;
+            scratch = (const phjo_tuple**)realloc((void*)scratch, scratch_cap * sizeof(*scratch));
+            k = phjo_table_get_all(table, S[i].id, scratch, scratch_cap);
+        }
+        for (size_t j = 0; j != k; ++j, ++n)
+            if (out && n < cap) {
+                out[n].id = S[i].id;
+                out[n].payloadA = scratch[j]->payload;
+                out[n].payloadB = S[i].payload;
+            }
+    }
+    free((void*)scratch);
+    phjo_table_free(table);
+    return n;
+}
+
 /* HashJoiner::GetPartitioningConfiguration (src/RadixCluster/HashJoin.hpp:149-188), including its
  * quirk: when a batch falls below MinBatchSize the worker count is re-derived from that relation
  * and then applies to BOTH relations, while the other relation keeps its old batch size. */

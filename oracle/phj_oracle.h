@@ -70,6 +70,20 @@ typedef struct {
 int phjo_join_no_partitioning(const phjo_tuple* R, size_t nR, const phjo_tuple* S, size_t nS,
                               int table_kind, int hash_id, uint64_t seed_table, phjo_result* out);
 
+/* src/Common/Table.hpp:27-33 */
+typedef struct {
+    int64_t id;
+    int64_t payloadA;
+    int64_t payloadB;
+} phjo_joined;
+
+/* The joined table the reference declares but never fills: one row per (probe tuple, equal-key
+ * build tuple), via GetAll (src/HashTables/LinearProbing.hpp:183-200). Returns the row count;
+ * writes at most cap rows. UINT64_MAX if the chaining allocator overflowed. */
+uint64_t phjo_join_materialize(const phjo_tuple* R, size_t nR, const phjo_tuple* S, size_t nS,
+                               int table_kind, int hash_id, uint64_t seed_table, phjo_joined* out,
+                               uint64_t cap);
+
 /* src/RadixCluster/HashJoin.hpp:149-188 -- worker count / batch sizes for both relations. */
 void phjo_partitioning_configuration(size_t sizeA, size_t sizeB, size_t pool_workers,
                                      size_t min_batch, size_t* workers, size_t* batchA,

@@ -5,7 +5,7 @@ Layout: ``csrc/`` CUDA kernels + the C ABI of ``include/phj.h`` (-> ``libphj_b20
 by tests and bench. Importing this package requires the built shared library (no CPU fallback).
 """
 from ._lib import (ALGO_NO_PARTITIONING, ALGO_RADIX_PARTITIONING, FLAG_FUSE_HIST2, FLAG_NO_TMA_STORE, HASH_CITY,
-                   HASH_MURMUR3, HASH_NAMES, HASH_XXH3, LIB_PATH, TUPLE_DTYPE, PhjError)
+                   HASH_MURMUR3, HASH_NAMES, HASH_XXH3, JOINED_DTYPE, LIB_PATH, TUPLE_DTYPE, PhjError)
 from .engine import (Engine, Hasher, HashJoinTimer, HashJoinTimingResult, NoOpHashJoinTimer,
                      NoPartitioningConfiguration, NoPartitioningHashJoiner, PinnedTuples,
                      RadixClusteringConfiguration, RadixClusteringHashJoiner, as_tuples,

@@ -17,6 +17,9 @@ LIB_PATH = os.environ.get("PHJ_LIB") or os.path.join(PKG_DIR, "libphj_b200.so")
 #: numpy view of ``phj_tuple`` == reference ``Common::Tuple`` (src/Common/Table.hpp:20-25)
 TUPLE_DTYPE = np.dtype([("id", "<i8"), ("payload", "<i8")], align=True)
 assert TUPLE_DTYPE.itemsize == 16
+#: ``phj_joined_tuple`` == reference ``Common::JoinedTuple`` (src/Common/Table.hpp:27-33)
+JOINED_DTYPE = np.dtype([("id", "<i8"), ("payloadA", "<i8"), ("payloadB", "<i8")])
+assert JOINED_DTYPE.itemsize == 24
 
 ALGO_NO_PARTITIONING = 0
 ALGO_RADIX_PARTITIONING = 1
@@ -65,6 +68,8 @@ class PhjResult(C.Structure):
         ("fallback_partitions", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("joined_tuples", C.c_uint64),
+        ("materialize_ns", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -97,6 +102,9 @@ SIGNATURES = {
     "phj_bind_device_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                               C.c_void_p, C.c_void_p, C.c_uint32]),
     "phj_join": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
+    "phj_join_materialize": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
+    "phj_read_joined": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "phj_device_joined": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "phj_join_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                 C.POINTER(PhjResult)]),
     "phj_hash_batch": (C.c_int, [C.c_int32, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32]),

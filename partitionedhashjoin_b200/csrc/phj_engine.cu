@@ -153,6 +153,10 @@ struct phj_handle {
     uint64_t* d_gt = nullptr;
     uint64_t gt_buckets = 0;
 
+    // joined table (phj_join_materialize)
+    int64_t* d_joined = nullptr;
+    uint64_t cap_joined = 0, n_joined = 0;
+
     // host staging (pinned)
     uint64_t* h_out = nullptr;  // [0] matches, [1] scalars copy...
     uint64_t* h_cta_times = nullptr;
@@ -1113,7 +1117,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1249,6 +1253,97 @@ int phj_join(phj_handle* h, phj_result* out) {
     int rc = h->cfg.algo == PHJ_ALGO_NO_PARTITIONING ? join_no_partitioning(h, out) : join_radix(h, out);
     out->kernel_launches = h->launches;
     return rc;
+}
+
+int phj_join_materialize(phj_handle* h, phj_result* out) {
+    if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING)
+        return fail(PHJ_ERR_STATE, "the joined table is produced by the radix-partitioning joiner");
+    int rc = phj_join(h, out);  // partitions both relations (and counts, as the reference does)
+    if (rc != PHJ_OK) return rc;
+    const bool two = h->b2 > 0;
+    constexpr int kTpb = 512;
+    MatParams mp{};
+    mp.build = two ? h->d_buf_b[0] : h->prepart ? h->d_in[0] : h->d_buf_a[0];
+    mp.probe = two ? h->d_buf_b[1] : h->prepart ? h->d_in[1] : h->d_buf_a[1];
+    mp.bounds_build = h->d_bounds2[0];
+    mp.bounds_probe = h->d_bounds2[1];
+    mp.n_probe = h->n[1];
+    mp.npart = (uint32_t)h->nparts;
+    // table chunk: 4096 build tuples (64 KB) + 8192 index slots (32 KB): two CTAs per SM
+    mp.cap_tuples = 4096;
+    const uint32_t slots = 8192;
+    mp.slot_mask = slots - 1;
+    mp.slot_shift = 64 - ilog2_ceil(slots);
+    mp.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;
+    if (h->cfg.table_seed == 0) mp.table_mul = 0xBF58476D1CE4E5B9ULL;
+    const uint32_t grid = (uint32_t)h->sm_count * 2 * 4;
+    mp.slice_len = h->n[1] / grid;
+    mp.slice_rem = h->n[1] % grid;
+    mp.cursor = h->d_matches + 1;
+    const size_t smem = (size_t)mp.cap_tuples * 16 + (size_t)slots * 4;
+    auto count_kern = join_materialize<kTpb, false>;
+    auto write_kern = join_materialize<kTpb, true>;
+    PHJ_CUDA(cudaFuncSetAttribute(count_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PHJ_CUDA(cudaFuncSetAttribute(write_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
+    PHJ_CUDA(cudaMemsetAsync(h->d_matches + 1, 0, 8, h->stream));
+    {
+        KernelScope ks(h, "join_materialize[count]");
+        count_kern<<<grid, kTpb, smem, h->stream>>>(mp);
+    }
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 2, h->d_matches + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    const uint64_t rows = h->h_out[2];
+    if (rows > h->cap_joined) {
+        if (h->d_joined) cudaFree(h->d_joined);
+        h->d_joined = nullptr;
+        h->cap_joined = 0;
+        PHJ_CUDA(cudaMalloc(&h->d_joined, rows * 24));
+        h->cap_joined = rows;
+    }
+    mp.out = h->d_joined;
+    mp.out_cap = h->cap_joined;
+    PHJ_CUDA(cudaMemsetAsync(h->d_matches + 1, 0, 8, h->stream));
+    if (rows) {
+        KernelScope ks(h, "join_materialize[write]");
+        write_kern<<<grid, kTpb, smem, h->stream>>>(mp);
+    }
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 2, h->d_matches + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    if (rows && h->h_out[2] != rows)
+        return fail(PHJ_ERR_CUDA, "internal: the write pass produced %llu rows, the count pass %llu",
+                    (unsigned long long)h->h_out[2], (unsigned long long)rows);
+    h->n_joined = rows;
+    out->joined_tuples = rows;
+    out->materialize_ns = (uint64_t)(ev_ms(h->ev[5], h->ev[4]) * 1e6);
+    out->total_ns += out->materialize_ns;
+    out->kernel_launches = h->launches;
+    out->d2h_bytes += 16;
+    // probe read twice + build read + rows written
+    out->hbm_bytes_alg += 2 * 16ull * h->n[1] + 2 * 16ull * h->n[0] + 24ull * rows;
+    return PHJ_OK;
+}
+
+int phj_read_joined(phj_handle* h, phj_joined_tuple* out, uint64_t first, uint64_t count) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (first + count > h->n_joined) return fail(PHJ_ERR_INVALID, "rows [%llu, %llu) exceed the joined table (%llu rows)",
+                                                 (unsigned long long)first, (unsigned long long)(first + count),
+                                                 (unsigned long long)h->n_joined);
+    if (count && !out) return fail(PHJ_ERR_INVALID, "out is null");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    if (count) PHJ_CUDA(cudaMemcpy(out, h->d_joined + first * 3, count * 24, cudaMemcpyDeviceToHost));
+    return PHJ_OK;
+}
+
+int phj_device_joined(phj_handle* h, const void** d_joined, uint64_t* rows) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (d_joined) *d_joined = h->d_joined;
+    if (rows) *rows = h->n_joined;
+    return PHJ_OK;
 }
 
 int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,

@@ -953,6 +953,139 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
     }
 }
 
+// =================================================================================================
+// K5m  join_materialize: the joined table the reference declares but leaves empty
+// (Table<JoinedTuple>{id, payloadA, payloadB}, src/Common/Table.hpp:27-33; Run() returns it empty,
+// src/RadixCluster/HashJoin.hpp:226-227), filled with GetAll semantics
+// (src/HashTables/LinearProbing.hpp:183-200): one row per (probe tuple, equal-key build tuple).
+//
+// Same slicing as join_partitions. Per partition the CTA copies up to cap_tuples build TUPLES into
+// shared memory and links them into an open-addressing table of 32-bit slots holding tuple index + 1
+// (0 = free), so duplicate build keys each keep their slot and no key value is reserved. A build
+// side larger than cap_tuples is processed chunk by chunk against the same probe slice (block
+// nested loop), so any partition size and any duplication is handled.
+// WRITE = false only counts the rows (sizes the output); WRITE = true appends them: the lanes of a
+// warp that found a match in the same probe step reserve their rows with ONE atomicAdd on the
+// global cursor and write them side by side (24-byte rows, contiguous per warp step).
+// =================================================================================================
+struct MatParams {
+    const ulonglong2* build;
+    const ulonglong2* probe;
+    const uint64_t* bounds_build;
+    const uint64_t* bounds_probe;
+    uint64_t n_probe;
+    uint64_t slice_len, slice_rem;
+    uint32_t npart;
+    uint32_t cap_tuples;   // build tuples per table chunk
+    uint32_t slot_mask;    // slots - 1, slots = power of two >= 2 * cap_tuples
+    uint32_t slot_shift;   // slot = table_bucket(key) >> ... (64 - log2 slots)
+    uint64_t table_mul;
+    unsigned long long* cursor;  // WRITE = false: row count; WRITE = true: append cursor
+    int64_t* out;                // rows of 3 x int64
+    uint64_t out_cap;            // rows
+};
+
+template <int TPB, bool WRITE>
+__global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ulonglong2* tup = reinterpret_cast<ulonglong2*>(smem_raw);                  // [cap_tuples]
+    uint32_t* slots = reinterpret_cast<uint32_t*>(tup + p.cap_tuples);           // [slot_mask + 1]
+    __shared__ unsigned long long block_count;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = lanemask_lt();
+
+    const uint64_t lo = p.slice_len * blockIdx.x + min((uint64_t)blockIdx.x, p.slice_rem);
+    const uint64_t hi = lo + p.slice_len + (blockIdx.x < p.slice_rem ? 1 : 0);
+    if (tid == 0) block_count = 0;
+    unsigned long long count = 0;
+
+    if (lo < hi) {
+        uint32_t a = 0, b = p.npart;
+        while (b - a > 1) {
+            const uint32_t m = (a + b) >> 1;
+            if (p.bounds_probe[m] <= lo) a = m; else b = m;
+        }
+        for (uint32_t part = a; part < p.npart; ++part) {
+            const uint64_t ps0 = p.bounds_probe[part];
+            if (ps0 >= hi) break;
+            const uint64_t s0 = max(lo, ps0), s1 = min(hi, p.bounds_probe[part + 1]);
+            if (s0 >= s1) continue;
+            const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
+            for (uint64_t c0 = r0; c0 < r1; c0 += p.cap_tuples) {
+                const uint32_t nb = (uint32_t)min((uint64_t)p.cap_tuples, r1 - c0);
+                cta_sync();  // the previous chunk's probes are done with the table
+                for (uint32_t i = tid; i <= p.slot_mask; i += TPB) slots[i] = 0;
+                for (uint32_t i = tid; i < nb; i += TPB) tup[i] = p.build[c0 + i];
+                cta_sync();
+                // ---- build: every tuple claims the first free slot of its probe sequence ----
+                for (uint32_t i0 = 0; i0 < nb; i0 += TPB) {
+                    const uint32_t i = i0 + tid;
+                    bool pending = i < nb;
+                    uint32_t slot = pending ? table_bucket(tup[i].x, p.table_mul, p.slot_shift) & p.slot_mask : 0;
+                    while (__any_sync(0xffffffffu, pending)) {
+                        if (pending) {
+                            uint32_t cur = slots[slot];
+                            if (cur == 0) cur = atomicCAS(&slots[slot], 0u, i + 1);
+                            if (cur == 0) pending = false;
+                            else slot = (slot + 1) & p.slot_mask;
+                        }
+                    }
+                }
+                cta_sync();
+                // ---- probe: walk the sequence to the first free slot, every equal key is a row ----
+                for (uint64_t i0 = s0; i0 < s1; i0 += TPB) {
+                    const uint64_t i = i0 + tid;
+                    bool pending = i < s1;
+                    ulonglong2 s = make_ulonglong2(0, 0);
+                    if (pending) s = ld_stream_v2(p.probe + i);
+                    uint32_t slot = table_bucket(s.x, p.table_mul, p.slot_shift) & p.slot_mask;
+                    while (__any_sync(0xffffffffu, pending)) {
+                        bool hit = false;
+                        ulonglong2 r = make_ulonglong2(0, 0);
+                        if (pending) {
+                            const uint32_t cur = slots[slot];
+                            if (cur == 0) {
+                                pending = false;
+                            } else {
+                                r = tup[cur - 1];
+                                hit = r.x == s.x;
+                                slot = (slot + 1) & p.slot_mask;
+                            }
+                        }
+                        if (WRITE) {
+                            const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                            if (hits) {
+                                unsigned long long base = 0;
+                                if (lane == __ffs(hits) - 1) base = atomicAdd(p.cursor, (unsigned long long)__popc(hits));
+                                base = __shfl_sync(0xffffffffu, base, __ffs(hits) - 1);
+                                if (hit) {
+                                    const unsigned long long row = base + __popc(hits & lt);
+                                    if (row < p.out_cap) {
+                                        int64_t* o = p.out + row * 3;
+                                        o[0] = (int64_t)s.x;
+                                        o[1] = (int64_t)r.y;
+                                        o[2] = (int64_t)s.y;
+                                    }
+                                }
+                            }
+                        } else {
+                            count += hit;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!WRITE) {
+        cta_sync();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if (lane == 0 && count) atomicAdd(&block_count, count);
+        cta_sync();
+        if (tid == 0 && block_count) atomicAdd(p.cursor, block_count);
+    }
+}
+
 // Counts the partitions join_partitions skipped (build side larger than the smem table).
 __global__ void count_oversize(const uint64_t* __restrict__ bounds_build, uint32_t npart,
                                uint32_t max_keys, uint32_t* __restrict__ oversize) {

@@ -194,6 +194,20 @@ class Engine:
         check(lib.phj_join(self._h, C.byref(res)))
         return res.as_dict()
 
+    def join_materialize(self) -> dict:
+        """The join with its result: res['joined_tuples'] rows wait on the device (read_joined)."""
+        res = PhjResult()
+        check(lib.phj_join_materialize(self._h, C.byref(res)))
+        self._joined = int(res.joined_tuples)
+        return res.as_dict()
+
+    def read_joined(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Rows [first, first + count) of the last join_materialize as a JOINED_DTYPE array."""
+        count = self._joined - first if count is None else count
+        out = np.empty(count, dtype=_lib.JOINED_DTYPE)
+        check(lib.phj_read_joined(self._h, out.ctypes.data, first, count))
+        return out
+
     def join_host(self, build: np.ndarray, probe: np.ndarray) -> dict:
         build, probe = as_tuples(build), as_tuples(probe)
         res = PhjResult()
@@ -284,8 +298,9 @@ class HashJoinTimer(NoOpHashJoinTimer):
 
 
 class _JoinerBase:
-    def __init__(self, engine: Engine):
+    def __init__(self, engine: Engine, materialize: bool = False):
         self._engine = engine
+        self._materialize = materialize
         self.last_result: Optional[dict] = None
 
     def Run(self, tableA, tableB, timer=None):
@@ -294,12 +309,14 @@ class _JoinerBase:
         ``self.last_result['matches']``."""
         timer = timer or NoOpHashJoinTimer()
         self._engine.upload(tableA, tableB)
-        res = self._engine.join()
+        res = self._engine.join_materialize() if self._materialize else self._engine.join()
         self.last_result = res
         timer.SetPartitionPhaseDuration(res["partition_ns"])
         timer.SetBuildPhaseDuration(res["build_ns"])
         timer.SetProbePhaseDuration(res["probe_ns"])
-        return np.empty(0, dtype=[("id", "<i8"), ("payloadA", "<i8"), ("payloadB", "<i8")])
+        if self._materialize:  # the Table<JoinedTuple> the reference declares but leaves empty
+            return self._engine.read_joined()
+        return np.empty(0, dtype=_lib.JOINED_DTYPE)
 
     def close(self):
         self._engine.close()
@@ -315,12 +332,13 @@ class NoPartitioningHashJoiner(_JoinerBase):
 
 class RadixClusteringHashJoiner(_JoinerBase):
     def __init__(self, configuration: Optional[RadixClusteringConfiguration] = None,
-                 hasher: Optional[Hasher] = None, device: int = 0, radix_bits=(0, 0), flags: int = 0):
+                 hasher: Optional[Hasher] = None, device: int = 0, radix_bits=(0, 0), flags: int = 0,
+                 materialize: bool = False):
         configuration = configuration or RadixClusteringConfiguration()
         hasher = hasher or Hasher()
         if configuration.NumberOfPartitions < 0:
             raise ValueError("NumberOfPartitions must be >= 0")
         super().__init__(Engine("radix-partitioning", partitions=configuration.NumberOfPartitions,
                                 radix_bits=radix_bits, hash=hasher.name, hash_seed=hasher.seed,
-                                device=device, flags=flags))
+                                device=device, flags=flags), materialize=materialize)
         self.configuration = configuration

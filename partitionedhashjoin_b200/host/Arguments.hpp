@@ -1,7 +1,7 @@
 // Command-line surface of phjoin: the reference's flags, spellings, defaults and validation
 // (reference src/main.cpp:141-208, src/Arguments.hpp:7-19) parsed without Boost, plus the flags
 // that only make sense for the GPU engine (--hash, --seed, --table-seed, --data-seed,
-// --radix-bits, --device, --gpus, --repeat, --no-tma-store).
+// --radix-bits, --device, --gpus, --repeat, --no-tma-store, --materialize).
 #pragma once
 #include <cstdlib>
 #include <iostream>
@@ -43,7 +43,9 @@ inline std::string HelpText() {
          "  --device arg (=0)                     CUDA device.\n"
          "  --gpus arg (=1)                       Number of GPUs (radix join sharded by partition).\n"
          "  --repeat arg (=1)                     Joins per run; the fastest is reported.\n"
-         "  --no-tma-store                        Flush scatter tiles with st.global instead of TMA bulk stores.\n";
+         "  --no-tma-store                        Flush scatter tiles with st.global instead of TMA bulk stores.\n"
+         "  --materialize                         Radix join only: also produce the joined table {id, payloadA,\n"
+         "                                        payloadB} (the reference returns it empty) and log its size.\n";
     return o.str();
 }
 
@@ -81,7 +83,7 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     static const std::set<std::string> kValued = {
         "primary", "secondary", "skew", "log", "join", "format", "unit", "output", "filename", "partitions",
         "hash", "seed", "table-seed", "data-seed", "radix-bits", "device", "gpus", "repeat"};
-    static const std::set<std::string> kFlags = {"help", "no-tma-store"};
+    static const std::set<std::string> kFlags = {"help", "no-tma-store", "materialize"};
 
     Common::Configuration c{};
     std::map<std::string, std::string> seen;
@@ -142,6 +144,7 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
         c.Gpu.RadixBits[1] = static_cast<unsigned>(ParseUnsigned("radix-bits", v->substr(comma + 1)));
     }
     c.Gpu.NoTmaStore = seen.count("no-tma-store") != 0;
+    c.Gpu.Materialize = seen.count("materialize") != 0;
     // --join is required (reference src/main.cpp:162-165)
     if (!get("join")) throw std::invalid_argument("the option '--join' is required but missing");
     c.JoinType = Common::GetJoinAlgorithmTypeFromString(*get("join"));
@@ -152,6 +155,8 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     if (c.JoinType != Common::JoinAlgorithmType::RadixParitioning && get("partitions"))
         throw std::invalid_argument(
             "validateParsedConfiguration: number of partitions can be specified only for RadixParitioning.");
+    if (c.Gpu.Materialize && c.JoinType != Common::JoinAlgorithmType::RadixParitioning)
+        throw std::invalid_argument("--materialize: the joined table is produced by the RadixParitioning joiner.");
     if (c.Gpu.Gpus != 1)
         throw std::invalid_argument("--gpus > 1 is driven through torch.distributed (bench.py --gpus N); "
                                     "this binary joins on one device");

@@ -101,6 +101,7 @@ struct GpuConfiguration {
     unsigned RadixBits[2] = {0, 0};
     int Repeat = 1;             // joins per run; the best is reported
     bool NoTmaStore = false;
+    bool Materialize = false;   // fill the returned Table<JoinedTuple> (the reference leaves it empty)
 };
 
 struct Configuration {

@@ -42,6 +42,8 @@ class Table {
     size_t GetCapacity() const { return m_tuples.capacity(); }
     const std::string& GetID() const { return m_id; }
 
+    void Resize(size_t size) { m_tuples.resize(size); }
+
     // What crosses the C ABI: &(*table)[0] and GetSize().
     TupleType* Data() { return m_tuples.data(); }
     const TupleType* Data() const { return m_tuples.data(); }

@@ -89,10 +89,12 @@ int main(int argc, char** argv) {
             params.SetParameter("NumberOfPartitions", std::to_string(config.RadixClusteringConfig.NumberOfPartitions));
             timer = std::make_shared<Common::HashJoinTimer>(params);
             Gpu::RadixClustering::HashJoiner joiner(config.RadixClusteringConfig, config.Gpu);
-            joiner.Run(primary, secondary, timer);
+            auto joined = joiner.Run(primary, secondary, timer);
             matches = joiner.GetLastResult().matches;
             total_ns = joiner.GetLastResult().total_ns;
             alg_bytes = joiner.GetLastResult().hbm_bytes_alg;
+            if (config.Gpu.Materialize)
+                log(Common::info, "Joined table holds " + std::to_string(joined->GetSize()) + " rows.");
         }
         result = timer->GetResult();
     } catch (std::exception& e) {

@@ -71,3 +71,24 @@ GENERATOR_CASES = {
     "gen_small_uniform": (20000, 200000, 0.01, 99, 3),
     "gen_ragged": (12347, 100003, 0.99, 4242, 7),
 }
+
+
+def joined_reference(R, S):
+    """Brute-force definition of the joined table (id, payloadA, payloadB), canonically sorted:
+    one row per (probe tuple, equal-key build tuple). numpy only; for the tests of the oracle."""
+    order = np.argsort(R["id"], kind="stable")
+    keys, pay = R["id"][order], R["payload"][order]
+    lo = np.searchsorted(keys, S["id"], side="left")
+    hi = np.searchsorted(keys, S["id"], side="right")
+    cnt = hi - lo
+    rows = np.empty(int(cnt.sum()), dtype=[("id", "<i8"), ("payloadA", "<i8"), ("payloadB", "<i8")])
+    probe_idx = np.repeat(np.arange(S.shape[0]), cnt)
+    within = np.arange(rows.shape[0]) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    rows["id"] = S["id"][probe_idx]
+    rows["payloadA"] = pay[lo[probe_idx] + within]
+    rows["payloadB"] = S["payload"][probe_idx]
+    return np.sort(rows, order=["id", "payloadB", "payloadA"])
+
+
+def sorted_rows(rows):
+    return np.sort(np.asarray(rows), order=["id", "payloadB", "payloadA"])

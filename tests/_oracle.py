@@ -24,6 +24,9 @@ TUPLE = np.dtype([("id", "<i8"), ("payload", "<i8")], align=True)
 u64, i64, sz, dbl, vp = C.c_uint64, C.c_int64, C.c_size_t, C.c_double, C.c_void_p
 
 
+JOINED = np.dtype([("id", "<i8"), ("payloadA", "<i8"), ("payloadB", "<i8")])
+
+
 class OResult(C.Structure):
     _fields_ = [("matches", u64), ("partition_ns", u64), ("build_ns", u64), ("probe_ns", u64)]
 
@@ -86,6 +89,7 @@ class Oracle:
         _sig(lib, "phjo_radix_partition", None, [vp, sz, sz, C.c_int, u64, sz, sz, vp, vp, vp])
         _sig(lib, "phjo_join_radix", C.c_int, [vp, sz, vp, sz, sz, sz, C.c_int, C.c_int, u64, u64, C.POINTER(OResult)])
         _sig(lib, "phjo_count_by_sort", u64, [vp, sz, vp, sz])
+        _sig(lib, "phjo_join_materialize", u64, [vp, sz, vp, sz, C.c_int, C.c_int, u64, vp, u64])
 
     # hashing
     def hash_raw(self, hash_id, key, seed):
@@ -156,6 +160,16 @@ class Oracle:
         w, a, b = sz(), sz(), sz()
         self.lib.phjo_partitioning_configuration(sizeA, sizeB, pool_workers, min_batch, C.byref(w), C.byref(a), C.byref(b))
         return int(w.value), int(a.value), int(b.value)
+
+    def join_materialize(self, R, S, table_kind=0, hash_id=0, seed_table=1):
+        """All (probe tuple, equal-key build tuple) rows as a JOINED array (probe order)."""
+        R, S = np.ascontiguousarray(R), np.ascontiguousarray(S)
+        args = (R.ctypes.data, R.shape[0], S.ctypes.data, S.shape[0], table_kind, hash_id, u64(seed_table))
+        n = int(self.lib.phjo_join_materialize(*args, None, 0))
+        assert n != 2**64 - 1
+        out = np.empty(n, dtype=JOINED)
+        assert int(self.lib.phjo_join_materialize(*args, out.ctypes.data, n)) == n
+        return out
 
     def count_by_sort(self, R, S):
         R, S = np.ascontiguousarray(R), np.ascontiguousarray(S)

@@ -44,6 +44,7 @@ def test_help_lists_reference_flags(phjoin):
     (("--join", "radix-partitioning", "--primary", "ten"), "option '--primary' is invalid"),
     (("--join", "radix-partitioning", "--bogus", "1"), "unrecognised option '--bogus'"),
     (("--join", "radix-partitioning", "--hash", "sha1"), "Unrecognized hash function: sha1."),
+    (("--join", "no-partitioning", "--materialize"), "the joined table is produced by the RadixParitioning joiner."),
 ])
 def test_argument_errors_exit_1_with_option_table(phjoin, args, message):
     """Any parse/validation error: message, option table, exit(1) (reference src/main.cpp:199-205)."""
@@ -89,3 +90,13 @@ def test_cli_end_to_end(phjoin, tmp_path, join, extra, typ):
     assert list(d["results"]) == ["partition", "build", "probe"]
     assert int(d["results"]["probe"]) > 0 and int(d["results"]["build"]) > 0
     assert (int(d["results"]["partition"]) > 0) == (join == "radix-partitioning")
+
+
+@pytest.mark.gpu
+def test_cli_materialize(phjoin, tmp_path):
+    """--materialize: Run() returns the filled Table<JoinedTuple>; generator data joins 1:1."""
+    out = tmp_path / "result.txt"
+    r = run(phjoin, "--join", "radix-partitioning", "--primary", "100000", "--secondary", "1500000", "-p", "256",
+            "--materialize", "--log", "info", "-f", str(out))
+    assert r.returncode == 0, r.stderr
+    assert "Joined table holds 1500000 rows." in r.stderr

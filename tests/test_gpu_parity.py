@@ -185,6 +185,54 @@ def test_prepartitioned_bind_equals_plain_join(phj, oracle, P, bits):
             pre.bind_device_partitioned(ptr[0], n[0], ptr[1], n[1], bnd[0][:-1], bnd[1][:-1])
 
 
+# ---- the joined table -----------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(_cases.adversarial_cases()) + ["gen_small_105", "gen_ragged"])
+def test_materialized_join_equals_oracle(phj, oracle, name):
+    """phj_join_materialize: every (probe tuple, equal-key build tuple) row, as a multiset, equals
+    the oracle's GetAll join; matches stays the count-only figure."""
+    R, S = cases_for(phj, name)
+    want = _cases.sorted_rows(oracle.join_materialize(R, S))
+    for P, bits in ((0, (0, 0)), (64, (0, 0)), (1024, (5, 5)), (4, (2, 0))):
+        with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits) as e:
+            e.upload(R, S)
+            for _ in range(2):
+                res = e.join_materialize()
+                assert res["joined_tuples"] == want.shape[0], (name, P)
+                assert res["matches"] == oracle.count_by_sort(R, S)
+                got = _cases.sorted_rows(e.read_joined())
+                assert (got == want).all(), (name, P)
+            if want.shape[0] > 10:
+                assert (_cases.sorted_rows(e.read_joined(3, 5)).shape[0]) == 5
+
+
+def test_materialized_join_large_partitions_and_duplicates(phj, oracle):
+    """Build partitions far beyond one shared-memory table chunk (block nested loop over chunks)
+    and a build key repeated 30 000 times (a 30 000-row fan-out per matching probe tuple)."""
+    r = np.concatenate([_cases.splitmix64(60_000, 41).astype(np.int64) % 50_000, np.full(30_000, 123)])
+    s = np.concatenate([_cases.splitmix64(200_000, 42).astype(np.int64) % 80_000, np.full(7, 123)])
+    R, S = _cases.tuples(r), _cases.tuples(s)
+    want = _cases.joined_reference(R, S)
+    with phj.Engine("radix-partitioning", partitions=2) as e:
+        e.upload(R, S)
+        res = e.join_materialize()
+        assert res["joined_tuples"] == want.shape[0]
+        assert (_cases.sorted_rows(e.read_joined()) == want).all()
+
+
+def test_joiner_run_returns_the_joined_table(phj, oracle):
+    """RadixClusteringHashJoiner(materialize=True).Run returns the filled Table<JoinedTuple>."""
+    R, S = cases_for(phj, "gen_small_125")
+    j = phj.RadixClusteringHashJoiner(phj.RadixClusteringConfiguration(NumberOfPartitions=256), materialize=True)
+    table = j.Run(R, S)
+    assert table.dtype == phj.JOINED_DTYPE and table.shape[0] == S.shape[0]
+    assert (_cases.sorted_rows(table) == _cases.sorted_rows(oracle.join_materialize(R, S))).all()
+    j.close()
+    with phj.Engine("no-partitioning") as e:
+        e.upload(R, S)
+        with pytest.raises(phj.PhjError):
+            e.join_materialize()
+
+
 def test_partition_layout_skewed_generator_data(phj, oracle):
     nr, ns = 100000, 1500000
     R = np.empty(nr, dtype=phj.TUPLE_DTYPE)

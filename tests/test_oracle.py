@@ -108,6 +108,22 @@ def test_join_counts_golden(oracle, name):
         assert oracle.join_radix(R, S, 64, workers=2, hash_id=hash_id) == want["matches"]
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+def test_materialized_join_is_the_getall_join(oracle, kind):
+    """phjo_join_materialize (the joined table the reference declares, filled through GetAll) against
+    the brute-force definition, on every adversarial case and a generator case; its distinct-probe
+    projection is the reference's count."""
+    cases = dict(_cases.adversarial_cases())
+    R = oracle.fill_sequential(3000, 1)
+    cases["gen"] = (R, oracle.fill_zipf(20000, 1.05, 1, 6000, 4242, 3))
+    for name, (R, S) in cases.items():
+        got = oracle.join_materialize(R, S, table_kind=kind)
+        want = _cases.joined_reference(R, S)
+        assert got.shape[0] == want.shape[0], name
+        assert (_cases.sorted_rows(got) == want).all(), name
+        assert np.unique(got["payloadB"]).shape[0] == oracle.count_by_sort(R, S), name
+
+
 def test_npj_empty_build_is_an_error(oracle):
     # LinearProbingHashTable's constructor throws for 0 objects (src/HashTables/LinearProbing.hpp:106-110)
     with pytest.raises(ValueError):
