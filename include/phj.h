@@ -232,6 +232,16 @@ int phj_shared_open(int32_t device, const unsigned char* ipc_handle, void** d_pt
 int phj_shared_close(int32_t device, void* d_ptr);
 int phj_shared_free(int32_t device, void* d_ptr);
 
+/* Device-side input generation for scale runs (the 160 M x 3.2 B configuration): the reference's
+ * Sequential / Zipf generators (src/DataGenerator/Sequential.cpp:20-25, Zipf.cpp:14-56,80-92) with
+ * the batch / seed scheme of phj_fill_zipf, one GPU thread per batch, written to device memory
+ * (phj_shared_alloc or any device pointer), ready for phj_bind_device. CUDA's pow() is not glibc's:
+ * a sample may differ from phj_fill_zipf's where an intermediate lands within an ulp of an integer,
+ * so parity runs use the host generators and upload. */
+int phj_device_fill_sequential(int32_t device, void* d_out, size_t n, int64_t start);
+int phj_device_fill_zipf(int32_t device, void* d_out, size_t n, double alpha, int64_t range_first,
+                         int64_t range_second, int64_t base_seed, size_t batches);
+
 /* Plain synchronous copies between host memory and memory from phj_shared_alloc (input arenas of
  * the multi-GPU path, test read-back of the windows). */
 int phj_memcpy_h2d(int32_t device, void* d_dst, const void* h_src, size_t bytes);

@@ -6,7 +6,7 @@ by tests and bench. Importing this package requires the built shared library (no
 """
 from ._lib import (ALGO_NO_PARTITIONING, ALGO_RADIX_PARTITIONING, FLAG_FUSE_HIST2, FLAG_NO_TMA_STORE, HASH_CITY,
                    HASH_MURMUR3, HASH_NAMES, HASH_XXH3, JOINED_DTYPE, LIB_PATH, TUPLE_DTYPE, PhjError)
-from .engine import (Engine, Hasher, HashJoinTimer, HashJoinTimingResult, NoOpHashJoinTimer,
+from .engine import (DeviceTuples, Engine, Hasher, HashJoinTimer, HashJoinTimingResult, NoOpHashJoinTimer,
                      NoPartitioningConfiguration, NoPartitioningHashJoiner, PinnedTuples,
                      RadixClusteringConfiguration, RadixClusteringHashJoiner, as_tuples,
                      device_count, device_info, fill_sequential, fill_zipf, hash_batch, hash_host,

@@ -119,6 +119,9 @@ SIGNATURES = {
     "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),
     "phj_shared_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "phj_device_fill_sequential": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_int64]),
+    "phj_device_fill_zipf": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_double, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_size_t]),
     "phj_memcpy_h2d": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "phj_memcpy_d2h": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "phj_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),

@@ -156,6 +156,7 @@ struct phj_handle {
     // joined table (phj_join_materialize)
     int64_t* d_joined = nullptr;
     uint64_t cap_joined = 0, n_joined = 0;
+    unsigned long long* d_cta_rows = nullptr;  // rows per CTA of join_materialize, then their scan
 
     // host staging (pinned)
     uint64_t* h_out = nullptr;  // [0] matches, [1] scalars copy...
@@ -1117,7 +1118,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1277,10 +1278,12 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     mp.slot_shift = 64 - ilog2_ceil(slots);
     mp.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;
     if (h->cfg.table_seed == 0) mp.table_mul = 0xBF58476D1CE4E5B9ULL;
-    const uint32_t grid = (uint32_t)h->sm_count * 2 * 4;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)h->sm_count * 2 * 4, 8192);
     mp.slice_len = h->n[1] / grid;
     mp.slice_rem = h->n[1] % grid;
     mp.cursor = h->d_matches + 1;
+    if (!h->d_cta_rows) PHJ_CUDA(cudaMalloc(&h->d_cta_rows, 8192 * sizeof(unsigned long long)));
+    mp.cta_rows = h->d_cta_rows;
     const size_t smem = (size_t)mp.cap_tuples * 16 + (size_t)slots * 4;
     auto count_kern = join_materialize<kTpb, false>;
     auto write_kern = join_materialize<kTpb, true>;
@@ -1305,18 +1308,14 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     }
     mp.out = h->d_joined;
     mp.out_cap = h->cap_joined;
-    PHJ_CUDA(cudaMemsetAsync(h->d_matches + 1, 0, 8, h->stream));
     if (rows) {
         KernelScope ks(h, "join_materialize[write]");
+        scan_cta_rows<<<1, 1024, 0, h->stream>>>(h->d_cta_rows, grid);
         write_kern<<<grid, kTpb, smem, h->stream>>>(mp);
     }
-    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 2, h->d_matches + 1, 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
-    if (rows && h->h_out[2] != rows)
-        return fail(PHJ_ERR_CUDA, "internal: the write pass produced %llu rows, the count pass %llu",
-                    (unsigned long long)h->h_out[2], (unsigned long long)rows);
     h->n_joined = rows;
     out->joined_tuples = rows;
     out->materialize_ns = (uint64_t)(ev_ms(h->ev[5], h->ev[4]) * 1e6);
@@ -1556,6 +1555,46 @@ int phj_shared_close(int32_t device, void* d_ptr) {
 int phj_shared_free(int32_t device, void* d_ptr) {
     PHJ_CUDA(cudaSetDevice(device));
     if (d_ptr) PHJ_CUDA(cudaFree(d_ptr));
+    return PHJ_OK;
+}
+
+int phj_device_fill_sequential(int32_t device, void* d_out, size_t n, int64_t start) {
+    if (n && !d_out) return fail(PHJ_ERR_INVALID, "null argument");
+    PHJ_CUDA(cudaSetDevice(device));
+    if (n) gen_sequential<<<1184, 256>>>(reinterpret_cast<ulonglong2*>(d_out), n, start);
+    PHJ_CUDA(cudaDeviceSynchronize());
+    PHJ_CUDA(cudaGetLastError());
+    return PHJ_OK;
+}
+
+int phj_device_fill_zipf(int32_t device, void* d_out, size_t n, double alpha, int64_t range_first,
+                         int64_t range_second, int64_t base_seed, size_t batches) {
+    if (n && !d_out) return fail(PHJ_ERR_INVALID, "null argument");
+    if (alpha < 0.01) return fail(PHJ_ERR_INVALID, "Zipf: alpha must be >= 0.01");  // Zipf.cpp:18-20
+    if (range_first >= range_second) return fail(PHJ_ERR_INVALID, "Zipf: empty range");  // Zipf.cpp:61-67
+    if (batches == 0) return fail(PHJ_ERR_INVALID, "Zipf: batches must be > 0");
+    if (base_seed <= 0 || (uint64_t)base_seed + batches >= 2147483647ull)
+        return fail(PHJ_ERR_INVALID, "Zipf: seeds base_seed .. base_seed + batches must lie in (0, 2^31 - 1)");
+    PHJ_CUDA(cudaSetDevice(device));
+    ZipfGenParams zp{};
+    zp.out = reinterpret_cast<ulonglong2*>(d_out);
+    zp.n = n;
+    zp.batches = batches;
+    zp.batch = n / batches;
+    zp.alpha = alpha;
+    zp.sd = 1.001 - alpha;
+    const double diff = 1.0 - alpha;
+    if (std::abs(diff) < 0.01) {
+        zp.sd = 0.01 * (diff < 0 ? 1 : -1);
+        zp.alpha = 1.0 - zp.sd;
+    }
+    const uint64_t cardinality = (uint64_t)(range_second - range_first + 1);
+    zp.norm = (std::pow((double)cardinality, zp.sd) - zp.alpha) / zp.sd;
+    zp.base_seed = base_seed;
+    zp.correction = range_first - 1;
+    if (n) gen_zipf<<<(uint32_t)((batches + 127) / 128), 128>>>(zp);
+    PHJ_CUDA(cudaDeviceSynchronize());
+    PHJ_CUDA(cudaGetLastError());
     return PHJ_OK;
 }
 

@@ -964,9 +964,11 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
 // (0 = free), so duplicate build keys each keep their slot and no key value is reserved. A build
 // side larger than cap_tuples is processed chunk by chunk against the same probe slice (block
 // nested loop), so any partition size and any duplication is handled.
-// WRITE = false only counts the rows (sizes the output); WRITE = true appends them: the lanes of a
-// warp that found a match in the same probe step reserve their rows with ONE atomicAdd on the
-// global cursor and write them side by side (24-byte rows, contiguous per warp step).
+// WRITE = false only counts the rows, per CTA (sizes the output; a scan of the per-CTA counts gives
+// every CTA its own output range). WRITE = true appends them: the lanes of a warp that found a
+// match in the same probe step reserve their rows with ONE shared-memory atomicAdd on the CTA's
+// cursor and write them side by side (24-byte rows, contiguous per warp step). (A single global
+// cursor was tried first: 6 M same-address L2 atomics took 15 ms, measured.)
 // =================================================================================================
 struct MatParams {
     const ulonglong2* build;
@@ -980,7 +982,9 @@ struct MatParams {
     uint32_t slot_mask;    // slots - 1, slots = power of two >= 2 * cap_tuples
     uint32_t slot_shift;   // slot = table_bucket(key) >> ... (64 - log2 slots)
     uint64_t table_mul;
-    unsigned long long* cursor;  // WRITE = false: row count; WRITE = true: append cursor
+    unsigned long long* cursor;  // WRITE = false: total row count
+    unsigned long long* cta_rows;  // WRITE = false: out, rows of every CTA; WRITE = true: in, their
+                                   // exclusive scan = where every CTA's rows start
     int64_t* out;                // rows of 3 x int64
     uint64_t out_cap;            // rows
 };
@@ -996,7 +1000,7 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
 
     const uint64_t lo = p.slice_len * blockIdx.x + min((uint64_t)blockIdx.x, p.slice_rem);
     const uint64_t hi = lo + p.slice_len + (blockIdx.x < p.slice_rem ? 1 : 0);
-    if (tid == 0) block_count = 0;
+    if (tid == 0) block_count = WRITE ? p.cta_rows[blockIdx.x] : 0;  // WRITE: this CTA's append cursor
     unsigned long long count = 0;
 
     if (lo < hi) {
@@ -1056,7 +1060,7 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
                             const uint32_t hits = __ballot_sync(0xffffffffu, hit);
                             if (hits) {
                                 unsigned long long base = 0;
-                                if (lane == __ffs(hits) - 1) base = atomicAdd(p.cursor, (unsigned long long)__popc(hits));
+                                if (lane == __ffs(hits) - 1) base = atomicAdd(&block_count, (unsigned long long)__popc(hits));
                                 base = __shfl_sync(0xffffffffu, base, __ffs(hits) - 1);
                                 if (hit) {
                                     const unsigned long long row = base + __popc(hits & lt);
@@ -1082,7 +1086,29 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(&block_count, count);
         cta_sync();
-        if (tid == 0 && block_count) atomicAdd(p.cursor, block_count);
+        if (tid == 0) {
+            p.cta_rows[blockIdx.x] = block_count;
+            if (block_count) atomicAdd(p.cursor, block_count);
+        }
+    }
+}
+
+// Exclusive scan of the per-CTA row counts (<= 8192 CTAs), in place. One CTA.
+__global__ void __launch_bounds__(1024) scan_cta_rows(unsigned long long* rows, uint32_t n) {
+    __shared__ uint64_t sh[33];
+    uint64_t v[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t idx = threadIdx.x * 8 + i;
+        v[i] = idx < n ? rows[idx] : 0;
+        s += v[i];
+    }
+    uint64_t excl = block_excl_scan_u64(s, sh, nullptr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t idx = threadIdx.x * 8 + i;
+        if (idx < n) rows[idx] = excl;
+        excl += v[i];
     }
 }
 
@@ -1270,6 +1296,56 @@ __global__ void split_starts(SplitStartsParams p) {
         else v = p.n[rel];
     }
     p.starts[i] = v;
+}
+
+// =================================================================================================
+// Device-side input generators: the reference's Sequential and Zipf generators
+// (src/DataGenerator/Sequential.cpp:20-25, src/DataGenerator/Zipf.cpp:14-56,80-92) with the same
+// batch / seed scheme as the host generator (batch b = an LCG seeded base_seed + b,
+// src/Common/Random.cpp:9-30), one thread per batch. For scale runs: the arithmetic is the
+// reference's, but pow() here is CUDA's, not glibc's, so a sample can differ from the host
+// generator's where an intermediate lands within an ulp of an integer -- parity runs keep the host
+// generator (phj_fill_zipf) and upload.
+// =================================================================================================
+__global__ void gen_sequential(ulonglong2* __restrict__ out, uint64_t n, int64_t start) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = make_ulonglong2((uint64_t)(start + (int64_t)i), i);
+}
+
+struct ZipfGenParams {
+    ulonglong2* out;
+    uint64_t n, batches, batch;  // batch = n / batches tuples, the last batch takes the remainder
+    double alpha, sd, norm;      // as set up by Zipf::generate (Zipf.cpp:22-28)
+    int64_t base_seed, correction;
+};
+
+__device__ __forceinline__ double lcg_next(int64_t& state) {
+    const int64_t a = 16807, m = 2147483647, q = 127773, r = 2836;
+    const int64_t t = a * (state % q) - r * (state / q);
+    state = t > 0 ? t : t + m;
+    return (double)state / (double)m;
+}
+
+__global__ void __launch_bounds__(128) gen_zipf(ZipfGenParams p) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batches) return;
+    const uint64_t first = p.batch * b, last = (b + 1 == p.batches) ? p.n : p.batch * (b + 1);
+    int64_t state = p.base_seed + (int64_t)b;
+    for (uint64_t i = first; i < last; ++i) {
+        double sample;
+        for (;;) {
+            const double u1 = lcg_next(state);
+            const double u2 = lcg_next(state);
+            const double x = u1 * p.norm;
+            const double inv = x <= 1.0 ? x : pow(x * p.sd + p.alpha, 1.0 / p.sd);
+            sample = floor(inv + 1);
+            const double p_target = pow(sample, -p.alpha);
+            const double p_proposal = sample <= 1.0 ? 1.0 / p.norm : pow(inv, -p.alpha) / p.norm;
+            if (u2 < p_target / (p_proposal * p.norm)) break;
+        }
+        p.out[i] = make_ulonglong2((uint64_t)((int64_t)sample + p.correction), i);
+    }
 }
 
 // Test hook: raw hashes of a key array.

@@ -88,6 +88,52 @@ def fill_zipf(out: np.ndarray, alpha: float, range_first: int, range_second: int
     return out
 
 
+class DeviceTuples:
+    """A relation in device memory (phj_shared_alloc): target of the device-side generators, source
+    of Engine.bind_device, mappable by peer processes."""
+
+    def __init__(self, n: int, device: int = 0):
+        self.n, self.device = int(n), device
+        self._ptr, self.ipc_handle = C.c_void_p(), (C.c_ubyte * 64)()
+        check(lib.phj_shared_alloc(device, max(self.n, 1) * 16, C.byref(self._ptr), self.ipc_handle))
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr.value or 0
+
+    def fill_sequential(self, start: int = 1):
+        check(lib.phj_device_fill_sequential(self.device, self._ptr, self.n, start))
+        return self
+
+    def fill_zipf(self, alpha: float, range_first: int, range_second: int, base_seed: int, batches: int):
+        check(lib.phj_device_fill_zipf(self.device, self._ptr, self.n, alpha, range_first, range_second, base_seed,
+                                       batches))
+        return self
+
+    def upload(self, rel: np.ndarray):
+        rel = as_tuples(rel)
+        assert rel.shape[0] == self.n
+        check(lib.phj_memcpy_h2d(self.device, self._ptr, rel.ctypes.data, self.n * 16))
+        return self
+
+    def download(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        out = np.empty(count, dtype=TUPLE_DTYPE)
+        check(lib.phj_memcpy_d2h(self.device, out.ctypes.data, C.c_void_p(self.ptr + first * 16), count * 16))
+        return out
+
+    def close(self):
+        if self._ptr:
+            lib.phj_shared_free(self.device, self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def hash_host(hash_id: int, seed: int, key: int) -> int:
     return int(lib.phj_hash_host(hash_id, C.c_uint64(seed & (2**64 - 1)), key))
 

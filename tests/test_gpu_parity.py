@@ -185,6 +185,32 @@ def test_prepartitioned_bind_equals_plain_join(phj, oracle, P, bits):
             pre.bind_device_partitioned(ptr[0], n[0], ptr[1], n[1], bnd[0][:-1], bnd[1][:-1])
 
 
+# ---- device-side generators ------------------------------------------------------
+@pytest.mark.parametrize("alpha", [0.01, 1.05, 1.25])
+def test_device_generators(phj, oracle, alpha):
+    """Same algorithm, seeds and batch split as the host generators; only pow() differs (CUDA vs
+    glibc), so nearly every sample is identical and all of them lie in the key range."""
+    nr, ns, batches = 50_000, 1_000_000, 500
+    dR = phj.DeviceTuples(nr).fill_sequential(1)
+    dS = phj.DeviceTuples(ns).fill_zipf(alpha, 1, nr, 4242, batches)
+    R, S = dR.download(), dS.download()
+    hostR = np.empty(nr, dtype=phj.TUPLE_DTYPE)
+    hostS = np.empty(ns, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(hostR, 1)
+    phj.fill_zipf(hostS, alpha, 1, nr, 4242, batches)
+    assert (R["id"] == hostR["id"]).all() and (R["payload"] == hostR["payload"]).all()
+    assert (S["payload"] == np.arange(ns)).all()
+    assert S["id"].min() >= 1 and S["id"].max() <= nr
+    same = float((S["id"] == hostS["id"]).mean())
+    assert same > 0.999, same
+    with phj.Engine("radix-partitioning", partitions=256) as e:  # joined in place, no upload
+        e.bind_device(dR.ptr, nr, dS.ptr, ns, keepalive=(dR, dS))
+        assert e.join()["matches"] == ns == oracle.count_by_sort(R, S)
+    with pytest.raises(phj.PhjError):
+        phj.DeviceTuples(10).fill_zipf(0.001, 1, 10, 1, 1)
+    dR.close(), dS.close()
+
+
 # ---- the joined table (SURVEY 8f rank 1) -----------------------------------------------------------
 @pytest.mark.parametrize("name", sorted(_cases.adversarial_cases()) + ["gen_small_105", "gen_ragged"])
 def test_materialized_join_equals_oracle(phj, oracle, name):
