@@ -98,6 +98,9 @@ typedef struct {
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
 #define PHJ_FLAG_SPLIT_REMOTE_ONLY 0x8u /* SHARD_SPLIT handle used only through phj_shard_scatter with
                                            both destinations given: no local output buffers */
+#define PHJ_FLAG_CHAINED_TABLE 0x10u /* NO_PARTITIONING: bucket-chained global table (the reference's
+                                        SeparateChainingHashTable, src/HashTables/SeparateChaining.hpp)
+                                        instead of the open-addressing one (LinearProbing.hpp) */
 #define PHJ_FLAG_FUSE_HIST2 0x4u   /* experimental: the pass-1 scatter also accumulates the pass-2
                                       histogram (saves one read of both relations, costs shared
                                       memory; slower on B200 as measured) */

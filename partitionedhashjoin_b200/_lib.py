@@ -29,6 +29,7 @@ HASH_NAMES = {"xxh3": HASH_XXH3, "xxhash": HASH_XXH3, "murmur3": HASH_MURMUR3, "
 FLAG_NO_TMA_STORE = 0x2
 FLAG_FUSE_HIST2 = 0x4
 FLAG_SPLIT_REMOTE_ONLY = 0x8
+FLAG_CHAINED_TABLE = 0x10
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

@@ -80,6 +80,7 @@ enum Scalar : int {  // device-resident uint32 scalars
     kNcounts2,
     kOversize,
     kGtFlags,
+    kCtCursor,
     kNumScalars = 8
 };
 
@@ -152,6 +153,10 @@ struct phj_handle {
     uint32_t join_grid = 0, join_slots = 0, join_max_keys = 0;
     uint64_t* d_gt = nullptr;
     uint64_t gt_buckets = 0;
+    // bucket-chained table (PHJ_FLAG_CHAINED_TABLE)
+    uint32_t* d_ct_heads = nullptr;
+    phj::ChainBucket* d_ct_buckets = nullptr;
+    uint32_t ct_nheads = 0, ct_pool = 0;
 
     // joined table (phj_join_materialize)
     int64_t* d_joined = nullptr;
@@ -609,6 +614,26 @@ int build_plan(phj_handle* h) {
             h->cap_cta_times = cap;
         }
     }
+    // ---- bucket-chained table: ceil(0.25 n) heads rounded to a power of two, one preallocated
+    // bucket per head + ceil(n / 3) overflow buckets (SeparateChaining.hpp:150-181, SeparateChaining.cpp) ----
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING && (h->cfg.flags & PHJ_FLAG_CHAINED_TABLE)) {
+        const uint64_t n0 = std::max<size_t>(h->n[0], 1);
+        uint64_t heads = 64;
+        while (heads < (n0 + 3) / 4) heads <<= 1;
+        const uint64_t pool = heads + (n0 + 2) / 3 + 1024;
+        if (pool >= 0xfffffff0ull) return fail(PHJ_ERR_INVALID, "build relation too large for the chained table");
+        if (heads > h->ct_nheads || pool > h->ct_pool) {
+            if (h->d_ct_heads) cudaFree(h->d_ct_heads);
+            if (h->d_ct_buckets) cudaFree(h->d_ct_buckets);
+            h->d_ct_heads = nullptr;
+            h->d_ct_buckets = nullptr;
+            PHJ_CUDA(cudaMalloc(&h->d_ct_heads, heads * 4));
+            PHJ_CUDA(cudaMalloc(&h->d_ct_buckets, pool * sizeof(ChainBucket)));
+        }
+        h->ct_nheads = (uint32_t)heads;
+        h->ct_pool = (uint32_t)pool;
+        return PHJ_OK;
+    }
     // ---- global table: always for NPJ; for radix it is allocated on first need ----
     if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING) {
         uint64_t want = (uint64_t)std::ceil((double)std::max<size_t>(h->n[0], 1) / 2.8);
@@ -716,6 +741,52 @@ int run_gt(phj_handle* h, bool select, const ulonglong2* build, const ulonglong2
     return PHJ_OK;
 }
 
+template <int HASH>
+void launch_ct_t(phj_handle* h, bool build, const CtParams& cp, uint32_t grid) {
+    if (build) ct_build<HASH><<<grid, 256, 0, h->stream>>>(cp);
+    else ct_probe<HASH><<<grid, 256, 0, h->stream>>>(cp);
+}
+
+// No-partitioning join through the bucket-chained table.
+int run_ct(phj_handle* h, const ulonglong2* build, const ulonglong2* probe) {
+    CtParams cp{};
+    cp.heads = h->d_ct_heads;
+    cp.buckets = h->d_ct_buckets;
+    cp.nheads_mask = h->ct_nheads - 1;
+    cp.hash_shift = 0;
+    cp.pool = h->ct_pool;
+    cp.cursor = h->d_scalars + kCtCursor;
+    cp.overflow = h->d_scalars + kGtFlags;
+    cp.hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
+    cp.matches = h->d_matches;
+    const uint32_t grid = (uint32_t)h->sm_count * 8;
+    auto launch = [&](bool is_build) {
+        switch (h->cfg.hash) {
+            case PHJ_HASH_MURMUR3: launch_ct_t<kMurmur3>(h, is_build, cp, grid); break;
+            case PHJ_HASH_CITY: launch_ct_t<kCity>(h, is_build, cp, grid); break;
+            default: launch_ct_t<kXXH3>(h, is_build, cp, grid); break;
+        }
+    };
+    {
+        KernelScope ks(h, "ct_init");
+        ct_init<<<grid, 256, 0, h->stream>>>(cp);
+    }
+    {
+        KernelScope ks(h, "ct_build");
+        cp.rel = build;
+        cp.n = h->n[0];
+        launch(true);
+    }
+    PHJ_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    {
+        KernelScope ks(h, "ct_probe");
+        cp.rel = probe;
+        cp.n = h->n[1];
+        launch(false);
+    }
+    return PHJ_OK;
+}
+
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
@@ -727,13 +798,17 @@ int join_no_partitioning(phj_handle* h, phj_result* out) {
     // (src/HashTables/LinearProbing.hpp:106-110); here an empty R simply joins to 0.
     PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
     PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 8, h->stream));
-    int rc = run_gt(h, false, h->d_in[0], h->d_in[1]);
+    const bool chained = (h->cfg.flags & PHJ_FLAG_CHAINED_TABLE) != 0;
+    int rc = chained ? run_ct(h, h->d_in[0], h->d_in[1]) : run_gt(h, false, h->d_in[0], h->d_in[1]);
     if (rc != PHJ_OK) return rc;
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kGtFlags, 4, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
+    if (chained && (h->h_out[1] & 0xffffffffu))
+        return fail(PHJ_ERR_NOMEM, "BucketAllocator exceeded its limit.");  // SeparateChaining.hpp:114-118
     out->matches = h->h_out[0];
     out->partition_ns = 0;
     out->build_ns = (uint64_t)(ev_ms(h->ev[0], h->ev[2]) * 1e6);
@@ -997,6 +1072,8 @@ int validate_config(const phj_config* c) {
         if (c->split_chunks > (uint32_t)kMaxSplitChunks)
             return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
     }
+    if ((c->flags & PHJ_FLAG_CHAINED_TABLE) && c->algo != PHJ_ALGO_NO_PARTITIONING)
+        return fail(PHJ_ERR_INVALID, "the bucket-chained table serves the no-partitioning join only");
     if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
         return fail(PHJ_ERR_INVALID, "Unrecognized hash function: %d.", c->hash);
     if (c->algo == PHJ_ALGO_NO_PARTITIONING && (c->partitions != 0 || c->radix_bits[0] || c->radix_bits[1]))
@@ -1118,7 +1195,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows, h->d_ct_heads, h->d_ct_buckets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);

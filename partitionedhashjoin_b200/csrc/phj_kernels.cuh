@@ -1036,44 +1036,61 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
                     }
                 }
                 cta_sync();
-                // ---- probe: walk the sequence to the first free slot, every equal key is a row ----
-                for (uint64_t i0 = s0; i0 < s1; i0 += TPB) {
-                    const uint64_t i = i0 + tid;
-                    bool pending = i < s1;
-                    ulonglong2 s = make_ulonglong2(0, 0);
-                    if (pending) s = ld_stream_v2(p.probe + i);
-                    uint32_t slot = table_bucket(s.x, p.table_mul, p.slot_shift) & p.slot_mask;
-                    while (__any_sync(0xffffffffu, pending)) {
-                        bool hit = false;
-                        ulonglong2 r = make_ulonglong2(0, 0);
-                        if (pending) {
-                            const uint32_t cur = slots[slot];
-                            if (cur == 0) {
-                                pending = false;
-                            } else {
-                                r = tup[cur - 1];
-                                hit = r.x == s.x;
-                                slot = (slot + 1) & p.slot_mask;
-                            }
+                // ---- probe: walk the sequence to the first free slot, every equal key is a row.
+                // U probe tuples per thread are in flight (independent shared-memory chains).
+                constexpr int U = 4;
+                for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
+                    ulonglong2 s[U];
+                    uint32_t slot[U];
+                    bool pending[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint64_t i = i0 + (uint64_t)u * TPB + tid;
+                        pending[u] = i < s1;
+                        s[u] = make_ulonglong2(0, 0);
+                        if (pending[u]) {
+                            if (WRITE) s[u] = ld_stream_v2(p.probe + i);
+                            else s[u].x = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i));
                         }
-                        if (WRITE) {
-                            const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-                            if (hits) {
-                                unsigned long long base = 0;
-                                if (lane == __ffs(hits) - 1) base = atomicAdd(&block_count, (unsigned long long)__popc(hits));
-                                base = __shfl_sync(0xffffffffu, base, __ffs(hits) - 1);
-                                if (hit) {
-                                    const unsigned long long row = base + __popc(hits & lt);
-                                    if (row < p.out_cap) {
-                                        int64_t* o = p.out + row * 3;
-                                        o[0] = (int64_t)s.x;
-                                        o[1] = (int64_t)r.y;
-                                        o[2] = (int64_t)s.y;
-                                    }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) slot[u] = table_bucket(s[u].x, p.table_mul, p.slot_shift) & p.slot_mask;
+                    while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            bool hit = false;
+                            ulonglong2 r = make_ulonglong2(0, 0);
+                            if (pending[u]) {
+                                const uint32_t cur = slots[slot[u]];
+                                if (cur == 0) {
+                                    pending[u] = false;
+                                } else {
+                                    if (WRITE) r = tup[cur - 1];
+                                    else r.x = tup[cur - 1].x;
+                                    hit = r.x == s[u].x;
+                                    slot[u] = (slot[u] + 1) & p.slot_mask;
                                 }
                             }
-                        } else {
-                            count += hit;
+                            if (WRITE) {
+                                const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                                if (hits) {
+                                    unsigned long long base = 0;
+                                    if (lane == __ffs(hits) - 1)
+                                        base = atomicAdd(&block_count, (unsigned long long)__popc(hits));
+                                    base = __shfl_sync(0xffffffffu, base, __ffs(hits) - 1);
+                                    if (hit) {
+                                        const unsigned long long row = base + __popc(hits & lt);
+                                        if (row < p.out_cap) {
+                                            int64_t* o = p.out + row * 3;
+                                            o[0] = (int64_t)s[u].x;
+                                            o[1] = (int64_t)r.y;
+                                            o[2] = (int64_t)s[u].y;
+                                        }
+                                    }
+                                }
+                            } else {
+                                count += hit;
+                            }
                         }
                     }
                 }
@@ -1240,6 +1257,136 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
                     } else {
                         bucket[u] = (bucket[u] + 1) & p.bucket_mask;
                     }
+                }
+            }
+        }
+    }
+    __shared__ unsigned long long block_count;
+    if (threadIdx.x == 0) block_count = 0;
+    cta_sync();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
+    cta_sync();
+    if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
+}
+
+// =================================================================================================
+// K6c/K7c  bucket-chained global table: the GPU counterpart of SeparateChainingHashTable
+// (src/HashTables/SeparateChaining.hpp:143-277). A key hashes to one of `nheads` chain heads; a
+// bucket is one 32-byte sector {3 keys, next, count} -- the reference's 3-slot bucket
+// (SeparateChaining.hpp:22-101) shrunk from 64 to 32 bytes because only keys are stored; the first
+// bucket of every chain is preallocated (bucket i belongs to head i, :176-181), overflow buckets
+// come from a bump allocator (BucketAllocator, :103-135) and are pushed at the chain HEAD (:226-237).
+// Insert: claim a slot of the head bucket with atomicAdd on its count; when it is full, ONE inserter
+// wins the head's lock (atomicCAS to kChainLocked), links a fresh bucket holding its key and
+// publishes it; the others retry on the new head. All loops are warp-converged (see cta_sync()).
+// Duplicates keep their own slots (GetAll semantics); the count-only probe stops at the first hit.
+// =================================================================================================
+constexpr uint32_t kChainLocked = 0xffffffffu;
+
+struct __align__(32) ChainBucket {
+    uint64_t key[3];
+    uint32_t next;   // bucket index + 1 of the next (older) bucket, 0 = end of chain
+    uint32_t count;  // slots claimed (may exceed 3 transiently; valid slots = min(count, 3))
+};
+
+struct CtParams {
+    const ulonglong2* rel;
+    uint64_t n;
+    uint32_t* heads;        // [nheads]: bucket index + 1 of the newest bucket of the chain
+    ChainBucket* buckets;   // [pool]
+    uint32_t nheads_mask;
+    uint32_t hash_shift;
+    uint32_t pool;          // buckets available
+    uint32_t* cursor;       // bump allocator: next free bucket (starts at nheads)
+    uint32_t* overflow;     // set when the allocator ran out ("BucketAllocator exceeded its limit.")
+    HashParams hp;
+    unsigned long long* matches;
+};
+
+__global__ void ct_init(CtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= p.nheads_mask; i += stride) {
+        p.heads[i] = (uint32_t)i + 1;
+        p.buckets[i].next = 0;
+        p.buckets[i].count = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *p.cursor = p.nheads_mask + 1;
+        *p.overflow = 0;
+    }
+}
+
+template <int HASH>
+__global__ void __launch_bounds__(256) ct_build(CtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        bool pending = i < p.n;
+        const uint64_t key = pending ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
+        const uint32_t h = (uint32_t)(hash_key<HASH>(key, p.hp) >> p.hash_shift) & p.nheads_mask;
+        volatile uint32_t* head = p.heads + h;
+        while (__any_sync(0xffffffffu, pending)) {
+            if (pending) {
+                const uint32_t hb = *head;
+                if (hb != kChainLocked) {
+                    ChainBucket* b = p.buckets + (hb - 1);
+                    uint32_t c = *reinterpret_cast<volatile uint32_t*>(&b->count);
+                    if (c < 3) c = atomicAdd(&b->count, 1u);
+                    if (c < 3) {
+                        b->key[c] = key;
+                        pending = false;
+                    } else if (atomicCAS(p.heads + h, hb, kChainLocked) == hb) {
+                        // this inserter extends the chain: new bucket at the head, holding its key
+                        const uint32_t nb = atomicAdd(p.cursor, 1u);
+                        if (nb < p.pool) {
+                            ChainBucket* fresh = p.buckets + nb;
+                            fresh->key[0] = key;
+                            fresh->next = hb;
+                            fresh->count = 1;
+                            __threadfence();
+                            *head = nb + 1;
+                        } else {
+                            *p.overflow = 1;  // allocator exhausted: the key is dropped, the join fails
+                            __threadfence();
+                            *head = hb;
+                        }
+                        pending = false;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int HASH>
+__global__ void __launch_bounds__(256) ct_probe(CtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t count = 0;
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += stride * U) {
+        uint64_t key[U];
+        uint32_t b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = base + (uint64_t)u * stride + threadIdx.x;
+            const bool valid = i < p.n;
+            key[u] = valid ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
+            b[u] = 0;
+            if (valid) b[u] = __ldg(p.heads + ((uint32_t)(hash_key<HASH>(key[u], p.hp) >> p.hash_shift) & p.nheads_mask));
+        }
+        while (__any_sync(0xffffffffu, (b[0] | b[1] | b[2] | b[3]) != 0)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (b[u]) {
+                    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p.buckets + (b[u] - 1));
+                    const ulonglong2 k01 = __ldg(q), k2m = __ldg(q + 1);
+                    const uint32_t next = (uint32_t)k2m.y, cnt = (uint32_t)(k2m.y >> 32);
+                    const bool hit = (cnt > 0 && k01.x == key[u]) | (cnt > 1 && k01.y == key[u]) |
+                                     (cnt > 2 && k2m.x == key[u]);
+                    count += hit;
+                    b[u] = hit ? 0 : next;
                 }
             }
         }

@@ -369,10 +369,19 @@ class _JoinerBase:
 
 
 class NoPartitioningHashJoiner(_JoinerBase):
+    """``table``: 'linear-probing' (HashTables::LinearProbingHashTable, what the reference's main
+    instantiates, src/main.cpp:216-217) or 'separate-chaining' (HashTables::SeparateChainingHashTable,
+    src/HashTables/SeparateChaining.hpp) -- the HashTableFactory template argument of the reference."""
+
+    TABLES = {"linear-probing": 0, "separate-chaining": _lib.FLAG_CHAINED_TABLE}
+
     def __init__(self, configuration: Optional[NoPartitioningConfiguration] = None,
-                 hasher: Optional[Hasher] = None, device: int = 0):
+                 hasher: Optional[Hasher] = None, device: int = 0, table: str = "linear-probing"):
         hasher = hasher or Hasher()
-        super().__init__(Engine("no-partitioning", hash=hasher.name, hash_seed=hasher.seed, device=device))
+        if table not in self.TABLES:
+            raise ValueError(f"Unrecognized hash table type: {table}.")
+        super().__init__(Engine("no-partitioning", hash=hasher.name, hash_seed=hasher.seed, device=device,
+                                flags=self.TABLES[table]))
         self.configuration = configuration or NoPartitioningConfiguration()
 
 

@@ -44,6 +44,8 @@ inline std::string HelpText() {
          "  --gpus arg (=1)                       Number of GPUs (radix join sharded by partition).\n"
          "  --repeat arg (=1)                     Joins per run; the fastest is reported.\n"
          "  --no-tma-store                        Flush scatter tiles with st.global instead of TMA bulk stores.\n"
+         "  --table arg (=linear-probing)         Hash table of the no-partitioning join: linear-probing or\n"
+         "                                        separate-chaining (the reference's two HashTables).\n"
          "  --materialize                         Radix join only: also produce the joined table {id, payloadA,\n"
          "                                        payloadB} (the reference returns it empty) and log its size.\n";
     return o.str();
@@ -82,7 +84,7 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
         {"-h", "help"}, {"-u", "unit"}, {"-o", "output"}, {"-f", "filename"}, {"-p", "partitions"}};
     static const std::set<std::string> kValued = {
         "primary", "secondary", "skew", "log", "join", "format", "unit", "output", "filename", "partitions",
-        "hash", "seed", "table-seed", "data-seed", "radix-bits", "device", "gpus", "repeat"};
+        "hash", "seed", "table-seed", "data-seed", "radix-bits", "device", "gpus", "repeat", "table"};
     static const std::set<std::string> kFlags = {"help", "no-tma-store", "materialize"};
 
     Common::Configuration c{};
@@ -136,6 +138,10 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     if (auto v = get("data-seed")) c.Gpu.DataSeed = static_cast<int64_t>(ParseUnsigned("data-seed", *v));
     if (auto v = get("device")) c.Gpu.Device = static_cast<int>(ParseUnsigned("device", *v));
     if (auto v = get("gpus")) c.Gpu.Gpus = static_cast<int>(ParseUnsigned("gpus", *v));
+    if (auto v = get("table")) {
+        if (*v == "separate-chaining") c.Gpu.ChainedTable = true;
+        else if (*v != "linear-probing") throw std::invalid_argument("Unrecognized hash table type: " + *v + ".");
+    }
     if (auto v = get("repeat")) c.Gpu.Repeat = static_cast<int>(ParseUnsigned("repeat", *v));
     if (auto v = get("radix-bits")) {
         auto comma = v->find(',');

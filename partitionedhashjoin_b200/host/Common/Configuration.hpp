@@ -101,6 +101,8 @@ struct GpuConfiguration {
     unsigned RadixBits[2] = {0, 0};
     int Repeat = 1;             // joins per run; the best is reported
     bool NoTmaStore = false;
+    bool ChainedTable = false;  // no-partitioning join: bucket-chained table (SeparateChaining) instead of
+                                // the open-addressing one (LinearProbing)
     bool Materialize = false;   // fill the returned Table<JoinedTuple> (the reference leaves it empty)
 };
 

@@ -48,6 +48,7 @@ class Engine {
         cfg.table_seed = gpu.TableSeed;
         cfg.device = gpu.Device;
         cfg.flags = gpu.NoTmaStore ? PHJ_FLAG_NO_TMA_STORE : 0;
+        if (gpu.ChainedTable && algo == PHJ_ALGO_NO_PARTITIONING) cfg.flags |= PHJ_FLAG_CHAINED_TABLE;
         Check(phj_create(&cfg, &m_handle));
     }
     ~Engine() { phj_destroy(m_handle); }

@@ -44,6 +44,7 @@ def test_help_lists_reference_flags(phjoin):
     (("--join", "radix-partitioning", "--primary", "ten"), "option '--primary' is invalid"),
     (("--join", "radix-partitioning", "--bogus", "1"), "unrecognised option '--bogus'"),
     (("--join", "radix-partitioning", "--hash", "sha1"), "Unrecognized hash function: sha1."),
+    (("--join", "no-partitioning", "--table", "cuckoo"), "Unrecognized hash table type: cuckoo."),
     (("--join", "no-partitioning", "--materialize"), "the joined table is produced by the RadixParitioning joiner."),
 ])
 def test_argument_errors_exit_1_with_option_table(phjoin, args, message):
@@ -74,6 +75,7 @@ def test_json_rendering_matches_reference(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("join,extra,typ", [("no-partitioning", [], "NoPartitioning"),
+                                             ("no-partitioning", ["--table", "separate-chaining"], "NoPartitioning"),
                                              ("radix-partitioning", ["-p", "64"], "RadixParitioning"),
                                              ("radix-partitioning", ["--partitions=4096", "--hash", "city", "--repeat", "2"], "RadixParitioning")])
 def test_cli_end_to_end(phjoin, tmp_path, join, extra, typ):

@@ -185,6 +185,32 @@ def test_prepartitioned_bind_equals_plain_join(phj, oracle, P, bits):
             pre.bind_device_partitioned(ptr[0], n[0], ptr[1], n[1], bnd[0][:-1], bnd[1][:-1])
 
 
+# ---- bucket-chained table ---------------------------------------------------
+@pytest.mark.parametrize("hash", HASHES)
+def test_chained_table_counts(phj, oracle, hash):
+    """No-partitioning join through the bucket-chained table: the oracle's separate-chaining count
+    (= the linear-probing count = the independent sort count) on every case, incl. 5000 equal build
+    keys (one long chain built under contention) and the int64 extremes (no reserved key value)."""
+    cases = dict(_cases.adversarial_cases())
+    for name in ("gen_small_105", "gen_ragged"):
+        cases[name] = cases_for(phj, name)
+    big_r = _cases.tuples(_cases.splitmix64(300_000, 51).astype(np.int64) % 200_003)
+    big_s = _cases.tuples(_cases.splitmix64(2_000_000, 52).astype(np.int64) % 300_007)
+    cases["big_random"] = (big_r, big_s)
+    for name, (R, S) in cases.items():
+        want = oracle.count_by_sort(R, S)
+        if R.shape[0]:
+            assert oracle.join_npj(R, S, table_kind=1) == want
+        got = run(phj, R, S, "no-partitioning", hash=hash, flags=phj.FLAG_CHAINED_TABLE)
+        assert got["matches"] == want, (name, got["matches"], want)
+    j = phj.NoPartitioningHashJoiner(table="separate-chaining")
+    j.Run(*cases["big_random"])
+    assert j.last_result["matches"] == oracle.count_by_sort(*cases["big_random"])
+    j.close()
+    with pytest.raises(phj.PhjError):
+        phj.Engine("radix-partitioning", flags=phj.FLAG_CHAINED_TABLE)
+
+
 # ---- device-side generators (SURVEY 8f rank 3) ------------------------------------------------------
 @pytest.mark.parametrize("alpha", [0.01, 1.05, 1.25])
 def test_device_generators(phj, oracle, alpha):
