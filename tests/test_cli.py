@@ -102,3 +102,17 @@ def test_cli_materialize(phjoin, tmp_path):
             "--materialize", "--log", "info", "-f", str(out))
     assert r.returncode == 0, r.stderr
     assert "Joined table holds 1500000 rows." in r.stderr
+
+
+@pytest.mark.gpu
+def test_partition_sweep_writes_figure_dat(phjoin, tmp_path):
+    """tools/sweep.py = scripts/generate.sh:66-80: figure.dat with one column per run."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "-s", "1.05", "--primary", "100000",
+                        "--secondary", "1000000", "--outdir", str(tmp_path), "--repeat", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l.split() for l in open(tmp_path / "figure.dat").read().splitlines()]
+    assert rows[0] == ["NumberOfPartitions", "NoPartitioning"] + [f"Radix{p}" for p in (32, 64, 128, 256, 512, 1024, 2048, 4096, 8192)]
+    assert [r_[0] for r_ in rows[1:]] == ["Partition", "Build", "Probe"]
+    assert rows[1][1] == "0" and all(int(v) > 0 for v in rows[1][2:])  # only radix runs partition
