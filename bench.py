@@ -263,6 +263,17 @@ def gpu_arm(args):
                     others[f"radix_{h}_Gtuples_s"] = few(e2)
         with phj.Engine("no-partitioning", device=local) as e2:
             others["no_partitioning_Gtuples_s"] = few(e2)
+        with phj.Engine("no-partitioning", device=local, flags=phj.FLAG_CHAINED_TABLE) as e2:
+            others["no_partitioning_chained_table_Gtuples_s"] = few(e2)
+        with phj.Engine("radix-partitioning", partitions=64, hash=args.hash, device=local) as e2:
+            others["radix_1pass_64_partitions_Gtuples_s"] = few(e2)
+        with phj.Engine("radix-partitioning", partitions=args.partitions, hash=args.hash, device=local) as e2:
+            e2.upload(R, S)
+            e2.join_materialize()
+            rm = min((e2.join_materialize() for _ in range(3)), key=lambda r: r["total_ns"])
+            assert rm["joined_tuples"] == S.shape[0]
+            others["radix_materialized_Gtuples_s"] = round(n_tuples / (rm["total_ns"] / 1e9) / 1e9, 2)
+            others["radix_materialized_rows"] = rm["joined_tuples"]
         for skew in (1.05, 1.25):
             if abs(skew - args.skew) > 1e-9:
                 phj.fill_zipf(S, skew, 1, N_BUILD, BASE_SEED, BATCHES)
@@ -304,6 +315,9 @@ def main():
     ap.add_argument("--hash", default="xxh3", choices=["xxh3", "murmur3", "city"])
     ap.add_argument("--partitions", type=int, default=4096)
     ap.add_argument("--ref-partitions", type=int, default=2048)
+    ap.add_argument("--workload", default="default", choices=["default", "scaled"],
+                    help="N > 1 only: scaled = BASELINE.json configs[4], 160M x 3.2B in total sharded over the ranks "
+                         "(strong scaling), generated on the device; use --partitions 8192")
     ap.add_argument("--chunks", type=int, default=4, help="N > 1, pipelined shuffle: probe chunks")
     ap.add_argument("--split-ctas", type=int, default=96,
                     help="N > 1, pipelined shuffle: CTAs of the NVLink-bound split scatter (0 = all)")

@@ -995,6 +995,8 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
     ulonglong2* tup = reinterpret_cast<ulonglong2*>(smem_raw);                  // [cap_tuples]
     uint32_t* slots = reinterpret_cast<uint32_t*>(tup + p.cap_tuples);           // [slot_mask + 1]
     __shared__ unsigned long long block_count;
+    __shared__ uint64_t wstage_all[WRITE ? (TPB / 32) * 96 : 1];                 // 32 rows x 3 words per warp
+    uint64_t* wstage = wstage_all + (WRITE ? (threadIdx.x >> 5) * 96 : 0);
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt = lanemask_lt();
 
@@ -1078,15 +1080,24 @@ __global__ void __launch_bounds__(TPB) join_materialize(MatParams p) {
                                     if (lane == __ffs(hits) - 1)
                                         base = atomicAdd(&block_count, (unsigned long long)__popc(hits));
                                     base = __shfl_sync(0xffffffffu, base, __ffs(hits) - 1);
+                                    // rows -> the warp's staging words, then consecutive lanes store
+                                    // consecutive 8-byte words: full 32-byte sectors instead of three
+                                    // strided partial-sector stores per row
+                                    const uint32_t nh = __popc(hits);
                                     if (hit) {
-                                        const unsigned long long row = base + __popc(hits & lt);
-                                        if (row < p.out_cap) {
-                                            int64_t* o = p.out + row * 3;
-                                            o[0] = (int64_t)s[u].x;
-                                            o[1] = (int64_t)r.y;
-                                            o[2] = (int64_t)s[u].y;
-                                        }
+                                        uint64_t* w = wstage + 3 * __popc(hits & lt);
+                                        w[0] = s[u].x;
+                                        w[1] = r.y;
+                                        w[2] = s[u].y;
                                     }
+                                    __syncwarp();
+                                    if (base + nh <= p.out_cap) {
+                                        uint64_t* o = reinterpret_cast<uint64_t*>(p.out) + base * 3;
+#pragma unroll
+                                        for (int k = 0; k < 3; ++k)
+                                            if (lane + 32 * k < 3 * nh) o[lane + 32 * k] = wstage[lane + 32 * k];
+                                    }
+                                    __syncwarp();
                                 }
                             } else {
                                 count += hit;

@@ -52,6 +52,10 @@ class GpuBackend:
     def upload(self, R, S):
         self.split_engine.upload(R, S)
 
+    def bind_device(self, d_build, n_build, d_probe, n_probe, keepalive=None):
+        """Shards that already live on this rank's GPU (e.g. DeviceTuples from the device generators)."""
+        self.split_engine.bind_device(d_build, n_build, d_probe, n_probe, keepalive=keepalive)
+
     def split(self):
         """-> ([send tensor R, send tensor S] ordered by owner, counts[2][world], device ns)."""
         res = self.split_engine.join()
@@ -571,8 +575,19 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     import torch
 
     import partitionedhashjoin_b200 as phj
-    n_build, n_probe = 10_000_000, 200_000_000
-    Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
+    scaled = getattr(args, "workload", "default") == "scaled"
+    if scaled:
+        # BASELINE.json configs[4]: 160 M x 3.2 B in total, row-sharded over the ranks (strong scaling),
+        # generated ON the device (the host generator would need minutes and a 51 GB upload)
+        total_build, total_probe = 160_000_000, 3_200_000_000
+        n_build, n_probe = total_build // world, total_probe // world
+        dR = phj.DeviceTuples(n_build, local).fill_sequential(1 + rank * n_build)
+        dS = phj.DeviceTuples(n_probe, local).fill_zipf(args.skew, 1, total_build, 12345 + 100_003 * rank, 1 << 16)
+        # local fan-out for build partitions of ~2.4 K keys, like the single-GPU default
+        args.partitions = 1 << max(2, (n_build // 2400).bit_length())
+    else:
+        n_build, n_probe = 10_000_000, 200_000_000
+        Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
     mode = getattr(args, "shuffle", "pass1")
     fused = mode in ("fused", "pass1", "pipelined")
     if mode == "pipelined":  # chunked: the NVLink shuffle of chunk c + 1 overlaps the local join of chunk c
@@ -586,7 +601,10 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     else:      # split locally, then one NCCL all-to-all per relation
         backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
         job = ShardedRadixJoin(dist, rank, world, backend)
-    job.upload(Rp.array, Sp.array)
+    if scaled:
+        backend.bind_device(dR.ptr, n_build, dS.ptr, n_probe, keepalive=(dR, dS))
+    else:
+        job.upload(Rp.array, Sp.array)
     for _ in range(args.warmup):
         res = job.join()
     want = world * n_probe
@@ -613,17 +631,20 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     elapsed = float(t.item())
     assert res["matches"] == want
 
-    # e2e: the host shards are uploaded inside the timed region
+    # e2e: the host shards are uploaded inside the timed region (the scaled workload is generated on
+    # the device and has no host copy, hence no end-to-end number)
     e2e_steps = max(3, min(args.steps, 5))
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        job.upload(Rp.array, Sp.array)
-        r2 = job.join()
-    sync()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    assert r2["matches"] == want
+    te = torch.tensor([0.0], dtype=torch.float64, device=f"cuda:{local}")
+    if not scaled:
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            job.upload(Rp.array, Sp.array)
+            r2 = job.join()
+        sync()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert r2["matches"] == want
     launches = torch.tensor([backend.launches - launches0], dtype=torch.int64, device=f"cuda:{local}")
     dist.all_reduce(launches)
 
@@ -633,8 +654,12 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         peak, peak_src = measured_hbm_peak()
         lr = res["local_result"]
         cfg = workload_config(args)
-        cfg["workload"] = (f"radix join sharded over {world} B200: {world} x (10M x 200M) row shards = "
-                           f"{world * 10}M x {world * 200}M, partition shuffle "
+        cfg["primary"], cfg["secondary"] = world * n_build, world * n_probe
+        if scaled:
+            cfg["l2_flush"] = f"inputs ({16 * (n_build + n_probe) / 1e9:.1f} GB per GPU) are larger than L2"
+        cfg["workload"] = (f"radix join sharded over {world} B200: {world} x ({n_build // 10**6}M x {n_probe // 10**6}M) "
+                           f"row shards = {world * n_build // 10**6}M x {world * n_probe // 10**6}M"
+                           f"{' (device-generated)' if scaled else ''}, partition shuffle "
                            f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
                            f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}"
                            f"{f', pipelined over {args.chunks} probe chunks' if mode == 'pipelined' else ''}, then local "
@@ -644,10 +669,11 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         line = {
             "metric": metric, "value": n_tuples / (elapsed / args.steps), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": cfg,
-            "e2e": {"value": n_tuples / (float(te.item()) / e2e_steps), "unit": unit,
-                    "h2d_bytes_per_step": 16 * n_tuples, "d2h_bytes_per_step": int(lr["d2h_bytes"] + 8 * (2 * world + 2)) * world,
-                    "steps": e2e_steps},
+            "scaling": "strong" if scaled else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": cfg,
+            "e2e": None if scaled else {
+                "value": n_tuples / (float(te.item()) / e2e_steps), "unit": unit, "h2d_bytes_per_step": 16 * n_tuples,
+                "d2h_bytes_per_step": int(lr["d2h_bytes"] + 8 * (2 * world + 2)) * world, "steps": e2e_steps},
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "kernel": "local radix join (per GPU)", "unit": "GB/s", "peak": peak,
                          "peak_source": peak_src, "achieved": lr["hbm_bytes_alg"] / lr["total_ns"],
