@@ -584,7 +584,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         dR = phj.DeviceTuples(n_build, local).fill_sequential(1 + rank * n_build)
         dS = phj.DeviceTuples(n_probe, local).fill_zipf(args.skew, 1, total_build, 12345 + 100_003 * rank, 1 << 16)
         # local fan-out for build partitions of ~2.4 K keys, like the single-GPU default
-        args.partitions = 1 << max(2, (n_build // 2400).bit_length())
+        args.partitions = 1 << max(2, (n_build // 1800).bit_length() - 1)
     else:
         n_build, n_probe = 10_000_000, 200_000_000
         Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
