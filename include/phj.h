@@ -101,9 +101,10 @@ typedef struct {
 #define PHJ_FLAG_CHAINED_TABLE 0x10u /* NO_PARTITIONING: bucket-chained global table (the reference's
                                         SeparateChainingHashTable, src/HashTables/SeparateChaining.hpp)
                                         instead of the open-addressing one (LinearProbing.hpp) */
-#define PHJ_FLAG_FUSE_HIST2 0x4u   /* experimental: the pass-1 scatter also accumulates the pass-2
-                                      histogram (saves one read of both relations, costs shared
-                                      memory; slower on B200 as measured) */
+#define PHJ_FLAG_FUSE_HIST2 0x4u   /* accepted for compatibility: the fused pass-2 histogram is the default */
+#define PHJ_FLAG_NO_FUSE_HIST2 0x20u /* pass 2 reads its own histogram instead of having the pass-1
+                                        scatter count it (the default for two passes of <= 6 bits; saves
+                                        one read of both relations) */
 
 
 /* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the

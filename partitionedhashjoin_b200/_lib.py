@@ -30,6 +30,7 @@ FLAG_NO_TMA_STORE = 0x2
 FLAG_FUSE_HIST2 = 0x4
 FLAG_SPLIT_REMOTE_ONLY = 0x8
 FLAG_CHAINED_TABLE = 0x10
+FLAG_NO_FUSE_HIST2 = 0x20
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

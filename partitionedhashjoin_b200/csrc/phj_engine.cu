@@ -118,7 +118,9 @@ struct phj_handle {
     uint64_t nparts = 0;      // d1 * d2 (>= P)
     uint32_t nsegs1 = 0, max_segs2 = 0, target_segs2[2] = {0, 0};
     uint32_t nseg1_rel[2] = {0, 0}, cnt_base1_rel[2] = {0, 0};
-    uint64_t seg_len[2] = {0, 0};   // tuples per segment (both passes)
+    uint64_t seg_len[2] = {0, 0};   // tuples per pass-1 segment
+    uint64_t seg_len2[2] = {0, 0};  // tuples per pass-2 segment (shorter: parents end ragged, more and
+                                    // shorter segments balance the CTAs better)
     phj::Parent2* d_parents2[2] = {nullptr, nullptr};
     size_t cap_parents2 = 0;
     bool fuse2 = false;             // pass-2 histogram accumulated by the pass-1 scatter
@@ -532,12 +534,19 @@ int build_plan(phj_handle* h) {
         size_t ncounts_max = ncounts1;
         h->fuse2 = false;
         if (h->b2 > 0) {
-            for (int rel = 0; rel < 2; ++rel)
-                h->target_segs2[rel] = std::max<uint32_t>(1, nseg_plan[rel]);
+            uint32_t div = 1;
+            if (const char* x = getenv("PHJ_SEG2_DIV")) div = (uint32_t)std::max(1, atoi(x));
+            for (int rel = 0; rel < 2; ++rel) {
+                h->seg_len2[rel] = ((h->seg_len[rel] / div + kScatTile - 1) / kScatTile) * kScatTile;
+                h->target_segs2[rel] = std::max<uint32_t>(1, nseg_plan[rel]) * div + div;
+            }
             h->max_segs2 = h->target_segs2[0] + h->target_segs2[1] + 2 * h->d1;
-            // Opt-in: measured slower than the separate histogram read on B200 (the extra 33 KB of
-            // shared memory shrinks L1, which bounds the loads in flight).
-            h->fuse2 = h->b1 <= 6 && h->b2 <= 6 && (h->cfg.flags & PHJ_FLAG_FUSE_HIST2);
+            // The pass-1 scatter also counts every tuple into its pass-2 segment, so pass 2 needs no
+            // histogram read of its own: 4.39 -> 4.28 ms at 10 M x 200 M (uniform), 4.40 -> 4.33 ms at
+            // Zipf 1.25. On by default for two 6-bit passes since the counters are packed 16-bit (two
+            // CTAs per SM); with 32-bit counters only one CTA fit and it was slower than the extra read.
+            h->fuse2 = h->b1 <= 6 && h->b2 <= 6 && !(h->cfg.flags & PHJ_FLAG_NO_FUSE_HIST2) && div == 1 &&
+                       h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING;
             if (h->d1 > h->cap_parents2 || !h->d_parents2[0]) {
                 for (int rel = 0; rel < 2; ++rel) {
                     if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
@@ -859,7 +868,7 @@ int join_radix(phj_handle* h, phj_result* out) {
             pl.parents2[rel] = h->d_parents2[rel];
             pl.cnt_base1[rel] = h->cnt_base1_rel[rel];
             pl.nseg1[rel] = h->nseg1_rel[rel];
-            pl.seg_len[rel] = h->seg_len[rel];
+            pl.seg_len[rel] = h->seg_len2[rel];
             pl.n[rel] = h->n[rel];
             pl.target_segs[rel] = h->target_segs2[rel];
             fe.bounds1[rel] = h->d_bounds1[rel];
@@ -925,7 +934,7 @@ int join_radix(phj_handle* h, phj_result* out) {
             PHJ_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->max_segs2 * h->d2 * sizeof(uint32_t), h->stream));
             for (int rel = 0; rel < 2; ++rel) {
                 p1.parents2[rel] = h->d_parents2[rel];
-                p1.seg_len2[rel] = h->seg_len[rel];
+                p1.seg_len2[rel] = h->seg_len2[rel];
             }
             p1.counts2 = h->d_counts;
             p1.df2 = digit_fn(h, 2);
@@ -984,6 +993,14 @@ int join_radix(phj_handle* h, phj_result* out) {
     jp.max_keys = h->join_max_keys;
     jp.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;  // odd
     if (h->cfg.table_seed == 0) jp.table_mul = 0xBF58476D1CE4E5B9ULL;
+    jp.table_mul |= 1ULL << 32;  // both 32-bit multipliers odd
+    jp.shift32 = 32 - ilog2_ceil(h->join_slots / PHJ_JOIN_BUCKET);
+    {
+        // the partition the free-slot marker (INT64_MIN) belongs to, in the final partition numbering
+        const uint64_t hs = hash_key_dyn(h->cfg.hash, kEmptyKey, hp);
+        const uint64_t full = h->pow2 ? (hs & (h->P - 1)) : (hs % h->P);
+        jp.sentinel_part = (uint32_t)full;
+    }
     jp.matches = h->d_matches;
     jp.cta_times = h->d_cta_times;
     {

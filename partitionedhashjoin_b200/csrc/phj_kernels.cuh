@@ -321,7 +321,9 @@ struct ScatterSmem {
     static constexpr size_t total =
         (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 16 * 4 + 64 + 15) / 16 * 16;
     // extra shared memory of the fused pass-2 histogram: counters + split positions + counter indices
-    static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 4 + (size_t)D * 8 + (size_t)D * 8;
+    // 16-bit counters packed in pairs (flushed before they can overflow): with 32-bit counters the CTA
+    // needed 127 KB and only ONE fit an SM, which is what made the first fused version slow
+    static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 2 + (size_t)D * 8 + (size_t)D * 8;
 };
 
 template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT, bool FUSE2,
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     uint16_t* sdig = reinterpret_cast<uint16_t*>(dbase + D + 4);
     // FUSE2: [2][D][d2] pass-2 counters of this segment + per-digit split position / first segment
     uint32_t* h2 = reinterpret_cast<uint32_t*>(smem_raw + L::total);
-    uint64_t* split_pos = reinterpret_cast<uint64_t*>(h2 + 2 * D * kFuse2MaxD2);
+    uint64_t* split_pos = reinterpret_cast<uint64_t*>(h2 + D * kFuse2MaxD2);  // h2: 2 * D * 64 / 2 words
     uint32_t* h2_first = reinterpret_cast<uint32_t*>(split_pos + D);  // counter index of (digit 0, first seg)
     uint32_t* h2_stride = h2_first + D;
 
@@ -379,8 +381,27 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         }
     }
     if (FUSE2) {
-        for (int i = tid; i < 2 * D * (int)kFuse2MaxD2; i += TPB) h2[i] = 0;
+        for (int i = tid; i < D * (int)kFuse2MaxD2; i += TPB) h2[i] = 0;
     }
+
+    // FUSE2: add the CTA's packed 16-bit pass-2 counts to the global counters and clear them.
+    auto flush_h2 = [&]() {
+        cta_sync();
+        for (uint32_t w = tid; w < (uint32_t)D * kFuse2MaxD2; w += TPB) {
+            const uint32_t pair = h2[w];
+            if (pair) {
+                h2[w] = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t c = (pair >> (16 * half)) & 0xffffu, i = 2 * w + half;
+                    const uint32_t d2 = i % kFuse2MaxD2, d = (i / kFuse2MaxD2) % D, slot = i / (kFuse2MaxD2 * D);
+                    if (c) atomicAdd(&p.counts2[h2_first[d] + d2 * h2_stride[d] + slot], c);
+                }
+            }
+        }
+        cta_sync();
+    };
+    uint32_t tiles_since_flush = 0;
 
     ulonglong2 v[IPT];
     auto load_tile = [&](uint64_t tile) {
@@ -400,6 +421,10 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     for (uint64_t tile = seg.begin; tile < seg.end; tile += T) {
         const uint32_t n_valid = (uint32_t)min((uint64_t)T, seg.end - tile);
         const uint32_t n_mine = n_valid - min(n_valid, (uint32_t)(warp * (32 * IPT) + lane));  // > i*32 <=> valid
+        if (FUSE2 && ++tiles_since_flush * T > 65535u) {  // a 16-bit counter could overflow in this tile
+            flush_h2();
+            tiles_since_flush = 1;
+        }
         const bool full = n_valid == T;
 
         for (int i = lane; i <= D; i += 32) wcw[i] = 0;
@@ -470,7 +495,8 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
                 if (!TMA_STORE) sdig[pos] = (uint16_t)d;
                 if (FUSE2) {
                     const uint32_t slot = gbase[d] + pos >= split_pos[d];
-                    atomicAdd(&h2[(slot * D + d) * kFuse2MaxD2 + ((dr[i] >> 9) & 0x7fu)], 1u);
+                    const uint32_t c2 = (slot * D + d) * kFuse2MaxD2 + ((dr[i] >> 9) & 0x7fu);
+                    atomicAdd(&h2[c2 >> 1], 1u << ((c2 & 1) * 16));
                 }
             }
         }
@@ -498,17 +524,7 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         }
         // The next iteration's barriers separate this flush from the next stage step.
     }
-    if (FUSE2) {
-        // flush this segment's pass-2 counts (<= 2 * D * d2 non-zero entries)
-        cta_sync();
-        for (uint32_t i = tid; i < 2u * D * kFuse2MaxD2; i += TPB) {
-            const uint32_t c = h2[i];
-            if (c) {
-                const uint32_t d2 = i % kFuse2MaxD2, d = (i / kFuse2MaxD2) % D, slot = i / (kFuse2MaxD2 * D);
-                atomicAdd(&p.counts2[h2_first[d] + d2 * h2_stride[d] + slot], c);
-            }
-        }
-    }
+    if (FUSE2) flush_h2();  // this segment's remaining pass-2 counts
     }  // segments of this CTA
     if (TMA_STORE) bulk_wait_all0();
 }
@@ -802,7 +818,10 @@ struct JoinParams {
     uint32_t bucket_mask;   // table buckets - 1 (a bucket = BK 8-byte keys, read with 16-byte loads)
     uint32_t bucket_shift;  // bucket = table_hash(key) >> bucket_shift
     uint32_t max_keys;      // largest build partition the table accepts
-    uint64_t table_mul;     // odd multiplier of the table hash (derived from the table seed)
+    uint64_t table_mul;     // odd multipliers of the table hash (derived from the table seed): low / high word
+    uint32_t shift32;       // 32 - log2(buckets)
+    uint32_t sentinel_part; // the one partition kEmptyKey hashes to: only there can a key equal the
+                            // free-slot marker, every other partition runs without that check
     unsigned long long* matches;
     uint64_t* cta_times;  // 2 per CTA: build ns, probe ns
 };
@@ -813,6 +832,11 @@ struct JoinParams {
 // (src/main.cpp:215-217) it only influences speed, never the count.
 __device__ __forceinline__ uint32_t table_bucket(uint64_t key, uint64_t mul, uint32_t shift) {
     return (uint32_t)(((key ^ (key >> 29)) * mul) >> shift);
+}
+// The same role with two 32-bit multiplies (multiply-shift over the key's halves): the probe loop of
+// join_partitions is issue-bound (ncu: 72 % issue slots busy), a 64-bit IMAD chain costs 4 slots.
+__device__ __forceinline__ uint32_t table_bucket32(uint64_t key, uint32_t mul_lo, uint32_t mul_hi, uint32_t shift32) {
+    return ((uint32_t)key * mul_lo + (uint32_t)(key >> 32) * mul_hi) >> shift32;
 }
 
 template <int TPB, int BK>
@@ -855,6 +879,8 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             }
             if (tid == 0) has_empty_key = 0;
             cta_sync();
+            const bool careful = part == p.sentinel_part;  // only here can a key equal kEmptyKey
+            const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
             // ---- build: first free slot of the home bucket, overflowing into the next bucket.
             // Warp-converged: every lane runs the same number of loop trips (vote on `pending`),
             // so no per-lane loop ever splits the warp (see cta_sync()).
@@ -864,12 +890,12 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                 bool pending = i < r1;
                 if (pending) {
                     key = __ldg(reinterpret_cast<const unsigned long long*>(p.build + i));
-                    if (key == kEmptyKey) {
+                    if (careful && key == kEmptyKey) {
                         has_empty_key = 1;
                         pending = false;
                     }
                 }
-                uint32_t slot = (table_bucket(key, p.table_mul, p.bucket_shift) & p.bucket_mask) * BK;
+                uint32_t slot = (table_bucket32(key, mul_lo, mul_hi, p.shift32) & p.bucket_mask) * BK;
                 while (__any_sync(0xffffffffu, pending)) {
                     if (pending) {
                         unsigned long long cur = table[slot];
@@ -886,11 +912,13 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
 
             // ---- probe: one bucket (BK keys) per step; a bucket whose last slot is free ends the
             // search (slots fill in order, LinearProbing.hpp:172-174 analogue). The first step is
-            // peeled: at the table's load factor nearly every search ends there, and the converged
-            // loop only runs for the few that overflow.
+            // peeled and branch-free: at the table's load factor nearly every search ends there, and
+            // the converged loop only runs for the few that overflow. Full blocks of TPB * U probe
+            // tuples skip the bounds checks; outside the sentinel partition no key can equal the
+            // free-slot marker, so that test is skipped too (the loop is issue-bound: every
+            // instruction removed here is time).
             constexpr int U = 4;
-            auto probe_step = [&](uint64_t key, uint32_t& bucket, bool& pending) {
-                bool hit, full;
+            auto probe_bucket = [&](uint64_t key, uint32_t bucket, bool& hit, bool& full) {
                 if (BK == 2) {
                     const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(table + bucket * 2);
                     hit = (k.x == key) | (k.y == key);
@@ -901,11 +929,43 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                     hit = (k01.x == key) | (k01.y == key) | (k23.x == key) | (k23.y == key);
                     full = k23.y != kEmptyKey;
                 }
-                count += hit;
-                pending = !hit && full;
-                bucket = (bucket + 1) & p.bucket_mask;
             };
-            for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
+            auto overflow_walk = [&](uint64_t (&key)[U], uint32_t (&bucket)[U], bool (&pending)[U]) {
+                bool any = pending[0] | pending[1] | pending[2] | pending[3];
+                while (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (pending[u]) {
+                            bucket[u] = (bucket[u] + 1) & p.bucket_mask;
+                            bool hit, full;
+                            probe_bucket(key[u], bucket[u], hit, full);
+                            count += hit;
+                            pending[u] = !hit && full;
+                        }
+                    any = pending[0] | pending[1] | pending[2] | pending[3];
+                }
+            };
+            uint64_t i0 = s0;
+            if (!careful) {
+                for (; i0 + (uint64_t)TPB * U <= s1; i0 += (uint64_t)TPB * U) {
+                    uint64_t key[U];
+                    uint32_t bucket[U];
+                    bool pending[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        key[u] = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i0 + (uint64_t)u * TPB + tid));
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, p.shift32) & p.bucket_mask;
+                        bool hit, full;
+                        probe_bucket(key[u], bucket[u], hit, full);
+                        count += hit;
+                        pending[u] = !hit && full;
+                    }
+                    overflow_walk(key, bucket, pending);
+                }
+            }
+            for (; i0 < s1; i0 += (uint64_t)TPB * U) {  // tail block, and the sentinel partition
                 uint64_t key[U];
                 uint32_t bucket[U];
                 bool pending[U];
@@ -921,18 +981,15 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                         count += sentinel_hit;
                         pending[u] = false;
                     }
-                    bucket[u] = table_bucket(key[u], p.table_mul, p.bucket_shift) & p.bucket_mask;
+                    bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, p.shift32) & p.bucket_mask;
+                    if (pending[u]) {
+                        bool hit, full;
+                        probe_bucket(key[u], bucket[u], hit, full);
+                        count += hit;
+                        pending[u] = !hit && full;
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (pending[u]) probe_step(key[u], bucket[u], pending[u]);
-                bool any = pending[0] | pending[1] | pending[2] | pending[3];
-                while (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (pending[u]) probe_step(key[u], bucket[u], pending[u]);
-                    any = pending[0] | pending[1] | pending[2] | pending[3];
-                }
+                overflow_walk(key, bucket, pending);
             }
             const uint64_t t2 = globaltimer_ns();
             build_ns += t1 - t0;

@@ -138,7 +138,7 @@ def test_partition_layout_equals_oracle(phj, oracle, P, bits, hash_id, hash):
     R = _cases.tuples(_cases.splitmix64(30011, 9).astype(np.int64) % 5003)
     S = _cases.tuples(_cases.splitmix64(250007, 10).astype(np.int64) % 7001)
     want_count = oracle.count_by_sort(R, S)
-    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_FUSE_HIST2, True)):
+    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_NO_FUSE_HIST2, True)):
         with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P,
                         flags=flags) as e:
             e.upload(R, S)
@@ -292,7 +292,7 @@ def test_partition_layout_skewed_generator_data(phj, oracle):
     phj.fill_sequential(R, 1)
     phj.fill_zipf(S, 1.25, 1, nr, 4711, 16)
     want, wb = oracle.radix_partition(S, 4096, 0, SEED_P, workers=1)
-    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_FUSE_HIST2, True)):
+    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_NO_FUSE_HIST2, True)):
         with phj.Engine("radix-partitioning", partitions=4096, hash_seed=SEED_P, flags=flags) as e:
             e.upload(R, S)
             assert e.join()["matches"] == ns

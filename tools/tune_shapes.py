@@ -48,7 +48,7 @@ def child():
     phj.fill_sequential(R, 1)
     for alpha in [float(a) for a in os.environ.get("ALPHAS", "0.01").split(",")]:
         phj.fill_zipf(S, alpha, 1, nr, 12345, 64)
-        for flags in (0, phj.FLAG_FUSE_HIST2):
+        for flags in (phj.FLAG_NO_FUSE_HIST2, 0):
             with phj.Engine("radix-partitioning", partitions=4096, radix_bits=(6, 6), flags=flags) as e:
                 e.upload(R, S)
                 runs = []
@@ -58,7 +58,7 @@ def child():
                 assert res["matches"] == ns
                 runs.sort(key=lambda r: r[0])
                 med, kt = runs[len(runs) // 2]
-                print(f"  alpha={alpha} fuse2={int(bool(flags))}: median {med / 1e6:.3f} ms best {runs[0][0] / 1e6:.3f} | " +
+                print(f"  alpha={alpha} fuse2={int(not flags)}: median {med / 1e6:.3f} ms best {runs[0][0] / 1e6:.3f} | " +
                       " ".join(f"{n.replace('radix_', '')}={t / 1e3:.0f}" for n, t in kt if t > 15000), flush=True)
 
 
