@@ -161,14 +161,18 @@ int phj_upload(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_
 int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
                     size_t n_probe);
 
-/* Same, for device-resident relations that are ALREADY partitioned by the pass-1 digit of this
- * handle's plan (partition id = hash % partitions, pass-1 digit = its top radix_bits[0] bits):
- * parent d lies at [bounds[d], bounds[d + 1]), nparents + 1 host boundaries per relation. The join
- * then starts at pass 2 (or, for a one-pass plan, at build + probe). This is how the multi-GPU path
- * makes the NVLink shuffle double as pass 1 (the split digit is owner rank x pass-1 digit). */
+/* Same, for device-resident relations that are ALREADY partitioned by pass-1 digit: parent d lies at
+ * [bounds[d], bounds[d + 1]), nparents + 1 host boundaries per relation, and holds the tuples whose
+ * digit (hash >> radix_bits[1]) % parent_space equals first_parent + d. The join then starts at
+ * pass 2 (or, for a one-pass plan, at build + probe) and produces nparents x 2^radix_bits[1]
+ * partitions. parent_space = 0 means this handle's own 2^radix_bits[0]; a plain single-GPU use binds
+ * all of them (first_parent 0, nparents = 2^radix_bits[0]). The multi-GPU path makes the NVLink
+ * shuffle double as pass 1: the split digit space is ranks x local digits, and every rank owns a
+ * contiguous digit range chosen to balance the tuple counts. Needs an explicit power-of-two
+ * config.partitions; nparents <= 256. */
 int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
                                 size_t n_probe, const uint64_t* bounds_build, const uint64_t* bounds_probe,
-                                uint32_t nparents);
+                                uint32_t nparents, uint32_t first_parent, uint32_t parent_space);
 
 /* ---- the join ---------------------------------------------------------------------------------
  * Stands in for HashJoiner::Run(tableA, tableB, timer) (src/NoPartitioning/HashJoin.hpp:54-74,

@@ -102,7 +102,7 @@ SIGNATURES = {
     "phj_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "phj_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "phj_bind_device_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                              C.c_void_p, C.c_void_p, C.c_uint32]),
+                                              C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "phj_join": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
     "phj_join_materialize": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
     "phj_read_joined": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),

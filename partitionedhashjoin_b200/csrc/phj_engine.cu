@@ -134,6 +134,9 @@ struct phj_handle {
     size_t segs_n[2] = {0, 0};                    // relation sizes the pass-1 segment table covers
     // relations bound already partitioned by the pass-1 digit (phj_bind_device_partitioned)
     bool prepart = false;
+    uint32_t prepart_parents = 0;      // plan built for this many pre-partitioned parents (0 = the plan's own)
+    uint32_t prepart_first = 0;        // full-digit-space index of the first parent bound
+    uint64_t prepart_space = 0;        // size of that digit space (a power of two; 0 = this plan's 2^b1)
     uint64_t* d_pre_bounds = nullptr;  // [2][d1 + 1]
     size_t cap_pre_bounds = 0;
     phj::Segment* d_segs1 = nullptr;
@@ -434,6 +437,9 @@ int plan_radix(phj_handle* h) {
     h->b2 = b2;
     h->d2 = 1u << b2;
     h->d1 = (uint32_t)((P + h->d2 - 1) >> b2);  // pass-1 digits actually populated
+    // A pre-partitioned bind may own any contiguous range of the pass-1 digits (the multi-GPU path
+    // balances digit ranges over ranks by their tuple counts): pass 2 and the join only need the count.
+    if (h->prepart_parents) h->d1 = h->prepart_parents;
     h->nparts = (uint64_t)h->d1 * h->d2;
     return PHJ_OK;
 }
@@ -716,7 +722,13 @@ int run_gt(phj_handle* h, bool select, const ulonglong2* build, const ulonglong2
     gp.part_fn.modulus = h->P;
     gp.part_fn.shift = 0;
     gp.part_fn.mask = ~0u;
-    if (select && h->pow2 && h->bits_total > 0) {
+    if (select && h->prepart) {
+        const uint64_t space = h->prepart_space ? h->prepart_space : ((uint64_t)1 << h->b1);
+        gp.pre_space_mask = space - 1 ? space - 1 : 0;
+        gp.pre_first = h->prepart_first;
+        gp.pre_b2 = (uint32_t)h->b2;
+    }
+    if (select && h->pow2 && h->bits_total > 0 && !(h->prepart && h->prepart_parents != (1u << h->b1))) {
         // partition-local table regions (at most 1024 of them, never smaller than 1024 buckets)
         uint32_t rb = (uint32_t)std::min(h->bits_total, 10);
         const uint32_t bucket_bits = (uint32_t)ilog2_ceil(h->gt_buckets);
@@ -1000,6 +1012,15 @@ int join_radix(phj_handle* h, phj_result* out) {
         const uint64_t hs = hash_key_dyn(h->cfg.hash, kEmptyKey, hp);
         const uint64_t full = h->pow2 ? (hs & (h->P - 1)) : (hs % h->P);
         jp.sentinel_part = (uint32_t)full;
+        if (h->prepart) {
+            // local parents 0 .. d1 - 1 are digits [first, first + d1) of a pass-1 digit space that may
+            // be wider than this handle's own (the owner-rank bits of the multi-GPU split sit above it)
+            const uint64_t space = h->prepart_space ? h->prepart_space : ((uint64_t)1 << h->b1);
+            const uint64_t digit = (hs >> h->b2) & (space - 1);
+            jp.sentinel_part = digit >= h->prepart_first && digit < (uint64_t)h->prepart_first + h->d1
+                                   ? (uint32_t)((digit - h->prepart_first) * h->d2 + (hs & (h->d2 - 1)))
+                                   : 0xffffffffu;
+        }
     }
     jp.matches = h->d_matches;
     jp.cta_times = h->d_cta_times;
@@ -1229,7 +1250,8 @@ void phj_destroy(phj_handle* h) {
 }
 
 static int set_relations(phj_handle* h, const void* build, size_t n_build, const void* probe,
-                         size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool prepartitioned = false) {
+                         size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool prepartitioned = false,
+                         uint32_t parents = 0) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     if ((n_build && !build) || (n_probe && !probe))
         return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
@@ -1241,7 +1263,9 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
     // A pre-partitioned bind (shrink_ok) keeps a plan that has room; everything else needs the pass-1
     // segment table to cover exactly these sizes.
     const bool replan = !h->have_data || nn[0] > h->plan_n[0] || nn[1] > h->plan_n[1] ||
+                        parents != h->prepart_parents ||
                         (!prepartitioned && (nn[0] != h->segs_n[0] || nn[1] != h->segs_n[1]));
+    h->prepart_parents = parents;
     const bool resized = nn[0] != h->n[0] || nn[1] != h->n[1];
     for (int rel = 0; rel < 2; ++rel) {
         if (device_resident) {
@@ -1307,11 +1331,17 @@ int phj_bind_device(phj_handle* h, const void* d_build, size_t n_build, const vo
 
 int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_build, const void* d_probe,
                                 size_t n_probe, const uint64_t* bounds_build, const uint64_t* bounds_probe,
-                                uint32_t nparents) {
+                                uint32_t nparents, uint32_t first_parent, uint32_t parent_space) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (parent_space & (parent_space - 1)) return fail(PHJ_ERR_INVALID, "parent_space must be a power of two (or 0)");
     if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING)
         return fail(PHJ_ERR_STATE, "pre-partitioned relations need a radix-partitioning handle");
     if (!bounds_build || !bounds_probe) return fail(PHJ_ERR_INVALID, "partition boundaries are null");
+    const uint64_t P = h->cfg.partitions;
+    if (P == 0 || (P & (P - 1)))
+        return fail(PHJ_ERR_INVALID, "pre-partitioned relations need an explicit power-of-two `partitions`");
+    if (nparents == 0 || nparents > (uint32_t)kMaxSplitDigits)
+        return fail(PHJ_ERR_INVALID, "nparents must be in [1, %d]", kMaxSplitDigits);
     const uint64_t* hb[2] = {bounds_build, bounds_probe};
     const size_t nn[2] = {n_build, n_probe};
     for (int rel = 0; rel < 2; ++rel) {
@@ -1320,15 +1350,11 @@ int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_bui
         for (uint32_t d = 0; d < nparents; ++d)
             if (hb[rel][d] > hb[rel][d + 1]) return fail(PHJ_ERR_INVALID, "boundaries must not decrease");
     }
-    int rc = set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr, true);
+    int rc = set_relations(h, d_build, n_build, d_probe, n_probe, true, nullptr, true, nparents);
     if (rc != PHJ_OK) return rc;
     if ((rc = ensure_buffers(h, false, h->b2 > 0)) != PHJ_OK) return rc;
-    if (!h->pow2 || nparents != h->d1) {
-        h->have_data = false;
-        return fail(PHJ_ERR_INVALID, "relations are partitioned %u ways but this handle's pass 1 has %u digits "
-                                     "(partitions and radix_bits must be powers of two that match the split)",
-                    nparents, h->d1);
-    }
+    h->prepart_first = first_parent;
+    h->prepart_space = parent_space;
     if ((rc = dev_reserve(&h->d_pre_bounds, &h->cap_pre_bounds, 2 * ((size_t)h->d1 + 1))) != PHJ_OK) return rc;
     for (int rel = 0; rel < 2; ++rel)
         PHJ_CUDA(cudaMemcpyAsync(h->d_pre_bounds + rel * (h->d1 + 1), hb[rel], (h->d1 + 1) * 8,

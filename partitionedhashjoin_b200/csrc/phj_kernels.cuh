@@ -1222,6 +1222,10 @@ struct GtParams {
     const uint64_t* bounds_build;  // select == 1: partition sizes of R
     uint32_t max_keys;
     DigitFn part_fn;           // select == 1: tuple -> partition id (shift 0, mask = all)
+    // pre-partitioned relations: partition = (pass-1 digit - pre_first) * 2^pre_b2 + low bits, with
+    // the pass-1 digit = (hash >> pre_b2) & pre_space_mask (pre_space_mask == 0: not pre-partitioned)
+    uint64_t pre_space_mask;
+    uint32_t pre_first, pre_b2;
     uint32_t region_bits;      // select == 1: the table is cut into 2^region_bits regions, one per
                                // group of partitions, so a partition's keys share a small, L2-sized
                                // piece of the table and the partition-ordered probe stays in L2
@@ -1240,17 +1244,24 @@ __global__ void gt_clear(uint64_t* __restrict__ table, uint64_t nkeys) {
 }
 
 template <bool POW2>
+__device__ __forceinline__ uint64_t gt_part(const GtParams& p, uint64_t h) {
+    if (p.pre_space_mask)
+        return ((((h >> p.pre_b2) & p.pre_space_mask) - p.pre_first) << p.pre_b2) | (h & ((1ull << p.pre_b2) - 1));
+    return POW2 ? (h & p.part_fn.pmask) : (h % p.part_fn.modulus);
+}
+
+template <bool POW2>
 __device__ __forceinline__ uint64_t gt_bucket(const GtParams& p, uint64_t h) {
     const uint64_t local = h >> p.hash_shift;
     if (!p.select || p.region_bits == 0) return local & p.bucket_mask;
-    const uint64_t part = POW2 ? (h & p.part_fn.pmask) : (h % p.part_fn.modulus);
+    const uint64_t part = gt_part<POW2>(p, h);
     return (((part >> p.region_shift) & ((1ull << p.region_bits) - 1)) * (p.local_mask + 1)) | (local & p.local_mask);
 }
 
 template <bool POW2>
 __device__ __forceinline__ bool gt_selected(const GtParams& p, uint64_t h) {
     if (!p.select) return true;
-    const uint64_t part = POW2 ? (h & p.part_fn.pmask) : (h % p.part_fn.modulus);
+    const uint64_t part = gt_part<POW2>(p, h);  // every tuple of a bound relation lies in a bound parent
     return p.bounds_build[part + 1] - p.bounds_build[part] > p.max_keys;
 }
 

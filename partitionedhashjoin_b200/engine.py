@@ -223,15 +223,17 @@ class Engine:
         self._n = (n_build, n_probe)
 
     def bind_device_partitioned(self, d_build: int, n_build: int, d_probe: int, n_probe: int, bounds_build,
-                                bounds_probe, keepalive=None):
-        """Device-resident relations already partitioned by this plan's pass-1 digit; bounds_* are
-        the parents + 1 host boundaries of each relation."""
+                                bounds_probe, keepalive=None, first_parent: int = 0, parent_space: int = 0):
+        """Device-resident relations already partitioned by pass-1 digit; bounds_* are the parents + 1
+        host boundaries of each relation. The parents are digits [first_parent, first_parent + parents)
+        of a digit space of `parent_space` values (0 = this plan's own 2^b1)."""
         bb = np.ascontiguousarray(bounds_build, dtype=np.uint64)
         bp = np.ascontiguousarray(bounds_probe, dtype=np.uint64)
         if bb.shape != bp.shape or bb.ndim != 1 or bb.shape[0] < 2:
             raise ValueError("bounds_build and bounds_probe must both hold parents + 1 boundaries")
         check(lib.phj_bind_device_partitioned(self._h, C.c_void_p(d_build), n_build, C.c_void_p(d_probe), n_probe,
-                                              bb.ctypes.data, bp.ctypes.data, bb.shape[0] - 1))
+                                              bb.ctypes.data, bp.ctypes.data, bb.shape[0] - 1, first_parent,
+                                              parent_space))
         self._keep = [keepalive]
         self._n = (n_build, n_probe)
 
