@@ -234,13 +234,14 @@ class FusedGpuBackend(GpuBackend):
         self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
         return counts.astype(np.int64)
 
-    def scatter(self, offsets):
-        """offsets[rel][digit]: first row of this rank's piece of `digit` inside its owner's window."""
+    def scatter(self, offsets, owner_of):
+        """offsets[rel][digit]: first row of this rank's piece of `digit` inside the window of
+        owner_of[digit]."""
         from ._lib import PhjResult
         C = self._C
         arrs = []
         for which in (0, 1):
-            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[which][d // self.d1]) for d in range(self.ndig)])
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[which][int(owner_of[d])]) for d in range(self.ndig)])
             offs = np.ascontiguousarray(offsets[which], dtype=np.uint64)
             arrs += [ptrs, offs]
         res = PhjResult()
@@ -249,12 +250,15 @@ class FusedGpuBackend(GpuBackend):
         self.launches += res.kernel_launches
         return int(res.total_ns)
 
-    def local_join_window(self, rows, bounds):
-        """rows[rel] tuples have landed in this rank's windows; bounds[rel] are the d1 + 1 boundaries
-        of the local pass-1 digits inside them."""
+    def local_join_window(self, rows, bounds, first_digit=0):
+        """rows[rel] tuples have landed in this rank's windows; bounds[rel] are the boundaries of the
+        split digits first_digit, first_digit + 1, ... this rank owns, in window order."""
         ptr = [self.win[w] if rows[w] else 0 for w in (0, 1)]
+        if self.b1 and len(bounds[0]) < 2:
+            return 0, {"kernel_launches": 0, "hbm_bytes_alg": 0, "total_ns": 1, "d2h_bytes": 0}  # owns no digit
         if self.b1:
-            self.local_engine.bind_device_partitioned(ptr[0], rows[0], ptr[1], rows[1], bounds[0], bounds[1])
+            self.local_engine.bind_device_partitioned(ptr[0], rows[0], ptr[1], rows[1], bounds[0], bounds[1],
+                                                      first_parent=first_digit, parent_space=self.ndig)
         else:
             self.local_engine.bind_device(ptr[0], rows[0], ptr[1], rows[1])
         res = self.local_engine.join()
@@ -278,10 +282,10 @@ class FusedShardedRadixJoin:
 
     GROW = 1.125
 
-    def __init__(self, dist, rank, world, backend):
+    def __init__(self, dist, rank, world, backend, balance=True):
         if world & (world - 1):
             raise ValueError("the number of ranks must be a power of two")
-        self.dist, self.rank, self.world, self.backend = dist, rank, world, backend
+        self.dist, self.rank, self.world, self.backend, self.balance = dist, rank, world, backend, balance
         self.caps = np.zeros((3, world), dtype=np.int64)  # rows of every rank's windows (same on all ranks)
         self.last = {}
 
@@ -328,17 +332,44 @@ class FusedShardedRadixJoin:
         return True
 
     @staticmethod
-    def layout(M, world, rank):
-        """From M[source][rel][digit] (digit = owner : local digit): rows arriving at every owner,
-        this rank's write offsets per digit, and the local-digit boundaries of this rank's windows."""
+    def ownership(M, world, balance=True):
+        """first[o] = first split digit owned by rank o (first[world] = digits). Equal digit ranges, or
+        -- balance -- contiguous ranges cut where the cumulative tuple count crosses o / world of the
+        total, so that a rank whose range holds heavy-hitter digits owns fewer of them (SURVEY 8e
+        "skew caveat"). M[source][rel][digit]; every rank computes the same cut from the same M."""
         ndig = M.shape[2]
-        d1 = ndig // world
-        tot = M.sum(axis=0).reshape(2, world, d1)              # [rel][owner][local digit]
-        need = tot.sum(axis=2)                                 # [rel][owner]
-        base = np.cumsum(tot, axis=2) - tot                    # start of a digit inside its owner's window
-        offsets = base.reshape(2, ndig) + M[:rank].sum(axis=0)  # lower ranks' pieces come first
-        bounds = np.concatenate([base[:, rank, :], need[:, rank:rank + 1]], axis=1)  # [rel][d1 + 1]
-        return need, offsets, bounds
+        if not balance or world == 1 or ndig == world:
+            return np.arange(world + 1, dtype=np.int64) * (ndig // world)
+        cum = np.cumsum(M.sum(axis=(0, 1)))
+        first = [0]
+        for o in range(1, world):
+            target = cum[-1] * o / world
+            i = int(np.searchsorted(cum, target, side="left"))          # cum[i] >= target
+            below = cum[i - 1] if i > 0 else 0
+            b = i + 1 if i < ndig and abs(cum[i] - target) < abs(target - below) else i
+            first.append(min(max(b, first[-1]), ndig))
+        first.append(ndig)
+        return np.asarray(first, dtype=np.int64)
+
+    @staticmethod
+    def layout(M, world, rank, first=None):
+        """From M[source][rel][digit] and the ownership cut: rows arriving at every owner, this rank's
+        write offsets per digit, the boundaries of this rank's own digits inside its windows, and the
+        owner of every digit."""
+        ndig = M.shape[2]
+        if first is None:
+            first = np.arange(world + 1, dtype=np.int64) * (ndig // world)
+        owner_of = np.searchsorted(first[1:], np.arange(ndig), side="right")
+        tot = M.sum(axis=0)                                     # [rel][digit]
+        excl = np.cumsum(tot, axis=1) - tot                     # global exclusive prefix over digits
+        start = np.concatenate([excl, tot.sum(axis=1, keepdims=True)], axis=1)[:, first]  # [rel][world + 1]
+        need = np.diff(start, axis=1)                           # [rel][owner]
+        base = excl - start[:, owner_of]                        # start of a digit inside its owner's window
+        offsets = base + M[:rank].sum(axis=0)                   # lower ranks' pieces come first
+        lo, hi = int(first[rank]), int(first[rank + 1])
+        bounds = np.concatenate([base[:, lo:hi], need[:, rank:rank + 1]], axis=1) if hi > lo else \
+            np.zeros((2, 1), dtype=np.int64)
+        return need, offsets, bounds, owner_of
 
     def join(self) -> dict:
         be, world, rank = self.backend, self.world, self.rank
@@ -346,24 +377,25 @@ class FusedShardedRadixJoin:
         counts = be.count()                                   # [rel][digit]
         t1 = time.perf_counter()
         M = self._gather_counts(counts)                       # [source][rel][digit]
-        need, offsets, bounds = self.layout(M, world, rank)
+        first = self.ownership(M, world, self.balance)
+        need, offsets, bounds, owner_of = self.layout(M, world, rank, first)
         regrown = self._ensure_windows({0: need[0], 1: need[1]})
         t2 = time.perf_counter()
-        scatter_ns = be.scatter(offsets)
+        scatter_ns = be.scatter(offsets, owner_of)
         if world > 1:
             self.dist.barrier()                               # every rank's stores are complete
         t3 = time.perf_counter()
         rows = [int(need[0][rank]), int(need[1][rank])]
-        local_matches, res = be.local_join_window(rows, bounds)
+        local_matches, res = be.local_join_window(rows, bounds, int(first[rank]))
         t4 = time.perf_counter()
         total = be.count_tensor(local_matches)
         if world > 1:
             self.dist.all_reduce(total)
         matches = int(total.item())
         t5 = time.perf_counter()
-        d1 = counts.shape[1] // world
-        mine = counts[:, rank * d1:(rank + 1) * d1].sum()
+        mine = counts[:, int(first[rank]):int(first[rank + 1])].sum()
         self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
+                     "first_digit": first.tolist(),
                      "exchange_s": t3 - t1, "sizes_s": t2 - t1, "scatter_s": t3 - t2, "local_s": t4 - t3,
                      "reduce_s": t5 - t4, "total_s": t5 - t0, "recv_rows": rows, "regrown": regrown,
                      "send_bytes_remote": int(16 * (counts.sum() - mine)) if world > 1 else 0,
@@ -434,12 +466,12 @@ class PipelinedGpuBackend(FusedGpuBackend):
         self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
         return counts.astype(np.int64)
 
-    def scatter(self, c, offsets):
+    def scatter(self, c, offsets, owner_of):
         from ._lib import PhjResult
         C = self._C
         arrs = []
         for which, w in ((0, 0), (1, 1 + c % 2)):
-            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][d // self.d1]) for d in range(self.ndig)])
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][int(owner_of[d])]) for d in range(self.ndig)])
             arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
         res = PhjResult()
         t0 = time.perf_counter()
@@ -450,12 +482,14 @@ class PipelinedGpuBackend(FusedGpuBackend):
             self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
         return int(res.total_ns)
 
-    def local_join(self, c, rows, bounds):
+    def local_join(self, c, rows, bounds, first_digit=0):
         w = 1 + c % 2
         eng = self.locals[c % 2]
         t0 = time.perf_counter()
+        if len(bounds[0]) < 2:
+            return 0, {"kernel_launches": 0, "hbm_bytes_alg": 0, "total_ns": 1, "d2h_bytes": 0}  # owns no digit
         eng.bind_device_partitioned(self.win[0] if rows[0] else 0, rows[0], self.win[w] if rows[1] else 0, rows[1],
-                                    bounds[0], bounds[1])
+                                    bounds[0], bounds[1], first_parent=first_digit, parent_space=self.ndig)
         t1 = time.perf_counter()
         res = eng.join()
         self.launches += res["kernel_launches"]
@@ -484,7 +518,8 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
         t1 = time.perf_counter()
         M = self._gather_counts(counts)                        # [source][chunk * 2 + rel][digit]
         M = M.reshape(world, K, 2, -1)
-        plans = [self.layout(M[:, c], world, rank) for c in range(K)]   # (need, offsets, bounds) per chunk
+        first = self.ownership(M.sum(axis=1), world, self.balance)      # one cut for all chunks
+        plans = [self.layout(M[:, c], world, rank, first) for c in range(K)]  # (need, offsets, bounds, owner) per chunk
         want = {0: plans[0][0][0]}
         for slot in (0, 1):
             needs = [plans[c][0][1] for c in range(slot, K, 2)]
@@ -510,8 +545,8 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
                         if abort.is_set():
                             return
                     ts = time.perf_counter()
-                    need, offsets, bounds = plans[c]
-                    stats["scatter_device_ns"] += be.scatter(c, offsets)
+                    need, offsets, bounds, owner_of = plans[c]
+                    stats["scatter_device_ns"] += be.scatter(c, offsets, owner_of)
                     if world > 1:
                         self.dist.barrier()                    # every rank's stores of chunk c have landed
                     stats["scatter_s"] += time.perf_counter() - ts
@@ -530,7 +565,7 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
                     raise item
                 c, rows, bounds = item
                 tj = time.perf_counter()
-                m, res = be.local_join(c, rows, bounds)
+                m, res = be.local_join(c, rows, bounds, int(first[rank]))
                 local_matches += m
                 free[c % 2].release()
                 local_s += time.perf_counter() - tj
@@ -547,8 +582,7 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
             self.dist.all_reduce(total)
         matches = int(total.item())
         t5 = time.perf_counter()
-        d1 = counts.shape[2] // world
-        mine = counts[:, :, rank * d1:(rank + 1) * d1].sum()
+        mine = counts[:, :, int(first[rank]):int(first[rank + 1])].sum()
         self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
                      "exchange_s": (t2 - t1) + stats["scatter_s"], "sizes_s": t2 - t1,
                      "scatter_s": stats["scatter_s"], "local_s": local_s, "wait_s": wait_s, "reduce_s": t5 - t4,

@@ -63,10 +63,11 @@ def main():
             shift = be.b2 if be.b1 else multigpu.SHARD_SHIFT
             digit = ((oracle.hash_batch(0, 0x9E3779B97F4A7C15, rel["id"]) >> np.uint64(shift))
                      & np.uint64(be.ndig - 1)).astype(np.int64)
-            mine = digit // be.d1 == rank
+            lo, hi = res["first_digit"][rank], res["first_digit"][rank + 1]  # the digits this rank owns
+            mine = (digit >= lo) & (digit < hi)
             # digit-major, then global input order (= source-rank order, then input order): a stable sort
             expect = rel[mine][np.argsort(digit[mine], kind="stable")]
-            assert np.diff(res["bounds"][which]).tolist() == np.bincount(digit[mine] % be.d1, minlength=be.d1).tolist()
+            assert np.diff(res["bounds"][which]).tolist() == np.bincount(digit[mine] - lo, minlength=hi - lo).tolist()
             assert got.shape[0] == expect.shape[0], (got.shape, expect.shape)
             assert (got[:, 0] == expect["id"]).all() and (got[:, 1] == expect["payload"]).all()
         # bigger shards: windows regrow collectively

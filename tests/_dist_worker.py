@@ -104,19 +104,20 @@ class OracleFusedBackend(OracleBackend):
             counts.append(np.bincount(dig, minlength=self.ndig))
         return np.stack(counts).astype(np.int64)
 
-    def scatter(self, offsets):
+    def scatter(self, offsets, owner_of):
+        self.owner_of = np.asarray(owner_of)
         for which in (0, 1):
             for d in range(self.ndig):
                 piece = self.pieces[which][d]
                 if piece.shape[0]:
-                    shm = self.peer[which][d // self.d1]
+                    shm = self.peer[which][int(owner_of[d])]
                     win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
                     o = int(offsets[which][d])
                     win[o:o + piece.shape[0]] = piece
                     del win
         return 0
 
-    def local_join_window(self, rows, bounds, windows=(0, 1)):
+    def local_join_window(self, rows, bounds, first_digit=0, windows=(0, 1)):
         got = []
         for which in (0, 1):
             n = rows[which]
@@ -124,12 +125,11 @@ class OracleFusedBackend(OracleBackend):
             win = np.ndarray((n,), dtype=_cases.TUPLE, buffer=shm.buf) if n else np.empty(0, _cases.TUPLE)
             got.append(win.copy())
             del win
-            # the window is partitioned by the local pass-1 digit exactly as `bounds` says
+            # the window is partitioned by split digit exactly as `bounds` says, starting at first_digit
             b = np.asarray(bounds[which])
-            assert b.shape[0] == self.d1 + 1 and b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+            assert b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
             if n:
-                local = self.digit(got[which]["id"]) & (self.d1 - 1)
-                assert (local == np.repeat(np.arange(self.d1), np.diff(b))).all()
+                assert (self.digit(got[which]["id"]) == first_digit + np.repeat(np.arange(b.shape[0] - 1), np.diff(b))).all()
         self.received = tuple(got)
         return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
 
@@ -162,20 +162,21 @@ class OraclePipelinedBackend(OracleFusedBackend):
             counts.append(np.stack(cc))
         return np.stack(counts).astype(np.int64)
 
-    def scatter(self, c, offsets):
+    def scatter(self, c, offsets, owner_of):
+        self.owner_of = np.asarray(owner_of)
         for which, w in ((0, 0), (1, 1 + c % 2)):
             for d in range(self.ndig):
                 piece = self.chunk_pieces[c][which][d]
                 if piece.shape[0]:
-                    shm = self.peer[w][d // self.d1]
+                    shm = self.peer[w][int(owner_of[d])]
                     win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
                     o = int(offsets[which][d])
                     win[o:o + piece.shape[0]] = piece
                     del win
         return 0
 
-    def local_join(self, c, rows, bounds):
-        m, res = self.local_join_window(rows, bounds, windows=(0, 1 + c % 2))
+    def local_join(self, c, rows, bounds, first_digit=0):
+        m, res = self.local_join_window(rows, bounds, first_digit, windows=(0, 1 + c % 2))
         self.joined.append(self.received)
         return m, res
 
@@ -233,7 +234,7 @@ def main():
     for rel in (got_R, got_S):
         if rel.shape[0]:
             if fused:
-                owner = backend.digit(rel["id"]) // backend.d1
+                owner = backend.owner_of[backend.digit(rel["id"])]
             else:
                 owner = (oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT)) & np.uint64(world - 1)
             assert (owner == rank).all()

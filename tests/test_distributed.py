@@ -49,6 +49,42 @@ def test_fused_shuffle_over_gloo(world, case, mode):
     assert line["world"] == world and line["fused"] and line["matches"] == line["want"] and line["want"] > 0
 
 
+@pytest.mark.parametrize("world,ndig", [(2, 8), (4, 16), (2, 128), (8, 256), (1, 64)])
+def test_window_layout_against_brute_force(world, ndig):
+    """FusedShardedRadixJoin.ownership / layout: window sizes, write offsets (digit-major, then source
+    rank) and local boundaries for equal and for count-balanced digit ownership, against a direct
+    enumeration of where every piece lands."""
+    import numpy as np
+
+    from partitionedhashjoin_b200.multigpu import FusedShardedRadixJoin as F
+    rng = np.random.default_rng(world * 1000 + ndig)
+    M = rng.integers(0, 50, size=(world, 2, ndig))
+    M[:, 1, 3] += 2000  # a heavy-hitter digit on the probe side
+    for balance in (False, True):
+        first = F.ownership(M, world, balance)
+        assert first[0] == 0 and first[-1] == ndig and (np.diff(first) >= 0).all()
+        if not balance:
+            assert (np.diff(first) == ndig // world).all()
+        for rank in range(world):
+            need, offsets, bounds, owner = F.layout(M, world, rank, first)
+            assert (owner == np.repeat(np.arange(world), np.diff(first))).all()
+            for rel in (0, 1):
+                for o in range(world):
+                    pos = 0
+                    for d in range(first[o], first[o + 1]):
+                        if o == rank:
+                            assert bounds[rel][d - first[o]] == pos
+                        for src in range(world):
+                            if src == rank:
+                                assert offsets[rel][d] == pos
+                            pos += M[src][rel][d]
+                    assert need[rel][o] == pos
+                assert bounds[rel][-1] == need[rel][rank]
+        if balance and world > 1:  # the cut is no worse than the equal split
+            load = lambda f: max(M[:, :, f[o]:f[o + 1]].sum() for o in range(world))
+            assert load(first) <= load(F.ownership(M, world, False))
+
+
 def test_world_must_be_power_of_two():
     from partitionedhashjoin_b200 import multigpu
     with pytest.raises(ValueError):
