@@ -1480,23 +1480,6 @@ __global__ void __launch_bounds__(256) ct_probe(CtParams p) {
     if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
 }
 
-// Partition boundaries straight from the scanned cursors (single-pass plans that need them before
-// the scatter runs): bounds[rel][d] = cursors[cnt_base[rel] + d * nseg[rel]] - bias[rel].
-struct BoundsParams {
-    const uint64_t* cursors;
-    uint64_t* bounds[2];
-    uint32_t cnt_base[2], nseg[2];
-    uint64_t bias[2];
-    uint32_t ndigits;
-};
-__global__ void bounds_from_cursors(BoundsParams p) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * p.ndigits) return;
-    const int rel = i / p.ndigits;
-    const uint32_t d = i % p.ndigits;
-    if (p.nseg[rel]) p.bounds[rel][d] = p.cursors[p.cnt_base[rel] + (uint64_t)d * p.nseg[rel]] - p.bias[rel];
-}
-
 // Multi-GPU split in K row chunks: where chunk c's tuples of digit d start in the (virtual) split
 // output, starts[(rel * ndigits + d) * (K + 1) + c]; entry K is the end of the digit. Chunk c of a
 // relation is the segment range [first_seg[rel][c], first_seg[rel][c + 1]).
