@@ -158,6 +158,8 @@ def split_plan(world, partitions_local, pass1_in_shuffle=True):
     if not pass1_in_shuffle or partitions_local < 4 or (1 << bits) != partitions_local:
         return 0, 0, world
     b1 = min((bits + 1) // 2, 8 - (world.bit_length() - 1))
+    if os.environ.get("PHJ_SPLIT_B1"):  # experiments: fewer split digits = longer NVLink runs, wider pass 2
+        b1 = min(b1, int(os.environ["PHJ_SPLIT_B1"]))
     b2 = bits - b1
     if b1 < 1 or b2 > 8:
         return 0, 0, world

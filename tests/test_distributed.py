@@ -85,6 +85,21 @@ def test_window_layout_against_brute_force(world, ndig):
             assert load(first) <= load(F.ownership(M, world, False))
 
 
+def test_split_plan():
+    """The split digit (owner rank : local pass-1 digit) never exceeds 256 values and the local plan
+    keeps passes of <= 8 bits; otherwise the split falls back to owner-only."""
+    from partitionedhashjoin_b200.multigpu import split_plan
+    assert split_plan(2, 4096) == (6, 6, 128)
+    assert split_plan(4, 4096) == (6, 6, 256)
+    assert split_plan(8, 4096) == (5, 7, 256)
+    assert split_plan(8, 8192) == (5, 8, 256)
+    assert split_plan(1, 4096) == (6, 6, 64)
+    assert split_plan(2, 256) == (4, 4, 32)
+    assert split_plan(8, 16384) == (0, 0, 8)       # would need a 9-bit pass 2
+    assert split_plan(2, 100) == (0, 0, 2)         # not a power of two
+    assert split_plan(2, 4096, pass1_in_shuffle=False) == (0, 0, 2)
+
+
 def test_world_must_be_power_of_two():
     from partitionedhashjoin_b200 import multigpu
     with pytest.raises(ValueError):
