@@ -318,6 +318,8 @@ def main():
     ap.add_argument("--workload", default="default", choices=["default", "scaled"],
                     help="N > 1 only: scaled = BASELINE.json configs[4], 160M x 3.2B in total sharded over the ranks "
                          "(strong scaling), generated on the device; use --partitions 8192")
+    ap.add_argument("--sm-shuffle", action="store_true",
+                    help="N > 1, pipelined shuffle: NVLink stores from the split scatter instead of copy-engine pushes")
     ap.add_argument("--chunks", type=int, default=4, help="N > 1, pipelined shuffle: probe chunks")
     ap.add_argument("--split-ctas", type=int, default=96,
                     help="N > 1, pipelined shuffle: CTAs of the NVLink-bound split scatter (0 = all)")

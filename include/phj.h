@@ -233,6 +233,15 @@ int phj_shard_count(phj_handle* h, uint64_t* counts);
 int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
                       void* const* dst_probe, const uint64_t* off_probe, phj_result* out);
 
+/* The same shuffle on the copy engines: after a LOCAL phj_shard_scatter of `chunk` (both dst null:
+ * the pieces sit in the handle's split buffer), phj_shard_push enqueues one device-to-device copy
+ * per (relation, digit) piece to dst[rel][d] + off[rel][d] on the handle's copy stream and returns;
+ * phj_shard_push_wait blocks until they have landed. The SMs stay free meanwhile -- for the split of
+ * the next chunk and the local join of the previous one (multigpu.PipelinedShardedRadixJoin). */
+int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
+                   void* const* dst_probe, const uint64_t* off_probe, uint64_t* bytes);
+int phj_shard_push_wait(phj_handle* h);
+
 /* Device memory that other processes on the node can map (CUDA IPC): the receive buffers of the
  * fused shuffle. `ipc_handle` is 64 opaque bytes to hand to the peers (any transport). */
 int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* ipc_handle);

@@ -117,6 +117,9 @@ SIGNATURES = {
     "phj_shard_count": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phj_shard_scatter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(PhjResult)]),
+    "phj_shard_push": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_uint64)]),
+    "phj_shard_push_wait": (C.c_int, [C.c_void_p]),
     "phj_shared_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),

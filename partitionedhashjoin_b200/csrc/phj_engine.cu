@@ -98,6 +98,7 @@ struct phj_handle {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // phj_shard_push: device-to-device copies on the copy engines
 
     // relations: 0 = build (R), 1 = probe (S)
     ulonglong2* d_in[2] = {nullptr, nullptr};
@@ -1245,6 +1246,7 @@ void phj_destroy(phj_handle* h) {
         if (k.begin) cudaEventDestroy(k.begin);
         if (k.end) cudaEventDestroy(k.end);
     }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1580,8 +1582,6 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
     if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
     if (!h->shard_counted) return fail(PHJ_ERR_STATE, "phj_shard_scatter needs a preceding phj_shard_count");
     if (chunk >= h->nchunks) return fail(PHJ_ERR_INVALID, "chunk %u out of range [0, %u)", chunk, h->nchunks);
-    if ((!dst_build || !dst_probe) && h->nchunks > 1)
-        return fail(PHJ_ERR_INVALID, "a chunked split needs destinations for both relations");
     PHJ_CUDA(cudaSetDevice(h->device));
     memset(out, 0, sizeof(*out));
     const uint32_t w = h->d1, K = h->nchunks;
@@ -1638,6 +1638,42 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
     h->launches = 0;
     if (chunk + 1 == K) h->shard_counted = false;
     h->joined_radix = K == 1 && (!dst_build || !dst_probe);
+    return PHJ_OK;
+}
+
+int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
+                   void* const* dst_probe, const uint64_t* off_probe, uint64_t* bytes_out) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
+    if (chunk >= h->nchunks) return fail(PHJ_ERR_INVALID, "chunk %u out of range [0, %u)", chunk, h->nchunks);
+    if (!h->h_shard_starts || !h->d_buf_a[0] || !h->d_buf_a[1])
+        return fail(PHJ_ERR_STATE, "phj_shard_push needs a local phj_shard_scatter of this chunk first");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    if (!h->copy_stream) PHJ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    const uint32_t w = h->d1, K = h->nchunks;
+    void* const* dst[2] = {dst_build, dst_probe};
+    const uint64_t* off[2] = {off_build, off_probe};
+    uint64_t bytes = 0;
+    for (int rel = 0; rel < 2; ++rel) {
+        if (!dst[rel]) continue;
+        for (uint32_t d = 0; d < w; ++d) {
+            // piece (digit d, this chunk) of the local split output: [starts[d][chunk], starts[d][chunk + 1])
+            const uint64_t* st = h->h_shard_starts + ((size_t)rel * w + d) * (K + 1);
+            const uint64_t len = st[chunk + 1] - st[chunk];
+            if (!len) continue;
+            PHJ_CUDA(cudaMemcpyAsync(reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0),
+                                     h->d_buf_a[rel] + st[chunk], len * 16, cudaMemcpyDeviceToDevice, h->copy_stream));
+            bytes += len * 16;
+        }
+    }
+    if (bytes_out) *bytes_out = bytes;
+    return PHJ_OK;
+}
+
+int phj_shard_push_wait(phj_handle* h) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    if (h->copy_stream) PHJ_CUDA(cudaStreamSynchronize(h->copy_stream));
     return PHJ_OK;
 }
 

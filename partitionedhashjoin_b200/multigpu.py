@@ -425,12 +425,16 @@ class PipelinedGpuBackend(FusedGpuBackend):
     chunks, double-buffered."""
 
     def __init__(self, world, device, partitions_local=4096, hash="xxh3", hash_seed=0x9E3779B97F4A7C15,
-                 chunks=4, split_ctas=0):
+                 chunks=4, split_ctas=0, copy_engines=True):
         import ctypes
         import torch
 
         from . import _lib, engine
         self.torch, self.world, self.device, self.chunks = torch, world, device, chunks
+        # copy_engines: every chunk is split LOCALLY at HBM speed and its pieces travel as device-to-
+        # device copies on the copy engines, so the SMs never wait on NVLink; otherwise the split
+        # scatter stores into the peers' windows itself (and shares the SMs with the local join)
+        self.copy_engines = copy_engines
         self.b1, self.b2, self.ndig = split_plan(world, partitions_local, True)
         if not self.b1:
             raise ValueError("the pipelined shuffle needs a power-of-two local fan-out >= 4 (two-level digit)")
@@ -439,8 +443,9 @@ class PipelinedGpuBackend(FusedGpuBackend):
             "radix-partitioning", partitions=partitions_local, radix_bits=(self.b1, self.b2), hash=hash,
             hash_seed=hash_seed, device=device, reserve=reserve)
         self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
-                                          device=device, shard_shift=self.b2, flags=_lib.FLAG_SPLIT_REMOTE_ONLY,
-                                          split_ctas=split_ctas, split_chunks=chunks)
+                                          device=device, shard_shift=self.b2,
+                                          flags=0 if copy_engines else _lib.FLAG_SPLIT_REMOTE_ONLY,
+                                          split_ctas=0 if copy_engines else split_ctas, split_chunks=chunks)
         self.locals = [None, None]
         self.local_reserve = (0, 0)
         self.trace = None   # set to [] to record per-call host times and per-kernel device times
@@ -483,6 +488,32 @@ class PipelinedGpuBackend(FusedGpuBackend):
         if self.trace is not None:
             self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
         return int(res.total_ns)
+
+    def scatter_local(self, c):
+        """Split chunk c into the handle's own buffer (no destinations)."""
+        from ._lib import PhjResult
+        res = PhjResult()
+        t0 = time.perf_counter()
+        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, None, None, None, None, self._C.byref(res)))
+        self.launches += res.kernel_launches
+        if self.trace is not None:
+            self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
+        return int(res.total_ns)
+
+    def push(self, c, offsets, owner_of):
+        """Enqueue the copies of chunk c's pieces into their owners' windows (copy engines)."""
+        C = self._C
+        arrs = []
+        for which, w in ((0, 0), (1, 1 + c % 2)):
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][int(owner_of[d])]) for d in range(self.ndig)])
+            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
+        nbytes = C.c_uint64()
+        self._check(self._lib.phj_shard_push(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
+                                             arrs[3].ctypes.data, C.byref(nbytes)))
+        return int(nbytes.value)
+
+    def push_wait(self):
+        self._check(self._lib.phj_shard_push_wait(self.split_engine._h))
 
     def local_join(self, c, rows, bounds, first_digit=0):
         w = 1 + c % 2
@@ -538,19 +569,36 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
         abort = threading.Event()
         stats = {"scatter_s": 0.0, "scatter_device_ns": 0}
 
+        def acquire(slot):
+            while not free[slot].acquire(timeout=0.05):
+                if abort.is_set():
+                    raise RuntimeError("aborted")
+
         def producer():
+            # Chunk c goes into window slot c % 2 of EVERY rank, so that slot must be free everywhere
+            # before anyone writes: each rank waits for its own consumer to release the slot of chunk
+            # c + 1 before entering the barrier that ends chunk c.
             try:
                 if hasattr(be, "thread_init"):
                     be.thread_init()
+                ce = getattr(be, "copy_engines", False)
+                acquire(0)
+                if ce:
+                    stats["scatter_device_ns"] += be.scatter_local(0)
                 for c in range(K):
-                    while not free[c % 2].acquire(timeout=0.05):
-                        if abort.is_set():
-                            return
                     ts = time.perf_counter()
                     need, offsets, bounds, owner_of = plans[c]
-                    stats["scatter_device_ns"] += be.scatter(c, offsets, owner_of)
+                    if ce:
+                        be.push(c, offsets, owner_of)              # copy engines, asynchronous
+                        if c + 1 < K:
+                            stats["scatter_device_ns"] += be.scatter_local(c + 1)   # SMs, meanwhile
+                        be.push_wait()
+                    else:
+                        stats["scatter_device_ns"] += be.scatter(c, offsets, owner_of)
+                    if c + 1 < K:
+                        acquire((c + 1) % 2)
                     if world > 1:
-                        self.dist.barrier()                    # every rank's stores of chunk c have landed
+                        self.dist.barrier()    # chunk c has landed everywhere; slot (c + 1) % 2 is free everywhere
                     stats["scatter_s"] += time.perf_counter() - ts
                     ready.put((c, [build_rows, int(need[1][rank])], [build_bounds, bounds[1]]))
             except BaseException as e:  # hand the failure to the consumer
@@ -628,7 +676,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     fused = mode in ("fused", "pass1", "pipelined")
     if mode == "pipelined":  # chunked: the NVLink shuffle of chunk c + 1 overlaps the local join of chunk c
         backend = PipelinedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
-                                      chunks=args.chunks, split_ctas=args.split_ctas)
+                                      chunks=args.chunks, split_ctas=args.split_ctas,
+                                      copy_engines=not getattr(args, "sm_shuffle", False))
         job = PipelinedShardedRadixJoin(dist, rank, world, backend)
     elif fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
         backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,

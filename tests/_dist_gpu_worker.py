@@ -37,9 +37,9 @@ def main():
         return rel[lo:hi]
 
     fused = mode in ("pass1", "fused")
-    if mode == "pipelined":
+    if mode.startswith("pipelined"):
         job = multigpu.PipelinedShardedRadixJoin(dist, rank, world, multigpu.PipelinedGpuBackend(
-            world, local, partitions_local=256, chunks=3, split_ctas=64))
+            world, local, partitions_local=256, chunks=3, split_ctas=64, copy_engines=(mode == "pipelined")))
     elif fused:
         job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(
             world, local, partitions_local=256, pass1_in_shuffle=(mode == "pass1")))
@@ -74,7 +74,7 @@ def main():
         job.upload(shard(R), np.concatenate([shard(S)] * 2))
         res = job.join()
         assert res["matches"] == 2 * want and res["regrown"]
-    if mode == "pipelined":
+    if mode.startswith("pipelined"):
         assert not res["regrown"] and res["chunks"] == 3
         job.upload(shard(R), np.concatenate([shard(S)] * 2))
         res = job.join()

@@ -138,10 +138,25 @@ class OraclePipelinedBackend(OracleFusedBackend):
     """CPU stand-in for multigpu.PipelinedGpuBackend: the probe shard travels in row chunks through
     two alternating windows, the build shard with chunk 0 into window 0."""
 
-    def __init__(self, world, oracle, partitions_local, chunks):
+    def __init__(self, world, oracle, partitions_local, chunks, copy_engines=False):
         super().__init__(world, oracle, partitions_local, True)
         self.chunks = chunks
+        self.copy_engines = copy_engines
         self.joined = []
+        self.split_done = set()
+
+    # copy-engine flavour: a local split per chunk, then the pieces are pushed
+    def scatter_local(self, c):
+        self.split_done.add(c)
+        return 0
+
+    def push(self, c, offsets, owner_of):
+        assert c in self.split_done  # a chunk is pushed only after its local split
+        self.scatter(c, offsets, owner_of)
+        return 0
+
+    def push_wait(self):
+        pass
 
     def upload(self, R, S):
         super().upload(R, S)
@@ -183,9 +198,9 @@ class OraclePipelinedBackend(OracleFusedBackend):
 
 def main():
     case = sys.argv[1]
-    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1", "pipelined")
-    pass1 = fused and sys.argv[2] in ("pass1", "pipelined")
-    pipelined = fused and sys.argv[2] == "pipelined"
+    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1", "pipelined", "pipelined-ce")
+    pass1 = fused and sys.argv[2] in ("pass1", "pipelined", "pipelined-ce")
+    pipelined = fused and sys.argv[2] in ("pipelined", "pipelined-ce")
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     oracle = _oracle.Oracle()
@@ -213,7 +228,7 @@ def main():
         return rel[lo:hi]
 
     if pipelined:
-        backend = OraclePipelinedBackend(world, oracle, 256, chunks=3)
+        backend = OraclePipelinedBackend(world, oracle, 256, chunks=3, copy_engines=sys.argv[2] == "pipelined-ce")
         job = multigpu.PipelinedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
     elif fused:
         backend = OracleFusedBackend(world, oracle, 256, pass1)

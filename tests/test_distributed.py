@@ -38,7 +38,8 @@ def test_sharded_join_over_gloo(world, case):
                                              (4, "random", "pass1"), (1, "random", "pass1"), (2, "random", "fused"),
                                              (2, "random", "pipelined"), (2, "skewed", "pipelined"),
                                              (2, "tiny", "pipelined"), (4, "random", "pipelined"),
-                                             (1, "random", "pipelined")])
+                                             (1, "random", "pipelined"), (2, "skewed", "pipelined-ce"),
+                                             (4, "random", "pipelined-ce")])
 def test_fused_shuffle_over_gloo(world, case, mode):
     """FusedShardedRadixJoin: sizes all-gather -> window offsets -> every rank writes its pieces into
     the owners' windows (shared memory stands in for the CUDA-IPC-mapped NVLink windows). pass1:
@@ -166,7 +167,7 @@ def test_fused_shuffle_single_gpu(phj, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"),
+@pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pipelined-sm"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"),
                                         (8, "pass1"), (8, "pipelined")])
 def test_sharded_join_on_gpus(phj, world, mode):
     """One rank per GPU over NCCL: the fused NVLink-store shuffle (and the all-to-all variant)

@@ -20,7 +20,8 @@ local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 Rp, Sp = multigpu.shard_inputs(phj, rank, world, 10_000_000, 200_000_000, 0.01, 12345, 64)
-be = multigpu.PipelinedGpuBackend(world, local, partitions_local=4096, chunks=chunks, split_ctas=ctas)
+be = multigpu.PipelinedGpuBackend(world, local, partitions_local=4096, chunks=chunks, split_ctas=ctas,
+                                  copy_engines=(len(sys.argv) <= 3 or sys.argv[3] != "sm"))
 job = multigpu.PipelinedShardedRadixJoin(dist, rank, world, be)
 job.upload(Rp.array, Sp.array)
 for _ in range(3):
