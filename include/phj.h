@@ -98,6 +98,8 @@ typedef struct {
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
 #define PHJ_FLAG_SPLIT_REMOTE_ONLY 0x8u /* SHARD_SPLIT handle used only through phj_shard_scatter with
                                            both destinations given: no local output buffers */
+#define PHJ_FLAG_SPLIT_LOCAL_TILES 0x40u /* SHARD_SPLIT: keep the HBM-tuned 4096-tuple tiles even when every
+                                            digit has a destination (the split mostly writes local memory) */
 #define PHJ_FLAG_CHAINED_TABLE 0x10u /* NO_PARTITIONING: bucket-chained global table (the reference's
                                         SeparateChainingHashTable, src/HashTables/SeparateChaining.hpp)
                                         instead of the open-addressing one (LinearProbing.hpp) */
@@ -226,8 +228,8 @@ int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, con
  * chunk, digit d's piece of relation `rel` written straight to dst[rel][d] + off[rel][d] tuples --
  * typically a peer GPU's receive window mapped with phj_shared_open, i.e. the partition shuffle
  * happens as NVLink stores from the scatter kernel (TMA bulk stores) instead of a separate
- * all-to-all. A null dst keeps that relation local (split into the handle's own buffer, chunk
- * count 1 only). Call order per join: phj_shard_count, exchange the counts, then per chunk:
+ * all-to-all. A null dst array keeps that relation local (split into the handle's own buffer); a
+ * null ENTRY keeps that digit local (phj_shard_push sends it later). Call order per join: phj_shard_count, exchange the counts, then per chunk:
  * phj_shard_scatter + a barrier across ranks. */
 int phj_shard_count(phj_handle* h, uint64_t* counts);
 int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,

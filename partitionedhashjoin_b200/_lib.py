@@ -31,6 +31,7 @@ FLAG_FUSE_HIST2 = 0x4
 FLAG_SPLIT_REMOTE_ONLY = 0x8
 FLAG_CHAINED_TABLE = 0x10
 FLAG_NO_FUSE_HIST2 = 0x20
+FLAG_SPLIT_LOCAL_TILES = 0x40
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

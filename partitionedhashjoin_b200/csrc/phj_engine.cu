@@ -72,6 +72,7 @@ constexpr int kMaxBitsPerPass = 8;
 constexpr int kMaxKernelTimes = 24;
 constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
 constexpr int kMaxSplitChunks = 16;
+constexpr int kCopyStreams = 4;
 
 enum Scalar : int {  // device-resident uint32 scalars
     kNsegs1 = 0,
@@ -98,7 +99,7 @@ struct phj_handle {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // phj_shard_push: device-to-device copies on the copy engines
+    cudaStream_t copy_streams[kCopyStreams] = {};  // phj_shard_push: device-to-device copies on the copy engines
 
     // relations: 0 = build (R), 1 = probe (S)
     ulonglong2* d_in[2] = {nullptr, nullptr};
@@ -1246,7 +1247,8 @@ void phj_destroy(phj_handle* h) {
         if (k.begin) cudaEventDestroy(k.begin);
         if (k.end) cudaEventDestroy(k.end);
     }
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& cs : h->copy_streams)
+        if (cs) cudaStreamDestroy(cs);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1597,10 +1599,23 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
     for (int rel = 0; rel < 2; ++rel) {
         if (!dst[rel]) continue;  // this relation stays local (split into buf_a)
         if (!h->d_outd[rel]) PHJ_CUDA(cudaMalloc(&h->d_outd[rel], kMaxSplitDigits * sizeof(void*)));
+        bool any_local = false;
         for (uint32_t d = 0; d < w; ++d) {
-            // this chunk's run of digit d starts at cursor == starts[rel][d][chunk]: rebase it to off[d]
+            // this chunk's run of digit d starts at cursor == starts[rel][d][chunk]: rebase it to off[d];
+            // a null destination keeps that digit in the handle's own split buffer (for phj_shard_push)
             const uint64_t start = h->h_shard_starts[((size_t)rel * w + d) * (K + 1) + chunk];
-            host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) - start;
+            if (dst[rel][d]) {
+                host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) - start;
+            } else {
+                any_local = true;
+                host_ptrs[rel][d] = nullptr;
+            }
+        }
+        if (any_local) {
+            int rc = ensure_buffers(h, true, false);
+            if (rc != PHJ_OK) return rc;
+            for (uint32_t d = 0; d < w; ++d)
+                if (!host_ptrs[rel][d]) host_ptrs[rel][d] = h->d_buf_a[rel];
         }
         PHJ_CUDA(cudaMemcpyAsync(h->d_outd[rel], host_ptrs[rel], w * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
         p1.outd[rel] = h->d_outd[rel];
@@ -1621,7 +1636,7 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
         const uint32_t grid = h->cfg.split_ctas ? std::min<uint32_t>(count, h->cfg.split_ctas) : count;
         KernelScope ks(h, "radix_scatter[split]");
         // remote destinations: the wide-tile kernel; a purely local split keeps the HBM-tuned shape
-        if (dst_build && dst_probe && !(h->cfg.flags & PHJ_FLAG_NO_TMA_STORE))
+        if (dst_build && dst_probe && !(h->cfg.flags & (PHJ_FLAG_NO_TMA_STORE | PHJ_FLAG_SPLIT_LOCAL_TILES)))
             PHJ_CUDA(launch_split_scatter(h, h->b1, p1, grid));
         else
             PHJ_CUDA(launch_pass(h, true, h->b1, p1, grid));
@@ -1647,10 +1662,12 @@ int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const 
     if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
     if (chunk >= h->nchunks) return fail(PHJ_ERR_INVALID, "chunk %u out of range [0, %u)", chunk, h->nchunks);
     if (!h->h_shard_starts || !h->d_buf_a[0] || !h->d_buf_a[1])
-        return fail(PHJ_ERR_STATE, "phj_shard_push needs a local phj_shard_scatter of this chunk first");
+        return fail(PHJ_ERR_STATE, "phj_shard_push needs a phj_shard_scatter of this chunk with local digits first");
     PHJ_CUDA(cudaSetDevice(h->device));
-    if (!h->copy_stream) PHJ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& cs : h->copy_streams)
+        if (!cs) PHJ_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     const uint32_t w = h->d1, K = h->nchunks;
+    uint32_t next = 0;
     void* const* dst[2] = {dst_build, dst_probe};
     const uint64_t* off[2] = {off_build, off_probe};
     uint64_t bytes = 0;
@@ -1660,9 +1677,11 @@ int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const 
             // piece (digit d, this chunk) of the local split output: [starts[d][chunk], starts[d][chunk + 1])
             const uint64_t* st = h->h_shard_starts + ((size_t)rel * w + d) * (K + 1);
             const uint64_t len = st[chunk + 1] - st[chunk];
-            if (!len) continue;
+            if (!len || !dst[rel][d]) continue;  // null: that digit was scattered straight to its window
+            // round-robin over a few streams: the copies spread over the device's copy engines
             PHJ_CUDA(cudaMemcpyAsync(reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0),
-                                     h->d_buf_a[rel] + st[chunk], len * 16, cudaMemcpyDeviceToDevice, h->copy_stream));
+                                     h->d_buf_a[rel] + st[chunk], len * 16, cudaMemcpyDeviceToDevice,
+                                     h->copy_streams[next++ % kCopyStreams]));
             bytes += len * 16;
         }
     }
@@ -1673,7 +1692,8 @@ int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const 
 int phj_shard_push_wait(phj_handle* h) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     PHJ_CUDA(cudaSetDevice(h->device));
-    if (h->copy_stream) PHJ_CUDA(cudaStreamSynchronize(h->copy_stream));
+    for (auto& cs : h->copy_streams)
+        if (cs) PHJ_CUDA(cudaStreamSynchronize(cs));
     return PHJ_OK;
 }
 

@@ -288,6 +288,8 @@ class FusedShardedRadixJoin:
         if world & (world - 1):
             raise ValueError("the number of ranks must be a power of two")
         self.dist, self.rank, self.world, self.backend, self.balance = dist, rank, world, backend, balance
+        if backend is not None:
+            backend.rank = rank
         self.caps = np.zeros((3, world), dtype=np.int64)  # rows of every rank's windows (same on all ranks)
         self.last = {}
 
@@ -444,7 +446,7 @@ class PipelinedGpuBackend(FusedGpuBackend):
             hash_seed=hash_seed, device=device, reserve=reserve)
         self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
                                           device=device, shard_shift=self.b2,
-                                          flags=0 if copy_engines else _lib.FLAG_SPLIT_REMOTE_ONLY,
+                                          flags=_lib.FLAG_SPLIT_LOCAL_TILES if copy_engines else _lib.FLAG_SPLIT_REMOTE_ONLY,
                                           split_ctas=0 if copy_engines else split_ctas, split_chunks=chunks)
         self.locals = [None, None]
         self.local_reserve = (0, 0)
@@ -489,12 +491,27 @@ class PipelinedGpuBackend(FusedGpuBackend):
             self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
         return int(res.total_ns)
 
-    def scatter_local(self, c):
-        """Split chunk c into the handle's own buffer (no destinations)."""
+    def _dst_arrays(self, c, offsets, owner_of, own):
+        """Per-digit destination pointers of chunk c: this rank's own digits (own=True) or the other
+        ranks' digits (own=False); the rest are null."""
+        C = self._C
+        arrs = []
+        for which, w in ((0, 0), (1, 1 + c % 2)):
+            ptrs = (C.c_void_p * self.ndig)(*[
+                C.c_void_p(self.peer[w][int(owner_of[d])]) if (int(owner_of[d]) == self.rank) == own else C.c_void_p(None)
+                for d in range(self.ndig)])
+            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
+        return arrs
+
+    def scatter_local(self, c, offsets, owner_of):
+        """Split chunk c at HBM speed: this rank's own digits go straight into its window, the others
+        into the handle's split buffer, from where push() sends them."""
         from ._lib import PhjResult
         res = PhjResult()
         t0 = time.perf_counter()
-        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, None, None, None, None, self._C.byref(res)))
+        arrs = self._dst_arrays(c, offsets, owner_of, own=True)
+        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
+                                                arrs[3].ctypes.data, self._C.byref(res)))
         self.launches += res.kernel_launches
         if self.trace is not None:
             self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
@@ -503,10 +520,7 @@ class PipelinedGpuBackend(FusedGpuBackend):
     def push(self, c, offsets, owner_of):
         """Enqueue the copies of chunk c's pieces into their owners' windows (copy engines)."""
         C = self._C
-        arrs = []
-        for which, w in ((0, 0), (1, 1 + c % 2)):
-            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][int(owner_of[d])]) for d in range(self.ndig)])
-            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
+        arrs = self._dst_arrays(c, offsets, owner_of, own=False)
         nbytes = C.c_uint64()
         self._check(self._lib.phj_shard_push(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
                                              arrs[3].ctypes.data, C.byref(nbytes)))
@@ -584,19 +598,20 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
                 ce = getattr(be, "copy_engines", False)
                 acquire(0)
                 if ce:
-                    stats["scatter_device_ns"] += be.scatter_local(0)
+                    stats["scatter_device_ns"] += be.scatter_local(0, plans[0][1], plans[0][3])
                 for c in range(K):
                     ts = time.perf_counter()
                     need, offsets, bounds, owner_of = plans[c]
                     if ce:
                         be.push(c, offsets, owner_of)              # copy engines, asynchronous
                         if c + 1 < K:
-                            stats["scatter_device_ns"] += be.scatter_local(c + 1)   # SMs, meanwhile
+                            acquire((c + 1) % 2)                   # the split writes this rank's own digits there
+                            stats["scatter_device_ns"] += be.scatter_local(c + 1, plans[c + 1][1], plans[c + 1][3])
                         be.push_wait()
                     else:
                         stats["scatter_device_ns"] += be.scatter(c, offsets, owner_of)
-                    if c + 1 < K:
-                        acquire((c + 1) % 2)
+                        if c + 1 < K:
+                            acquire((c + 1) % 2)
                     if world > 1:
                         self.dist.barrier()    # chunk c has landed everywhere; slot (c + 1) % 2 is free everywhere
                     stats["scatter_s"] += time.perf_counter() - ts

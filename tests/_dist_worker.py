@@ -146,13 +146,26 @@ class OraclePipelinedBackend(OracleFusedBackend):
         self.split_done = set()
 
     # copy-engine flavour: a local split per chunk, then the pieces are pushed
-    def scatter_local(self, c):
+    def _write(self, c, offsets, owner_of, own):
+        self.owner_of = np.asarray(owner_of)
+        for which, w in ((0, 0), (1, 1 + c % 2)):
+            for d in range(self.ndig):
+                piece = self.chunk_pieces[c][which][d]
+                if piece.shape[0] and (int(owner_of[d]) == self.rank) == own:
+                    shm = self.peer[w][int(owner_of[d])]
+                    win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
+                    o = int(offsets[which][d])
+                    win[o:o + piece.shape[0]] = piece
+                    del win
+
+    def scatter_local(self, c, offsets, owner_of):
+        self._write(c, offsets, owner_of, own=True)  # own digits straight into the own window
         self.split_done.add(c)
         return 0
 
     def push(self, c, offsets, owner_of):
         assert c in self.split_done  # a chunk is pushed only after its local split
-        self.scatter(c, offsets, owner_of)
+        self._write(c, offsets, owner_of, own=False)
         return 0
 
     def push_wait(self):
@@ -229,6 +242,7 @@ def main():
 
     if pipelined:
         backend = OraclePipelinedBackend(world, oracle, 256, chunks=3, copy_engines=sys.argv[2] == "pipelined-ce")
+        backend.rank = rank
         job = multigpu.PipelinedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
     elif fused:
         backend = OracleFusedBackend(world, oracle, 256, pass1)
