@@ -176,6 +176,12 @@ int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_bui
                                 size_t n_probe, const uint64_t* bounds_build, const uint64_t* bounds_probe,
                                 uint32_t nparents, uint32_t first_parent, uint32_t parent_space);
 
+/* Optional, after phj_bind_device_partitioned: the digit of every bound parent when they are not the
+ * contiguous range first_parent .. (the multi-GPU path appends replicas of heavy-hitter digits owned
+ * by other ranks). Only the handling of the reserved key value needs it; build partitions too large
+ * for the shared-memory table are an error in this mode. */
+int phj_set_parent_digits(phj_handle* h, const uint32_t* digits, uint32_t n);
+
 /* ---- the join ---------------------------------------------------------------------------------
  * Stands in for HashJoiner::Run(tableA, tableB, timer) (src/NoPartitioning/HashJoin.hpp:54-74,
  * src/RadixCluster/HashJoin.hpp:190-241) on the relations given to phj_upload / phj_bind_device.
@@ -265,6 +271,7 @@ int phj_device_fill_zipf(int32_t device, void* d_out, size_t n, double alpha, in
  * the multi-GPU path, test read-back of the windows). */
 int phj_memcpy_h2d(int32_t device, void* d_dst, const void* h_src, size_t bytes);
 int phj_memcpy_d2h(int32_t device, void* h_dst, const void* d_src, size_t bytes);
+int phj_memcpy_d2d(int32_t device, void* d_dst, const void* d_src, size_t bytes); /* incl. mapped peer memory */
 
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
  * names[i] points to a static string. */

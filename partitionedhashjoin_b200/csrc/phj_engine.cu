@@ -139,6 +139,7 @@ struct phj_handle {
     uint32_t prepart_parents = 0;      // plan built for this many pre-partitioned parents (0 = the plan's own)
     uint32_t prepart_first = 0;        // full-digit-space index of the first parent bound
     uint64_t prepart_space = 0;        // size of that digit space (a power of two; 0 = this plan's 2^b1)
+    std::vector<uint32_t> parent_digits;  // optional: digit of every bound parent (else first + index)
     uint64_t* d_pre_bounds = nullptr;  // [2][d1 + 1]
     size_t cap_pre_bounds = 0;
     phj::Segment* d_segs1 = nullptr;
@@ -1019,9 +1020,13 @@ int join_radix(phj_handle* h, phj_result* out) {
             // be wider than this handle's own (the owner-rank bits of the multi-GPU split sit above it)
             const uint64_t space = h->prepart_space ? h->prepart_space : ((uint64_t)1 << h->b1);
             const uint64_t digit = (hs >> h->b2) & (space - 1);
-            jp.sentinel_part = digit >= h->prepart_first && digit < (uint64_t)h->prepart_first + h->d1
-                                   ? (uint32_t)((digit - h->prepart_first) * h->d2 + (hs & (h->d2 - 1)))
-                                   : 0xffffffffu;
+            jp.sentinel_part = 0xffffffffu;
+            if (!h->parent_digits.empty()) {
+                for (uint32_t i = 0; i < h->d1; ++i)
+                    if (h->parent_digits[i] == digit) jp.sentinel_part = (uint32_t)(i * h->d2 + (hs & (h->d2 - 1)));
+            } else if (digit >= h->prepart_first && digit < (uint64_t)h->prepart_first + h->d1) {
+                jp.sentinel_part = (uint32_t)((digit - h->prepart_first) * h->d2 + (hs & (h->d2 - 1)));
+            }
         }
     }
     jp.matches = h->d_matches;
@@ -1060,6 +1065,9 @@ int join_radix(phj_handle* h, phj_result* out) {
 
     const uint32_t oversize = (uint32_t)(h->h_out[1] & 0xffffffffu);
     float extra_ms = 0;
+    if (oversize && h->prepart && !h->parent_digits.empty())
+        return fail(PHJ_ERR_INVALID, "%u build partitions exceed the shared-memory table; with explicitly numbered "
+                                     "parents raise `partitions` instead", oversize);
     if (oversize) {
         // Build partitions too large for shared memory: join them through the global table.
         int rc = ensure_gt_for_fallback(h);
@@ -1359,12 +1367,28 @@ int phj_bind_device_partitioned(phj_handle* h, const void* d_build, size_t n_bui
     if ((rc = ensure_buffers(h, false, h->b2 > 0)) != PHJ_OK) return rc;
     h->prepart_first = first_parent;
     h->prepart_space = parent_space;
+    h->parent_digits.clear();
     if ((rc = dev_reserve(&h->d_pre_bounds, &h->cap_pre_bounds, 2 * ((size_t)h->d1 + 1))) != PHJ_OK) return rc;
     for (int rel = 0; rel < 2; ++rel)
         PHJ_CUDA(cudaMemcpyAsync(h->d_pre_bounds + rel * (h->d1 + 1), hb[rel], (h->d1 + 1) * 8,
                                  cudaMemcpyHostToDevice, h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     h->prepart = true;
+    return PHJ_OK;
+}
+
+int phj_set_parent_digits(phj_handle* h, const uint32_t* digits, uint32_t n) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (!h->prepart) return fail(PHJ_ERR_STATE, "phj_set_parent_digits follows phj_bind_device_partitioned");
+    if (n != h->d1 || !digits) return fail(PHJ_ERR_INVALID, "expected the digit of each of the %u bound parents", h->d1);
+    h->parent_digits.assign(digits, digits + n);
+    return PHJ_OK;
+}
+
+int phj_memcpy_d2d(int32_t device, void* d_dst, const void* d_src, size_t bytes) {
+    if (bytes && (!d_dst || !d_src)) return fail(PHJ_ERR_INVALID, "null argument");
+    PHJ_CUDA(cudaSetDevice(device));
+    if (bytes) PHJ_CUDA(cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice));
     return PHJ_OK;
 }
 

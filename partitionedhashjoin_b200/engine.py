@@ -223,7 +223,8 @@ class Engine:
         self._n = (n_build, n_probe)
 
     def bind_device_partitioned(self, d_build: int, n_build: int, d_probe: int, n_probe: int, bounds_build,
-                                bounds_probe, keepalive=None, first_parent: int = 0, parent_space: int = 0):
+                                bounds_probe, keepalive=None, first_parent: int = 0, parent_space: int = 0,
+                                parent_digits=None):
         """Device-resident relations already partitioned by pass-1 digit; bounds_* are the parents + 1
         host boundaries of each relation. The parents are digits [first_parent, first_parent + parents)
         of a digit space of `parent_space` values (0 = this plan's own 2^b1)."""
@@ -234,6 +235,9 @@ class Engine:
         check(lib.phj_bind_device_partitioned(self._h, C.c_void_p(d_build), n_build, C.c_void_p(d_probe), n_probe,
                                               bb.ctypes.data, bp.ctypes.data, bb.shape[0] - 1, first_parent,
                                               parent_space))
+        if parent_digits is not None:  # parents that are not the contiguous range first_parent ..
+            pd = np.ascontiguousarray(parent_digits, dtype=np.uint32)
+            check(lib.phj_set_parent_digits(self._h, pd.ctypes.data, pd.shape[0]))
         self._keep = [keepalive]
         self._n = (n_build, n_probe)
 

@@ -238,12 +238,16 @@ class FusedGpuBackend(GpuBackend):
 
     def scatter(self, offsets, owner_of):
         """offsets[rel][digit]: first row of this rank's piece of `digit` inside the window of
-        owner_of[digit]."""
+        owner_of[digit] (or owner_of[rel][digit] when the two relations go different ways)."""
         from ._lib import PhjResult
         C = self._C
+        owner_of = np.asarray(owner_of)
+        if owner_of.ndim == 1:
+            owner_of = np.stack([owner_of, owner_of])
         arrs = []
         for which in (0, 1):
-            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[which][int(owner_of[d])]) for d in range(self.ndig)])
+            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[which][int(owner_of[which][d])])
+                                              for d in range(self.ndig)])
             offs = np.ascontiguousarray(offsets[which], dtype=np.uint64)
             arrs += [ptrs, offs]
         res = PhjResult()
@@ -252,15 +256,23 @@ class FusedGpuBackend(GpuBackend):
         self.launches += res.kernel_launches
         return int(res.total_ns)
 
-    def local_join_window(self, rows, bounds, first_digit=0):
+    def pull(self, which, owner, src_row, dst_row, rows):
+        """Copy `rows` tuples from rank `owner`'s window (mapped here) into this rank's own window."""
+        if rows:
+            self._check(self._lib.phj_memcpy_d2d(self.device, self._C.c_void_p(self.win[which] + 16 * dst_row),
+                                                 self._C.c_void_p(self.peer[which][owner] + 16 * src_row), 16 * rows))
+
+    def local_join_window(self, rows, bounds, first_digit=0, parent_digits=None):
         """rows[rel] tuples have landed in this rank's windows; bounds[rel] are the boundaries of the
-        split digits first_digit, first_digit + 1, ... this rank owns, in window order."""
+        split digits first_digit, first_digit + 1, ... this rank owns, in window order (or of the
+        explicitly listed parent_digits)."""
         ptr = [self.win[w] if rows[w] else 0 for w in (0, 1)]
         if self.b1 and len(bounds[0]) < 2:
             return 0, {"kernel_launches": 0, "hbm_bytes_alg": 0, "total_ns": 1, "d2h_bytes": 0}  # owns no digit
         if self.b1:
             self.local_engine.bind_device_partitioned(ptr[0], rows[0], ptr[1], rows[1], bounds[0], bounds[1],
-                                                      first_parent=first_digit, parent_space=self.ndig)
+                                                      first_parent=first_digit, parent_space=self.ndig,
+                                                      parent_digits=parent_digits)
         else:
             self.local_engine.bind_device(ptr[0], rows[0], ptr[1], rows[1])
         res = self.local_engine.join()
@@ -356,6 +368,54 @@ class FusedShardedRadixJoin:
         return np.asarray(first, dtype=np.int64)
 
     @staticmethod
+    def hot_digits(M, world):
+        """Split digits whose probe side alone is heavier than a quarter of one rank's fair share of the
+        probe relation (never the case for uniform keys: a digit is at most 1/32 of a share): an
+        ownership cut cannot balance those (key 1 at Zipf 1.25 is 22 % of S). Their probe tuples stay
+        on the rank that holds them -- no NVLink traffic at all -- and the (small, never skewed) build
+        side of the digit is replicated to every rank instead: SURVEY 8e "skew caveat"."""
+        tot_s = M[:, 1, :].sum(axis=0)
+        if world == 1 or M.shape[2] == world:
+            return np.zeros(M.shape[2], dtype=bool)
+        return tot_s * world * 4 > max(int(tot_s.sum()), 1)   # heavier than a quarter of a fair share
+
+    @staticmethod
+    def layout_hot(M, world, rank, first, hot):
+        """layout() with replicated heavy-hitter digits. Window of rank o: its owned digits first
+        (build side from every source; probe side from every source, but only o's own piece of a hot
+        digit), then one slot per hot digit owned by another rank (build side pulled from the owner
+        after the exchange, probe side = o's own piece). Returns rows per window, this rank's write
+        offsets and destination ranks per relation, its local boundaries, the digit of every local
+        parent, and the pulls (owner, source row, destination row, rows) of the build side."""
+        ndig = M.shape[2]
+        owner = np.searchsorted(first[1:], np.arange(ndig), side="right")
+        tot = M.sum(axis=0)
+        hot_list = [int(d) for d in np.nonzero(hot)[0]]
+        need = np.zeros((2, world), dtype=np.int64)
+        base = np.full((2, world, ndig), -1, dtype=np.int64)
+        parents = []
+        for o in range(world):
+            plist = list(range(int(first[o]), int(first[o + 1]))) + [d for d in hot_list if owner[d] != o]
+            pos = [0, 0]
+            for d in plist:
+                base[0, o, d], base[1, o, d] = pos
+                pos[0] += int(tot[0, d])
+                pos[1] += int(M[o, 1, d]) if hot[d] else int(tot[1, d])
+            need[:, o] = pos
+            parents.append(plist)
+        before = M[:rank].sum(axis=0)                          # lower ranks' pieces come first
+        dst = np.stack([owner, np.where(hot, rank, owner)])    # hot probe pieces stay here
+        offsets = np.zeros((2, ndig), dtype=np.int64)
+        for d in range(ndig):
+            offsets[0, d] = base[0, owner[d], d] + before[0, d]
+            offsets[1, d] = base[1, rank, d] if hot[d] else base[1, owner[d], d] + before[1, d]
+        mine = parents[rank]
+        bounds = np.array([[base[rel, rank, d] for d in mine] + [need[rel, rank]] for rel in (0, 1)], dtype=np.int64)
+        pulls = [(int(owner[d]), int(base[0, owner[d], d]), int(base[0, rank, d]), int(tot[0, d]))
+                 for d in mine if owner[d] != rank]
+        return need, offsets, dst, bounds, np.asarray(mine, dtype=np.int64), pulls
+
+    @staticmethod
     def layout(M, world, rank, first=None):
         """From M[source][rel][digit] and the ownership cut: rows arriving at every owner, this rank's
         write offsets per digit, the boundaries of this rank's own digits inside its windows, and the
@@ -381,25 +441,39 @@ class FusedShardedRadixJoin:
         counts = be.count()                                   # [rel][digit]
         t1 = time.perf_counter()
         M = self._gather_counts(counts)                       # [source][rel][digit]
-        first = self.ownership(M, world, self.balance)
-        need, offsets, bounds, owner_of = self.layout(M, world, rank, first)
+        hot = self.hot_digits(M, world) if self.balance and getattr(be, "b1", 0) else np.zeros(M.shape[2], dtype=bool)
+        if hot.any():
+            # heavy hitters: their probe tuples do not travel, their build side is replicated
+            W = M.copy()
+            W[:, 1, hot] = 0
+            first = self.ownership(W, world, True)
+            need, offsets, owner_of, bounds, parent_digits, pulls = self.layout_hot(M, world, rank, first, hot)
+        else:
+            first = self.ownership(M, world, self.balance)
+            need, offsets, bounds, owner_of = self.layout(M, world, rank, first)
+            parent_digits, pulls = None, []
         regrown = self._ensure_windows({0: need[0], 1: need[1]})
         t2 = time.perf_counter()
         scatter_ns = be.scatter(offsets, owner_of)
         if world > 1:
             self.dist.barrier()                               # every rank's stores are complete
+        for owner, src_row, dst_row, nrows in pulls:          # replicate the hot digits' build side
+            be.pull(0, owner, src_row, dst_row, nrows)
         t3 = time.perf_counter()
         rows = [int(need[0][rank]), int(need[1][rank])]
-        local_matches, res = be.local_join_window(rows, bounds, int(first[rank]))
+        local_matches, res = be.local_join_window(rows, bounds, int(first[rank]), parent_digits)
         t4 = time.perf_counter()
         total = be.count_tensor(local_matches)
         if world > 1:
             self.dist.all_reduce(total)
         matches = int(total.item())
         t5 = time.perf_counter()
-        mine = counts[:, int(first[rank]):int(first[rank + 1])].sum()
+        stay = np.asarray(owner_of)
+        stay = (stay if stay.ndim == 2 else np.stack([stay, stay])) == rank   # pieces that do not leave this GPU
+        mine = (counts * stay).sum()
         self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
-                     "first_digit": first.tolist(),
+                     "first_digit": first.tolist(), "hot_digits": [int(d) for d in np.nonzero(hot)[0]],
+                     "parent_digits": None if parent_digits is None else parent_digits.tolist(),
                      "exchange_s": t3 - t1, "sizes_s": t2 - t1, "scatter_s": t3 - t2, "local_s": t4 - t3,
                      "reduce_s": t5 - t4, "total_s": t5 - t0, "recv_rows": rows, "regrown": regrown,
                      "send_bytes_remote": int(16 * (counts.sum() - mine)) if world > 1 else 0,

@@ -64,10 +64,21 @@ def main():
             digit = ((oracle.hash_batch(0, 0x9E3779B97F4A7C15, rel["id"]) >> np.uint64(shift))
                      & np.uint64(be.ndig - 1)).astype(np.int64)
             lo, hi = res["first_digit"][rank], res["first_digit"][rank + 1]  # the digits this rank owns
-            mine = (digit >= lo) & (digit < hi)
-            # digit-major, then global input order (= source-rank order, then input order): a stable sort
-            expect = rel[mine][np.argsort(digit[mine], kind="stable")]
-            assert np.diff(res["bounds"][which]).tolist() == np.bincount(digit[mine] - lo, minlength=hi - lo).tolist()
+            parents = res["parent_digits"] if res["parent_digits"] is not None else list(range(lo, hi))
+            hot = set(res["hot_digits"])
+            per = rel.shape[0] // world
+            in_my_shard = np.zeros(rel.shape[0], dtype=bool)
+            in_my_shard[rank * per:(rel.shape[0] if rank == world - 1 else (rank + 1) * per)] = True
+            # parent by parent: the tuples of that digit in global input order (= source-rank order,
+            # then input order); of a heavy-hitter digit the probe side holds this rank's own piece only
+            pieces = []
+            for d in parents:
+                sel = digit == d
+                if which == 1 and d in hot:
+                    sel &= in_my_shard
+                pieces.append(rel[sel])
+            expect = np.concatenate(pieces) if pieces else rel[:0]
+            assert np.diff(res["bounds"][which]).tolist() == [p.shape[0] for p in pieces]
             assert got.shape[0] == expect.shape[0], (got.shape, expect.shape)
             assert (got[:, 0] == expect["id"]).all() and (got[:, 1] == expect["payload"]).all()
         # bigger shards: windows regrow collectively

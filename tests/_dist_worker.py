@@ -105,19 +105,30 @@ class OracleFusedBackend(OracleBackend):
         return np.stack(counts).astype(np.int64)
 
     def scatter(self, offsets, owner_of):
-        self.owner_of = np.asarray(owner_of)
+        owner_of = np.asarray(owner_of)
+        if owner_of.ndim == 1:
+            owner_of = np.stack([owner_of, owner_of])
+        self.owner_of = owner_of[0]
         for which in (0, 1):
             for d in range(self.ndig):
                 piece = self.pieces[which][d]
                 if piece.shape[0]:
-                    shm = self.peer[which][int(owner_of[d])]
+                    shm = self.peer[which][int(owner_of[which][d])]
                     win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
                     o = int(offsets[which][d])
                     win[o:o + piece.shape[0]] = piece
                     del win
         return 0
 
-    def local_join_window(self, rows, bounds, first_digit=0, windows=(0, 1)):
+    def pull(self, which, owner, src_row, dst_row, rows):
+        if rows:
+            src = np.ndarray((self.peer[which][owner].size // 16,), dtype=_cases.TUPLE, buffer=self.peer[which][owner].buf)
+            dst = np.ndarray((self.win[which].size // 16,), dtype=_cases.TUPLE, buffer=self.win[which].buf)
+            dst[dst_row:dst_row + rows] = src[src_row:src_row + rows]
+            del src, dst
+            self.pulled = getattr(self, "pulled", 0) + rows
+
+    def local_join_window(self, rows, bounds, first_digit=0, parent_digits=None, windows=(0, 1)):
         got = []
         for which in (0, 1):
             n = rows[which]
@@ -129,7 +140,8 @@ class OracleFusedBackend(OracleBackend):
             b = np.asarray(bounds[which])
             assert b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
             if n:
-                assert (self.digit(got[which]["id"]) == first_digit + np.repeat(np.arange(b.shape[0] - 1), np.diff(b))).all()
+                digits = first_digit + np.arange(b.shape[0] - 1) if parent_digits is None else np.asarray(parent_digits)
+                assert (self.digit(got[which]["id"]) == np.repeat(digits, np.diff(b))).all()
         self.received = tuple(got)
         return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
 
@@ -204,7 +216,7 @@ class OraclePipelinedBackend(OracleFusedBackend):
         return 0
 
     def local_join(self, c, rows, bounds, first_digit=0):
-        m, res = self.local_join_window(rows, bounds, first_digit, windows=(0, 1 + c % 2))
+        m, res = self.local_join_window(rows, bounds, first_digit, None, windows=(0, 1 + c % 2))
         self.joined.append(self.received)
         return m, res
 
@@ -262,15 +274,19 @@ def main():
         got_R, got_S = backend.received
     for rel in (got_R, got_S):
         if rel.shape[0]:
+            if fused and res.get("hot_digits"):
+                continue  # heavy-hitter digits are replicated (build) / stay where they are (probe)
             if fused:
                 owner = backend.owner_of[backend.digit(rel["id"])]
             else:
                 owner = (oracle.hash_batch(0, SEED, rel["id"]) >> np.uint64(multigpu.SHARD_SHIFT)) & np.uint64(world - 1)
             assert (owner == rank).all()
-    rows = torch.tensor([got_R.shape[0], got_S.shape[0]], dtype=torch.int64)
+    rows = torch.tensor([got_R.shape[0] - getattr(backend, "pulled", 0), got_S.shape[0]], dtype=torch.int64)
     if world > 1:
         dist.all_reduce(rows)
-    assert rows.tolist() == [R.shape[0], S.shape[0]], rows.tolist()
+    assert rows.tolist() == [R.shape[0], S.shape[0]], rows.tolist()  # nothing lost; only replicas added
+    if case == "skewed" and pass1 and not pipelined and world > 1:
+        assert res["hot_digits"], "the 70 % key must be recognised as a heavy hitter"
     assert res["matches"] == want, (res["matches"], want)
     res2 = job.join()  # the job is reusable
     assert res2["matches"] == want
