@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PHJ_ABI_VERSION 2
+#define PHJ_ABI_VERSION 3
 
 /* Common::Tuple (src/Common/Table.hpp:20-25): alignas(16) {int64 id; int64 payload}. */
 typedef struct {
@@ -92,7 +92,9 @@ typedef struct {
     uint32_t split_chunks;  /* PHJ_ALGO_SHARD_SPLIT: the probe relation is split in this many row chunks
                                (1..16, 0 = 1) that phj_shard_scatter sends one at a time; the build
                                relation travels with chunk 0 */
-    uint32_t reserved;      /* must be 0 */
+    uint32_t upload_chunks; /* phj_join_host: row chunks the probe relation is uploaded in, each joined
+                               as soon as it has landed (1 = upload everything, then join; 0 = choose:
+                               ~256 MB chunks when the probe relation is large, else 1; <= 32) */
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
@@ -131,6 +133,9 @@ typedef struct {
     uint64_t d2h_bytes; /* bytes copied device -> host by this call (count, per-CTA phase times) */
     uint64_t joined_tuples;  /* phj_join_materialize: rows of the joined table, else 0 */
     uint64_t materialize_ns; /* phj_join_materialize: device time of the count + write kernels */
+    uint64_t e2e_ns;         /* phj_join_host: device time, first upload .. match count on the host */
+    uint32_t upload_chunks;  /* phj_join_host: probe chunks actually used (1 = not streamed), else 0 */
+    uint32_t reserved;
 } phj_result;
 
 typedef struct phj_handle phj_handle;
@@ -201,7 +206,16 @@ int phj_join_materialize(phj_handle* h, phj_result* out);
 int phj_read_joined(phj_handle* h, phj_joined_tuple* out, uint64_t first, uint64_t count);
 int phj_device_joined(phj_handle* h, const void** d_joined, uint64_t* rows);
 
-/* Upload + join in one call, the end-to-end path (host buffers in, count out). */
+/* Upload + join in one call, the end-to-end path (host buffers in, count out) -- what the host
+ * mirrors' Run(tableA, tableB) calls. With config.upload_chunks != 1 and a large probe relation the
+ * call is STREAMED: the probe relation goes up in row chunks on a copy stream and every chunk is
+ * joined against the whole build relation as soon as it has landed (counts are additive over a
+ * partition of the probe relation), so only the last chunk's join is not hidden behind PCIe. Then
+ * partition/build/probe/join/total_ns, hbm_bytes_alg and kernel_launches are sums over the chunks
+ * (the build side is re-partitioned per chunk), h2d_ns is the device time of all uploads and
+ * e2e_ns the device time of the whole call. Works from pageable memory too (uploads are issued by
+ * a helper thread); pinned memory (phj_host_alloc) uploads faster. Both relations are resident
+ * afterwards, as after phj_upload; phj_read_partitions needs a phj_join first. */
 int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
                   size_t n_probe, phj_result* out);
 

@@ -51,7 +51,7 @@ class PhjConfig(C.Structure):
         ("shard_shift", C.c_uint32),
         ("split_ctas", C.c_uint32),
         ("split_chunks", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("upload_chunks", C.c_uint32),
     ]
 
 
@@ -73,6 +73,9 @@ class PhjResult(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("joined_tuples", C.c_uint64),
         ("materialize_ns", C.c_uint64),
+        ("e2e_ns", C.c_uint64),
+        ("upload_chunks", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
     def as_dict(self):

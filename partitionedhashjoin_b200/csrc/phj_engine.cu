@@ -10,12 +10,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/phj.h"
@@ -73,6 +75,8 @@ constexpr int kMaxKernelTimes = 24;
 constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
 constexpr int kMaxSplitChunks = 16;
 constexpr int kCopyStreams = 4;
+constexpr int kMaxUploadChunks = 32;                     // streamed phj_join_host
+constexpr size_t kUploadChunkBytes = (size_t)256 << 20;  // ... automatic chunking: ~256 MB of probe tuples
 
 enum Scalar : int {  // device-resident uint32 scalars
     kNsegs1 = 0,
@@ -174,6 +178,12 @@ struct phj_handle {
     // host staging (pinned)
     uint64_t* h_out = nullptr;  // [0] matches, [1] scalars copy...
     uint64_t* h_cta_times = nullptr;
+
+    // streamed phj_join_host: the probe relation is uploaded in row chunks on `upload_stream` while
+    // `stream_child` joins the chunks that have landed against the whole build relation
+    phj_handle* stream_child = nullptr;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t upload_ev[kMaxUploadChunks + 2] = {};  // [0] begin, [1] build landed, [2 + c] chunk c landed
 
     cudaEvent_t ev[6] = {};
     KernelTime ktimes[kMaxKernelTimes] = {};
@@ -1120,6 +1130,8 @@ int validate_config(const phj_config* c) {
         if (c->split_chunks > (uint32_t)kMaxSplitChunks)
             return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
     }
+    if (c->upload_chunks > (uint32_t)kMaxUploadChunks)
+        return fail(PHJ_ERR_INVALID, "upload_chunks must be <= %d", kMaxUploadChunks);
     if ((c->flags & PHJ_FLAG_CHAINED_TABLE) && c->algo != PHJ_ALGO_NO_PARTITIONING)
         return fail(PHJ_ERR_INVALID, "the bucket-chained table serves the no-partitioning join only");
     if (c->hash < PHJ_HASH_XXH3 || c->hash > PHJ_HASH_CITY)
@@ -1233,6 +1245,13 @@ int phj_create(const phj_config* config, phj_handle** out) {
 void phj_destroy(phj_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->stream_child) phj_destroy(h->stream_child);
+    if (h->upload_stream) {
+        cudaStreamSynchronize(h->upload_stream);
+        cudaStreamDestroy(h->upload_stream);
+    }
+    for (auto& e : h->upload_ev)
+        if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int rel = 0; rel < 2; ++rel) {
         if (h->owns_in[rel] && h->d_in[rel]) cudaFree(h->d_in[rel]);
@@ -1263,7 +1282,7 @@ void phj_destroy(phj_handle* h) {
 
 static int set_relations(phj_handle* h, const void* build, size_t n_build, const void* probe,
                          size_t n_probe, bool device_resident, uint64_t* h2d_ns, bool prepartitioned = false,
-                         uint32_t parents = 0) {
+                         uint32_t parents = 0, bool defer_copy = false) {
     if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
     if ((n_build && !build) || (n_probe && !probe))
         return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
@@ -1310,7 +1329,7 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
         int rc = upload_tail_bounds(h);
         if (rc != PHJ_OK) return rc;
     }
-    if (!device_resident) {
+    if (!device_resident && !defer_copy) {  // defer_copy: the streamed phj_join_host uploads by itself
         PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
         for (int rel = 0; rel < 2; ++rel)
             if (nn[rel])
@@ -1388,7 +1407,13 @@ int phj_set_parent_digits(phj_handle* h, const uint32_t* digits, uint32_t n) {
 int phj_memcpy_d2d(int32_t device, void* d_dst, const void* d_src, size_t bytes) {
     if (bytes && (!d_dst || !d_src)) return fail(PHJ_ERR_INVALID, "null argument");
     PHJ_CUDA(cudaSetDevice(device));
-    if (bytes) PHJ_CUDA(cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice));
+    // A device-to-device cudaMemcpy returns before the copy has run, and the engine's streams are
+    // non-blocking (not ordered behind the legacy stream): wait here, so that a join launched next
+    // sees the data.
+    if (bytes) {
+        PHJ_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, cudaStreamPerThread));
+        PHJ_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    }
     return PHJ_OK;
 }
 
@@ -1493,15 +1518,123 @@ int phj_device_joined(phj_handle* h, const void** d_joined, uint64_t* rows) {
     return PHJ_OK;
 }
 
+// Streamed host join: the build relation and then the probe relation in `chunks` row chunks go up
+// on their own stream (issued by a helper thread, so that pageable memory, whose "async" copies
+// block the issuing thread, overlaps as well); as soon as a chunk has landed the child handle joins
+// it against the whole build relation. Counts are additive over a partition of the probe relation,
+// so the sum is the count of the whole join (SURVEY.md 8d uses the same identity for config 5). The
+// build side is re-partitioned for every chunk: redundant work on SMs that would otherwise idle
+// behind PCIe. Only the last chunk's join is not hidden behind the upload.
+static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
+                              size_t n_probe, uint32_t chunks, phj_result* out) {
+    int rc = set_relations(h, build, n_build, probe, n_probe, false, nullptr, false, 0, /*defer_copy=*/true);
+    if (rc != PHJ_OK) return rc;
+    h->have_data = false;  // until the uploads below have landed
+    const size_t chunk_len = (n_probe + chunks - 1) / chunks;
+    if (!h->stream_child) {
+        phj_config cc = h->cfg;
+        cc.upload_chunks = 1;
+        cc.reserve_build = std::max<uint64_t>(cc.reserve_build, n_build);
+        cc.reserve_probe = chunk_len;
+        if ((rc = phj_create(&cc, &h->stream_child)) != PHJ_OK) return rc;
+    }
+    if (!h->upload_stream) {
+        PHJ_CUDA(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+        for (auto& e : h->upload_ev) PHJ_CUDA(cudaEventCreate(&e));
+    }
+    phj_handle* child = h->stream_child;
+
+    struct Uploader {
+        std::atomic<int> published{0};  // chunks whose "landed" event has been recorded
+        std::atomic<bool> failed{false};
+        std::string error;
+        std::thread thread;
+        ~Uploader() {
+            if (thread.joinable()) thread.join();
+        }
+    } up;
+    up.thread = std::thread([&]() {
+        auto check = [&](cudaError_t e, const char* what) {
+            if (e == cudaSuccess) return true;
+            up.error = std::string(what) + " failed: " + cudaGetErrorString(e);
+            up.failed.store(true);
+            return false;
+        };
+        if (!check(cudaSetDevice(h->device), "cudaSetDevice")) return;
+        if (!check(cudaEventRecord(h->upload_ev[0], h->upload_stream), "cudaEventRecord")) return;
+        if (n_build && !check(cudaMemcpyAsync(h->d_in[0], build, n_build * 16, cudaMemcpyHostToDevice,
+                                              h->upload_stream), "upload of the build relation")) return;
+        if (!check(cudaEventRecord(h->upload_ev[1], h->upload_stream), "cudaEventRecord")) return;
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const size_t first = std::min(n_probe, (size_t)c * chunk_len);
+            const size_t len = std::min(n_probe - first, chunk_len);
+            if (len && !check(cudaMemcpyAsync(h->d_in[1] + first, probe + first, len * 16, cudaMemcpyHostToDevice,
+                                              h->upload_stream), "upload of a probe chunk")) return;
+            if (!check(cudaEventRecord(h->upload_ev[2 + c], h->upload_stream), "cudaEventRecord")) return;
+            up.published.store((int)c + 1, std::memory_order_release);
+        }
+    });
+
+    memset(out, 0, sizeof(*out));
+    for (uint32_t c = 0; c < chunks; ++c) {
+        const size_t first = std::min(n_probe, (size_t)c * chunk_len);
+        const size_t len = std::min(n_probe - first, chunk_len);
+        // plan for this chunk while it is still on its way
+        if ((rc = phj_bind_device(child, h->d_in[0], n_build, h->d_in[1] + first, len)) != PHJ_OK) return rc;
+        while (up.published.load(std::memory_order_acquire) <= (int)c && !up.failed.load()) std::this_thread::yield();
+        if (up.failed.load()) break;
+        PHJ_CUDA(cudaStreamWaitEvent(child->stream, h->upload_ev[2 + c], 0));
+        phj_result r;
+        if ((rc = phj_join(child, &r)) != PHJ_OK) return rc;
+        out->matches += r.matches;
+        out->partition_ns += r.partition_ns;
+        out->build_ns += r.build_ns;
+        out->probe_ns += r.probe_ns;
+        out->join_ns += r.join_ns;
+        out->total_ns += r.total_ns;
+        out->hbm_bytes_alg += r.hbm_bytes_alg;
+        out->kernel_launches += r.kernel_launches;
+        out->d2h_bytes += r.d2h_bytes;
+        out->fallback_partitions = std::max(out->fallback_partitions, r.fallback_partitions);
+        out->passes = r.passes;
+        out->partitions = r.partitions;
+    }
+    up.thread.join();
+    if (up.failed.load()) return fail(PHJ_ERR_CUDA, "%s", up.error.c_str());
+    PHJ_CUDA(cudaEventRecord(h->ev[4], child->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->upload_stream));
+    PHJ_CUDA(cudaEventSynchronize(h->ev[4]));
+    out->h2d_ns = (uint64_t)(ev_ms(h->upload_ev[0], h->upload_ev[1 + chunks]) * 1e6);
+    out->e2e_ns = (uint64_t)(ev_ms(h->upload_ev[0], h->ev[4]) * 1e6);
+    out->h2d_bytes = 16ull * (n_build + n_probe);
+    out->upload_chunks = chunks;
+    h->have_data = true;  // both relations are resident: phj_join may follow
+    return PHJ_OK;
+}
+
 int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
                   size_t n_probe, phj_result* out) {
+    if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    uint32_t chunks = h->cfg.upload_chunks;
+    if (chunks == 0) {
+        // automatic: chunks of ~256 MB once the probe relation is worth overlapping, but never so short
+        // that redoing the build side per chunk (radix: partitioning it, ~14x faster per tuple than
+        // PCIe delivers tuples; no-partitioning: building the table) takes longer than the chunk's upload
+        const size_t by_bytes = (n_probe * 16 + kUploadChunkBytes - 1) / kUploadChunkBytes;
+        const size_t min_len = std::max<size_t>(1, h->cfg.algo == PHJ_ALGO_NO_PARTITIONING ? n_build : n_build / 4);
+        chunks = (uint32_t)std::min<size_t>(std::min<size_t>(kMaxUploadChunks, by_bytes), n_probe / min_len);
+    }
+    if (h->cfg.algo == PHJ_ALGO_SHARD_SPLIT || n_probe < chunks) chunks = 1;
+    if (chunks > 1) return join_host_streamed(h, build, n_build, probe, n_probe, chunks, out);
     uint64_t h2d = 0;
     int rc = set_relations(h, build, n_build, probe, n_probe, false, &h2d);
     if (rc != PHJ_OK) return rc;
     rc = phj_join(h, out);
     if (rc == PHJ_OK) {
         out->h2d_ns = h2d;
+        out->e2e_ns = h2d + out->total_ns;
         out->h2d_bytes = 16ull * (n_build + n_probe);
+        out->upload_chunks = 1;
     }
     return rc;
 }

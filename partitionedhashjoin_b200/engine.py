@@ -172,7 +172,7 @@ class Engine:
     def __init__(self, algo="radix-partitioning", partitions: int = 0, radix_bits=(0, 0), hash="xxh3",
                  hash_seed: int = 0x9E3779B97F4A7C15, table_seed: int = 1, device: int = 0,
                  flags: int = 0, shard_shift: int = 0, split_ctas: int = 0, reserve=(0, 0),
-                 split_chunks: int = 0):
+                 split_chunks: int = 0, upload_chunks: int = 0):
         cfg = PhjConfig()
         if isinstance(algo, str):
             if algo not in self.ALGOS:
@@ -189,6 +189,7 @@ class Engine:
         cfg.shard_shift = shard_shift
         cfg.split_ctas = split_ctas
         cfg.split_chunks = split_chunks
+        cfg.upload_chunks = upload_chunks  # join_host: 0 = automatic, 1 = upload then join, k = k probe chunks
         cfg.reserve_build, cfg.reserve_probe = reserve
         self._h = C.c_void_p()
         check(lib.phj_create(C.byref(cfg), C.byref(self._h)))
@@ -261,6 +262,8 @@ class Engine:
         return out
 
     def join_host(self, build: np.ndarray, probe: np.ndarray) -> dict:
+        """Host relations in, count out (phj_join_host): the uploads are part of the call, and for a
+        large probe relation they overlap the joins of the chunks that have already landed."""
         build, probe = as_tuples(build), as_tuples(probe)
         res = PhjResult()
         check(lib.phj_join_host(self._h, build.ctypes.data, build.shape[0], probe.ctypes.data,
@@ -350,9 +353,10 @@ class HashJoinTimer(NoOpHashJoinTimer):
 
 
 class _JoinerBase:
-    def __init__(self, engine: Engine, materialize: bool = False):
+    def __init__(self, engine: Engine, materialize: bool = False, stream_upload: bool = False):
         self._engine = engine
         self._materialize = materialize
+        self._stream_upload = stream_upload and not materialize
         self.last_result: Optional[dict] = None
 
     def Run(self, tableA, tableB, timer=None):
@@ -360,8 +364,11 @@ class _JoinerBase:
         joined table is empty (count-only join, reference Readme.md:10); the count is in
         ``self.last_result['matches']``."""
         timer = timer or NoOpHashJoinTimer()
-        self._engine.upload(tableA, tableB)
-        res = self._engine.join_materialize() if self._materialize else self._engine.join()
+        if self._stream_upload:  # one call; the upload of tableB overlaps the joins of its landed chunks
+            res = self._engine.join_host(tableA, tableB)
+        else:
+            self._engine.upload(tableA, tableB)
+            res = self._engine.join_materialize() if self._materialize else self._engine.join()
         self.last_result = res
         timer.SetPartitionPhaseDuration(res["partition_ns"])
         timer.SetBuildPhaseDuration(res["build_ns"])
@@ -382,24 +389,25 @@ class NoPartitioningHashJoiner(_JoinerBase):
     TABLES = {"linear-probing": 0, "separate-chaining": _lib.FLAG_CHAINED_TABLE}
 
     def __init__(self, configuration: Optional[NoPartitioningConfiguration] = None,
-                 hasher: Optional[Hasher] = None, device: int = 0, table: str = "linear-probing"):
+                 hasher: Optional[Hasher] = None, device: int = 0, table: str = "linear-probing",
+                 stream_upload: bool = False):
         hasher = hasher or Hasher()
         if table not in self.TABLES:
             raise ValueError(f"Unrecognized hash table type: {table}.")
         super().__init__(Engine("no-partitioning", hash=hasher.name, hash_seed=hasher.seed, device=device,
-                                flags=self.TABLES[table]))
+                                flags=self.TABLES[table]), stream_upload=stream_upload)
         self.configuration = configuration or NoPartitioningConfiguration()
 
 
 class RadixClusteringHashJoiner(_JoinerBase):
     def __init__(self, configuration: Optional[RadixClusteringConfiguration] = None,
                  hasher: Optional[Hasher] = None, device: int = 0, radix_bits=(0, 0), flags: int = 0,
-                 materialize: bool = False):
+                 materialize: bool = False, stream_upload: bool = False):
         configuration = configuration or RadixClusteringConfiguration()
         hasher = hasher or Hasher()
         if configuration.NumberOfPartitions < 0:
             raise ValueError("NumberOfPartitions must be >= 0")
         super().__init__(Engine("radix-partitioning", partitions=configuration.NumberOfPartitions,
                                 radix_bits=radix_bits, hash=hasher.name, hash_seed=hasher.seed,
-                                device=device, flags=flags), materialize=materialize)
+                                device=device, flags=flags), materialize=materialize, stream_upload=stream_upload)
         self.configuration = configuration

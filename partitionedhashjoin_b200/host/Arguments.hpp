@@ -1,7 +1,7 @@
 // Command-line surface of phjoin: the reference's flags, spellings, defaults and validation
 // (reference src/main.cpp:141-208, src/Arguments.hpp:7-19) parsed without Boost, plus the flags
 // that only make sense for the GPU engine (--hash, --seed, --table-seed, --data-seed,
-// --radix-bits, --device, --gpus, --repeat, --no-tma-store, --materialize).
+// --radix-bits, --device, --gpus, --repeat, --no-tma-store, --materialize, --stream-upload).
 #pragma once
 #include <cstdlib>
 #include <iostream>
@@ -47,7 +47,11 @@ inline std::string HelpText() {
          "  --table arg (=linear-probing)         Hash table of the no-partitioning join: linear-probing or\n"
          "                                        separate-chaining (the reference's two HashTables).\n"
          "  --materialize                         Radix join only: also produce the joined table {id, payloadA,\n"
-         "                                        payloadB} (the reference returns it empty) and log its size.\n";
+         "                                        payloadB} (the reference returns it empty) and log its size.\n"
+         "  --stream-upload                       Overlap the host-to-device upload with the join: the secondary\n"
+         "                                        relation goes up in chunks that are joined as they land; phase\n"
+         "                                        timings are then sums over the chunks and the end-to-end time\n"
+         "                                        is logged.\n";
     return o.str();
 }
 
@@ -85,7 +89,7 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     static const std::set<std::string> kValued = {
         "primary", "secondary", "skew", "log", "join", "format", "unit", "output", "filename", "partitions",
         "hash", "seed", "table-seed", "data-seed", "radix-bits", "device", "gpus", "repeat", "table"};
-    static const std::set<std::string> kFlags = {"help", "no-tma-store", "materialize"};
+    static const std::set<std::string> kFlags = {"help", "no-tma-store", "materialize", "stream-upload"};
 
     Common::Configuration c{};
     std::map<std::string, std::string> seen;
@@ -151,6 +155,7 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     }
     c.Gpu.NoTmaStore = seen.count("no-tma-store") != 0;
     c.Gpu.Materialize = seen.count("materialize") != 0;
+    c.Gpu.StreamUpload = seen.count("stream-upload") != 0;
     // --join is required (reference src/main.cpp:162-165)
     if (!get("join")) throw std::invalid_argument("the option '--join' is required but missing");
     c.JoinType = Common::GetJoinAlgorithmTypeFromString(*get("join"));
@@ -163,6 +168,8 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
             "validateParsedConfiguration: number of partitions can be specified only for RadixParitioning.");
     if (c.Gpu.Materialize && c.JoinType != Common::JoinAlgorithmType::RadixParitioning)
         throw std::invalid_argument("--materialize: the joined table is produced by the RadixParitioning joiner.");
+    if (c.Gpu.StreamUpload && (c.Gpu.Materialize || c.Gpu.Repeat > 1))
+        throw std::invalid_argument("--stream-upload joins once and count-only: not with --materialize or --repeat.");
     if (c.Gpu.Gpus != 1)
         throw std::invalid_argument("--gpus > 1 is driven through torch.distributed (bench.py --gpus N); "
                                     "this binary joins on one device");

@@ -104,6 +104,8 @@ struct GpuConfiguration {
     bool ChainedTable = false;  // no-partitioning join: bucket-chained table (SeparateChaining) instead of
                                 // the open-addressing one (LinearProbing)
     bool Materialize = false;   // fill the returned Table<JoinedTuple> (the reference leaves it empty)
+    bool StreamUpload = false;  // Run() through phj_join_host: the upload of tableB overlaps the join of the
+                                // chunks that have landed (phase timings become sums over the chunks)
 };
 
 struct Configuration {

@@ -56,8 +56,14 @@ class Engine {
     Engine& operator=(const Engine&) = delete;
 
     phj_result Join(const Common::Table<Common::Tuple>& build, const Common::Table<Common::Tuple>& probe,
-                    int repeat, bool materialize = false) {
+                    int repeat, bool materialize = false, bool stream_upload = false) {
         static_assert(sizeof(Common::Tuple) == sizeof(phj_tuple) && alignof(Common::Tuple) == 16, "layout");
+        if (stream_upload && !materialize) {  // one call: uploads overlapped with the joins of landed chunks
+            phj_result r{};
+            Check(phj_join_host(m_handle, reinterpret_cast<const phj_tuple*>(build.Data()), build.GetSize(),
+                                reinterpret_cast<const phj_tuple*>(probe.Data()), probe.GetSize(), &r));
+            return r;
+        }
         Check(phj_upload(m_handle, reinterpret_cast<const phj_tuple*>(build.Data()), build.GetSize(),
                          reinterpret_cast<const phj_tuple*>(probe.Data()), probe.GetSize()));
         phj_result best{};
@@ -103,7 +109,7 @@ class HashJoiner {
     std::shared_ptr<Common::Table<Common::JoinedTuple>> Run(
         std::shared_ptr<Common::Table<Common::Tuple>> tableA, std::shared_ptr<Common::Table<Common::Tuple>> tableB,
         std::shared_ptr<Common::IHashJoinTimer> timer = std::make_shared<Common::NoOpHashJoinTimer>()) {
-        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat);
+        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat, false, m_gpu.StreamUpload);
         return internal::Report(m_last, timer);
     }
     const phj_result& GetLastResult() const { return m_last; }
@@ -130,7 +136,7 @@ class HashJoiner {
     std::shared_ptr<Common::Table<Common::JoinedTuple>> Run(
         std::shared_ptr<Common::Table<Common::Tuple>> tableA, std::shared_ptr<Common::Table<Common::Tuple>> tableB,
         std::shared_ptr<Common::IHashJoinTimer> timer = std::make_shared<Common::NoOpHashJoinTimer>()) {
-        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat, m_gpu.Materialize);
+        m_last = m_engine.Join(*tableA, *tableB, m_gpu.Repeat, m_gpu.Materialize, m_gpu.StreamUpload);
         auto joined = internal::Report(m_last, timer);
         if (m_gpu.Materialize) m_engine.ReadJoined(*joined, m_last.joined_tuples);
         return joined;

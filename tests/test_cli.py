@@ -46,6 +46,8 @@ def test_help_lists_reference_flags(phjoin):
     (("--join", "radix-partitioning", "--hash", "sha1"), "Unrecognized hash function: sha1."),
     (("--join", "no-partitioning", "--table", "cuckoo"), "Unrecognized hash table type: cuckoo."),
     (("--join", "no-partitioning", "--materialize"), "the joined table is produced by the RadixParitioning joiner."),
+    (("--join", "radix-partitioning", "--stream-upload", "--repeat", "2"), "--stream-upload joins once and count-only"),
+    (("--join", "radix-partitioning", "--stream-upload", "--materialize"), "--stream-upload joins once and count-only"),
 ])
 def test_argument_errors_exit_1_with_option_table(phjoin, args, message):
     """Any parse/validation error: message, option table, exit(1) (reference src/main.cpp:199-205)."""
@@ -92,6 +94,20 @@ def test_cli_end_to_end(phjoin, tmp_path, join, extra, typ):
     assert list(d["results"]) == ["partition", "build", "probe"]
     assert int(d["results"]["probe"]) > 0 and int(d["results"]["build"]) > 0
     assert (int(d["results"]["partition"]) > 0) == (join == "radix-partitioning")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("join,extra", [("no-partitioning", []), ("radix-partitioning", ["-p", "1024"])])
+def test_cli_stream_upload(phjoin, tmp_path, join, extra):
+    """--stream-upload: Run() through phj_join_host (24 MB probe chunks do not stream by themselves at
+    this size, so the count and the end-to-end log line are what is checked; the chunked path itself
+    is covered by test_gpu_parity.py::test_join_host_streamed)."""
+    out = tmp_path / "result.txt"
+    r = run(phjoin, "--join", join, "--primary", "200000", "--secondary", "3000000", "--stream-upload", "--log", "info",
+            "-f", str(out), *extra)
+    assert r.returncode == 0, r.stderr
+    assert "End to end (upload in 1 chunk(s) + join)" in r.stderr
+    assert json.load(open(out))["parameters"]["SecondaryRelationSize"] == "3000000"
 
 
 @pytest.mark.gpu

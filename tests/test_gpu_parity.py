@@ -115,6 +115,67 @@ def test_reuse_handle_and_reupload(phj, oracle):
             assert e.join_host(R, S)["matches"] == want
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("algo,kw", [("radix-partitioning", {"partitions": 512}), ("radix-partitioning", {"partitions": 0}),
+                                     ("radix-partitioning", {"partitions": 100}), ("no-partitioning", {}),
+                                     ("no-partitioning", {"flags": 0x10})])
+def test_join_host_streamed(phj, oracle, algo, kw, pinned):
+    """phj_join_host with the probe relation uploaded in chunks, each joined as it lands: the sum of
+    the chunk counts is the count of the whole join, from pageable and from pinned memory, for every
+    chunk count (also more chunks than tuples, ragged last chunks, an empty probe relation), and the
+    relations are resident afterwards (a plain phj_join gives the same count)."""
+    R = _cases.tuples(_cases.splitmix64(30011, 5).astype(np.int64) % 50000)
+    S = _cases.tuples(_cases.splitmix64(400009, 6).astype(np.int64) % 70000)
+    want = oracle.count_by_sort(R, S)
+    assert 0 < want < S.shape[0]
+    keep = []
+    if pinned:
+        keep = [phj.PinnedTuples(R.shape[0]), phj.PinnedTuples(S.shape[0])]
+        keep[0].array[:] = R
+        keep[1].array[:] = S
+        R, S = keep[0].array, keep[1].array
+    for chunks in (1, 2, 3, 7, 32):
+        with phj.Engine(algo, upload_chunks=chunks, **kw) as e:
+            for _ in range(2):  # the second call reuses the child handle, streams and events
+                res = e.join_host(R, S)
+                assert res["matches"] == want, (chunks, res)
+                assert res["upload_chunks"] == chunks and res["h2d_bytes"] == 16 * (R.shape[0] + S.shape[0])
+                assert res["e2e_ns"] >= res["h2d_ns"] > 0
+            assert e.join()["matches"] == want          # both relations are resident
+            # other sizes on the same handle: fewer tuples than chunks, nothing to probe, a larger relation
+            assert e.join_host(R, S[:5])["matches"] == oracle.count_by_sort(R, S[:5])
+            assert e.join_host(R, S[:0])["matches"] == 0
+            S2 = np.concatenate([S, S[:1000]])
+            assert e.join_host(R[:777], S2)["matches"] == oracle.count_by_sort(R[:777], S2)
+    # automatic chunking leaves a probe relation of a few MB alone
+    with phj.Engine(algo, **kw) as e:
+        res = e.join_host(R, S)
+        assert res["matches"] == want and res["upload_chunks"] == 1
+
+
+def test_join_host_streamed_generator_data(phj):
+    """Streamed host join at 2 M x 40 M generator tuples (Zipf 1.05: every probe key has a match), the
+    automatic chunk count, pinned memory: what bench.py's e2e leg does, at a fifth of its size."""
+    Rp, Sp = phj.PinnedTuples(2_000_000), phj.PinnedTuples(40_000_000)
+    phj.fill_sequential(Rp.array, 1)
+    phj.fill_zipf(Sp.array, 1.05, 1, 2_000_000, 777, 16)
+    with phj.Engine("radix-partitioning", partitions=1024) as e:
+        res = e.join_host(Rp.array, Sp.array)
+        assert res["matches"] == 40_000_000 and res["upload_chunks"] == 3, res
+        plain = e.join()
+        assert plain["matches"] == 40_000_000
+    with phj.Engine("no-partitioning") as e:
+        res = e.join_host(Rp.array, Sp.array)
+        assert res["matches"] == 40_000_000 and res["upload_chunks"] == 3, res
+    # the joiner interface with the same option
+    j = phj.RadixClusteringHashJoiner(phj.RadixClusteringConfiguration(NumberOfPartitions=1024), stream_upload=True)
+    timer = phj.HashJoinTimer()
+    assert j.Run(Rp.array, Sp.array, timer).shape[0] == 0
+    assert j.last_result["matches"] == 40_000_000 and j.last_result["upload_chunks"] == 3
+    assert timer.GetResult().partitioning_ns > 0
+    j.close()
+
+
 # ---- intermediate state: the partitioned relations equal the reference algorithm's ---------------
 def assert_same_partitioning(got, gb, want, wb, n, exact_order):
     """Boundaries identical; partition contents identical -- in input order when `exact_order`,

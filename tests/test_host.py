@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(phj):
     for name in names:
         assert hasattr(raw, name), f"{name} is declared in include/phj.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert phj._lib.lib.phj_abi_version() == 2
+    assert phj._lib.lib.phj_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(phj, tmp_path):
@@ -115,6 +115,9 @@ def test_configuration_errors(phj):
     cfg.algo, cfg.hash, cfg.partitions = 0, 0, 32
     assert _lib.lib.phj_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID
     assert b"only for RadixParitioning" in _lib.lib.phj_last_error()
+    cfg.algo, cfg.partitions, cfg.upload_chunks = 1, 64, 33
+    assert _lib.lib.phj_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID
+    assert b"upload_chunks" in _lib.lib.phj_last_error()
     with pytest.raises(ValueError, match="Unrecognized join algorithm type: hash-join."):
         phj.Engine("hash-join")  # src/Common/Configuration.cpp:4-12
     assert _lib.lib.phj_join(None, None) == _lib.ERR_INVALID
