@@ -323,7 +323,7 @@ struct ScatterSmem {
     // extra shared memory of the fused pass-2 histogram: counters + split positions + counter indices
     // 16-bit counters packed in pairs (flushed before they can overflow): with 32-bit counters the CTA
     // needed 127 KB and only ONE fit an SM, which is what made the first fused version slow
-    static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 2 + (size_t)D * 8 + (size_t)D * 8;
+    static constexpr size_t fuse2_bytes = (size_t)2 * D * 64 * 2 + (size_t)D * 8 + (size_t)D * 8 + (size_t)D * 4;
 };
 
 template <int BITS, int HASH, bool POW2, int TPB, int IPT, bool TMA_STORE, bool BALLOT, bool FUSE2,
@@ -345,6 +345,9 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     uint64_t* split_pos = reinterpret_cast<uint64_t*>(h2 + D * kFuse2MaxD2);  // h2: 2 * D * 64 / 2 words
     uint32_t* h2_first = reinterpret_cast<uint32_t*>(split_pos + D);  // counter index of (digit 0, first seg)
     uint32_t* h2_stride = h2_first + D;
+    // per tile: tile-local base of the digit | (tile slot at which its pass-2 segment changes) << 16
+    uint32_t* dthr = h2_stride + D;
+    static_assert(!FUSE2 || T <= 0x8000, "tile slots must fit 16 bits");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* wcw = wc + warp * (D + 1);
@@ -481,6 +484,14 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
             dbase[tid] = excl;
             if (tid == D - 1) dbase[D] = n_valid;
             gbase[tid] = gcur[tid] - excl;  // out index of tile slot j of this digit = gbase + j
+            if (FUSE2) {
+                // tile slot j of this digit goes to the run's second pass-2 segment iff gbase + j >=
+                // split_pos, i.e. j >= thr: one packed 32-bit word per digit for the stage step
+                // instead of two 64-bit loads and a 64-bit compare per tuple
+                const int64_t t = (int64_t)(split_pos[tid] - gbase[tid]);
+                const uint32_t thr = t < 0 ? 0u : t > 0xffff ? 0xffffu : (uint32_t)t;
+                dthr[tid] = excl | (thr << 16);
+            }
             gcur[tid] += tot;
         }
         cta_sync();
@@ -490,11 +501,12 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = dr[i] & 0x1ffu;
             if (full || d < D) {
-                const uint32_t pos = dbase[d] + wcw[d] + (dr[i] >> 16);
+                const uint32_t db = FUSE2 ? dthr[d] : dbase[d];
+                const uint32_t pos = (FUSE2 ? db & 0xffffu : db) + wcw[d] + (dr[i] >> 16);
                 stage[pos] = v[i];
                 if (!TMA_STORE) sdig[pos] = (uint16_t)d;
                 if (FUSE2) {
-                    const uint32_t slot = gbase[d] + pos >= split_pos[d];
+                    const uint32_t slot = pos >= (db >> 16);
                     const uint32_t c2 = (slot * D + d) * kFuse2MaxD2 + ((dr[i] >> 9) & 0x7fu);
                     atomicAdd(&h2[c2 >> 1], 1u << ((c2 & 1) * 16));
                 }
