@@ -245,21 +245,28 @@ def gpu_arm(args):
     # Streamed by default: the probe relation goes up in ~256 MB chunks, each joined as soon as it has
     # landed, so only the last chunk's join is not hidden behind PCIe. The unstreamed call (upload
     # everything, then join) is timed beside it for comparison.
-    e2e_steps = max(3, min(args.steps, 8))
-    eng.join_host(R, S)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r2 = eng.join_host(R, S)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    assert r2["matches"] == S.shape[0]
-    with phj.Engine("radix-partitioning", partitions=args.partitions, hash=args.hash, device=local,
-                    upload_chunks=1) as e1:
-        e1.join_host(R, S)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 8))
+        eng.join_host(R, S)
         t0 = time.perf_counter()
-        for _ in range(3):
-            r1 = e1.join_host(R, S)
-        e2e_plain_s = (time.perf_counter() - t0) / 3
-        assert r1["matches"] == S.shape[0] and r1["upload_chunks"] == 1
+        for _ in range(e2e_steps):
+            r2 = eng.join_host(R, S)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        assert r2["matches"] == S.shape[0]
+        with phj.Engine("radix-partitioning", partitions=args.partitions, hash=args.hash, device=local,
+                        upload_chunks=1) as e1:
+            e1.join_host(R, S)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                r1 = e1.join_host(R, S)
+            e2e_plain_s = (time.perf_counter() - t0) / 3
+            assert r1["matches"] == S.shape[0] and r1["upload_chunks"] == 1
+        e2e = {"value": n_tuples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]),
+               "d2h_bytes_per_step": int(r2["d2h_bytes"]), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "upload_chunks": int(r2["upload_chunks"]), "h2d_ms": r2["h2d_ns"] / 1e6,
+               "device_ms": r2["e2e_ns"] / 1e6, "unstreamed_ms_per_step": e2e_plain_s * 1e3,
+               "unstreamed_h2d_ms": r1["h2d_ns"] / 1e6}
 
     # ---- the other configurations of BASELINE.json, a few steps each (informational) ----
     others = {}
@@ -302,11 +309,7 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic", "config": workload_config(args),
-        "e2e": {"value": n_tuples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]),
-                "d2h_bytes_per_step": int(r2["d2h_bytes"]),
-                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "upload_chunks": int(r2["upload_chunks"]),
-                "h2d_ms": r2["h2d_ns"] / 1e6, "device_ms": r2["e2e_ns"] / 1e6,
-                "unstreamed_ms_per_step": e2e_plain_s * 1e3, "unstreamed_h2d_ms": r1["h2d_ns"] / 1e6},
+        "e2e": e2e,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "radix_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": SCATTER_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
@@ -344,6 +347,8 @@ def main():
                          "owner only; nccl = local split + NCCL all-to-all")
     ap.add_argument("--quick", action="store_true", help="skip the informational extra configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the end-to-end leg (profiling runs: keeps the ncu launch list to the timed joins)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -1,12 +1,13 @@
 """Turn ncu captures under gpurun_out/ into the tracked summaries under profiles/.
 
-  python tools/make_profile_summary.py r01 gpurun_out/r01_launches.csv gpurun_out/prof_r01_top.ncu-rep
+  python tools/make_profile_summary.py r01 gpurun_out/r01_launches.csv gpurun_out/prof_r01_top.ncu-rep ["bench.py flags"]
 """
 import csv, io, json, subprocess, sys, collections
 
 tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+flags = sys.argv[4] if len(sys.argv) > 4 else "--steps 2 --warmup 3 --quick --no-cpu-baseline"
 out = [f"# ncu summary {tag}", "",
-       "Command: `python bench.py --steps 2 --warmup 3 --quick --no-cpu-baseline` on one B200 (gpurun); both ncu passes",
+       f"Command: `python bench.py {flags}` on one B200 (gpurun); both ncu passes",
        "ran only after the same command had exited 0 without ncu. Times under ncu are serialised and",
        "cold-cache: compare SHARES, not absolutes (the live CUDA-event numbers are in the bench line).", ""]
 
