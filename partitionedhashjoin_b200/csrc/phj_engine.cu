@@ -38,6 +38,9 @@
 #ifndef PHJ_SCAT_MINB
 #define PHJ_SCAT_MINB 2  // two 512-thread CTAs per SM: caps the scatter at 64 registers (no spills)
 #endif
+#ifndef PHJ_SCAT_MINB_PLAIN
+#define PHJ_SCAT_MINB_PLAIN PHJ_SCAT_MINB  // CTAs per SM of the scatter without the fused pass-2 histogram
+#endif
 #ifndef PHJ_JOIN_TPB
 #define PHJ_JOIN_TPB 512
 #endif
@@ -259,9 +262,10 @@ void launch_hist_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
 template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT, bool FUSE2>
 cudaError_t launch_scatter_tbf(phj_handle* h, const PassParams& pp, uint32_t grid) {
     using L = ScatterSmem<BITS, PHJ_SCAT_TPB, PHJ_SCAT_IPT>;
-    size_t smem = L::total + (FUSE2 ? L::fuse2_bytes : 0);
+    size_t smem = L::bytes(TMA) + (FUSE2 ? L::fuse2_bytes : 0);
     if (const char* x = getenv("PHJ_SCAT_EXTRA_SMEM")) smem += (size_t)atoi(x);  // experiment: L1 sensitivity
-    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT, FUSE2>;
+    auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT, FUSE2,
+                              (FUSE2 || !TMA) ? PHJ_SCAT_MINB : PHJ_SCAT_MINB_PLAIN>;
     static bool configured[16] = {};
     if (!configured[h->device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -354,11 +358,11 @@ cudaError_t launch_split_scatter_t(phj_handle* h, const PassParams& pp, uint32_t
     auto kern = radix_scatter<BITS, HASH, true, kTpb, kIpt, true, true, false, 1>;
     static bool configured[16] = {};
     if (!configured[h->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total_tma);
         if (e != cudaSuccess) return e;
         configured[h->device & 15] = true;
     }
-    kern<<<grid, kTpb, L::total, h->stream>>>(pp);
+    kern<<<grid, kTpb, L::total_tma, h->stream>>>(pp);
     return cudaSuccess;
 }
 

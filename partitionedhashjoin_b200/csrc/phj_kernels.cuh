@@ -318,8 +318,10 @@ struct ScatterSmem {
     static constexpr size_t wc_bytes = (size_t)NW * (D + 1) * 4;
     static constexpr size_t dbase_bytes = (size_t)(D + 4) * 4;
     static constexpr size_t sdig_bytes = (size_t)T * 2;
-    static constexpr size_t total =
-        (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + sdig_bytes + 16 * 4 + 64 + 15) / 16 * 16;
+    static constexpr size_t total_tma =  // TMA bulk stores flush whole runs: no per-slot digit array
+        (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + 16 * 4 + 64 + 15) / 16 * 16;
+    static constexpr size_t total = total_tma + sdig_bytes;
+    static constexpr size_t bytes(bool tma_store) { return tma_store ? total_tma : total; }
     // extra shared memory of the fused pass-2 histogram: counters + split positions + counter indices
     // 16-bit counters packed in pairs (flushed before they can overflow): with 32-bit counters the CTA
     // needed 127 KB and only ONE fit an SM, which is what made the first fused version slow
@@ -339,9 +341,9 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     uint32_t* wtot_sh = reinterpret_cast<uint32_t*>(gbase + D);  // 16 entries: digit-scan warp totals
     uint32_t* wc = wtot_sh + 16;
     uint32_t* dbase = wc + NW * (D + 1);
-    uint16_t* sdig = reinterpret_cast<uint16_t*>(dbase + D + 4);
+    uint16_t* sdig = reinterpret_cast<uint16_t*>(smem_raw + L::total_tma);  // only without TMA stores
     // FUSE2: [2][D][d2] pass-2 counters of this segment + per-digit split position / first segment
-    uint32_t* h2 = reinterpret_cast<uint32_t*>(smem_raw + L::total);
+    uint32_t* h2 = reinterpret_cast<uint32_t*>(smem_raw + (TMA_STORE ? L::total_tma : L::total));
     uint64_t* split_pos = reinterpret_cast<uint64_t*>(h2 + D * kFuse2MaxD2);  // h2: 2 * D * 64 / 2 words
     uint32_t* h2_first = reinterpret_cast<uint32_t*>(split_pos + D);  // counter index of (digit 0, first seg)
     uint32_t* h2_stride = h2_first + D;

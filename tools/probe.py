@@ -31,6 +31,10 @@ def main():
                ("radix-partitioning", {"partitions": 65536, "radix_bits": (8, 8)}),
                ("radix-partitioning", {"partitions": 256, "radix_bits": (8, 0)}),
                ]
+    if os.environ.get("PROBE") == "fanout":
+        # one pass of 1..8 bits: how the scatter's time depends on the length of the runs it writes
+        # (tile of 4096 tuples / digits); the join behind it does not matter here
+        configs = [("radix-partitioning", {"partitions": 1 << b, "radix_bits": (b, 0)}) for b in (1, 2, 3, 4, 5, 6, 7, 8)]
     for algo, kw in configs:
         with phj.Engine(algo, **kw) as e:
             e.upload(R, S)

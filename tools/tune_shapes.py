@@ -12,6 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARDIR = os.path.join(ROOT, "partitionedhashjoin_b200", "variants")
 VARIANTS = {
     "s512x8m2": "",
+    "s512x8m2_plain3": "-DPHJ_SCAT_MINB_PLAIN=3",  # three CTAs/SM for the scatter without the fused histogram
+                                                   # (40 registers: ~20 spilled; 71 KB of shared memory each)
+    "s384x8m3": "-DPHJ_SCAT_TPB=384 -DPHJ_SCAT_MINB=3",  # 56 registers, no spills, three CTAs/SM (also fused)
+    "s256x8m5": "-DPHJ_SCAT_TPB=256 -DPHJ_SCAT_MINB=5",
     "s512x6m2": "-DPHJ_SCAT_IPT=6",
     "s512x4m3": "-DPHJ_SCAT_IPT=4 -DPHJ_SCAT_MINB=3",
     "s256x8m4": "-DPHJ_SCAT_TPB=256 -DPHJ_SCAT_MINB=4",
