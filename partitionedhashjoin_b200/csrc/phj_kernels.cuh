@@ -30,6 +30,7 @@ namespace phj {
 
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN marks a free table slot
 constexpr uint32_t kFuse2MaxD2 = 64;  // fused pass-2 histogram: pass 2 of at most 6 bits (with a 6-bit pass 1)
+constexpr uint32_t kFullD1 = 64, kFullD2 = 64;  // radix_histogram_full: two passes of at most 6 bits
 
 struct __align__(16) Segment {
     uint64_t begin, end;  // tuple range inside the relation's input array
@@ -79,6 +80,8 @@ struct PassParams {
     uint64_t seg_len2[2];               // pass-2 segment length per relation
     DigitFn df2;                        // pass-2 digit of the same hash
     uint32_t d2;                        // pass-2 digits
+    // radix_histogram_full: per pass-1 segment, the counts of all (pass-1 digit, pass-2 digit) pairs
+    uint32_t* hist12;                   // [segment][kFullD1 * kFullD2]
 };
 
 // Where pass-1 partition `parent` of a relation sits in pass 2's bookkeeping.
@@ -716,6 +719,65 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes8(PassParams p) {
 }
 
 // =================================================================================================
+// K1d  radix_histogram_full: ONE read of the input yields the histograms of BOTH passes (two passes
+// of <= 6 bits). Every CTA counts its pass-1 segment into a [pass-1 digit][pass-2 digit] table of
+// 4096 32-bit counters in shared memory (one shared-memory atomic per tuple: with 4096 bins two lanes
+// rarely meet in a counter, unlike a 64-bin table) and writes (a) the pass-1 counts = row sums, as
+// radix_histogram_lanes does, and (b) the table itself to hist12[segment]. The pass-1 scatter is
+// stable and segments are input slices, so in the pass-1 output partition d1 is the concatenation
+// over segments s of run (s, d1), whose pass-2 digit counts are exactly hist12[s][d1][*]: pass 2
+// gets its counters by summing rows (pass2_counts_from_hist12) instead of reading its input again
+// or having the pass-1 scatter count (FUSE2). The kernel stays HBM-bound: the atomics hide behind
+// the loads. HBM: reads 16 B/tuple (8 used), writes 16 KB per segment.
+// =================================================================================================
+template <int HASH, int TPB, int IPT>
+__global__ void __launch_bounds__(TPB) radix_histogram_full(PassParams p) {
+    constexpr int T = TPB * IPT;
+    constexpr int NB = kFullD1 * kFullD2;
+    __shared__ uint32_t cnt[NB];
+
+    if (blockIdx.x >= *p.nsegs) return;
+    const Segment seg = p.segs[blockIdx.x];
+    const ulonglong2* __restrict__ in = p.in[seg.rel];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < NB; i += TPB) cnt[i] = 0;
+    cta_sync();
+
+    auto count_key = [&](uint64_t key) {
+        const uint64_t h = hash_key<HASH>(key, p.hp);
+        atomicAdd(&cnt[digit_of<true>(h, p.df) * kFullD2 + digit_of<true>(h, p.df2)], 1u);
+    };
+    uint64_t tile = seg.begin;
+    for (; tile + T <= seg.end; tile += T) {  // full tiles: no bounds checks
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(in + tile + (uint64_t)warp * (32 * IPT) + lane);
+        uint64_t key[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) key[i] = ld_stream_u64(src + (size_t)i * 64);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) count_key(key[i]);
+    }
+    if (tile < seg.end) {  // tail tile
+        const uint64_t base = tile + (uint64_t)warp * (32 * IPT) + lane;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint64_t idx = base + (uint64_t)i * 32;
+            if (idx < seg.end) count_key(ld_stream_u64(reinterpret_cast<const uint64_t*>(in + idx)));
+        }
+    }
+    cta_sync();
+    // pass-1 counts: row sums (column index rotated by the row: the 64 threads hit 32 distinct banks twice)
+    if (threadIdx.x < p.ndigits) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (uint32_t k = 0; k < kFullD2; ++k) sum += cnt[threadIdx.x * kFullD2 + ((k + threadIdx.x) & (kFullD2 - 1))];
+        p.counts[seg.cnt_index + (uint64_t)threadIdx.x * seg.cnt_stride] = sum;
+    }
+    uint32_t* __restrict__ row = p.hist12 + (uint64_t)blockIdx.x * NB;
+    for (int i = threadIdx.x; i < NB; i += TPB) row[i] = cnt[i];
+}
+
+// =================================================================================================
 // plan_pass2: cut every pass-1 partition ("parent") of both relations into segments for pass 2.
 // Single CTA; runs on the device so the pipeline never waits for the host.
 // =================================================================================================
@@ -789,6 +851,91 @@ __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
         *p.nsegs = min(seg_base, p.max_segs);
         *p.ncounts = min(seg_base, p.max_segs) * p.d2;
     }
+}
+
+// =================================================================================================
+// With radix_histogram_full, pass 2's segments are aligned to RUNS of the pass-1 output: run (s, d)
+// = the tuples of pass-1 digit d that pass-1 segment s wrote, starting at its scanned cursor.
+// Segment j of parent d keeps plan_pass2's nominal window [lo + j L, lo + (j + 1) L) but holds exactly
+// the runs that START inside it, so its pass-2 digit counts are sums of hist12 rows.
+// align_pass2_segments moves every segment's begin / end to those run starts (binary search over
+// the parent's cursors); pass2_counts_from_hist12 adds the rows up into the pass-2 counters.
+// =================================================================================================
+struct Align2Params {
+    const uint64_t* cursors;  // scanned pass-1 cursors (as in Plan2Params)
+    uint32_t cnt_base1[2], nseg1[2];
+    uint64_t bias[2];
+    const uint64_t* bounds1[2];  // d1 + 1 per relation
+    const Parent2* parents2[2];
+    uint64_t seg_len[2];
+    Segment* segs;
+    const uint32_t* nsegs;
+};
+
+__global__ void align_pass2_segments(Align2Params p) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= *p.nsegs) return;
+    Segment sg = p.segs[gi];
+    const uint32_t rel = sg.rel, d = sg.parent_first & 0x7fffffffu;
+    const Parent2 par = p.parents2[rel][d];
+    const uint32_t j = sg.cnt_index - par.cnt_base, n1 = p.nseg1[rel];
+    const uint64_t lo = par.lo, hi = p.bounds1[rel][d + 1], bias = p.bias[rel];
+    const uint64_t* __restrict__ cur = p.cursors + p.cnt_base1[rel] + (uint64_t)d * n1;
+    // start of the first run that begins at or after `target` (the parent's end if there is none)
+    auto first_run_from = [&](uint64_t target) -> uint64_t {
+        uint32_t a = 0, b = n1;
+        while (a < b) {
+            const uint32_t m = (a + b) >> 1;
+            if (cur[m] - bias >= target) b = m;
+            else a = m + 1;
+        }
+        return a == n1 ? hi : cur[a] - bias;
+    };
+    sg.begin = j == 0 ? lo : first_run_from(lo + (uint64_t)j * p.seg_len[rel]);
+    sg.end = j + 1 == par.nseg ? hi : first_run_from(lo + (uint64_t)(j + 1) * p.seg_len[rel]);
+    p.segs[gi] = sg;
+}
+
+struct Counts2Params {
+    const uint32_t* hist12;   // [pass-1 segment][kFullD1][kFullD2]
+    const uint64_t* cursors;  // scanned pass-1 cursors
+    uint32_t cnt_base1[2], nseg1[2], seg_first1[2];  // seg_first1: index of the relation's first pass-1 segment
+    uint64_t bias[2];
+    const Parent2* parents2[2];
+    uint64_t seg_len[2];
+    uint32_t d1, d2;
+    uint32_t* counts2;  // zeroed before the launch
+};
+
+// grid (2 * d1 parents, s-chunks), 1024 threads = 16 segment lanes x 64 pass-2 digits: a thread walks
+// a few consecutive pass-1 segments of its parent, adds up hist12[s][d][d2] while the runs stay in
+// one pass-2 segment and flushes the sum with one atomic when it changes.
+__global__ void __launch_bounds__(1024) pass2_counts_from_hist12(Counts2Params p) {
+    const uint32_t rel = blockIdx.x / p.d1, d = blockIdx.x % p.d1;
+    const uint32_t d2 = threadIdx.x & (kFullD2 - 1), sl = threadIdx.x / kFullD2;
+    const uint32_t n1 = p.nseg1[rel];
+    const uint32_t lanes = gridDim.y * (1024 / kFullD2);
+    const uint32_t chunk = (n1 + lanes - 1) / lanes;
+    const uint32_t s0 = (blockIdx.y * (1024 / kFullD2) + sl) * chunk, s1 = min(n1, s0 + chunk);
+    if (d2 >= p.d2 || s0 >= s1) return;
+    const Parent2 par = p.parents2[rel][d];
+    if (par.nseg == 0) return;  // empty parent: nothing was counted
+    const uint64_t* __restrict__ cur = p.cursors + p.cnt_base1[rel] + (uint64_t)d * n1;
+    const uint32_t* __restrict__ hrow =
+        p.hist12 + ((uint64_t)p.seg_first1[rel] + s0) * (kFullD1 * kFullD2) + d * kFullD2 + d2;
+    const uint64_t base = p.bias[rel] + par.lo, len = p.seg_len[rel];
+    uint32_t acc = 0, jcur = 0;
+    for (uint32_t s = s0; s < s1; ++s, hrow += kFullD1 * kFullD2) {
+        const uint32_t c = *hrow;
+        const uint32_t j = (uint32_t)min((cur[s] - base) / len, (uint64_t)(par.nseg - 1));
+        if (j != jcur) {
+            if (acc) atomicAdd(&p.counts2[par.cnt_base + d2 * par.nseg + jcur], acc);
+            acc = 0;
+            jcur = j;
+        }
+        acc += c;
+    }
+    if (acc) atomicAdd(&p.counts2[par.cnt_base + d2 * par.nseg + jcur], acc);
 }
 
 // Boundaries of parents that received no segment (empty parents) are never written by

@@ -39,6 +39,29 @@ def cases_for(phj, name):
     return R, S
 
 
+class pass2_histogram:
+    """How pass 2 of a two-pass plan gets its histogram: 'full' = from the one 12-bit histogram read
+    (radix_histogram_full, the default), 'fused' = counted by the pass-1 scatter (PHJ_HIST12=0),
+    'separate' = its own histogram read (PHJ_FLAG_NO_FUSE_HIST2). Yields the engine flags."""
+    MODES = ("full", "fused", "separate")
+
+    def __init__(self, phj, mode):
+        self.mode, self.flags = mode, phj.FLAG_NO_FUSE_HIST2 if mode == "separate" else 0
+
+    def __enter__(self):
+        self.old = os.environ.get("PHJ_HIST12")
+        if self.mode == "fused":
+            os.environ["PHJ_HIST12"] = "0"
+        else:
+            os.environ.pop("PHJ_HIST12", None)
+        return self.flags
+
+    def __exit__(self, *exc):
+        os.environ.pop("PHJ_HIST12", None)
+        if self.old is not None:
+            os.environ["PHJ_HIST12"] = self.old
+
+
 def run(phj, R, S, algo, **kw):
     with phj.Engine(algo, **kw) as e:
         e.upload(R, S)
@@ -199,15 +222,16 @@ def test_partition_layout_equals_oracle(phj, oracle, P, bits, hash_id, hash):
     R = _cases.tuples(_cases.splitmix64(30011, 9).astype(np.int64) % 5003)
     S = _cases.tuples(_cases.splitmix64(250007, 10).astype(np.int64) % 7001)
     want_count = oracle.count_by_sort(R, S)
-    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_NO_FUSE_HIST2, True)):
-        with phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P,
-                        flags=flags) as e:
+    for mode, extra in (("full", 0), ("full", phj.FLAG_NO_TMA_STORE), ("fused", 0), ("separate", 0)):
+        with pass2_histogram(phj, mode) as flags, \
+                phj.Engine("radix-partitioning", partitions=P, radix_bits=bits, hash=hash, hash_seed=SEED_P,
+                           flags=flags | extra) as e:
             e.upload(R, S)
             assert e.join()["matches"] == want_count
             for which, rel in ((0, R), (1, S)):
                 got, gb = e.read_partitions(which, P)
                 want, wb = oracle.radix_partition(rel, P, hash_id, SEED_P, workers=1)
-                assert_same_partitioning(got, gb, want, wb, rel.shape[0], exact)
+                assert_same_partitioning(got, gb, want, wb, rel.shape[0], True)
 
 
 @pytest.mark.parametrize("P,bits", [(256, (4, 4)), (4096, (6, 6)), (4096, (5, 7)), (1 << 14, (8, 6)), (64, (6, 0))])
@@ -353,16 +377,16 @@ def test_partition_layout_skewed_generator_data(phj, oracle):
     phj.fill_sequential(R, 1)
     phj.fill_zipf(S, 1.25, 1, nr, 4711, 16)
     want, wb = oracle.radix_partition(S, 4096, 0, SEED_P, workers=1)
-    for flags, exact in ((0, True), (phj.FLAG_NO_TMA_STORE, True), (phj.FLAG_NO_FUSE_HIST2, True)):
-        with phj.Engine("radix-partitioning", partitions=4096, hash_seed=SEED_P, flags=flags) as e:
+    for mode, extra in (("full", 0), ("full", phj.FLAG_NO_TMA_STORE), ("fused", 0), ("separate", 0)):
+        with pass2_histogram(phj, mode) as flags, \
+                phj.Engine("radix-partitioning", partitions=4096, hash_seed=SEED_P, flags=flags | extra) as e:
             e.upload(R, S)
             assert e.join()["matches"] == ns
             got, gb = e.read_partitions(1, 4096)
-            assert_same_partitioning(got, gb, want, wb, ns, exact)
-            if not exact:  # deterministic: a second run gives the very same bytes
-                assert e.join()["matches"] == ns
-                again, _ = e.read_partitions(1, 4096)
-                assert (again["id"] == got["id"]).all() and (again["payload"] == got["payload"]).all()
+            assert_same_partitioning(got, gb, want, wb, ns, True)
+            assert e.join()["matches"] == ns   # deterministic: a second run gives the very same bytes
+            again, _ = e.read_partitions(1, 4096)
+            assert (again["id"] == got["id"]).all() and (again["payload"] == got["payload"]).all()
 
 
 def test_oversize_partitions_use_the_global_table(phj, oracle):
