@@ -39,9 +39,9 @@ N_BUILD, N_PROBE = 10_000_000, 200_000_000
 BASE_SEED, BATCHES = 12345, 64
 METRIC = "join throughput (|R|+|S|) tuples/sec"
 UNIT = "tuples/s"
-# ncu (profiles/r01c_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum of one
-# radix_scatter launch at this workload (6.681 GB pass 1 with the fused histogram, 6.688 GB pass 2)
-SCATTER_DRAM_TRAFFIC_BYTES = 6.685e9
+# ncu (profiles/r01f_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum of one
+# radix_scatter launch at this workload (3.371 GB read + 3.309 GB written)
+SCATTER_DRAM_TRAFFIC_BYTES = 6.680e9
 
 
 def measured_hbm_peak():

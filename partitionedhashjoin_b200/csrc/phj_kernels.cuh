@@ -881,18 +881,25 @@ __global__ void align_pass2_segments(Align2Params p) {
     const uint32_t j = sg.cnt_index - par.cnt_base, n1 = p.nseg1[rel];
     const uint64_t lo = par.lo, hi = p.bounds1[rel][d + 1], bias = p.bias[rel];
     const uint64_t* __restrict__ cur = p.cursors + p.cnt_base1[rel] + (uint64_t)d * n1;
-    // start of the first run that begins at or after `target` (the parent's end if there is none)
-    auto first_run_from = [&](uint64_t target) -> uint64_t {
-        uint32_t a = 0, b = n1;
-        while (a < b) {
-            const uint32_t m = (a + b) >> 1;
-            if (cur[m] - bias >= target) b = m;
-            else a = m + 1;
+    // Start of the first run that begins at or after a target position (the parent's end if there is
+    // none); the searches for this segment's begin and end advance together, so their dependent
+    // loads overlap.
+    const uint64_t t0 = lo + (uint64_t)j * p.seg_len[rel], t1 = t0 + p.seg_len[rel];
+    uint32_t a0 = 0, b0 = n1, a1 = 0, b1 = n1;
+    while (a0 < b0 || a1 < b1) {
+        const uint32_t m0 = min((a0 + b0) >> 1, n1 - 1), m1 = min((a1 + b1) >> 1, n1 - 1);
+        const uint64_t c0 = cur[m0] - bias, c1 = cur[m1] - bias;
+        if (a0 < b0) {
+            if (c0 >= t0) b0 = m0;
+            else a0 = m0 + 1;
         }
-        return a == n1 ? hi : cur[a] - bias;
-    };
-    sg.begin = j == 0 ? lo : first_run_from(lo + (uint64_t)j * p.seg_len[rel]);
-    sg.end = j + 1 == par.nseg ? hi : first_run_from(lo + (uint64_t)(j + 1) * p.seg_len[rel]);
+        if (a1 < b1) {
+            if (c1 >= t1) b1 = m1;
+            else a1 = m1 + 1;
+        }
+    }
+    sg.begin = j == 0 ? lo : a0 == n1 ? hi : cur[a0] - bias;
+    sg.end = j + 1 == par.nseg ? hi : a1 == n1 ? hi : cur[a1] - bias;
     p.segs[gi] = sg;
 }
 
@@ -924,14 +931,23 @@ __global__ void __launch_bounds__(1024) pass2_counts_from_hist12(Counts2Params p
     const uint32_t* __restrict__ hrow =
         p.hist12 + ((uint64_t)p.seg_first1[rel] + s0) * (kFullD1 * kFullD2) + d * kFullD2 + d2;
     const uint64_t base = p.bias[rel] + par.lo, len = p.seg_len[rel];
-    uint32_t acc = 0, jcur = 0;
+    // pass-2 segment of the first run (one division per thread), then only comparisons: run starts
+    // grow with s, so the segment index moves forward
+    const uint64_t pos0 = cur[s0] - base;
+    uint32_t jcur = (uint32_t)min(((pos0 | len) >> 32) ? pos0 / len : (uint64_t)((uint32_t)pos0 / (uint32_t)len),
+                                  (uint64_t)(par.nseg - 1));
+    uint64_t next = (uint64_t)(jcur + 1) * len;  // first position of the next segment's window
+    uint32_t acc = 0;
     for (uint32_t s = s0; s < s1; ++s, hrow += kFullD1 * kFullD2) {
         const uint32_t c = *hrow;
-        const uint32_t j = (uint32_t)min((cur[s] - base) / len, (uint64_t)(par.nseg - 1));
-        if (j != jcur) {
+        const uint64_t pos = cur[s] - base;
+        if (pos >= next && jcur + 1 < par.nseg) {
             if (acc) atomicAdd(&p.counts2[par.cnt_base + d2 * par.nseg + jcur], acc);
             acc = 0;
-            jcur = j;
+            do {
+                ++jcur;
+                next += len;
+            } while (pos >= next && jcur + 1 < par.nseg);
         }
         acc += c;
     }
