@@ -1626,7 +1626,7 @@ static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_bu
             if (thread.joinable()) thread.join();
         }
     } up;
-    up.thread = std::thread([&]() {
+    auto uploader = [&]() {
         auto check = [&](cudaError_t e, const char* what) {
             if (e == cudaSuccess) return true;
             up.error = std::string(what) + " failed: " + cudaGetErrorString(e);
@@ -1646,7 +1646,12 @@ static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_bu
             if (!check(cudaEventRecord(h->upload_ev[2 + c], h->upload_stream), "cudaEventRecord")) return;
             up.published.store((int)c + 1, std::memory_order_release);
         }
-    });
+    };
+    try {
+        up.thread = std::thread(uploader);
+    } catch (const std::exception&) {
+        uploader();  // no helper thread to be had: issue the uploads from here (pinned memory still overlaps)
+    }
 
     memset(out, 0, sizeof(*out));
     for (uint32_t c = 0; c < chunks; ++c) {
@@ -1672,7 +1677,7 @@ static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_bu
         out->passes = r.passes;
         out->partitions = r.partitions;
     }
-    up.thread.join();
+    if (up.thread.joinable()) up.thread.join();
     if (up.failed.load()) return fail(PHJ_ERR_CUDA, "%s", up.error.c_str());
     PHJ_CUDA(cudaEventRecord(h->ev[4], child->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->upload_stream));
