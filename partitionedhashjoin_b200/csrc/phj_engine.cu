@@ -230,8 +230,8 @@ struct KernelScope {
     phj_handle* h;
     int idx;
     const char* name_;
-    KernelScope(phj_handle* h_, const char* name) : h(h_), idx(-1), name_(name) {
-        ++h->launches;
+    KernelScope(phj_handle* h_, const char* name, uint32_t kernels = 1) : h(h_), idx(-1), name_(name) {
+        h->launches += kernels;  // kernels launched inside this scope (phj_result.kernel_launches)
         if (h->time_kernels && h->n_ktimes < kMaxKernelTimes) {
             idx = h->n_ktimes++;
             h->ktimes[idx].name = name;
@@ -958,7 +958,7 @@ int join_radix(phj_handle* h, phj_result* out) {
         p2.df = digit_fn(h, 2);
     }
     auto run_plan2 = [&]() {
-        KernelScope ks(h, "plan_pass2");
+        KernelScope ks(h, "plan_pass2", 2);
         plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
         fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
     };
@@ -1019,7 +1019,7 @@ int join_radix(phj_handle* h, phj_result* out) {
             cp.counts2 = h->d_counts;
             PHJ_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->max_segs2 * h->d2 * sizeof(uint32_t), h->stream));
             {
-                KernelScope ks(h, "pass2_counts");
+                KernelScope ks(h, "pass2_counts", 2);
                 align_pass2_segments<<<(h->max_segs2 + 255) / 256, 256, 0, h->stream>>>(ap);
                 const uint32_t max_nseg1 = std::max(h->nseg1_rel[0], h->nseg1_rel[1]);
                 const dim3 grid(2 * h->d1, std::max<uint32_t>(1, std::min<uint32_t>(8, (max_nseg1 + 63) / 64)));
@@ -1555,7 +1555,7 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     mp.out = h->d_joined;
     mp.out_cap = h->cap_joined;
     if (rows) {
-        KernelScope ks(h, "join_materialize[write]");
+        KernelScope ks(h, "join_materialize[write]", 2);
         scan_cta_rows<<<1, 1024, 0, h->stream>>>(h->d_cta_rows, grid);
         write_kern<<<grid, kTpb, smem, h->stream>>>(mp);
     }
