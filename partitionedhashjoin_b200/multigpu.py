@@ -789,20 +789,27 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         dist.barrier()
         torch.cuda.synchronize()
 
+    # Timed on the device: a CUDA event pair brackets the K joins (every join returns with its streams
+    # synchronised, so the closing event's timestamp lies after the last kernel), barrier +
+    # synchronize on both sides, max over ranks. The wall clock is kept beside it.
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = backend.launches
     with ClockSampler(local) as clocks:
         sync()
+        ev0.record()
         t0 = time.perf_counter()
         parts = {"split_s": 0.0, "exchange_s": 0.0, "local_s": 0.0, "reduce_s": 0.0}
         for _ in range(args.steps):
             res = job.join()
             for k in parts:
                 parts[k] += res[k]
+        ev1.record()
         sync()
-        elapsed = time.perf_counter() - t0
-    t = torch.tensor([elapsed], dtype=torch.float64, device=f"cuda:{local}")
+        wall = time.perf_counter() - t0
+    elapsed = ev0.elapsed_time(ev1) / 1e3
+    t = torch.tensor([elapsed, wall], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
+    elapsed, wall = float(t[0].item()), float(t[1].item())
     assert res["matches"] == want
 
     # e2e: the host shards are uploaded inside the timed region (the scaled workload is generated on
@@ -843,6 +850,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         line = {
             "metric": metric, "value": n_tuples / (elapsed / args.steps), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "timing": "CUDA events around the K joins, max over ranks", "wall_ms_per_step": wall / args.steps * 1e3,
             "scaling": "strong" if scaled else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": cfg,
             "e2e": None if scaled else {
