@@ -916,6 +916,7 @@ int join_radix(phj_handle* h, phj_result* out) {
     p1.ndigits = h->d1;
     p1.hp = hp;
     p1.df = digit_fn(h, 1);
+    if (const char* x = getenv("PHJ_SCAT_PREFETCH")) p1.prefetch_tiles = (uint32_t)std::max(0, atoi(x));
     // pass-2 bookkeeping (needed before scatter 1 when the pass-2 histogram is fused into it)
     Plan2Params pl{};
     FillEmptyParams fe{};
@@ -956,6 +957,7 @@ int join_radix(phj_handle* h, phj_result* out) {
         p2.ndigits = h->d2;
         p2.hp = hp;
         p2.df = digit_fn(h, 2);
+        p2.prefetch_tiles = p1.prefetch_tiles;
     }
     auto run_plan2 = [&]() {
         KernelScope ks(h, "plan_pass2", 2);

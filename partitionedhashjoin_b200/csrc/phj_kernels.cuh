@@ -82,6 +82,9 @@ struct PassParams {
     uint32_t d2;                        // pass-2 digits
     // radix_histogram_full: per pass-1 segment, the counts of all (pass-1 digit, pass-2 digit) pairs
     uint32_t* hist12;                   // [segment][kFullD1 * kFullD2]
+    // radix_scatter experiment (PHJ_SCAT_PREFETCH=k, default 0 = off): when a tile's loads are issued,
+    // one thread also asks for the tile k further on to be brought into L2 (cp.async.bulk.prefetch.L2)
+    uint32_t prefetch_tiles;
 };
 
 // Where pass-1 partition `parent` of a relation sits in pass 2's bookkeeping.
@@ -131,6 +134,10 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
+}
+// TMA prefetch of a contiguous piece of global memory into L2 (16-byte aligned, size % 16 == 0).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
@@ -519,6 +526,10 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         }
         // prefetch the next tile while this one is flushed
         if (tile + T < seg.end) load_tile(tile + T);
+        if (p.prefetch_tiles && tid == 0) {
+            const uint64_t pf = tile + (uint64_t)T * (1 + p.prefetch_tiles);
+            if (pf < seg.end) bulk_prefetch_l2(in + pf, (uint32_t)min((uint64_t)T, seg.end - pf) * 16u);
+        }
         if (TMA_STORE) fence_proxy_async_smem();
         cta_sync();
 
