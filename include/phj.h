@@ -105,10 +105,13 @@ typedef struct {
 #define PHJ_FLAG_CHAINED_TABLE 0x10u /* NO_PARTITIONING: bucket-chained global table (the reference's
                                         SeparateChainingHashTable, src/HashTables/SeparateChaining.hpp)
                                         instead of the open-addressing one (LinearProbing.hpp) */
-#define PHJ_FLAG_FUSE_HIST2 0x4u   /* accepted for compatibility: the fused pass-2 histogram is the default */
-#define PHJ_FLAG_NO_FUSE_HIST2 0x20u /* pass 2 reads its own histogram instead of having the pass-1
-                                        scatter count it (the default for two passes of <= 6 bits; saves
-                                        one read of both relations) */
+#define PHJ_FLAG_FUSE_HIST2 0x4u   /* accepted for compatibility: pass 2 never reads a histogram of its own by default */
+#define PHJ_FLAG_NO_FUSE_HIST2 0x20u /* pass 2 reads its own histogram. By default (two passes of <= 6 bits,
+                                        power-of-two fan-out) ONE read of the input yields the histograms of
+                                        both passes (radix_histogram_full: counts of (pass-1 digit, pass-2
+                                        digit) pairs per pass-1 segment, summed into pass 2's counters); for
+                                        other two-pass plans of <= 6 bits the pass-1 scatter counts them.
+                                        Saves one read of both relations, DESIGN.md section 4 */
 
 
 /* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the
