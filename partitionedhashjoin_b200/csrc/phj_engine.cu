@@ -171,6 +171,11 @@ struct phj_handle {
     uint32_t join_grid = 0, join_slots = 0, join_max_keys = 0;
     uint64_t* d_gt = nullptr;
     uint64_t gt_buckets = 0;
+    // EXPERIMENT (PHJ_L2JOIN=1): per-partition tables in global memory, probed out of L2 (pt_build / pt_probe)
+    bool l2join = false;
+    uint64_t* d_pt = nullptr;
+    size_t cap_pt = 0;
+    uint32_t pt_region_buckets = 0;
     // bucket-chained table (PHJ_FLAG_CHAINED_TABLE)
     uint32_t* d_ct_heads = nullptr;
     phj::ChainBucket* d_ct_buckets = nullptr;
@@ -667,6 +672,20 @@ int build_plan(phj_handle* h) {
         const size_t smem = (size_t)slots * 8;
         uint32_t resident = (uint32_t)std::max<size_t>(1, std::min<size_t>((h->smem_optin) / (smem + 1024), 2048 / PHJ_JOIN_TPB));
         h->join_grid = (uint32_t)h->sm_count * resident * 4;
+        {
+            // EXPERIMENT: L2-resident partition tables instead of shared-memory ones. A region of 32-byte
+            // buckets per partition, load <= 0.4 at the mean partition size; partitions beyond 75 % of a
+            // region's capacity take the oversize path like partitions too large for shared memory.
+            const char* x = getenv("PHJ_L2JOIN");
+            h->l2join = x && x[0] == '1' && h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING;
+            if (h->l2join) {
+                uint32_t rb = 64;
+                while ((uint64_t)rb * 8 < mean * 5) rb <<= 1;  // 4 rb >= 2.5 x mean
+                h->pt_region_buckets = rb;
+                h->join_max_keys = rb * 3;
+                if ((rc = dev_reserve(&h->d_pt, &h->cap_pt, (size_t)h->nparts * rb * 4)) != PHJ_OK) return rc;
+            }
+        }
         size_t cap = h->cap_cta_times;
         if ((rc = dev_reserve(&h->d_cta_times, &cap, (size_t)h->join_grid * 2)) != PHJ_OK) return rc;
         if (cap != h->cap_cta_times) {
@@ -1116,7 +1135,32 @@ int join_radix(phj_handle* h, phj_result* out) {
     }
     jp.matches = h->d_matches;
     jp.cta_times = h->d_cta_times;
-    {
+    if (h->l2join) {
+        PtParams q{};
+        q.j = jp;
+        const uint32_t grid = (uint32_t)h->sm_count * 8;
+        q.j.slice_len = h->n[1] / grid;
+        q.j.slice_rem = h->n[1] % grid;
+        q.table = h->d_pt;
+        q.n_build = h->n[0];
+        q.region_buckets = h->pt_region_buckets;
+        q.region_shift32 = 32 - (uint32_t)ilog2_ceil(h->pt_region_buckets);
+        q.flags = h->d_scalars + kGtFlags;
+        {
+            KernelScope ks(h, "pt_clear");
+            PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kGtFlags, 0, 4, h->stream));
+            gt_clear<<<grid, 256, 0, h->stream>>>(h->d_pt, (uint64_t)h->nparts * h->pt_region_buckets * 4);
+        }
+        {
+            KernelScope ks(h, "pt_build");
+            pt_build<256><<<grid, 256, 0, h->stream>>>(q);
+        }
+        PHJ_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        {
+            KernelScope ks(h, "pt_probe");
+            pt_probe<256><<<grid, 256, 0, h->stream>>>(q);
+        }
+    } else {
         KernelScope ks(h, "join_partitions");
         PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
     }
@@ -1181,6 +1225,10 @@ int join_radix(phj_handle* h, phj_result* out) {
     }
     out->build_ns = best_b;
     out->probe_ns = best_p;
+    if (h->l2join) {  // the table kernels do not time themselves: whole-kernel device times instead
+        out->build_ns = (uint64_t)(ev_ms(h->ev[1], h->ev[2]) * 1e6);
+        out->probe_ns = (uint64_t)(ev_ms(h->ev[2], h->ev[3]) * 1e6);
+    }
     out->passes = (two ? 2 : 1) - (h->prepart ? 1 : 0);
     out->partitions = h->P;
     out->fallback_partitions = oversize;
@@ -1337,7 +1385,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_hist12, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows, h->d_ct_heads, h->d_ct_buckets};
+                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_hist12, h->d_pt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows, h->d_ct_heads, h->d_ct_buckets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);

@@ -1393,6 +1393,152 @@ __global__ void count_oversize(const uint64_t* __restrict__ bounds_build, uint32
 }
 
 // =================================================================================================
+// K4g/K5g  EXPERIMENT (PHJ_L2JOIN=1, off by default; not measured yet): per-partition tables in GLOBAL
+// memory sized for L2 instead of shared memory. With few, large partitions (one radix pass of 6
+// bits: 156 K build keys each at 10 M x 200 M) a partition's table (32-byte buckets of four keys,
+// load <= 0.6) is a few MB; the probe relation is walked in partition order by all CTAs together, so
+// only the tables of the ~10 partitions being probed are hot and they stay in the 126 MB L2. Unlike
+// gt_build / gt_probe (the fallback for oversize partitions) the partition comes from the tuple's
+// POSITION (the boundaries), so the table hash is the 5-instruction multiply-shift of
+// join_partitions instead of a second XXH3, and there is no per-tuple selection test. What it could
+// buy: the second partitioning pass (1.36 ms + planning) for an L2-resident probe; to be measured.
+// Partitions whose build side exceeds max_keys are skipped and counted, as in join_partitions.
+// =================================================================================================
+struct PtParams {
+    JoinParams j;            // relations, boundaries, slicing of the probe side, hash multipliers
+    uint64_t* table;         // npart regions of region_buckets buckets of 4 keys
+    uint64_t n_build;
+    uint32_t region_shift32; // bucket inside a region = table_bucket32(...) >> nothing: shift32 = 32 - log2(region_buckets)
+    uint32_t region_buckets; // a power of two
+    uint32_t* flags;         // [0]: the sentinel partition's build side contains kEmptyKey
+};
+
+// First partition whose range [bounds[a], bounds[a + 1]) can contain position `pos`.
+__device__ __forceinline__ uint32_t partition_of(const uint64_t* __restrict__ bounds, uint32_t npart, uint64_t pos) {
+    uint32_t a = 0, b = npart;
+    while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (bounds[m] <= pos) a = m;
+        else b = m;
+    }
+    return a;
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB) pt_build(PtParams q) {
+    const JoinParams& p = q.j;
+    const uint64_t lo = q.n_build / gridDim.x * blockIdx.x + min((uint64_t)blockIdx.x, q.n_build % gridDim.x);
+    const uint64_t hi = lo + q.n_build / gridDim.x + (blockIdx.x < q.n_build % gridDim.x ? 1 : 0);
+    if (lo >= hi) return;
+    const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
+    const uint32_t bmask = q.region_buckets - 1;
+    for (uint32_t part = partition_of(p.bounds_build, p.npart, lo); part < p.npart; ++part) {
+        const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
+        if (r0 >= hi) break;
+        if (r1 - r0 > p.max_keys) continue;  // oversize: left to the global-table fallback
+        const uint64_t s0 = max(lo, r0), s1 = min(hi, r1);
+        uint64_t* __restrict__ region = q.table + (uint64_t)part * q.region_buckets * 4;
+        const bool careful = part == p.sentinel_part;
+        // warp-converged insert loop (see cta_sync()): first free slot of the home bucket, then the next bucket
+        for (uint64_t i0 = s0; i0 < s1; i0 += TPB) {
+            const uint64_t i = i0 + threadIdx.x;
+            uint64_t key = 0;
+            bool pending = i < s1;
+            if (pending) {
+                key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.build + i));
+                if (careful && key == kEmptyKey) {
+                    q.flags[0] = 1;
+                    pending = false;
+                }
+            }
+            uint32_t bucket = table_bucket32(key, mul_lo, mul_hi, q.region_shift32) & bmask, s = 0;
+            while (__any_sync(0xffffffffu, pending)) {
+                if (pending) {
+                    unsigned long long* slot = reinterpret_cast<unsigned long long*>(region + (uint64_t)bucket * 4 + s);
+                    unsigned long long cur = *slot;
+                    if (cur == kEmptyKey) cur = atomicCAS(slot, kEmptyKey, key);
+                    if (cur == kEmptyKey || cur == key) {
+                        pending = false;  // duplicates collapse
+                    } else if (++s == 4) {
+                        s = 0;
+                        bucket = (bucket + 1) & bmask;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB) pt_probe(PtParams q) {
+    const JoinParams& p = q.j;
+    __shared__ unsigned long long block_count;
+    if (threadIdx.x == 0) block_count = 0;
+    const uint64_t lo = p.slice_len * blockIdx.x + min((uint64_t)blockIdx.x, p.slice_rem);
+    const uint64_t hi = lo + p.slice_len + (blockIdx.x < p.slice_rem ? 1 : 0);
+    const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
+    const uint32_t bmask = q.region_buckets - 1;
+    const uint32_t sentinel_hit = q.flags[0];
+    uint32_t count = 0;
+    constexpr int U = 4;
+    if (lo < hi) {
+        for (uint32_t part = partition_of(p.bounds_probe, p.npart, lo); part < p.npart; ++part) {
+            const uint64_t ps0 = p.bounds_probe[part];
+            if (ps0 >= hi) break;
+            const uint64_t s0 = max(lo, ps0), s1 = min(hi, p.bounds_probe[part + 1]);
+            if (s0 >= s1) continue;
+            const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
+            if (r1 == r0 || r1 - r0 > p.max_keys) continue;
+            const uint64_t* __restrict__ region = q.table + (uint64_t)part * q.region_buckets * 4;
+            const bool careful = part == p.sentinel_part;
+            for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
+                uint64_t key[U];
+                uint32_t bucket[U];
+                bool pending[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t i = i0 + (uint64_t)u * TPB + threadIdx.x;
+                    pending[u] = i < s1;
+                    key[u] = pending[u] ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (careful && pending[u] && key[u] == kEmptyKey) {
+                        count += sentinel_hit;
+                        pending[u] = false;
+                    }
+                    bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, q.region_shift32) & bmask;
+                }
+                // one 32-byte bucket per step; a bucket whose last slot is free ends the search
+                while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pending[u]) {
+                            const ulonglong2* b = reinterpret_cast<const ulonglong2*>(region + (uint64_t)bucket[u] * 4);
+                            const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
+                            if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
+                                ++count;
+                                pending[u] = false;
+                            } else if (k23.y == kEmptyKey) {
+                                pending[u] = false;
+                            } else {
+                                bucket[u] = (bucket[u] + 1) & bmask;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cta_sync();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
+    cta_sync();
+    if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
+}
+
+// =================================================================================================
 // K6/K7  global open-addressing table: the no-partitioning join, and the fallback for oversize
 // radix partitions. Buckets are 32-byte sectors of four 8-byte keys; a key hashes to a bucket,
 // takes the first free slot (atomicCAS) and overflows into the next bucket -- the GPU analogue of
