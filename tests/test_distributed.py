@@ -35,7 +35,7 @@ def test_sharded_join_over_gloo(world, case):
 
 
 @pytest.mark.parametrize("world,case,mode", [(2, "random", "pass1"), (2, "skewed", "pass1"), (2, "tiny", "pass1"),
-                                             (4, "random", "pass1"), (1, "random", "pass1"), (2, "random", "fused"),
+                                             (4, "random", "pass1"), (4, "skewed", "pass1"), (1, "random", "pass1"), (2, "random", "fused"),
                                              (2, "random", "pipelined"), (2, "skewed", "pipelined"),
                                              (2, "tiny", "pipelined"), (4, "random", "pipelined"),
                                              (1, "random", "pipelined"), (2, "skewed", "pipelined-ce"),
@@ -84,6 +84,71 @@ def test_window_layout_against_brute_force(world, ndig):
         if balance and world > 1:  # the cut is no worse than the equal split
             load = lambda f: max(M[:, :, f[o]:f[o + 1]].sum() for o in range(world))
             assert load(first) <= load(F.ownership(M, world, False))
+
+
+@pytest.mark.parametrize("world,ndig,hot_on", [(2, 8, "all"), (4, 16, "all"), (8, 256, "all"), (4, 128, "some"),
+                                               (8, 64, "some"), (2, 128, "none")])
+def test_hot_digit_layout_simulation(world, ndig, hot_on):
+    """FusedShardedRadixJoin.hot_digits / layout_hot: a numpy simulation of the whole exchange -- every
+    rank scatters its pieces to the windows layout_hot names, non-owners pull the replicated build side
+    of the heavy-hitter digits -- after which every window is completely filled without overlap, every
+    local parent holds the WHOLE build side of its digit (all sources, source order) and, on the probe
+    side, all sources' pieces (normal digit, at its owner) or only the rank's own piece (hot digit, on
+    every rank): each probe tuple ends up on exactly one rank, next to every build tuple it can match."""
+    import numpy as np
+
+    from partitionedhashjoin_b200.multigpu import FusedShardedRadixJoin as F
+    rng = np.random.default_rng(7 * world + ndig)
+    M = rng.integers(0, 40, size=(world, 2, ndig))
+    M[:, 0, 5 % ndig] = 0                                  # a digit without build tuples
+    hot_want = []
+    if hot_on != "none":
+        hot_want = sorted({3 % ndig, (ndig // 2 + 1) % ndig})
+        for d in hot_want:
+            M[:, 1, d] = rng.integers(3000, 6000, size=world)
+        if hot_on == "some":                               # a heavy hitter that only some ranks hold
+            M[1:, 1, hot_want[0]] = 0
+            M[0, 1, hot_want[0]] = 20000
+    hot = F.hot_digits(M, world)
+    assert sorted(np.nonzero(hot)[0].tolist()) == hot_want
+    Wt = M.copy()
+    Wt[:, 1, hot] = 0
+    first = F.ownership(Wt, world, True)
+    plans = [F.layout_hot(M, world, r, first, hot) for r in range(world)]
+    need = plans[0][0]
+    for pl in plans:
+        assert (pl[0] == need).all()                       # every rank derives the same window sizes
+
+    def ids(rel, src, d):                                  # globally unique tuple ids of one piece
+        return ((rel * world + src) * ndig + d) * 100000 + np.arange(M[src][rel][d])
+
+    win = [[np.full(int(need[rel][o]), -1, dtype=np.int64) for o in range(world)] for rel in (0, 1)]
+    for src, (_, offsets, dst, _, _, _) in enumerate(plans):
+        for rel in (0, 1):
+            for d in range(ndig):
+                n, o, at = int(M[src][rel][d]), int(dst[rel][d]), int(offsets[rel][d])
+                assert (win[rel][o][at:at + n] == -1).all(), "pieces overlap"
+                win[rel][o][at:at + n] = ids(rel, src, d)
+    for r, (_, _, _, _, _, pulls) in enumerate(plans):     # after the exchange barrier
+        for owner, src_row, dst_row, rows in pulls:
+            assert owner != r and (win[0][r][dst_row:dst_row + rows] == -1).all()
+            win[0][r][dst_row:dst_row + rows] = win[0][owner][src_row:src_row + rows]
+    seen_probe = []
+    for r, (_, _, _, bounds, parents, _) in enumerate(plans):
+        assert (win[0][r] != -1).all() and (win[1][r] != -1).all(), "window not completely filled"
+        assert bounds[0][-1] == need[0][r] and bounds[1][-1] == need[1][r]
+        owned = set(range(int(first[r]), int(first[r + 1])))
+        assert set(parents.tolist()) == owned | set(hot_want)
+        for i, d in enumerate(parents.tolist()):
+            build = win[0][r][bounds[0][i]:bounds[0][i + 1]]
+            assert (build == np.concatenate([ids(0, src, d) for src in range(world)])).all()
+            probe = win[1][r][bounds[1][i]:bounds[1][i + 1]]
+            want = ids(1, r, d) if hot[d] else np.concatenate([ids(1, src, d) for src in range(world)])
+            assert (probe == want).all()
+            seen_probe.append(probe)
+    seen = np.sort(np.concatenate(seen_probe))
+    everything = np.sort(np.concatenate([ids(1, src, d) for src in range(world) for d in range(ndig)]))
+    assert (seen == everything).all()                      # every probe tuple on exactly one rank
 
 
 def test_split_plan():
