@@ -44,6 +44,9 @@
 #ifndef PHJ_JOIN_TPB
 #define PHJ_JOIN_TPB 512
 #endif
+#ifndef PHJ_JOIN_U
+#define PHJ_JOIN_U 4  // probe tuples in flight per thread of join_partitions (tools/tune_shapes.py: j*u6 / u8)
+#endif
 #ifndef PHJ_JOIN_BUCKET
 #define PHJ_JOIN_BUCKET 2  // keys per shared-memory bucket (2: one LDS.128 per probe step)
 #endif

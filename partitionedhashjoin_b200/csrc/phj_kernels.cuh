@@ -1105,7 +1105,7 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
             // tuples skip the bounds checks; outside the sentinel partition no key can equal the
             // free-slot marker, so that test is skipped too (the loop is issue-bound: every
             // instruction removed here is time).
-            constexpr int U = 4;
+            constexpr int U = PHJ_JOIN_U;  // probe tuples (loads) in flight per thread
             auto probe_bucket = [&](uint64_t key, uint32_t bucket, bool& hit, bool& full) {
                 if (BK == 2) {
                     const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(table + bucket * 2);
@@ -1119,7 +1119,13 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                 }
             };
             auto overflow_walk = [&](uint64_t (&key)[U], uint32_t (&bucket)[U], bool (&pending)[U]) {
-                bool any = pending[0] | pending[1] | pending[2] | pending[3];
+                auto any_pending = [&]() {
+                    bool a = false;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) a |= pending[u];
+                    return a;
+                };
+                bool any = any_pending();
                 while (__any_sync(0xffffffffu, any)) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
@@ -1130,7 +1136,7 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
                             count += hit;
                             pending[u] = !hit && full;
                         }
-                    any = pending[0] | pending[1] | pending[2] | pending[3];
+                    any = any_pending();
                 }
             };
             uint64_t i0 = s0;

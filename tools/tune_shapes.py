@@ -20,6 +20,8 @@ VARIANTS = {
     "s512x4m3": "-DPHJ_SCAT_IPT=4 -DPHJ_SCAT_MINB=3",
     "s256x8m4": "-DPHJ_SCAT_TPB=256 -DPHJ_SCAT_MINB=4",
     "s384x8m2": "-DPHJ_SCAT_TPB=384 -DPHJ_SCAT_MINB=2",
+    "s512x8m2_ju6": "-DPHJ_JOIN_U=6",   # more probe loads in flight per thread (ncu: 11.5 % of the join's
+    "s512x8m2_ju8": "-DPHJ_JOIN_U=8",   # stall samples wait on the first use of a loaded key)
     "s512x8m2_j256": "-DPHJ_JOIN_TPB=256",
     "s512x8m2_j1024": "-DPHJ_JOIN_TPB=1024",
     "s512x8m2_h1024": "-DPHJ_HIST_TPB=1024 -DPHJ_HIST_IPT=4",
