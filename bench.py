@@ -340,11 +340,12 @@ def main():
     ap.add_argument("--chunks", type=int, default=4, help="N > 1, pipelined shuffle: probe chunks")
     ap.add_argument("--split-ctas", type=int, default=96,
                     help="N > 1, pipelined shuffle: CTAs of the NVLink-bound split scatter (0 = all)")
-    ap.add_argument("--shuffle", default="pass1", choices=["pass1", "pipelined", "fused", "nccl"],
+    ap.add_argument("--shuffle", default="pass1", choices=["pass1", "pipelined", "fused", "nccl", "npj"],
                     help="N > 1: pipelined = pass1 cut into probe chunks, shuffle of chunk c+1 overlapping the local "
                          "join of chunk c; pass1 = the split scatter writes (owner : pass-1 digit) pieces into the owners' "
                          "windows over NVLink and the local join starts at pass 2; fused = same stores, split by "
-                         "owner only; nccl = local split + NCCL all-to-all")
+                         "owner only; nccl = local split + NCCL all-to-all; npj = the no-partitioning join instead: build shards "
+                         "gathered on every rank, probe shards stay (no shuffle)")
     ap.add_argument("--quick", action="store_true", help="skip the informational extra configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",

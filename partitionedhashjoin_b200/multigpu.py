@@ -150,6 +150,104 @@ class ShardedRadixJoin:
         self.backend.close()
 
 
+class NpjGpuBackend:
+    """Device side of the multi-GPU no-partitioning join: the rank's shards as device tensors and a
+    PHJ_ALGO_NO_PARTITIONING engine that joins the gathered build relation with the local probe shard."""
+
+    def __init__(self, world, device, hash="xxh3", hash_seed=0x9E3779B97F4A7C15, chained_table=False):
+        import torch
+
+        from . import _lib, engine
+        self.torch, self.world, self.device = torch, world, device
+        self.engine = engine.Engine("no-partitioning", hash=hash, hash_seed=hash_seed, device=device,
+                                    flags=_lib.FLAG_CHAINED_TABLE if chained_table else 0)
+        self._full = None
+        self.launches = 0
+
+    def upload(self, R, S):
+        from .engine import as_tuples
+        dev = f"cuda:{self.device}"
+        to_dev = lambda rel: self.torch.from_numpy(as_tuples(rel).view("<i8").reshape(-1, 2)).to(dev)
+        self.R, self.S = to_dev(R), to_dev(S)
+
+    def build_shard(self):
+        return self.R
+
+    def gather_buffer(self, rows):
+        if self._full is None or self._full.shape[0] < rows:
+            self._full = self.torch.empty((max(rows, 1), 2), dtype=self.torch.int64, device=f"cuda:{self.device}")
+        return self._full[:rows]
+
+    def local_join(self, full_R):
+        self.torch.cuda.current_stream().synchronize()  # the broadcasts have landed
+        self.engine.bind_device(full_R.data_ptr() if full_R.shape[0] else 0, full_R.shape[0],
+                                self.S.data_ptr() if self.S.shape[0] else 0, self.S.shape[0],
+                                keepalive=(full_R, self.S))
+        res = self.engine.join()
+        self.launches += res["kernel_launches"]
+        return res["matches"], res
+
+    def count_tensor(self, value):
+        return self.torch.tensor([value], dtype=self.torch.int64, device=f"cuda:{self.device}")
+
+    def int_tensor(self, array):
+        return self.torch.as_tensor(np.ascontiguousarray(array, dtype=np.int64), device=f"cuda:{self.device}")
+
+    def close(self):
+        self.engine.close()
+
+
+class ReplicatedNoPartitioningJoin:
+    """The no-partitioning join on several GPUs (last row): no shuffle. Every rank holds a
+    row shard of R and of S; the build shards are gathered so that every rank builds the table of the
+    WHOLE build relation (NoPartitioning::HashJoiner::Build, src/NoPartitioning/HashJoin.hpp:76-126,
+    replicated), probes it with its own shard of S (Probe, :128-187) and the counts are summed. Probe
+    tuples never move; the traffic is |R| x (world - 1) tuples per rank, once per join."""
+
+    def __init__(self, dist, rank, world, backend):
+        self.dist, self.rank, self.world, self.backend = dist, rank, world, backend
+        self.last = {}
+
+    def upload(self, R_shard, S_shard):
+        self.backend.upload(R_shard, S_shard)
+
+    def join(self) -> dict:
+        dist, be, world = self.dist, self.backend, self.world
+        t0 = time.perf_counter()
+        shard = be.build_shard()
+        if world > 1:
+            sizes = [be.int_tensor(np.zeros(1)) for _ in range(world)]
+            dist.all_gather(sizes, be.int_tensor(np.array([shard.shape[0]])))
+            rows = [int(x.item()) for x in sizes]
+            full = be.gather_buffer(sum(rows))
+            first = 0
+            for src, n in enumerate(rows):  # uneven shards: one broadcast per source into its slice
+                piece = full[first:first + n]
+                if src == self.rank:
+                    piece.copy_(shard)
+                if n:
+                    dist.broadcast(piece, src=src)
+                first += n
+        else:
+            rows, full = [int(shard.shape[0])], shard
+        t1 = time.perf_counter()
+        local_matches, res = be.local_join(full)
+        t2 = time.perf_counter()
+        total = be.count_tensor(local_matches)
+        if world > 1:
+            dist.all_reduce(total)
+        matches = int(total.item())
+        t3 = time.perf_counter()
+        self.last = {"matches": matches, "local_matches": int(local_matches), "build_rows": int(sum(rows)),
+                     "split_s": 0.0, "exchange_s": t1 - t0, "local_s": t2 - t1, "reduce_s": t3 - t2,
+                     "total_s": t3 - t0, "recv_bytes": int(16 * (sum(rows) - rows[self.rank])) if world > 1 else 0,
+                     "send_bytes_remote": int(16 * rows[self.rank] * (world - 1)), "local_result": res}
+        return self.last
+
+    def close(self):
+        self.backend.close()
+
+
 def split_plan(world, partitions_local, pass1_in_shuffle=True):
     """(b1, b2) of the local radix join and the number of split digits. With pass1_in_shuffle the
     split digit is owner rank x local pass-1 digit (<= 256 digits in all), so what a rank receives
@@ -772,6 +870,11 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
                                   pass1_in_shuffle=(mode == "pass1"))
         job = FusedShardedRadixJoin(dist, rank, world, backend)
+    elif mode == "npj":  # no-partitioning join: build shards gathered on every rank, probe shards stay
+        if scaled:
+            raise SystemExit("--shuffle npj joins the uploaded default workload only")
+        backend = NpjGpuBackend(world, local, hash=args.hash)
+        job = ReplicatedNoPartitioningJoin(dist, rank, world, backend)
     else:      # split locally, then one NCCL all-to-all per relation
         backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
         job = ShardedRadixJoin(dist, rank, world, backend)
@@ -838,14 +941,20 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         cfg["primary"], cfg["secondary"] = world * n_build, world * n_probe
         if scaled:
             cfg["l2_flush"] = f"inputs ({16 * (n_build + n_probe) / 1e9:.1f} GB per GPU) are larger than L2"
-        cfg["workload"] = (f"radix join sharded over {world} B200: {world} x ({n_build // 10**6}M x {n_probe // 10**6}M) "
-                           f"row shards = {world * n_build // 10**6}M x {world * n_probe // 10**6}M"
-                           f"{' (device-generated)' if scaled else ''}, partition shuffle "
-                           f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
-                           f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}"
-                           f"{f', pipelined over {args.chunks} probe chunks' if mode == 'pipelined' else ''}, then local "
-                           f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
-        cfg["parallelism"] = f"partition-sharded x{world}"
+        if mode == "npj":
+            cfg["workload"] = (f"no-partitioning join over {world} B200: build shards ({n_build // 10**6}M each) "
+                               f"gathered on every rank (NCCL broadcasts), probe shards ({n_probe // 10**6}M each) "
+                               f"stay, {args.hash}, Zipf skew {args.skew}")
+        else:
+            cfg["workload"] = (
+                f"radix join sharded over {world} B200: {world} x ({n_build // 10**6}M x {n_probe // 10**6}M) "
+                f"row shards = {world * n_build // 10**6}M x {world * n_probe // 10**6}M"
+                f"{' (device-generated)' if scaled else ''}, partition shuffle "
+                f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
+                f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}"
+                f"{f', pipelined over {args.chunks} probe chunks' if mode == 'pipelined' else ''}, then local "
+                f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
+        cfg["parallelism"] = f"build side replicated x{world}" if mode == "npj" else f"partition-sharded x{world}"
         exch_bytes = res["send_bytes_remote"]
         line = {
             "metric": metric, "value": n_tuples / (elapsed / args.steps), "unit": unit, "n_gpus": world,
@@ -857,7 +966,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
                 "value": n_tuples / (float(te.item()) / e2e_steps), "unit": unit, "h2d_bytes_per_step": 16 * n_tuples,
                 "d2h_bytes_per_step": int(lr["d2h_bytes"] + 8 * (2 * world + 2)) * world, "steps": e2e_steps},
             "gpu_launches": int(launches.item()),
-            "roofline": {"bound": "hbm", "kernel": "local radix join (per GPU)", "unit": "GB/s", "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "local join (per GPU)", "unit": "GB/s", "peak": peak,
                          "peak_source": peak_src, "achieved": lr["hbm_bytes_alg"] / lr["total_ns"],
                          "frac": lr["hbm_bytes_alg"] / lr["total_ns"] / peak, "traffic": None},
             "phases_ms_rank0": {k[:-2]: v / args.steps * 1e3 for k, v in parts.items()},

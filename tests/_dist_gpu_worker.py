@@ -37,6 +37,18 @@ def main():
         return rel[lo:hi]
 
     fused = mode in ("pass1", "fused")
+    if mode == "npj":  # no-partitioning join, build side gathered on every rank (not yet in the pytest matrix)
+        job = multigpu.ReplicatedNoPartitioningJoin(dist, rank, world, multigpu.NpjGpuBackend(world, local))
+        job.upload(shard(R), shard(S))
+        for _ in range(2):
+            res = job.join()
+            assert res["matches"] == want and res["build_rows"] == R.shape[0], (res, want)
+        if rank == 0:
+            print(json.dumps({"mode": mode, "world": world, "matches": res["matches"], "want": want}))
+        job.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if mode.startswith("pipelined"):
         job = multigpu.PipelinedShardedRadixJoin(dist, rank, world, multigpu.PipelinedGpuBackend(
             world, local, partitions_local=256, chunks=3, split_ctas=64, copy_engines=(mode == "pipelined")))

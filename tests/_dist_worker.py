@@ -57,6 +57,40 @@ class OracleBackend:
         pass
 
 
+class OracleNpjBackend:
+    """CPU stand-in for multigpu.NpjGpuBackend: the gathered build relation is joined with the local
+    probe shard by the oracle's no-partitioning join."""
+
+    def __init__(self, world, oracle):
+        self.world, self.oracle, self.launches = world, oracle, 0
+
+    def upload(self, R, S):
+        self.R = torch.from_numpy(np.ascontiguousarray(R).view("<i8").reshape(-1, 2).copy())
+        self.S = np.ascontiguousarray(S)
+
+    def build_shard(self):
+        return self.R
+
+    def gather_buffer(self, rows):
+        return torch.full((rows, 2), -1, dtype=torch.int64)
+
+    def local_join(self, full_R):
+        R = full_R.numpy().copy().view(_cases.TUPLE).reshape(-1)
+        self.gathered = R
+        count = self.oracle.join_npj(R, self.S) if R.shape[0] else 0  # the reference's table rejects n = 0
+        assert count == self.oracle.count_by_sort(R, self.S)
+        return count, {"kernel_launches": 0}
+
+    def count_tensor(self, value):
+        return torch.tensor([value], dtype=torch.int64)
+
+    def int_tensor(self, array):
+        return torch.from_numpy(np.ascontiguousarray(array, dtype=np.int64))
+
+    def close(self):
+        pass
+
+
 class OracleFusedBackend(OracleBackend):
     """CPU stand-in for multigpu.FusedGpuBackend: the receive windows are POSIX shared memory that
     the peers map by name (the role CUDA IPC plays on the device) and write their pieces into."""
@@ -252,6 +286,22 @@ def main():
             hi = n
         return rel[lo:hi]
 
+    if len(sys.argv) > 2 and sys.argv[2] == "npj":
+        # no-partitioning join: the build shards are gathered on every rank, the probe shards stay
+        job = multigpu.ReplicatedNoPartitioningJoin(dist if world > 1 else None, rank, world, OracleNpjBackend(world, oracle))
+        job.upload(shard(R), shard(S))
+        for _ in range(2):  # reusable
+            res = job.join()
+            assert res["matches"] == want, (res["matches"], want)
+            got = job.backend.gathered
+            assert got.shape[0] == R.shape[0] == res["build_rows"]
+            assert (got["id"] == R["id"]).all() and (got["payload"] == R["payload"]).all()  # shards in rank order
+        if rank == 0:
+            print(json.dumps({"case": case, "world": world, "matches": res["matches"], "want": want, "fused": False}))
+        if world > 1:
+            dist.barrier()
+        dist.destroy_process_group()
+        return
     if pipelined:
         backend = OraclePipelinedBackend(world, oracle, 256, chunks=3, copy_engines=sys.argv[2] == "pipelined-ce")
         backend.rank = rank

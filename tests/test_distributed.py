@@ -86,6 +86,17 @@ def test_window_layout_against_brute_force(world, ndig):
             assert load(first) <= load(F.ownership(M, world, False))
 
 
+@pytest.mark.parametrize("world,case", [(2, "random"), (2, "skewed"), (2, "tiny"), (4, "random"), (1, "random")])
+def test_replicated_no_partitioning_join_over_gloo(world, case):
+    """ReplicatedNoPartitioningJoin (NPJ on several GPUs): every rank gathers the whole build
+    relation (shards in rank order, uneven and empty shards included), probes it with its own probe
+    shard, and the summed counts equal the oracle's."""
+    r = torchrun(world, os.path.join(HERE, "_dist_worker.py"), case, "npj")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
+
+
 @pytest.mark.parametrize("world,ndig,hot_on", [(2, 8, "all"), (4, 16, "all"), (8, 256, "all"), (4, 128, "some"),
                                                (8, 64, "some"), (2, 128, "none")])
 def test_hot_digit_layout_simulation(world, ndig, hot_on):
