@@ -315,7 +315,14 @@ def gpu_arm(args):
                      "frac": achieved / peak, "traffic": SCATTER_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scat_ms,
                      "launches_per_step": len(scat) // args.steps, "share_of_step": kernel_share,
-                     "join_bytes_alg_96B_per_tuple_frac": 96.0 * n_tuples / (ms_per_step / 1e3) / 1e9 / peak},
+                     "join_bytes_alg_96B_per_tuple_frac": 96.0 * n_tuples / (ms_per_step / 1e3) / 1e9 / peak,
+                     "join_bytes_alg_96B_per_tuple_frac_of_nominal_8000GBs":
+                         96.0 * n_tuples / (ms_per_step / 1e3) / 1e9 / 8000.0},
+        # the reference's three phases (IHashJoinTimer) of the last timed join, device times: partitioning =
+        # histograms + scans + both scatters; build / probe = shares of the CTA with the largest build + probe
+        # (src/RadixCluster/HashJoin.hpp:67-87); join = the fused build + probe kernel as a whole
+        "phases_ms": {"partition": res["partition_ns"] / 1e6, "build": res["build_ns"] / 1e6,
+                      "probe": res["probe_ns"] / 1e6, "join": res["join_ns"] / 1e6},
         "cpu_baseline": cpu, "clocks": clocks.summary(), "kernel_us": per_kernel,
         "wall_ms_per_step": wall / args.steps * 1e3, "matches": res["matches"], "other_configs": others,
     }
