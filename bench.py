@@ -39,9 +39,27 @@ N_BUILD, N_PROBE = 10_000_000, 200_000_000
 BASE_SEED, BATCHES = 12345, 64
 METRIC = "join throughput (|R|+|S|) tuples/sec"
 UNIT = "tuples/s"
-# ncu (profiles/r01f_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum of one
-# radix_scatter launch at this workload (3.371 GB read + 3.309 GB written)
-SCATTER_DRAM_TRAFFIC_BYTES = 6.680e9
+
+
+def scatter_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one radix_scatter launch at this workload, read from the
+    newest profiles/*_ncu_summary.md (written by tools/make_profile_summary.py from an `ncu --set full` capture of
+    this command). Returns (bytes per launch or None, the file it came from)."""
+    import glob
+    import re
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.md"))):
+        in_scatter = False
+        for line in open(path):
+            if line.startswith("### "):
+                in_scatter = "radix_scatter" in line
+            m = re.search(r"traffic \(read\+write\) per launch: ([0-9.]+) (\w+)", line)
+            if in_scatter and m:
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(m.group(2))
+                if scale:
+                    best = (float(m.group(1)) * scale, os.path.relpath(path, ROOT))
+                in_scatter = False
+    return best
 
 
 def measured_hbm_peak():
@@ -128,42 +146,48 @@ def dist_setup(n_gpus):
 
 
 def reference_arm(args, rank):
-    """--impl reference: the unmodified reference radix join (oracle/_ref) on the host cores."""
+    """--impl reference: the UNMODIFIED reference radix join (oracle/_ref) on the host cores, on the FULL
+    workload of the GPU arm (10 M x 200 M, same skew, same seeds, the reference's own generators). Every step is
+    one RadixClustering::HashJoiner::Run, timed by the reference's own phase timers. The joins run in forked
+    children because the reference keeps its partitioned tables alive after Run (oracle/ref_harness.cpp)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
     ref = _oracle.Reference()  # nothing of the product is imported on this arm
-    # bounded sample: the whole build side and a prefix of the probe side, sized so that
-    # steps + warmup joins stay within ~2 minutes (and within the reference's per-join leak)
-    total = args.steps + args.warmup
-    n_probe = int(min(N_PROBE, max(10_000_000, N_PROBE * 6 // max(total, 1))))
-    n_probe -= n_probe % 1000
-    # inputs from the reference's own generators (Sequential + seeded Zipf batches)
-    R = ref.fill_sequential(N_BUILD, 1, threads=0)
-    S = ref.fill_zipf(n_probe, args.skew, 1, N_BUILD, BASE_SEED, BATCHES, threads=0)
+    hR, hS = ref.generate_tables(N_BUILD, N_PROBE, args.skew, BASE_SEED, BATCHES, threads=0)
     workers = ref.default_workers()
-    times, matches = [], None
-    for i in range(total):
-        res = ref.join(R, S, 1, partitions=args.ref_partitions, threads=0, seeded=False)
+    times, walls, matches = [], [], None
+    for i in range(args.steps + args.warmup):
+        res = ref.join_tables(hR, hS, 1, partitions=args.ref_partitions, threads=0, seeded=False)
         matches = res["matches"]
+        assert matches == N_PROBE, (matches, N_PROBE)
         if i >= args.warmup:
             times.append((res["partition_ns"] + res["build_ns"] + res["probe_ns"]) / 1e9)
-    assert matches == n_probe, (matches, n_probe)
+            walls.append(res["wall_ns"] / 1e9)
+    npj = ref.join_tables(hR, hS, 0, threads=0, seeded=False)
+    assert npj["matches"] == N_PROBE
     per_step = sum(times) / len(times)
-    value = (N_BUILD + n_probe) / per_step
-    sample = (f"reference RadixClustering::HashJoiner P={args.ref_partitions}, {N_BUILD} x {n_probe} "
-              f"(probe prefix of the 200 M workload), phase sum partition+build+probe, {workers} workers")
+    value = (N_BUILD + N_PROBE) / per_step
+    sample = (f"full workload {N_BUILD} x {N_PROBE}, reference RadixClustering::HashJoiner P={args.ref_partitions}, "
+              f"{workers} workers, {len(times)} timed runs: phase sum partition+build+probe (the reference's own timers; "
+              f"Run() incl. its untimed 3.36 GB of allocation takes {sum(walls) / len(walls):.2f} s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": workload_config(args, n_probe=n_probe),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference", "sample": sample,
+                         "no_partitioning": {"value": (N_BUILD + N_PROBE) / (npj["probe_ns"] / 1e9), "unit": UNIT,
+                                             "ms": npj["probe_ns"] / 1e6,
+                                             "note": "NoPartitioning::HashJoiner, 1 run; its 'probe' figure is "
+                                                     "build + probe (Results.hpp:202), used as the total"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "matches": matches,
     }
     print(json.dumps(line), flush=True)
+    ref.free_table(hR)
+    ref.free_table(hS)
 
 
 def workload_config(args, n_probe=N_PROBE, n_build=N_BUILD):
@@ -175,7 +199,8 @@ def workload_config(args, n_probe=N_PROBE, n_build=N_BUILD):
 
 
 def cpu_baseline_leg(args, R, S):
-    """The reference's own CPU radix join, timed on this box (rank 0, N = 1)."""
+    """The reference's own CPU joins -- radix (P = --ref-partitions) AND no-partitioning -- timed on this box's
+    host cores on the very arrays the GPU joined (rank 0, N = 1), each in a forked child (see reference_arm)."""
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import _oracle
@@ -183,16 +208,33 @@ def cpu_baseline_leg(args, R, S):
     except Exception as e:  # the checker is optional for the GPU arm
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     workers = ref.default_workers()
-    t0 = time.time()
-    res = ref.join(R, S, 1, partitions=args.ref_partitions, threads=0, seeded=False)
-    wall = time.time() - t0
-    assert res["matches"] == S.shape[0], res
-    phase = (res["partition_ns"] + res["build_ns"] + res["probe_ns"]) / 1e9
-    return {"value": (R.shape[0] + S.shape[0]) / phase, "unit": UNIT, "cores": workers, "kind": "reference",
-            "sample": f"full workload, 1 run of the reference RadixClustering::HashJoiner P={args.ref_partitions} "
-                      f"({workers} workers): phases {res['partition_ns'] / 1e6:.0f}/{res['build_ns'] / 1e6:.0f}/"
-                      f"{res['probe_ns'] / 1e6:.0f} ms, wall incl. copies and allocation {wall:.1f} s",
-            "matches": res["matches"]}
+    hR, hS = ref.new_table(R.shape[0]), ref.new_table(S.shape[0])
+    ref.table_view(hR, R.shape[0])[:] = R
+    ref.table_view(hS, S.shape[0])[:] = S
+    best = None
+    for _ in range(2):
+        res = ref.join_tables(hR, hS, 1, partitions=args.ref_partitions, threads=0, seeded=False)
+        assert res["matches"] == S.shape[0], res
+        if best is None or sum(res[k] for k in ("partition_ns", "build_ns", "probe_ns")) < \
+                sum(best[k] for k in ("partition_ns", "build_ns", "probe_ns")):
+            best = res
+    npj = ref.join_tables(hR, hS, 0, threads=0, seeded=False)
+    assert npj["matches"] == S.shape[0], npj
+    ref.free_table(hR)
+    ref.free_table(hS)
+    n = R.shape[0] + S.shape[0]
+    phase = (best["partition_ns"] + best["build_ns"] + best["probe_ns"]) / 1e9
+    return {"value": n / phase, "unit": UNIT, "cores": workers, "kind": "reference",
+            "sample": f"full workload, best of 2 runs of the reference RadixClustering::HashJoiner P={args.ref_partitions} "
+                      f"({workers} workers): phases {best['partition_ns'] / 1e6:.0f}/{best['build_ns'] / 1e6:.0f}/"
+                      f"{best['probe_ns'] / 1e6:.0f} ms (its own timers), Run() wall {best['wall_ns'] / 1e9:.2f} s",
+            "matches": best["matches"],
+            "no_partitioning": {"value": n / (npj["probe_ns"] / 1e9), "unit": UNIT, "cores": workers,
+                                "build_ms": npj["build_ns"] / 1e6, "total_ms": npj["probe_ns"] / 1e6,
+                                "matches": npj["matches"],
+                                "sample": "full workload, 1 run of the reference NoPartitioning::HashJoiner; its "
+                                          "'probe' figure already contains the build (Results.hpp:202) and is "
+                                          "used as the total"}}
 
 
 def gpu_arm(args):
@@ -238,6 +280,7 @@ def gpu_arm(args):
     scat_ms = sum(scat) / len(scat) / 1e6
     alg_bytes = 32.0 * n_tuples  # every tuple is read once and written once: 16 B + 16 B
     achieved = alg_bytes / (scat_ms / 1e3) / 1e9
+    traffic, traffic_src = scatter_dram_traffic()
     per_kernel = {name: round(sum(v) / len(v) / 1e3, 1) for name, v in kernel_ns.items()}
     kernel_share = sum(scat) / max(1, sum(sum(v) for v in kernel_ns.values()))
 
@@ -262,7 +305,21 @@ def gpu_arm(args):
                 r1 = e1.join_host(R, S)
             e2e_plain_s = (time.perf_counter() - t0) / 3
             assert r1["matches"] == S.shape[0] and r1["upload_chunks"] == 1
+        # the same call from PAGEABLE memory -- what a Common::Table (a std::vector, host/Common/Table.hpp) holds
+        # and what the `phjoin` CLI therefore delivers; the uploads are issued by the helper thread
+        Rq, Sq = np.array(R, copy=True), np.array(S, copy=True)
+        eng.join_host(Rq, Sq)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rq = eng.join_host(Rq, Sq)
+        e2e_pageable_s = (time.perf_counter() - t0) / 3
+        assert rq["matches"] == S.shape[0]
+        del Rq, Sq
         e2e = {"value": n_tuples / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]),
+               "host_memory": "pinned (phj_host_alloc)",
+               "pageable": {"value": n_tuples / e2e_pageable_s, "unit": UNIT, "ms_per_step": e2e_pageable_s * 1e3,
+                            "h2d_ms": rq["h2d_ns"] / 1e6, "steps": 3,
+                            "note": "same call from pageable numpy arrays (std::vector-like), as the phjoin CLI"},
                "d2h_bytes_per_step": int(r2["d2h_bytes"]), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "upload_chunks": int(r2["upload_chunks"]), "h2d_ms": r2["h2d_ns"] / 1e6,
                "device_ms": r2["e2e_ns"] / 1e6, "unstreamed_ms_per_step": e2e_plain_s * 1e3,
@@ -273,9 +330,10 @@ def gpu_arm(args):
     if not args.quick:
         def few(engine, n=3):
             engine.upload(R, S)
-            engine.join()
-            best = min(engine.join()["total_ns"] for _ in range(n))
-            return round(n_tuples / (best / 1e9) / 1e9, 2)
+            runs = [engine.join() for _ in range(n + 1)][1:]
+            for r in runs:  # generator data: every probe key has a build match
+                assert r["matches"] == S.shape[0], r
+            return round(n_tuples / (min(r["total_ns"] for r in runs) / 1e9) / 1e9, 2)
         for h in ("xxh3", "murmur3", "city"):
             if h != args.hash:
                 with phj.Engine("radix-partitioning", partitions=args.partitions, hash=h, device=local) as e2:
@@ -312,7 +370,7 @@ def gpu_arm(args):
         "e2e": e2e,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "radix_scatter", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": SCATTER_DRAM_TRAFFIC_BYTES, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scat_ms,
                      "launches_per_step": len(scat) // args.steps, "share_of_step": kernel_share,
                      "join_bytes_alg_96B_per_tuple_frac": 96.0 * n_tuples / (ms_per_step / 1e3) / 1e9 / peak,

@@ -219,6 +219,7 @@ class Reference:
         _sig(lib, "phjref_fill_zipf_seeded", C.c_int, [vp, dbl, i64, i64, C.c_long, sz, C.c_int])
         _sig(lib, "phjref_join_tables", C.c_int, [vp, vp, C.c_int, C.c_int, sz, C.c_int, C.c_int, u64, u64, C.POINTER(RefResult)])
         _sig(lib, "phjref_join", C.c_int, [vp, sz, vp, sz, C.c_int, C.c_int, sz, C.c_int, C.c_int, u64, u64, C.POINTER(RefResult)])
+        _sig(lib, "phjref_join_tables_forked", C.c_int, [vp, vp, C.c_int, C.c_int, sz, C.c_int, C.c_int, u64, u64, C.POINTER(RefResult)])
         _sig(lib, "phjref_table_probe", C.c_int, [C.c_int, dbl, u64, sz, vp, sz, C.c_int, vp, sz, vp, vp, vp])
         _sig(lib, "phjref_number_of_buckets", u64, [C.c_int, dbl, u64])
         _sig(lib, "phjref_format_json", C.c_int, [vp, vp, sz, u64, u64, u64, C.c_char_p, C.c_char_p, sz])
@@ -273,6 +274,38 @@ class Reference:
         rc = self.lib.phjref_join(R.ctypes.data, R.shape[0], S.ctypes.data, S.shape[0], algo, table_kind,
                                   partitions, threads, 1 if seeded else 0, u64(seed_partition), u64(seed_table),
                                   C.byref(res))
+        if rc:
+            raise RuntimeError(self.lib.phjref_last_error().decode())
+        return {n: int(getattr(res, n)) for n, _ in res._fields_}
+
+    # -- reference-owned tables: generated in place by the reference's generators and joined any number of
+    # -- times without copies (bench.py --impl reference / cpu_baseline)
+    def new_table(self, n):
+        return self.lib.phjref_table_new(n)
+
+    def free_table(self, h):
+        self.lib.phjref_table_free(h)
+
+    def table_view(self, h, n):
+        """numpy view (no copy) of a reference table's tuples; valid until free_table."""
+        return self._table_array(h, n)
+
+    def generate_tables(self, n_build, n_probe, alpha, base_seed, batches, threads=0):
+        """Sequential build side (ids 1..n) + seeded Zipf probe side over [1, n_build], as src/main.cpp:54-63."""
+        hR, hS = self.new_table(n_build), self.new_table(n_probe)
+        assert self.lib.phjref_fill_sequential(hR, 1, threads) == 0
+        if self.lib.phjref_fill_zipf_seeded(hS, alpha, 1, n_build, base_seed, batches, threads):
+            raise ValueError(self.lib.phjref_last_error().decode())
+        return hR, hS
+
+    def join_tables(self, hR, hS, algo, partitions=32, table_kind=0, threads=0, seeded=False,
+                    seed_partition=0x9E3779B97F4A7C15, seed_table=1, forked=True):
+        """Join two reference tables. forked: in a child process, because the reference's radix joiner keeps
+        its partitioned tables alive after Run (3.36 GB per 10 M x 200 M join; see ref_harness.cpp)."""
+        res = RefResult()
+        fn = self.lib.phjref_join_tables_forked if forked else self.lib.phjref_join_tables
+        rc = fn(hR, hS, algo, table_kind, partitions, threads, 1 if seeded else 0, u64(seed_partition),
+                u64(seed_table), C.byref(res))
         if rc:
             raise RuntimeError(self.lib.phjref_last_error().decode())
         return {n: int(getattr(res, n)) for n, _ in res._fields_}
