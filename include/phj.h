@@ -112,7 +112,14 @@ typedef struct {
                                         digit) pairs per pass-1 segment, summed into pass 2's counters); for
                                         other two-pass plans of <= 6 bits the pass-1 scatter counts them.
                                         Saves one read of both relations, DESIGN.md section 4 */
-
+#define PHJ_FLAG_L2_TABLES 0x80u  /* RADIX_PARTITIONING: build + probe through per-partition tables in GLOBAL
+                                     memory that stay hot in the 126 MB L2 (all CTAs walk the probe side in
+                                     partition order) instead of shared-memory tables. Made for FEW, LARGE
+                                     partitions: one radix pass (partitions = 32 .. 256) then needs no second
+                                     partitioning pass at all -- 3.41 ms against 3.95 ms for two passes + shared
+                                     memory at 10 M x 200 M. The multi-GPU path always joins this way. */
+#define PHJ_FLAG_NO_HIST12 0x100u /* two-pass plans: do not take both passes' histograms from one read
+                                     (radix_histogram_full); the pass-1 scatter counts for pass 2 instead */
 
 /* What the reference reports through IHashJoinTimer (src/Common/Results.hpp:131-149) plus the
  * count it only logs (src/NoPartitioning/HashJoin.hpp:184, src/RadixCluster/HashJoin.hpp:320). */

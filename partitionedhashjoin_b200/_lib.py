@@ -32,6 +32,8 @@ FLAG_SPLIT_REMOTE_ONLY = 0x8
 FLAG_CHAINED_TABLE = 0x10
 FLAG_NO_FUSE_HIST2 = 0x20
 FLAG_SPLIT_LOCAL_TILES = 0x40
+FLAG_L2_TABLES = 0x80
+FLAG_NO_HIST12 = 0x100
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

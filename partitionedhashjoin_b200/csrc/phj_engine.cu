@@ -174,7 +174,7 @@ struct phj_handle {
     uint32_t join_grid = 0, join_slots = 0, join_max_keys = 0;
     uint64_t* d_gt = nullptr;
     uint64_t gt_buckets = 0;
-    // EXPERIMENT (PHJ_L2JOIN=1): per-partition tables in global memory, probed out of L2 (pt_build / pt_probe)
+    // PHJ_FLAG_L2_TABLES: per-partition tables in global memory, probed out of L2 (pt_build / pt_probe)
     bool l2join = false;
     uint64_t* d_pt = nullptr;
     size_t cap_pt = 0;
@@ -274,7 +274,6 @@ template <int BITS, int HASH, bool POW2, bool TMA, bool BALLOT, bool FUSE2>
 cudaError_t launch_scatter_tbf(phj_handle* h, const PassParams& pp, uint32_t grid) {
     using L = ScatterSmem<BITS, PHJ_SCAT_TPB, PHJ_SCAT_IPT>;
     size_t smem = L::bytes(TMA) + (FUSE2 ? L::fuse2_bytes : 0);
-    if (const char* x = getenv("PHJ_SCAT_EXTRA_SMEM")) smem += (size_t)atoi(x);  // experiment: L1 sensitivity
     auto kern = radix_scatter<BITS, HASH, POW2, PHJ_SCAT_TPB, PHJ_SCAT_IPT, TMA, BALLOT, FUSE2,
                               (FUSE2 || !TMA) ? PHJ_SCAT_MINB : PHJ_SCAT_MINB_PLAIN>;
     static bool configured[16] = {};
@@ -583,8 +582,7 @@ int build_plan(phj_handle* h) {
         size_t ncounts_max = ncounts1;
         h->fuse2 = false;
         if (h->b2 > 0) {
-            uint32_t div = 1;
-            if (const char* x = getenv("PHJ_SEG2_DIV")) div = (uint32_t)std::max(1, atoi(x));
+            const uint32_t div = 1;
             for (int rel = 0; rel < 2; ++rel) {
                 h->seg_len2[rel] = ((h->seg_len[rel] / div + kScatTile - 1) / kScatTile) * kScatTile;
                 h->target_segs2[rel] = std::max<uint32_t>(1, nseg_plan[rel]) * div + div;
@@ -598,10 +596,10 @@ int build_plan(phj_handle* h) {
                        h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING;
             // Both passes' histograms from ONE read of the input (radix_histogram_full, K1d): the
             // pass-1 scatter then runs without the fused counting (1.57 -> 1.29 ms) for a histogram
-            // that takes 0.53 instead of 0.49 ms. PHJ_HIST12=0 falls back to the fused histogram.
+            // that takes 0.53 instead of 0.49 ms. PHJ_FLAG_NO_HIST12 falls back to the fused histogram.
             {
-                const char* x = getenv("PHJ_HIST12");
-                h->hist12 = !(x && x[0] == '0') && h->fuse2 && h->pow2 && h->d1 <= kFullD1 && h->d2 <= kFullD2;
+                h->hist12 = !(h->cfg.flags & PHJ_FLAG_NO_HIST12) && h->fuse2 && h->pow2 && h->d1 <= kFullD1 &&
+                            h->d2 <= kFullD2;
                 if (h->hist12 &&
                     (rc = dev_reserve(&h->d_hist12, &h->cap_hist12,
                                       (size_t)std::max<uint32_t>(h->nsegs1, 1) * kFullD1 * kFullD2)) != PHJ_OK)
@@ -676,11 +674,10 @@ int build_plan(phj_handle* h) {
         uint32_t resident = (uint32_t)std::max<size_t>(1, std::min<size_t>((h->smem_optin) / (smem + 1024), 2048 / PHJ_JOIN_TPB));
         h->join_grid = (uint32_t)h->sm_count * resident * 4;
         {
-            // EXPERIMENT: L2-resident partition tables instead of shared-memory ones. A region of 32-byte
-            // buckets per partition, load <= 0.4 at the mean partition size; partitions beyond 75 % of a
-            // region's capacity take the oversize path like partitions too large for shared memory.
-            const char* x = getenv("PHJ_L2JOIN");
-            h->l2join = x && x[0] == '1' && h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING;
+            // PHJ_FLAG_L2_TABLES: L2-resident partition tables instead of shared-memory ones. A region of
+            // 32-byte buckets per partition, load <= 0.4 at the mean partition size; partitions beyond 75 % of
+            // a region's capacity take the oversize path like partitions too large for shared memory.
+            h->l2join = (h->cfg.flags & PHJ_FLAG_L2_TABLES) && h->cfg.algo == PHJ_ALGO_RADIX_PARTITIONING;
             if (h->l2join) {
                 uint32_t rb = 64;
                 while ((uint64_t)rb * 8 < mean * 5) rb <<= 1;  // 4 rb >= 2.5 x mean
@@ -938,7 +935,6 @@ int join_radix(phj_handle* h, phj_result* out) {
     p1.ndigits = h->d1;
     p1.hp = hp;
     p1.df = digit_fn(h, 1);
-    if (const char* x = getenv("PHJ_SCAT_PREFETCH")) p1.prefetch_tiles = (uint32_t)std::max(0, atoi(x));
     // pass-2 bookkeeping (needed before scatter 1 when the pass-2 histogram is fused into it)
     Plan2Params pl{};
     FillEmptyParams fe{};
@@ -979,7 +975,6 @@ int join_radix(phj_handle* h, phj_result* out) {
         p2.ndigits = h->d2;
         p2.hp = hp;
         p2.df = digit_fn(h, 2);
-        p2.prefetch_tiles = p1.prefetch_tiles;
     }
     auto run_plan2 = [&]() {
         KernelScope ks(h, "plan_pass2", 2);
@@ -1140,15 +1135,20 @@ int join_radix(phj_handle* h, phj_result* out) {
     jp.cta_times = h->d_cta_times;
     if (h->l2join) {
         PtParams q{};
-        q.j = jp;
-        const uint32_t grid = (uint32_t)h->sm_count * 8;
-        q.j.slice_len = h->n[1] / grid;
-        q.j.slice_rem = h->n[1] % grid;
+        q.build = part_build;
+        q.probe = part_probe;
+        q.bounds_build = h->d_bounds2[0];
+        q.bounds_probe = h->d_bounds2[1];
+        q.npart = (uint32_t)h->nparts;
+        q.max_keys = h->join_max_keys;
+        q.table_mul = jp.table_mul;
+        q.sentinel_part = jp.sentinel_part;
         q.table = h->d_pt;
-        q.n_build = h->n[0];
         q.region_buckets = h->pt_region_buckets;
         q.region_shift32 = 32 - (uint32_t)ilog2_ceil(h->pt_region_buckets);
         q.flags = h->d_scalars + kGtFlags;
+        q.matches = h->d_matches;
+        const uint32_t grid = (uint32_t)h->sm_count * 8;
         {
             KernelScope ks(h, "pt_clear");
             PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kGtFlags, 0, 4, h->stream));
@@ -1173,20 +1173,6 @@ int join_radix(phj_handle* h, phj_result* out) {
             h->d_bounds2[0], (uint32_t)h->nparts, h->join_max_keys, h->d_scalars + kOversize);
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
-    if (const char* rj = getenv("PHJ_DEBUG_REJOIN")) {
-        // debugging aid: run only the join kernel again on the already partitioned relations
-        PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
-        PHJ_CUDA(cudaStreamSynchronize(h->stream));
-        fprintf(stderr, "[phj debug] first join: %llu\n", (unsigned long long)h->h_out[0]);
-        for (int i = 0; i < atoi(rj); ++i) {
-            PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 16, h->stream));
-            PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
-            PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 16, cudaMemcpyDeviceToHost, h->stream));
-            PHJ_CUDA(cudaStreamSynchronize(h->stream));
-            fprintf(stderr, "[phj debug] rejoin %d: %llu probed %llu\n", i, (unsigned long long)h->h_out[0],
-                    (unsigned long long)h->h_out[1]);
-        }
-    }
     PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 4, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_cta_times, h->d_cta_times, (size_t)h->join_grid * 16,

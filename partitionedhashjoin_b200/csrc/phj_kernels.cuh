@@ -82,9 +82,6 @@ struct PassParams {
     uint32_t d2;                        // pass-2 digits
     // radix_histogram_full: per pass-1 segment, the counts of all (pass-1 digit, pass-2 digit) pairs
     uint32_t* hist12;                   // [segment][kFullD1 * kFullD2]
-    // radix_scatter experiment (PHJ_SCAT_PREFETCH=k, default 0 = off): when a tile's loads are issued,
-    // one thread also asks for the tile k further on to be brought into L2 (cp.async.bulk.prefetch.L2)
-    uint32_t prefetch_tiles;
 };
 
 // Where pass-1 partition `parent` of a relation sits in pass 2's bookkeeping.
@@ -134,10 +131,6 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
-}
-// TMA prefetch of a contiguous piece of global memory into L2 (16-byte aligned, size % 16 == 0).
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
@@ -526,10 +519,6 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         }
         // prefetch the next tile while this one is flushed
         if (tile + T < seg.end) load_tile(tile + T);
-        if (p.prefetch_tiles && tid == 0) {
-            const uint64_t pf = tile + (uint64_t)T * (1 + p.prefetch_tiles);
-            if (pf < seg.end) bulk_prefetch_l2(in + pf, (uint32_t)min((uint64_t)T, seg.end - pf) * 16u);
-        }
         if (TMA_STORE) fence_proxy_async_smem();
         cta_sync();
 
@@ -1399,24 +1388,37 @@ __global__ void count_oversize(const uint64_t* __restrict__ bounds_build, uint32
 }
 
 // =================================================================================================
-// K4g/K5g  EXPERIMENT (PHJ_L2JOIN=1, off by default; not measured yet): per-partition tables in GLOBAL
-// memory sized for L2 instead of shared memory. With few, large partitions (one radix pass of 6
-// bits: 156 K build keys each at 10 M x 200 M) a partition's table (32-byte buckets of four keys,
-// load <= 0.6) is a few MB; the probe relation is walked in partition order by all CTAs together, so
-// only the tables of the ~10 partitions being probed are hot and they stay in the 126 MB L2. Unlike
-// gt_build / gt_probe (the fallback for oversize partitions) the partition comes from the tuple's
-// POSITION (the boundaries), so the table hash is the 5-instruction multiply-shift of
-// join_partitions instead of a second XXH3, and there is no per-tuple selection test. What it could
-// buy: the second partitioning pass (1.36 ms + planning) for an L2-resident probe; to be measured.
+// K4g/K5g  pt_build / pt_probe: per-partition tables in GLOBAL memory sized for the L2
+// (PHJ_FLAG_L2_TABLES, and the local join of the multi-GPU path). With few, large partitions (one
+// radix pass of 6 bits: 156 K build keys each at 10 M x 200 M) a partition's table (32-byte buckets of
+// four keys, load <= 0.5) is a few MB; the probe relation is walked in partition order by all CTAs
+// together, so only the tables of the partitions being probed are hot and they stay in the 126 MB L2.
+// Unlike gt_build / gt_probe (the fallback for oversize partitions) the partition comes from the
+// tuple's POSITION (the boundaries), so the table hash is the 5-instruction multiply-shift of
+// join_partitions instead of a second XXH3, and there is no per-tuple selection test. Measured
+// (round 2, 10 M x 200 M uniform): one 6-bit pass + this join 3.41 ms against 3.95 ms for two passes +
+// shared-memory tables -- the second partitioning pass (1.36 ms + planning) costs more than probing
+// out of L2 (0.37 + 1.14 ms) instead of shared memory (0.62 ms).
+// Everything the kernels need to know about sizes comes from the device-resident boundaries
+// (bounds[npart] is the relation's size), so the multi-GPU path can enqueue them before the host
+// knows how many tuples the shuffle delivered. Boundaries may be absolute positions inside a larger
+// window: the probe side is sliced over [bounds_probe[0], bounds_probe[npart]).
 // Partitions whose build side exceeds max_keys are skipped and counted, as in join_partitions.
 // =================================================================================================
 struct PtParams {
-    JoinParams j;            // relations, boundaries, slicing of the probe side, hash multipliers
-    uint64_t* table;         // npart regions of region_buckets buckets of 4 keys
-    uint64_t n_build;
-    uint32_t region_shift32; // bucket inside a region = table_bucket32(...) >> nothing: shift32 = 32 - log2(region_buckets)
-    uint32_t region_buckets; // a power of two
-    uint32_t* flags;         // [0]: the sentinel partition's build side contains kEmptyKey
+    const ulonglong2* build;       // partitioned R (or the build window of the shuffle)
+    const ulonglong2* probe;       // partitioned S (or one chunk's region of the probe window)
+    const uint64_t* bounds_build;  // npart + 1, device
+    const uint64_t* bounds_probe;  // npart + 1, device
+    uint32_t npart;
+    uint32_t max_keys;             // largest build partition a region accepts
+    uint64_t table_mul;            // odd multipliers of the table hash: low / high word
+    uint32_t sentinel_part;        // the one partition kEmptyKey hashes to (0xffffffff: none here)
+    uint32_t region_shift32;       // 32 - log2(region_buckets)
+    uint32_t region_buckets;       // a power of two
+    uint64_t* table;               // npart regions of region_buckets buckets of 4 keys
+    uint32_t* flags;               // [0]: the sentinel partition's build side contains kEmptyKey
+    unsigned long long* matches;
 };
 
 // First partition whose range [bounds[a], bounds[a + 1]) can contain position `pos`.
@@ -1430,20 +1432,26 @@ __device__ __forceinline__ uint32_t partition_of(const uint64_t* __restrict__ bo
     return a;
 }
 
+// Equal share of [first, first + n) for this CTA.
+__device__ __forceinline__ void cta_slice(uint64_t first, uint64_t n, uint64_t& lo, uint64_t& hi) {
+    const uint64_t len = n / gridDim.x, rem = n % gridDim.x;
+    lo = first + len * blockIdx.x + min((uint64_t)blockIdx.x, rem);
+    hi = lo + len + (blockIdx.x < rem ? 1 : 0);
+}
+
 template <int TPB>
-__global__ void __launch_bounds__(TPB) pt_build(PtParams q) {
-    const JoinParams& p = q.j;
-    const uint64_t lo = q.n_build / gridDim.x * blockIdx.x + min((uint64_t)blockIdx.x, q.n_build % gridDim.x);
-    const uint64_t hi = lo + q.n_build / gridDim.x + (blockIdx.x < q.n_build % gridDim.x ? 1 : 0);
+__global__ void __launch_bounds__(TPB) pt_build(PtParams p) {
+    uint64_t lo, hi;
+    cta_slice(p.bounds_build[0], p.bounds_build[p.npart] - p.bounds_build[0], lo, hi);
     if (lo >= hi) return;
     const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
-    const uint32_t bmask = q.region_buckets - 1;
+    const uint32_t bmask = p.region_buckets - 1;
     for (uint32_t part = partition_of(p.bounds_build, p.npart, lo); part < p.npart; ++part) {
         const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
         if (r0 >= hi) break;
         if (r1 - r0 > p.max_keys) continue;  // oversize: left to the global-table fallback
         const uint64_t s0 = max(lo, r0), s1 = min(hi, r1);
-        uint64_t* __restrict__ region = q.table + (uint64_t)part * q.region_buckets * 4;
+        uint64_t* __restrict__ region = p.table + (uint64_t)part * p.region_buckets * 4;
         const bool careful = part == p.sentinel_part;
         // warp-converged insert loop (see cta_sync()): first free slot of the home bucket, then the next bucket
         for (uint64_t i0 = s0; i0 < s1; i0 += TPB) {
@@ -1453,11 +1461,11 @@ __global__ void __launch_bounds__(TPB) pt_build(PtParams q) {
             if (pending) {
                 key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.build + i));
                 if (careful && key == kEmptyKey) {
-                    q.flags[0] = 1;
+                    p.flags[0] = 1;
                     pending = false;
                 }
             }
-            uint32_t bucket = table_bucket32(key, mul_lo, mul_hi, q.region_shift32) & bmask, s = 0;
+            uint32_t bucket = table_bucket32(key, mul_lo, mul_hi, p.region_shift32) & bmask, s = 0;
             while (__any_sync(0xffffffffu, pending)) {
                 if (pending) {
                     unsigned long long* slot = reinterpret_cast<unsigned long long*>(region + (uint64_t)bucket * 4 + s);
@@ -1476,15 +1484,14 @@ __global__ void __launch_bounds__(TPB) pt_build(PtParams q) {
 }
 
 template <int TPB>
-__global__ void __launch_bounds__(TPB) pt_probe(PtParams q) {
-    const JoinParams& p = q.j;
+__global__ void __launch_bounds__(TPB) pt_probe(PtParams p) {
     __shared__ unsigned long long block_count;
     if (threadIdx.x == 0) block_count = 0;
-    const uint64_t lo = p.slice_len * blockIdx.x + min((uint64_t)blockIdx.x, p.slice_rem);
-    const uint64_t hi = lo + p.slice_len + (blockIdx.x < p.slice_rem ? 1 : 0);
+    uint64_t lo, hi;
+    cta_slice(p.bounds_probe[0], p.bounds_probe[p.npart] - p.bounds_probe[0], lo, hi);
     const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
-    const uint32_t bmask = q.region_buckets - 1;
-    const uint32_t sentinel_hit = q.flags[0];
+    const uint32_t bmask = p.region_buckets - 1;
+    const uint32_t sentinel_hit = p.flags[0];
     uint32_t count = 0;
     constexpr int U = 4;
     if (lo < hi) {
@@ -1495,7 +1502,7 @@ __global__ void __launch_bounds__(TPB) pt_probe(PtParams q) {
             if (s0 >= s1) continue;
             const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
             if (r1 == r0 || r1 - r0 > p.max_keys) continue;
-            const uint64_t* __restrict__ region = q.table + (uint64_t)part * q.region_buckets * 4;
+            const uint64_t* __restrict__ region = p.table + (uint64_t)part * p.region_buckets * 4;
             const bool careful = part == p.sentinel_part;
             for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
                 uint64_t key[U];
@@ -1513,7 +1520,7 @@ __global__ void __launch_bounds__(TPB) pt_probe(PtParams q) {
                         count += sentinel_hit;
                         pending[u] = false;
                     }
-                    bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, q.region_shift32) & bmask;
+                    bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, p.region_shift32) & bmask;
                 }
                 // one 32-byte bucket per step; a bucket whose last slot is free ends the search
                 while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {

@@ -41,25 +41,19 @@ def cases_for(phj, name):
 
 class pass2_histogram:
     """How pass 2 of a two-pass plan gets its histogram: 'full' = from the one 12-bit histogram read
-    (radix_histogram_full, the default), 'fused' = counted by the pass-1 scatter (PHJ_HIST12=0),
+    (radix_histogram_full, the default), 'fused' = counted by the pass-1 scatter (PHJ_FLAG_NO_HIST12),
     'separate' = its own histogram read (PHJ_FLAG_NO_FUSE_HIST2). Yields the engine flags."""
     MODES = ("full", "fused", "separate")
 
     def __init__(self, phj, mode):
-        self.mode, self.flags = mode, phj.FLAG_NO_FUSE_HIST2 if mode == "separate" else 0
+        self.mode = mode
+        self.flags = {"full": 0, "fused": phj.FLAG_NO_HIST12, "separate": phj.FLAG_NO_FUSE_HIST2}[mode]
 
     def __enter__(self):
-        self.old = os.environ.get("PHJ_HIST12")
-        if self.mode == "fused":
-            os.environ["PHJ_HIST12"] = "0"
-        else:
-            os.environ.pop("PHJ_HIST12", None)
         return self.flags
 
     def __exit__(self, *exc):
-        os.environ.pop("PHJ_HIST12", None)
-        if self.old is not None:
-            os.environ["PHJ_HIST12"] = self.old
+        pass
 
 
 def run(phj, R, S, algo, **kw):
@@ -101,6 +95,10 @@ def test_counts_match_reference_golden(phj, oracle, name):
     for flags in (phj.FLAG_NO_TMA_STORE,):
         res = run(phj, R, S, "radix-partitioning", partitions=4096, flags=flags)
         assert res["matches"] == want, (name, flags, res)
+    # per-partition tables in global memory (L2-resident) instead of shared memory, any fan-out
+    for P in (1, 2, 32, 64, 100, 256, 4096):
+        res = run(phj, R, S, "radix-partitioning", partitions=P, flags=phj.FLAG_L2_TABLES)
+        assert res["matches"] == want, (name, P, "l2 tables", res)
 
 
 @pytest.mark.parametrize("hash", HASHES)

@@ -36,11 +36,12 @@ def main():
         # (tile of 4096 tuples / digits); the join behind it does not matter here
         configs = [("radix-partitioning", {"partitions": 1 << b, "radix_bits": (b, 0)}) for b in (1, 2, 3, 4, 5, 6, 7, 8)]
     if os.environ.get("PROBE") == "l2join":
-        # EXPERIMENT: one partitioning pass + L2-resident partition tables (PHJ_L2JOIN=1) against the
-        # default two passes + shared-memory tables. Check `matches` first: this path is unvalidated.
-        os.environ["PHJ_L2JOIN"] = "1"
-        configs = [("radix-partitioning", {"partitions": 1 << b, "radix_bits": (b, 0)}) for b in (5, 6, 7, 8)]
-        configs += [("radix-partitioning", {"partitions": 4096})]
+        # one partitioning pass + L2-resident partition tables (PHJ_FLAG_L2_TABLES) against the default two
+        # passes + shared-memory tables
+        configs = [("radix-partitioning", {"partitions": 1 << b, "radix_bits": (b, 0), "flags": phj.FLAG_L2_TABLES})
+                   for b in (3, 4, 5, 6, 7, 8)]
+        configs += [("radix-partitioning", {"partitions": 4096, "flags": phj.FLAG_L2_TABLES}),
+                    ("radix-partitioning", {"partitions": 4096})]
     for algo, kw in configs:
         with phj.Engine(algo, **kw) as e:
             e.upload(R, S)
