@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PHJ_ABI_VERSION 3
+#define PHJ_ABI_VERSION 4
 
 /* Common::Tuple (src/Common/Table.hpp:20-25): alignas(16) {int64 id; int64 payload}. */
 typedef struct {
@@ -95,6 +95,14 @@ typedef struct {
     uint32_t upload_chunks; /* phj_join_host: row chunks the probe relation is uploaded in, each joined
                                as soon as it has landed (1 = upload everything, then join; 0 = choose:
                                ~256 MB chunks when the probe relation is large, else 1; <= 32) */
+    int32_t num_gpus;       /* RADIX_PARTITIONING, 0 or 1 = one GPU. N > 1 (a power of two): this process drives
+                               GPUs device .. device + N - 1 -- phj_upload gives GPU g the rows [g n / N,
+                               (g + 1) n / N) of both relations, phj_join runs the sharded join below (one host
+                               thread per GPU, NCCL for sizes / barriers / the count, NVLink peer stores for the
+                               tuples) and returns the global count. `partitions` then is GPUs x local
+                               partitions (a power of two <= 256; 0 = 64) and split_chunks the number of probe
+                               chunks whose shuffle overlaps the local probe of the previous one (0 = 4). */
+    uint32_t reserved0;
 } phj_config;
 
 #define PHJ_FLAG_NO_TMA_STORE 0x2u /* scatter flush with st.global.v4 instead of TMA bulk stores */
@@ -145,7 +153,11 @@ typedef struct {
     uint64_t materialize_ns; /* phj_join_materialize: device time of the count + write kernels */
     uint64_t e2e_ns;         /* phj_join_host: device time, first upload .. match count on the host */
     uint32_t upload_chunks;  /* phj_join_host: probe chunks actually used (1 = not streamed), else 0 */
-    uint32_t reserved;
+    uint32_t gpus;           /* GPUs that took part (sharded join), else 0 */
+    uint64_t count_ns;       /* sharded join: histogram + scan + all-gather of the piece sizes */
+    uint64_t shuffle_ns;     /* sharded join: first store into a peer's window .. last barrier (the local
+                                probes of earlier chunks run inside this span) */
+    uint64_t shuffle_bytes;  /* sharded join: bytes this rank (num_gpus > 1: all GPUs) sent to other GPUs */
 } phj_result;
 
 typedef struct phj_handle phj_handle;
@@ -273,6 +285,48 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
 int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
                    void* const* dst_probe, const uint64_t* off_probe, uint64_t* bytes);
 int phj_shard_push_wait(phj_handle* h);
+
+/* ---- the sharded radix join, one process per GPU ---------------------------------------
+ * What RadixClustering::HashJoiner::Run (src/RadixCluster/HashJoin.hpp:190-241) becomes when R and S are
+ * row-sharded over the GPUs of a node: the exchange is the one partitioning pass (every digit run is
+ * stored straight into its owner's window over NVLink), the probe relation travels in chunks whose shuffle
+ * overlaps the local probe of the previous chunk (the reference overlaps its two partition pipelines the
+ * same way, :210-216), NCCL carries the piece sizes, the barriers and the count. All ranks call the same
+ * functions in the same order (they are collectives). phj_nccl_unique_id: rank 0 obtains 128 opaque bytes
+ * and hands them to the others over any transport (torch.distributed, MPI, a file). config as for
+ * phj_create (algo RADIX_PARTITIONING; partitions = GPUs x local partitions, a power of two <= 256, 0 = 64;
+ * split_chunks = probe chunks, 0 = 4; device = this rank's GPU). phj_dist_join returns the GLOBAL count on
+ * every rank. The same join inside ONE process: phj_config.num_gpus. */
+typedef struct phj_dist phj_dist;
+int phj_nccl_unique_id(unsigned char* id128);
+int phj_dist_create(const phj_config* config, int32_t rank, int32_t world, const unsigned char* id128,
+                    phj_dist** out);
+void phj_dist_destroy(phj_dist* d);
+int phj_dist_upload(phj_dist* d, const phj_tuple* build, size_t n_build, const phj_tuple* probe, size_t n_probe);
+int phj_dist_bind_device(phj_dist* d, const void* d_build, size_t n_build, const void* d_probe, size_t n_probe);
+int phj_dist_join(phj_dist* d, phj_result* out);
+int phj_dist_kernel_times(phj_dist* d, const char** names, uint64_t* ns, uint32_t cap);
+/* Same launches with their begin / end device times relative to the join's first event (needs
+ * PHJ_KERNEL_TIMES=1): shows which kernels of the two streams ran side by side. */
+int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, uint64_t* end_ns, uint32_t cap);
+
+/* How the last join laid this rank's data out, and test read-back of its windows: `which` 0 = build
+ * (bounds: local_partitions + 1), 1 = probe (bounds: chunks x (local_partitions + 1), absolute positions:
+ * chunk c's tuples of local partition l lie at [bounds[c][l], bounds[c][l + 1]), ordered by source rank,
+ * then input order). The window's used prefix (bounds' last entry) is copied to `out` when it is given. */
+typedef struct {
+    uint32_t world, rank;
+    uint32_t digits;            /* split digits = world x local_partitions; owner = digit / local_partitions */
+    uint32_t local_partitions;
+    uint32_t chunks;
+    uint32_t region_buckets;    /* 32-byte buckets per local partition's table */
+    uint64_t window_tuples[2];  /* capacity of this rank's build / probe window */
+    uint32_t resizes;           /* host-synchronous sizing passes that re-allocated a window so far */
+    uint32_t reserved;
+    uint64_t sent_remote_bytes;
+} phj_dist_layout;
+int phj_dist_info(phj_dist* d, phj_dist_layout* out);
+int phj_dist_read_window(phj_dist* d, int32_t which, phj_tuple* out, uint64_t cap_tuples, uint64_t* bounds);
 
 /* Device memory that other processes on the node can map (CUDA IPC): the receive buffers of the
  * fused shuffle. `ipc_handle` is 64 opaque bytes to hand to the peers (any transport). */

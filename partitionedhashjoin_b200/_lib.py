@@ -54,6 +54,8 @@ class PhjConfig(C.Structure):
         ("split_ctas", C.c_uint32),
         ("split_chunks", C.c_uint32),
         ("upload_chunks", C.c_uint32),
+        ("num_gpus", C.c_int32),
+        ("reserved0", C.c_uint32),
     ]
 
 
@@ -77,11 +79,29 @@ class PhjResult(C.Structure):
         ("materialize_ns", C.c_uint64),
         ("e2e_ns", C.c_uint64),
         ("upload_chunks", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("gpus", C.c_uint32),
+        ("count_ns", C.c_uint64),
+        ("shuffle_ns", C.c_uint64),
+        ("shuffle_bytes", C.c_uint64),
     ]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+class PhjDistLayout(C.Structure):
+    _fields_ = [
+        ("world", C.c_uint32),
+        ("rank", C.c_uint32),
+        ("digits", C.c_uint32),
+        ("local_partitions", C.c_uint32),
+        ("chunks", C.c_uint32),
+        ("region_buckets", C.c_uint32),
+        ("window_tuples", C.c_uint64 * 2),
+        ("resizes", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("sent_remote_bytes", C.c_uint64),
+    ]
 
 
 class PhjDeviceInfo(C.Structure):
@@ -126,6 +146,17 @@ SIGNATURES = {
     "phj_shard_push": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_uint64)]),
     "phj_shard_push_wait": (C.c_int, [C.c_void_p]),
+    "phj_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "phj_dist_create": (C.c_int, [C.POINTER(PhjConfig), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "phj_dist_destroy": (None, [C.c_void_p]),
+    "phj_dist_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "phj_dist_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "phj_dist_join": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
+    "phj_dist_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
+    "phj_dist_kernel_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.c_uint32]),
+    "phj_dist_info": (C.c_int, [C.c_void_p, C.POINTER(PhjDistLayout)]),
+    "phj_dist_read_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "phj_shared_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "phj_shared_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_shared_close": (C.c_int, [C.c_int32, C.c_void_p]),

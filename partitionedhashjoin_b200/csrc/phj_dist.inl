@@ -1,0 +1,906 @@
+// phj_dist.inl -- the radix join sharded over several GPUs; included by phj_engine.cu.
+//
+// The reference is one process on one machine (no communication backend at all). Radix
+// partitions are independent join units, so the join shards by partition with ONE exchange step, and
+// that exchange doubles as the (only) partitioning pass:
+//
+//   count     every rank histograms its row shard of R and S by the split digit
+//             (owner rank : local partition) = the low log2(world) + b bits of the partitioning hash,
+//             once for all row chunks of S                                      [stream A]
+//   sizes     NCCL all-gather of the chunk starts, device to device; a one-CTA kernel turns them into
+//             where each of this rank's pieces lands inside its owner's window (digit-major, then
+//             source rank: the reference's stable partition order, src/RadixCluster/HashJoin.hpp:394-412),
+//             into the boundaries of this rank's own partitions, and into an overflow flag    [A]
+//   scatter   the radix scatter kernel writes every digit run STRAIGHT INTO THE OWNER'S WINDOW over
+//             NVLink with its TMA bulk stores -- first R, then S chunk by chunk, each followed by a
+//             stream-ordered NCCL barrier ("everybody's chunk c has landed")                 [A]
+//   local     per-partition tables in global memory, hot in L2 (pt_build after R's barrier, pt_probe
+//             of chunk c after chunk c's barrier): it runs on stream B WHILE stream A scatters the
+//             next chunk -- NVLink-bound stores on one side, L2 / HBM-bound probes on the other
+//   reduce    NCCL all-reduce of {matches, overflow flags}; one 32-byte copy to the host
+//
+// The reference overlaps its two partition pipelines the same way before it waits on either
+// (src/RadixCluster/HashJoin.hpp:210-216). In steady state the host enqueues the whole join and waits
+// once: sizes never visit the host. Windows and tables are sized by a host-synchronous first pass
+// (dist_size) and re-sized only when the device-side overflow flag comes back set.
+//
+// Two launch modes share this code: one process per GPU (phj_dist_create: NCCL communicator from a
+// unique id the caller distributes, windows mapped through CUDA IPC) and one process driving all
+// GPUs (phj_config.num_gpus > 1: ncclCommInitAll, one host thread per GPU, peer access).
+// NCCL is bound at run time (dlopen), so the single-GPU library has no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <pthread.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+
+namespace {
+
+constexpr int kMaxRanks = 16;
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    std::string error;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // inside a torch process this resolves to the NCCL torch has already loaded (same SONAME)
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!api.lib) {
+            api.error = std::string("libnccl.so.2 not found: ") + dlerror();
+            return;
+        }
+        auto sym = [&](const char* name) {
+            void* p = dlsym(api.lib, name);
+            if (!p) api.error = std::string("NCCL symbol missing: ") + name;
+            return p;
+        };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    });
+    return api.error.empty() ? &api : nullptr;
+}
+
+#define PHJ_NCCL(call)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess)                                                                      \
+            return fail(PHJ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+// ---- the device-side layout ------------------------------------------------------------------------
+// all_starts[src][rel][digit][K + 1] (what every rank's split_starts produced, all-gathered). Thread d
+// owns split digit d = owner * d_local + local partition.
+struct LayoutParams {
+    const uint64_t* all_starts;
+    uint32_t world, rank, ndig, d_local, K;
+    ulonglong2* const* peer_build;  // [world]: base of every rank's build window, as mapped HERE
+    ulonglong2* const* peer_probe;
+    ulonglong2** outd;    // out [(1 + K)][ndig]: destination base of digit d for the R launch (0) and the
+                          // S launch of chunk c (1 + c), rebased so that base + scatter cursor is the slot
+    uint64_t* lb_build;   // out [d_local + 1]: boundaries of this rank's partitions in its build window
+    uint64_t* lb_probe;   // out [K][d_local + 1]: ... of chunk c's region of its probe window (absolute)
+    uint64_t cap_build, cap_probe;  // this rank's windows, tuples
+    uint32_t max_keys;              // largest build partition the tables accept
+    unsigned long long* flags;      // [1] += 1 if a window is too small, [2] += oversize partitions
+};
+
+__global__ void __launch_bounds__(256) dist_layout(LayoutParams p) {
+    __shared__ uint64_t tot_r[256];
+    __shared__ uint64_t tot_s[kMaxSplitChunks][256];
+    const uint32_t d = threadIdx.x, K = p.K, stride = K + 1;
+    uint64_t before_r = 0, before_s[kMaxSplitChunks];
+    if (d < p.ndig) {
+        uint64_t tr = 0;
+        uint64_t ts[kMaxSplitChunks];
+        for (uint32_t c = 0; c < K; ++c) ts[c] = before_s[c] = 0;
+        for (uint32_t src = 0; src < p.world; ++src) {
+            const uint64_t* r = p.all_starts + ((uint64_t)(src * 2 + 0) * p.ndig + d) * stride;
+            const uint64_t* s = p.all_starts + ((uint64_t)(src * 2 + 1) * p.ndig + d) * stride;
+            const uint64_t cr = r[K] - r[0];
+            tr += cr;
+            if (src < p.rank) before_r += cr;
+            for (uint32_t c = 0; c < K; ++c) {
+                const uint64_t cs = s[c + 1] - s[c];
+                ts[c] += cs;
+                if (src < p.rank) before_s[c] += cs;
+            }
+        }
+        tot_r[d] = tr;
+        for (uint32_t c = 0; c < K; ++c) tot_s[c][d] = ts[c];
+    }
+    __syncthreads();
+    if (d >= p.ndig) return;
+    const uint32_t owner = d / p.d_local, first = owner * p.d_local, l = d - first;
+    const uint64_t* my_r = p.all_starts + ((uint64_t)(p.rank * 2 + 0) * p.ndig + d) * stride;
+    const uint64_t* my_s = p.all_starts + ((uint64_t)(p.rank * 2 + 1) * p.ndig + d) * stride;
+    uint64_t base_r = 0;
+    for (uint32_t e = first; e < d; ++e) base_r += tot_r[e];
+    p.outd[d] = p.peer_build[owner] + base_r + before_r - my_r[0];
+    const bool mine = owner == p.rank, last = l + 1 == p.d_local;
+    if (mine) {
+        p.lb_build[l] = base_r;
+        if (last) {
+            p.lb_build[p.d_local] = base_r + tot_r[d];
+            if (base_r + tot_r[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
+        }
+        if (tot_r[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
+    }
+    uint64_t region = 0;  // start of chunk c's region in the owner's probe window
+    for (uint32_t c = 0; c < K; ++c) {
+        uint64_t pre = 0, size = 0;
+        for (uint32_t e = first; e < first + p.d_local; ++e) {
+            if (e < d) pre += tot_s[c][e];
+            size += tot_s[c][e];
+        }
+        const uint64_t base_s = region + pre;
+        p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base_s + before_s[c] - my_s[c];
+        if (mine) {
+            p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base_s;
+            if (last) p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base_s + tot_s[c][d];
+        }
+        region += size;
+    }
+    if (mine && last && region > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+}
+
+}  // namespace
+
+// ---- one rank -------------------------------------------------------------------------------------
+struct phj_group;
+
+struct phj_dist {
+    int rank = 0, world = 1, device = 0;
+    phj_config cfg{};
+    phj_group* group = nullptr;  // set when all ranks live in this process
+    ncclComm_t comm = nullptr;
+    bool own_comm = false;
+    phj_handle* split = nullptr;  // PHJ_ALGO_SHARD_SPLIT handle: stream A, histogram, scan, scatter
+    cudaStream_t sb = nullptr;    // stream B: the local join
+    uint32_t b_local = 0, d_local = 1, ndig = 1, K = 1;
+    // windows: 0 = build, 1 = probe
+    void* win[2] = {nullptr, nullptr};
+    unsigned char win_handle[2][64] = {};
+    void* peer[2][kMaxRanks] = {};
+    uint64_t caps[2][kMaxRanks] = {};  // tuples; tracked identically by every rank
+    // device-side plan
+    uint64_t* d_all_starts = nullptr;
+    uint64_t* h_all_starts = nullptr;  // pinned
+    ulonglong2** d_peer = nullptr;     // [2][kMaxRanks]
+    ulonglong2** d_outd = nullptr;     // [(1 + K)][ndig]
+    uint64_t* d_lb = nullptr;          // build [d_local + 1], then probe [K][d_local + 1]
+    unsigned long long* d_flags = nullptr;  // [4] local, [4..8) all-reduced
+    unsigned long long* h_flags = nullptr;  // pinned [8]
+    unsigned char* d_xchg = nullptr;        // handle exchange staging: [(1 + world)][128]
+    unsigned char* h_xchg = nullptr;        // pinned
+    // L2 tables
+    uint64_t* d_pt = nullptr;
+    size_t cap_pt = 0;
+    uint32_t region_buckets = 0, max_keys = 0;
+    uint32_t* d_ptflags = nullptr;
+    cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
+    bool sized = false, have_data = false;
+    size_t n[2] = {0, 0};
+    uint64_t sent_remote_bytes = 0;  // this rank's tuples that leave the GPU, from the last sizing pass
+    uint32_t resizes = 0;
+};
+
+struct phj_group {
+    int world = 0;
+    pthread_barrier_t bar;
+    bool bar_ok = false;
+    std::vector<phj_dist*> ranks;
+    void* win[2][kMaxRanks] = {};
+    struct Worker {
+        std::thread thread;
+        std::mutex m;
+        std::condition_variable cv;
+        std::function<int()> job;
+        bool has_job = false, done = false, stop = false;
+        int rc = 0;
+        std::string error;
+    };
+    std::vector<Worker*> workers;
+    // sharding of the host relations given to phj_upload
+    std::vector<ncclComm_t> comms;
+};
+
+namespace {
+
+int dist_host_barrier(phj_dist* D) {
+    // every rank's stream A has drained AND every rank has arrived
+    NcclApi* nc = nccl_api();
+    PHJ_NCCL(nc->AllReduce(D->d_flags + 8, D->d_flags + 8, 1, ncclUint64, ncclSum, D->comm, D->split->stream));
+    PHJ_CUDA(cudaStreamSynchronize(D->split->stream));
+    return PHJ_OK;
+}
+
+// Publish this rank's window pointers and map everybody else's.
+int dist_exchange_windows(phj_dist* D) {
+    NcclApi* nc = nccl_api();
+    const int W = D->world;
+    if (D->group) {
+        for (int w = 0; w < 2; ++w) D->group->win[w][D->rank] = D->win[w];
+        pthread_barrier_wait(&D->group->bar);
+        for (int w = 0; w < 2; ++w)
+            for (int r = 0; r < W; ++r) D->peer[w][r] = D->group->win[w][r];
+        pthread_barrier_wait(&D->group->bar);
+    } else {
+        memcpy(D->h_xchg, D->win_handle[0], 64);
+        memcpy(D->h_xchg + 64, D->win_handle[1], 64);
+        PHJ_CUDA(cudaMemcpyAsync(D->d_xchg, D->h_xchg, 128, cudaMemcpyHostToDevice, D->split->stream));
+        PHJ_NCCL(nc->AllGather(D->d_xchg, D->d_xchg + 128, 128, ncclUint8, D->comm, D->split->stream));
+        PHJ_CUDA(cudaMemcpyAsync(D->h_xchg + 128, D->d_xchg + 128, (size_t)128 * W, cudaMemcpyDeviceToHost,
+                                 D->split->stream));
+        PHJ_CUDA(cudaStreamSynchronize(D->split->stream));
+        for (int r = 0; r < W; ++r)
+            for (int w = 0; w < 2; ++w) {
+                if (r == D->rank) {
+                    D->peer[w][r] = D->win[w];
+                    continue;
+                }
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, D->h_xchg + 128 + (size_t)128 * r + 64 * w, 64);
+                PHJ_CUDA(cudaIpcOpenMemHandle(&D->peer[w][r], hd, cudaIpcMemLazyEnablePeerAccess));
+            }
+    }
+    ulonglong2* table[2][kMaxRanks] = {};
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < W; ++r) table[w][r] = reinterpret_cast<ulonglong2*>(D->peer[w][r]);
+    PHJ_CUDA(cudaMemcpyAsync(D->d_peer, table, sizeof(table), cudaMemcpyHostToDevice, D->split->stream));
+    PHJ_CUDA(cudaStreamSynchronize(D->split->stream));
+    return PHJ_OK;
+}
+
+int dist_close_peers(phj_dist* D) {
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < D->world; ++r) {
+            if (D->peer[w][r] && r != D->rank && !D->group) PHJ_CUDA(cudaIpcCloseMemHandle(D->peer[w][r]));
+            D->peer[w][r] = nullptr;
+        }
+    return PHJ_OK;
+}
+
+// The count phase on stream A: histogram, scan, chunk starts, all-gather of the starts.
+int dist_enqueue_count(phj_dist* D) {
+    NcclApi* nc = nccl_api();
+    phj_handle* h = D->split;
+    int rc = shard_count_enqueue(h);
+    if (rc != PHJ_OK) return rc;
+    const size_t per_rank = (size_t)2 * D->ndig * (D->K + 1);
+    PHJ_NCCL(nc->AllGather(h->d_shard_starts, D->d_all_starts, per_rank, ncclUint64, D->comm, h->stream));
+    h->launches += 1;
+    return PHJ_OK;
+}
+
+// Host-synchronous sizing pass (first join, new relations, or after an overflow): counts as the join
+// itself does, then every rank derives -- from the same all-gathered numbers, hence identically --
+// how large every rank's windows and tables must be, and the ranks whose windows are too small
+// re-allocate them; all windows are then (re)mapped.
+int dist_size(phj_dist* D) {
+    phj_handle* h = D->split;
+    const int W = D->world;
+    const uint32_t K = D->K, ndig = D->ndig, dl = D->d_local;
+    int rc = dist_enqueue_count(D);
+    if (rc != PHJ_OK) return rc;
+    const size_t total = (size_t)W * 2 * ndig * (K + 1);
+    PHJ_CUDA(cudaMemcpyAsync(D->h_all_starts, D->d_all_starts, total * 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaStreamSynchronize(h->stream));
+    PHJ_CUDA(cudaGetLastError());
+    uint64_t need[2][kMaxRanks] = {};
+    uint64_t max_part = 0, mine_remote = 0;
+    for (uint32_t d = 0; d < ndig; ++d) {
+        uint64_t tot[2] = {0, 0};
+        for (int src = 0; src < W; ++src)
+            for (int rel = 0; rel < 2; ++rel) {
+                const uint64_t* st = D->h_all_starts + (((size_t)src * 2 + rel) * ndig + d) * (K + 1);
+                tot[rel] += st[K] - st[0];
+                if (src == D->rank && (int)(d / dl) != D->rank) mine_remote += st[K] - st[0];
+            }
+        need[0][d / dl] += tot[0];
+        need[1][d / dl] += tot[1];
+        max_part = std::max(max_part, tot[0]);
+    }
+    D->sent_remote_bytes = 16 * mine_remote;
+    bool grow_any = false, grow_mine[2] = {false, false};
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < W; ++r)
+            if (need[w][r] > D->caps[w][r] || (D->caps[w][r] == 0)) {
+                D->caps[w][r] = need[w][r] + need[w][r] / 8 + 4096;
+                grow_any = true;
+                if (r == D->rank) grow_mine[w] = true;
+            }
+    if (grow_any || !D->peer[0][D->rank]) {
+        if ((rc = dist_close_peers(D)) != PHJ_OK) return rc;
+        if ((rc = dist_host_barrier(D)) != PHJ_OK) return rc;  // nobody maps a window that is about to go
+        for (int w = 0; w < 2; ++w)
+            if (grow_mine[w] || !D->win[w]) {
+                if (D->win[w]) PHJ_CUDA(cudaFree(D->win[w]));
+                D->win[w] = nullptr;
+                PHJ_CUDA(cudaMalloc(&D->win[w], D->caps[w][D->rank] * 16));
+                if (!D->group) {
+                    cudaIpcMemHandle_t hd;
+                    PHJ_CUDA(cudaIpcGetMemHandle(&hd, D->win[w]));
+                    memcpy(D->win_handle[w], &hd, 64);
+                }
+            }
+        if ((rc = dist_exchange_windows(D)) != PHJ_OK) return rc;
+        ++D->resizes;
+    }
+    // tables: load <= 0.5 at the largest build partition seen (duplicates only lower it), 10 % to spare
+    uint32_t rb = 64;
+    while ((uint64_t)rb * 2 < max_part + max_part / 10) rb <<= 1;
+    if (rb != D->region_buckets || !D->d_pt) {
+        const size_t want = (size_t)dl * rb * 4;
+        if (want > D->cap_pt) {
+            if (D->d_pt) PHJ_CUDA(cudaFree(D->d_pt));
+            D->d_pt = nullptr;
+            PHJ_CUDA(cudaMalloc(&D->d_pt, want * 8));
+            D->cap_pt = want;
+        }
+        D->region_buckets = rb;
+    }
+    D->max_keys = D->region_buckets * 3;
+    D->sized = true;
+    return PHJ_OK;
+}
+
+// The whole join, enqueued; `counted`: dist_size has just produced d_all_starts for these relations.
+int dist_enqueue_join(phj_dist* D, bool counted) {
+    NcclApi* nc = nccl_api();
+    phj_handle* h = D->split;
+    cudaStream_t sa = h->stream, sb = D->sb;
+    const uint32_t K = D->K, ndig = D->ndig, dl = D->d_local;
+    int rc;
+    PHJ_CUDA(cudaEventRecord(D->ev_t[0], sa));
+    PHJ_CUDA(cudaMemsetAsync(D->d_flags, 0, 4 * sizeof(unsigned long long), sa));
+    PHJ_CUDA(cudaMemsetAsync(D->d_ptflags, 0, 4, sa));
+    if (!counted && (rc = dist_enqueue_count(D)) != PHJ_OK) return rc;
+    PHJ_CUDA(cudaEventRecord(D->ev_t[1], sa));
+    {
+        LayoutParams lp{};
+        lp.all_starts = D->d_all_starts;
+        lp.world = (uint32_t)D->world;
+        lp.rank = (uint32_t)D->rank;
+        lp.ndig = ndig;
+        lp.d_local = dl;
+        lp.K = K;
+        lp.peer_build = D->d_peer;
+        lp.peer_probe = D->d_peer + kMaxRanks;
+        lp.outd = D->d_outd;
+        lp.lb_build = D->d_lb;
+        lp.lb_probe = D->d_lb + (dl + 1);
+        lp.cap_build = D->caps[0][D->rank];
+        lp.cap_probe = D->caps[1][D->rank];
+        lp.max_keys = D->max_keys;
+        lp.flags = D->d_flags;
+        KernelScope ks(h, "dist_layout");
+        dist_layout<<<1, 256, 0, sa>>>(lp);
+    }
+    // ---- stream B: clear the tables while stream A still scatters R ----
+    PHJ_CUDA(cudaEventRecord(D->ev_t[2], sa));
+    PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the layout (boundaries) is ready, the flags are zero
+    uint32_t grid_l = (uint32_t)h->sm_count * 8, scatter_cap = D->cfg.split_ctas;
+    if (const char* x = getenv("PHJ_DIST_PROBE_CTAS")) grid_l = (uint32_t)std::max(1, atoi(x));      // experiment
+    if (const char* x = getenv("PHJ_DIST_SCATTER_CTAS")) scatter_cap = (uint32_t)std::max(0, atoi(x));  // experiment
+    {
+        KernelScope ks(h, "pt_clear", 1, sb);
+        gt_clear<<<grid_l, 256, 0, sb>>>(D->d_pt, (uint64_t)dl * D->region_buckets * 4);
+    }
+
+    // ---- stream A: R, then S chunk by chunk, into the owners' windows; a barrier after each ----
+    PassParams p1{};
+    fill_pass1_params(h, p1);
+    const uint32_t nseg0 = h->nseg1_rel[0];
+    auto scatter = [&](uint32_t first, uint32_t count, uint32_t table) -> int {
+        PassParams pp = p1;
+        pp.seg_first = first;
+        pp.seg_count = count;
+        pp.outd[0] = pp.outd[1] = D->d_outd + (size_t)table * ndig;
+        if (count) {
+            KernelScope ks(h, table == 0 ? "radix_scatter[shuffle R]" : "radix_scatter[shuffle S]");
+            PHJ_CUDA(launch_split_scatter(h, h->b1, pp, scatter_cap ? std::min(count, scatter_cap) : count));
+        }
+        // stream-ordered barrier: when it completes HERE, every rank's scatter of this piece has completed
+        PHJ_NCCL(nc->AllReduce(D->d_flags + 8, D->d_flags + 8, 1, ncclUint64, ncclSum, D->comm, sa));
+        h->launches += 1;
+        return PHJ_OK;
+    };
+    if ((rc = scatter(0, nseg0, 0)) != PHJ_OK) return rc;
+    PHJ_CUDA(cudaEventRecord(D->ev_r, sa));
+
+    PtParams q{};
+    q.build = reinterpret_cast<const ulonglong2*>(D->win[0]);
+    q.probe = reinterpret_cast<const ulonglong2*>(D->win[1]);
+    q.bounds_build = D->d_lb;
+    q.npart = dl;
+    q.max_keys = D->max_keys;
+    q.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;
+    if (h->cfg.table_seed == 0) q.table_mul = 0xBF58476D1CE4E5B9ULL;
+    q.table_mul |= 1ULL << 32;
+    {
+        const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
+        const uint64_t digit = hash_key_dyn(h->cfg.hash, kEmptyKey, hp) & (ndig - 1);
+        q.sentinel_part = digit / dl == (uint64_t)D->rank ? (uint32_t)(digit % dl) : 0xffffffffu;
+    }
+    q.table = D->d_pt;
+    q.region_buckets = D->region_buckets;
+    q.region_shift32 = 32 - (uint32_t)ilog2_ceil(D->region_buckets);
+    q.flags = D->d_ptflags;
+    q.matches = D->d_flags;
+    PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_r, 0));
+    q.bounds_probe = D->d_lb + (dl + 1);
+    {
+        KernelScope ks(h, "pt_build", 1, sb);
+        pt_build<256><<<grid_l, 256, 0, sb>>>(q);
+    }
+    PHJ_CUDA(cudaEventRecord(D->ev_t[5], sb));
+
+    for (uint32_t c = 0; c < K; ++c) {
+        const uint32_t first = nseg0 + h->chunk_first_seg[1][c], last = nseg0 + h->chunk_first_seg[1][c + 1];
+        if ((rc = scatter(first, last - first, 1 + c)) != PHJ_OK) return rc;
+        PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
+        PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
+        q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
+        {
+            KernelScope ks(h, "pt_probe", 1, sb);
+            pt_probe<256><<<grid_l, 256, 0, sb>>>(q);
+        }
+    }
+    PHJ_CUDA(cudaEventRecord(D->ev_t[3], sa));  // the shuffle is complete
+    PHJ_CUDA(cudaEventRecord(D->ev_local, sb));
+    PHJ_CUDA(cudaStreamWaitEvent(sa, D->ev_local, 0));
+    // {matches, overflow, oversize}: summed over the ranks; also the barrier that keeps the next join's
+    // stores out of windows that are still being probed
+    PHJ_NCCL(nc->AllReduce(D->d_flags, D->d_flags + 4, 4, ncclUint64, ncclSum, D->comm, sa));
+    h->launches += 1;
+    PHJ_CUDA(cudaMemcpyAsync(D->h_flags, D->d_flags, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sa));
+    PHJ_CUDA(cudaEventRecord(D->ev_t[4], sa));
+    return PHJ_OK;
+}
+
+int dist_join_rank(phj_dist* D, phj_result* out) {
+    if (!D->have_data) return fail(PHJ_ERR_STATE, "join called before upload / bind_device");
+    PHJ_CUDA(cudaSetDevice(D->device));
+    phj_handle* h = D->split;
+    memset(out, 0, sizeof(*out));
+    h->launches = 0;
+    h->n_ktimes = 0;
+    int rc;
+    for (int attempt = 0;; ++attempt) {
+        // the sizing pass counts on its own; the join below counts again, so that every join runs -- and
+        // times -- the same work
+        if (!D->sized && (rc = dist_size(D)) != PHJ_OK) return rc;
+        h->n_ktimes = 0;
+        if ((rc = dist_enqueue_join(D, false)) != PHJ_OK) return rc;
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(D->sb));
+        PHJ_CUDA(cudaGetLastError());
+        if (D->h_flags[5] == 0 && D->h_flags[6] == 0) break;  // no window / table anywhere was too small
+        if (attempt == 1)
+            return fail(PHJ_ERR_INVALID, "sharded join: windows or tables still too small after re-sizing "
+                                         "(%llu window overflows, %llu oversize partitions)",
+                        (unsigned long long)D->h_flags[5], (unsigned long long)D->h_flags[6]);
+        D->sized = false;  // every rank saw the same all-reduced flags: all of them re-size
+    }
+    out->matches = D->h_flags[4];
+    out->partition_ns = (uint64_t)(ev_ms(D->ev_t[0], D->ev_t[3]) * 1e6);
+    out->count_ns = (uint64_t)(ev_ms(D->ev_t[0], D->ev_t[1]) * 1e6);
+    out->shuffle_ns = (uint64_t)(ev_ms(D->ev_t[2], D->ev_t[3]) * 1e6);
+    out->join_ns = (uint64_t)(ev_ms(D->ev_r, D->ev_local) * 1e6);  // tables + probes (overlapping the shuffle)
+    out->build_ns = (uint64_t)(ev_ms(D->ev_r, D->ev_t[5]) * 1e6);  // table build, once the build side has landed
+    out->probe_ns = (uint64_t)(ev_ms(D->ev_t[5], D->ev_local) * 1e6);  // the probes of all chunks (incl. waiting for them)
+    out->total_ns = (uint64_t)(ev_ms(D->ev_t[0], D->ev_t[4]) * 1e6);
+    out->passes = 1;
+    out->partitions = D->ndig;
+    out->gpus = (uint32_t)D->world;
+    out->shuffle_bytes = D->sent_remote_bytes;
+    out->kernel_launches = h->launches;
+    out->d2h_bytes = 8 * sizeof(unsigned long long);
+    // per rank: histogram read + scatter read + remote / local write + probe read
+    out->hbm_bytes_alg = 16ull * 4 * (D->n[0] + D->n[1]);
+    return PHJ_OK;
+}
+
+int dist_alloc(phj_dist* D) {
+    PHJ_CUDA(cudaSetDevice(D->device));
+    const size_t total = (size_t)D->world * 2 * D->ndig * (D->K + 1);
+    PHJ_CUDA(cudaMalloc(&D->d_all_starts, total * 8));
+    PHJ_CUDA(cudaMallocHost(&D->h_all_starts, total * 8));
+    PHJ_CUDA(cudaMalloc(&D->d_peer, sizeof(ulonglong2*) * 2 * kMaxRanks));
+    PHJ_CUDA(cudaMalloc(&D->d_outd, sizeof(ulonglong2*) * (size_t)(1 + D->K) * D->ndig));
+    PHJ_CUDA(cudaMalloc(&D->d_lb, 8 * (size_t)(1 + D->K) * (D->d_local + 1)));
+    PHJ_CUDA(cudaMalloc(&D->d_flags, 16 * sizeof(unsigned long long)));
+    PHJ_CUDA(cudaMemset(D->d_flags, 0, 16 * sizeof(unsigned long long)));
+    PHJ_CUDA(cudaMallocHost(&D->h_flags, 8 * sizeof(unsigned long long)));
+    PHJ_CUDA(cudaMalloc(&D->d_xchg, (size_t)128 * (1 + D->world)));
+    PHJ_CUDA(cudaMallocHost(&D->h_xchg, (size_t)128 * (1 + D->world)));
+    PHJ_CUDA(cudaMalloc(&D->d_ptflags, 16));
+    PHJ_CUDA(cudaStreamCreateWithFlags(&D->sb, cudaStreamNonBlocking));
+    PHJ_CUDA(cudaEventCreate(&D->ev_r));
+    PHJ_CUDA(cudaEventCreate(&D->ev_local));
+    for (auto& e : D->ev_c) PHJ_CUDA(cudaEventCreate(&e));
+    for (auto& e : D->ev_t) PHJ_CUDA(cudaEventCreate(&e));
+    return PHJ_OK;
+}
+
+// world x local partitions: the split digit space. The tables are probed out of L2, so few, large local
+// partitions are fine; what the choice trades is the length of the runs the scatter stores over
+// NVLink (tile / digits tuples) against the size of one table.
+int dist_plan(phj_dist* D) {
+    const int W = D->world;
+    if (W < 1 || W > kMaxRanks || (W & (W - 1))) return fail(PHJ_ERR_INVALID, "the number of GPUs must be a power of two <= %d", kMaxRanks);
+    uint32_t ndig = 64;
+    if (D->cfg.partitions) {
+        const uint64_t P = D->cfg.partitions;
+        if ((P & (P - 1)) || P < (uint64_t)W || P > (uint64_t)kMaxSplitDigits)
+            return fail(PHJ_ERR_INVALID, "sharded join: partitions = GPUs x local partitions must be a power of two "
+                                         "in [%d, %d] (0 = choose)", W, kMaxSplitDigits);
+        ndig = (uint32_t)P;
+    }
+    ndig = std::max<uint32_t>(ndig, (uint32_t)W);
+    D->ndig = ndig;
+    D->d_local = ndig / (uint32_t)W;
+    D->b_local = (uint32_t)ilog2_ceil(D->d_local);
+    D->K = D->cfg.split_chunks ? D->cfg.split_chunks : 4;
+    if (D->K > (uint32_t)kMaxSplitChunks) return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
+    return PHJ_OK;
+}
+
+int dist_make_split(phj_dist* D) {
+    phj_config sc = D->cfg;
+    sc.algo = PHJ_ALGO_SHARD_SPLIT;
+    sc.partitions = D->ndig;
+    sc.radix_bits[0] = sc.radix_bits[1] = 0;
+    sc.shard_shift = 0;
+    sc.split_chunks = D->K;
+    sc.split_ctas = 0;
+    sc.num_gpus = 0;
+    sc.flags = (D->cfg.flags & PHJ_FLAG_NO_TMA_STORE) | PHJ_FLAG_SPLIT_REMOTE_ONLY;
+    sc.device = D->device;
+    return phj_create(&sc, &D->split);
+}
+
+void dist_free(phj_dist* D) {
+    if (!D) return;
+    cudaSetDevice(D->device);
+    if (D->split && D->split->stream) cudaStreamSynchronize(D->split->stream);
+    if (D->sb) cudaStreamSynchronize(D->sb);
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < D->world; ++r)
+            if (D->peer[w][r] && r != D->rank && !D->group) cudaIpcCloseMemHandle(D->peer[w][r]);
+    if (D->comm && D->own_comm && nccl_api()) nccl_api()->CommDestroy(D->comm);
+    for (int w = 0; w < 2; ++w)
+        if (D->win[w]) cudaFree(D->win[w]);
+    void* dev[] = {D->d_all_starts, D->d_peer, D->d_outd, D->d_lb, D->d_flags, D->d_xchg, D->d_pt, D->d_ptflags};
+    for (void* p : dev)
+        if (p) cudaFree(p);
+    if (D->h_all_starts) cudaFreeHost(D->h_all_starts);
+    if (D->h_flags) cudaFreeHost(D->h_flags);
+    if (D->h_xchg) cudaFreeHost(D->h_xchg);
+    if (D->sb) cudaStreamDestroy(D->sb);
+    if (D->ev_r) cudaEventDestroy(D->ev_r);
+    if (D->ev_local) cudaEventDestroy(D->ev_local);
+    for (auto& e : D->ev_c)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : D->ev_t)
+        if (e) cudaEventDestroy(e);
+    if (D->split) phj_destroy(D->split);
+    delete D;
+}
+
+int dist_set_relations(phj_dist* D, const void* build, size_t n_build, const void* probe, size_t n_probe,
+                       bool device_resident) {
+    PHJ_CUDA(cudaSetDevice(D->device));
+    int rc = device_resident ? phj_bind_device(D->split, build, n_build, probe, n_probe)
+                             : phj_upload(D->split, reinterpret_cast<const phj_tuple*>(build), n_build,
+                                          reinterpret_cast<const phj_tuple*>(probe), n_probe);
+    if (rc != PHJ_OK) return rc;
+    D->n[0] = n_build;
+    D->n[1] = n_probe;
+    D->have_data = true;
+    D->sized = false;  // new relations: count on the host once, keep windows that are large enough
+    return PHJ_OK;
+}
+
+// ---- all ranks in one process -----------------------------------------------------------------------
+void worker_main(phj_group::Worker* w) {
+    std::unique_lock<std::mutex> lk(w->m);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->has_job || w->stop; });
+        if (w->stop) return;
+        std::function<int()> job = std::move(w->job);
+        w->has_job = false;
+        lk.unlock();
+        g_error.clear();
+        const int rc = job();
+        lk.lock();
+        w->rc = rc;
+        w->error = g_error;
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+
+// Run f(rank) on every rank's own host thread (the ranks synchronise with each other inside) and wait.
+int group_run(phj_group* g, const std::function<int(int)>& f) {
+    for (int r = 0; r < g->world; ++r) {
+        phj_group::Worker* w = g->workers[r];
+        std::lock_guard<std::mutex> lk(w->m);
+        w->job = [&f, r] { return f(r); };
+        w->has_job = true;
+        w->done = false;
+        w->cv.notify_all();
+    }
+    int rc = PHJ_OK;
+    for (int r = 0; r < g->world; ++r) {
+        phj_group::Worker* w = g->workers[r];
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != PHJ_OK && rc == PHJ_OK) {
+            rc = w->rc;
+            g_error = "GPU " + std::to_string(r) + ": " + w->error;
+        }
+    }
+    return rc;
+}
+
+}  // namespace
+
+void group_destroy(phj_group* g) {
+    if (!g) return;
+    for (auto* w : g->workers) {
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            w->stop = true;
+            w->cv.notify_all();
+        }
+        if (w->thread.joinable()) w->thread.join();
+        delete w;
+    }
+    for (phj_dist* D : g->ranks) dist_free(D);
+    if (nccl_api())
+        for (ncclComm_t c : g->comms)
+            if (c) nccl_api()->CommDestroy(c);
+    if (g->bar_ok) pthread_barrier_destroy(&g->bar);
+    delete g;
+}
+
+int group_create(const phj_config* cfg, phj_group** out) {
+    *out = nullptr;
+    if (cfg->algo != PHJ_ALGO_RADIX_PARTITIONING)
+        return fail(PHJ_ERR_INVALID, "num_gpus > 1 serves the radix-partitioning join");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(PHJ_ERR_CUDA, "num_gpus > 1 needs NCCL");
+    const int W = cfg->num_gpus;
+    int ndev = 0;
+    PHJ_CUDA(cudaGetDeviceCount(&ndev));
+    if (W > ndev) return fail(PHJ_ERR_INVALID, "num_gpus = %d but only %d CUDA devices are visible", W, ndev);
+    phj_group* g = new phj_group;
+    g->world = W;
+    auto cleanup = [&](int code) {
+        group_destroy(g);
+        return code;
+    };
+    if (pthread_barrier_init(&g->bar, nullptr, (unsigned)W) != 0) return cleanup(fail(PHJ_ERR_NOMEM, "pthread_barrier_init failed"));
+    g->bar_ok = true;
+    int devs[kMaxRanks];
+    for (int r = 0; r < W; ++r) devs[r] = cfg->device + r;
+    if (cfg->device + W > ndev) return cleanup(fail(PHJ_ERR_INVALID, "devices %d .. %d are not all visible", cfg->device, cfg->device + W - 1));
+    for (int r = 0; r < W; ++r) {  // peer access both ways (NCCL may already have enabled it)
+        cudaSetDevice(devs[r]);
+        for (int q = 0; q < W; ++q)
+            if (q != r) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devs[r], devs[q]);
+                if (!can) return cleanup(fail(PHJ_ERR_CUDA, "GPU %d cannot access GPU %d's memory", devs[r], devs[q]));
+                cudaError_t e = cudaDeviceEnablePeerAccess(devs[q], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return cleanup(fail(PHJ_ERR_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)));
+                cudaGetLastError();
+            }
+    }
+    g->comms.assign(W, nullptr);
+    {
+        ncclResult_t r_ = nc->CommInitAll(g->comms.data(), W, devs);
+        if (r_ != ncclSuccess) return cleanup(fail(PHJ_ERR_CUDA, "ncclCommInitAll failed: %s", nc->GetErrorString(r_)));
+    }
+    for (int r = 0; r < W; ++r) {
+        phj_dist* D = new phj_dist;
+        g->ranks.push_back(D);
+        D->rank = r;
+        D->world = W;
+        D->device = devs[r];
+        D->cfg = *cfg;
+        D->group = g;
+        D->comm = g->comms[r];
+        int rc = dist_plan(D);
+        if (rc == PHJ_OK) rc = dist_make_split(D);
+        if (rc == PHJ_OK) rc = dist_alloc(D);
+        if (rc != PHJ_OK) return cleanup(rc);
+    }
+    for (int r = 0; r < W; ++r) {
+        auto* w = new phj_group::Worker;
+        g->workers.push_back(w);
+        w->thread = std::thread(worker_main, w);
+    }
+    *out = g;
+    return PHJ_OK;
+}
+
+// Row shards: GPU r gets rows [r n / W, (r + 1) n / W) of both relations.
+int group_set_relations(phj_group* g, const void* build, size_t n_build, const void* probe, size_t n_probe,
+                        bool device_resident) {
+    if (device_resident)
+        return fail(PHJ_ERR_INVALID, "num_gpus > 1: relations come from host memory (phj_upload / phj_join_host)");
+    const int W = g->world;
+    return group_run(g, [&](int r) {
+        const size_t b0 = n_build * r / W, b1 = n_build * (r + 1) / W;
+        const size_t p0 = n_probe * r / W, p1 = n_probe * (r + 1) / W;
+        return dist_set_relations(g->ranks[r], reinterpret_cast<const phj_tuple*>(build) + b0, b1 - b0,
+                                  reinterpret_cast<const phj_tuple*>(probe) + p0, p1 - p0, false);
+    });
+}
+
+int group_join(phj_group* g, phj_result* out) {
+    std::vector<phj_result> res(g->world);
+    int rc = group_run(g, [&](int r) { return dist_join_rank(g->ranks[r], &res[r]); });
+    if (rc != PHJ_OK) return rc;
+    *out = res[0];
+    for (int r = 1; r < g->world; ++r) {  // the slowest rank defines the join's times
+        out->total_ns = std::max(out->total_ns, res[r].total_ns);
+        out->partition_ns = std::max(out->partition_ns, res[r].partition_ns);
+        out->shuffle_ns = std::max(out->shuffle_ns, res[r].shuffle_ns);
+        out->count_ns = std::max(out->count_ns, res[r].count_ns);
+        out->join_ns = std::max(out->join_ns, res[r].join_ns);
+        out->hbm_bytes_alg += res[r].hbm_bytes_alg;
+        out->kernel_launches += res[r].kernel_launches;
+        out->shuffle_bytes += res[r].shuffle_bytes;
+        out->d2h_bytes += res[r].d2h_bytes;
+    }
+    return PHJ_OK;
+}
+
+// =================================================================================================
+// C ABI of the sharded join, one process per GPU
+// =================================================================================================
+extern "C" {
+
+int phj_nccl_unique_id(unsigned char* id128) {
+    if (!id128) return fail(PHJ_ERR_INVALID, "id is null");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(PHJ_ERR_CUDA, "NCCL is not available");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    PHJ_NCCL(nc->GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return PHJ_OK;
+}
+
+int phj_dist_create(const phj_config* config, int32_t rank, int32_t world, const unsigned char* id128,
+                    phj_dist** out) {
+    if (!out || !config || !id128) return fail(PHJ_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (config->algo != PHJ_ALGO_RADIX_PARTITIONING)
+        return fail(PHJ_ERR_INVALID, "the sharded join is the radix-partitioning join");
+    if (rank < 0 || rank >= world) return fail(PHJ_ERR_INVALID, "rank %d out of range [0, %d)", rank, world);
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(PHJ_ERR_CUDA, "the sharded join needs NCCL (libnccl.so.2)");
+    phj_dist* D = new phj_dist;
+    D->rank = rank;
+    D->world = world;
+    D->device = config->device;
+    D->cfg = *config;
+    auto cleanup = [&](int code) {
+        dist_free(D);
+        return code;
+    };
+    int rc = dist_plan(D);
+    if (rc != PHJ_OK) return cleanup(rc);
+    if (cudaSetDevice(D->device) != cudaSuccess) return cleanup(fail(PHJ_ERR_CUDA, "cudaSetDevice(%d) failed", D->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    {
+        ncclResult_t r_ = nc->CommInitRank(&D->comm, world, id, rank);
+        if (r_ != ncclSuccess) return cleanup(fail(PHJ_ERR_CUDA, "ncclCommInitRank failed: %s", nc->GetErrorString(r_)));
+        D->own_comm = true;
+    }
+    if ((rc = dist_make_split(D)) != PHJ_OK) return cleanup(rc);
+    if ((rc = dist_alloc(D)) != PHJ_OK) return cleanup(rc);
+    *out = D;
+    return PHJ_OK;
+}
+
+void phj_dist_destroy(phj_dist* d) {
+    if (d && !d->group) dist_free(d);
+}
+
+int phj_dist_upload(phj_dist* d, const phj_tuple* build, size_t n_build, const phj_tuple* probe, size_t n_probe) {
+    if (!d) return fail(PHJ_ERR_INVALID, "handle is null");
+    return dist_set_relations(d, build, n_build, probe, n_probe, false);
+}
+
+int phj_dist_bind_device(phj_dist* d, const void* d_build, size_t n_build, const void* d_probe, size_t n_probe) {
+    if (!d) return fail(PHJ_ERR_INVALID, "handle is null");
+    return dist_set_relations(d, d_build, n_build, d_probe, n_probe, true);
+}
+
+int phj_dist_join(phj_dist* d, phj_result* out) {
+    if (!d || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    return dist_join_rank(d, out);
+}
+
+int phj_dist_kernel_times(phj_dist* d, const char** names, uint64_t* ns, uint32_t cap) {
+    return d ? phj_kernel_times(d->split, names, ns, cap) : 0;
+}
+
+int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, uint64_t* end_ns, uint32_t cap) {
+    if (!d) return 0;
+    phj_handle* h = d->split;
+    uint32_t n = 0;
+    for (int i = 0; i < h->n_ktimes && n < cap; ++i) {
+        if (!h->ktimes[i].used) continue;
+        names[n] = h->ktimes[i].name;
+        begin_ns[n] = (uint64_t)(ev_ms(d->ev_t[0], h->ktimes[i].begin) * 1e6);
+        end_ns[n] = (uint64_t)(ev_ms(d->ev_t[0], h->ktimes[i].end) * 1e6);
+        ++n;
+    }
+    return (int)n;
+}
+
+int phj_dist_info(phj_dist* d, phj_dist_layout* out) {
+    if (!d || !out) return fail(PHJ_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->world = (uint32_t)d->world;
+    out->rank = (uint32_t)d->rank;
+    out->digits = d->ndig;
+    out->local_partitions = d->d_local;
+    out->chunks = d->K;
+    out->region_buckets = d->region_buckets;
+    out->window_tuples[0] = d->caps[0][d->rank];
+    out->window_tuples[1] = d->caps[1][d->rank];
+    out->resizes = d->resizes;
+    out->sent_remote_bytes = d->sent_remote_bytes;
+    return PHJ_OK;
+}
+
+int phj_dist_read_window(phj_dist* d, int32_t which, phj_tuple* out, uint64_t cap_tuples, uint64_t* bounds) {
+    if (!d) return fail(PHJ_ERR_INVALID, "handle is null");
+    if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
+    if (!d->sized) return fail(PHJ_ERR_STATE, "no join has run yet");
+    PHJ_CUDA(cudaSetDevice(d->device));
+    const uint32_t dl = d->d_local;
+    const size_t nb = which == 0 ? dl + 1 : (size_t)d->K * (dl + 1);
+    std::vector<uint64_t> b(nb);
+    PHJ_CUDA(cudaMemcpy(b.data(), d->d_lb + (which == 0 ? 0 : dl + 1), nb * 8, cudaMemcpyDeviceToHost));
+    if (bounds) memcpy(bounds, b.data(), nb * 8);
+    const uint64_t used = b[nb - 1];
+    if (out) {
+        if (used > cap_tuples) return fail(PHJ_ERR_INVALID, "the window holds %llu tuples, room for %llu", (unsigned long long)used, (unsigned long long)cap_tuples);
+        if (used) PHJ_CUDA(cudaMemcpy(out, d->win[which], used * 16, cudaMemcpyDeviceToHost));
+    }
+    return PHJ_OK;
+}
+
+}  // extern "C"

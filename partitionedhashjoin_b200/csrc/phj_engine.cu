@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -77,7 +78,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kScatTile = PHJ_SCAT_TPB * PHJ_SCAT_IPT;
 constexpr int kMaxBitsPerPass = 8;
-constexpr int kMaxKernelTimes = 24;
+constexpr int kMaxKernelTimes = 48;
 constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
 constexpr int kMaxSplitChunks = 16;
 constexpr int kCopyStreams = 4;
@@ -103,8 +104,17 @@ struct KernelTime {
 
 }  // namespace
 
+// One process driving several GPUs (phj_config.num_gpus > 1): defined in phj_dist.inl.
+struct phj_group;
+int group_create(const phj_config* cfg, phj_group** out);
+void group_destroy(phj_group* g);
+int group_set_relations(phj_group* g, const void* build, size_t n_build, const void* probe, size_t n_probe,
+                        bool device_resident);
+int group_join(phj_group* g, phj_result* out);
+
 struct phj_handle {
     phj_config cfg{};
+    phj_group* group = nullptr;  // num_gpus > 1: every call on this handle is forwarded to the group
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -238,17 +248,19 @@ struct KernelScope {
     phj_handle* h;
     int idx;
     const char* name_;
-    KernelScope(phj_handle* h_, const char* name, uint32_t kernels = 1) : h(h_), idx(-1), name_(name) {
+    cudaStream_t stream;
+    KernelScope(phj_handle* h_, const char* name, uint32_t kernels = 1, cudaStream_t on = nullptr)
+        : h(h_), idx(-1), name_(name), stream(on ? on : h_->stream) {
         h->launches += kernels;  // kernels launched inside this scope (phj_result.kernel_launches)
         if (h->time_kernels && h->n_ktimes < kMaxKernelTimes) {
             idx = h->n_ktimes++;
             h->ktimes[idx].name = name;
             h->ktimes[idx].used = true;
-            cudaEventRecord(h->ktimes[idx].begin, h->stream);
+            cudaEventRecord(h->ktimes[idx].begin, stream);
         }
     }
     ~KernelScope() {
-        if (idx >= 0) cudaEventRecord(h->ktimes[idx].end, h->stream);
+        if (idx >= 0) cudaEventRecord(h->ktimes[idx].end, stream);
         if (h->debug_sync) {
             cudaError_t e = cudaStreamSynchronize(h->stream);
             if (e == cudaSuccess) e = cudaGetLastError();
@@ -1242,6 +1254,7 @@ int validate_config(const phj_config* c) {
         if (c->split_chunks > (uint32_t)kMaxSplitChunks)
             return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
     }
+    if (c->num_gpus < 0) return fail(PHJ_ERR_INVALID, "num_gpus must be >= 0");
     if (c->upload_chunks > (uint32_t)kMaxUploadChunks)
         return fail(PHJ_ERR_INVALID, "upload_chunks must be <= %d", kMaxUploadChunks);
     if ((c->flags & PHJ_FLAG_CHAINED_TABLE) && c->algo != PHJ_ALGO_NO_PARTITIONING)
@@ -1301,6 +1314,17 @@ int phj_create(const phj_config* config, phj_handle** out) {
     *out = nullptr;
     int rc = validate_config(config);
     if (rc != PHJ_OK) return rc;
+    if (config->num_gpus > 1) {  // the sharded join over the GPUs of this node, driven from this process
+        phj_handle* g = new phj_handle;
+        g->cfg = *config;
+        g->device = config->device;
+        if ((rc = group_create(config, &g->group)) != PHJ_OK) {
+            delete g;
+            return rc;
+        }
+        *out = g;
+        return PHJ_OK;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1356,6 +1380,11 @@ int phj_create(const phj_config* config, phj_handle** out) {
 
 void phj_destroy(phj_handle* h) {
     if (!h) return;
+    if (h->group) {
+        group_destroy(h->group);
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
     if (h->stream_child) phj_destroy(h->stream_child);
     if (h->upload_stream) {
@@ -1400,6 +1429,16 @@ static int set_relations(phj_handle* h, const void* build, size_t n_build, const
         return fail(PHJ_ERR_INVALID, "relation pointer is null but its size is not zero");
     if (((uintptr_t)build | (uintptr_t)probe) & 15)
         return fail(PHJ_ERR_INVALID, "relations must be 16-byte aligned (alignas(16) Tuple)");
+    if (h->group) {
+        if (prepartitioned) return fail(PHJ_ERR_STATE, "num_gpus > 1: pre-partitioned relations are not supported");
+        int rc = group_set_relations(h->group, build, n_build, probe, n_probe, device_resident);
+        if (rc == PHJ_OK) {
+            h->n[0] = n_build;
+            h->n[1] = n_probe;
+            h->have_data = true;
+        }
+        return rc;
+    }
     PHJ_CUDA(cudaSetDevice(h->device));
     const void* src[2] = {build, probe};
     const size_t nn[2] = {n_build, n_probe};
@@ -1532,6 +1571,7 @@ int phj_memcpy_d2d(int32_t device, void* d_dst, const void* d_src, size_t bytes)
 int phj_join(phj_handle* h, phj_result* out) {
     if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
     if (!h->have_data) return fail(PHJ_ERR_STATE, "phj_join called before phj_upload / phj_bind_device");
+    if (h->group) return group_join(h->group, out);
     PHJ_CUDA(cudaSetDevice(h->device));
     memset(out, 0, sizeof(*out));
     h->launches = 0;
@@ -1545,6 +1585,7 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
     if (h->cfg.algo != PHJ_ALGO_RADIX_PARTITIONING)
         return fail(PHJ_ERR_STATE, "the joined table is produced by the radix-partitioning joiner");
+    if (h->group) return fail(PHJ_ERR_STATE, "num_gpus > 1 counts only: the joined table needs a single-GPU handle");
     int rc = phj_join(h, out);  // partitions both relations (and counts, as the reference does)
     if (rc != PHJ_OK) return rc;
     const bool two = h->b2 > 0;
@@ -1732,6 +1773,20 @@ static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_bu
 int phj_join_host(phj_handle* h, const phj_tuple* build, size_t n_build, const phj_tuple* probe,
                   size_t n_probe, phj_result* out) {
     if (!h || !out) return fail(PHJ_ERR_INVALID, "handle or result is null");
+    if (h->group) {  // every GPU uploads its row shard (concurrently), then the sharded join
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = group_set_relations(h->group, build, n_build, probe, n_probe, false);
+        if (rc != PHJ_OK) return rc;
+        h->have_data = true;
+        const auto t1 = std::chrono::steady_clock::now();
+        if ((rc = group_join(h->group, out)) != PHJ_OK) return rc;
+        out->h2d_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        out->e2e_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                          std::chrono::steady_clock::now() - t0).count();
+        out->h2d_bytes = 16ull * (n_build + n_probe);
+        out->upload_chunks = 1;
+        return PHJ_OK;
+    }
     uint32_t chunks = h->cfg.upload_chunks;
     if (chunks == 0) {
         // automatic: chunks of ~256 MB once the probe relation is worth overlapping, but never so short
@@ -1801,13 +1856,11 @@ static void fill_pass1_params(phj_handle* h, PassParams& p1) {
     p1.df = digit_fn(h, 1);
 }
 
-int phj_shard_count(phj_handle* h, uint64_t* counts) {
-    if (!h || !counts) return fail(PHJ_ERR_INVALID, "handle or counts is null");
-    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
-    if (!h->have_data) return fail(PHJ_ERR_STATE, "phj_shard_count called before phj_upload / phj_bind_device");
-    PHJ_CUDA(cudaSetDevice(h->device));
-    h->launches = 0;
-    h->n_ktimes = 0;
+// Histogram + scan of the bound shard by split digit and the chunk starts of every digit, enqueued on
+// the handle's stream: d_shard_starts[(rel * digits + d) * (chunks + 1) + c] = where chunk c's tuples
+// of digit d start in the (virtual) digit-major split output of the relation; entry `chunks` is the
+// end of the digit. Nothing here waits for the device.
+static int shard_count_enqueue(phj_handle* h) {
     const uint32_t w = h->d1, K = h->nchunks;
     const size_t nstarts = (size_t)2 * w * (K + 1);
     if (!h->d_shard_starts) {
@@ -1817,7 +1870,6 @@ int phj_shard_count(phj_handle* h, uint64_t* counts) {
     }
     PassParams p1{};
     fill_pass1_params(h, p1);
-    PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (h->nsegs1 > 0) {
         KernelScope ks(h, "radix_histogram[split]");
         PHJ_CUDA(launch_pass(h, false, h->b1, p1, h->nsegs1));
@@ -1839,6 +1891,21 @@ int phj_shard_count(phj_handle* h, uint64_t* counts) {
         KernelScope ks(h, "split_starts");
         split_starts<<<(uint32_t)((nstarts + 255) / 256), 256, 0, h->stream>>>(sp);
     }
+    return PHJ_OK;
+}
+
+int phj_shard_count(phj_handle* h, uint64_t* counts) {
+    if (!h || !counts) return fail(PHJ_ERR_INVALID, "handle or counts is null");
+    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
+    if (!h->have_data) return fail(PHJ_ERR_STATE, "phj_shard_count called before phj_upload / phj_bind_device");
+    PHJ_CUDA(cudaSetDevice(h->device));
+    h->launches = 0;
+    h->n_ktimes = 0;
+    const uint32_t w = h->d1, K = h->nchunks;
+    const size_t nstarts = (size_t)2 * w * (K + 1);
+    PHJ_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    int rc = shard_count_enqueue(h);
+    if (rc != PHJ_OK) return rc;
     PHJ_CUDA(cudaMemcpyAsync(h->h_shard_starts, h->d_shard_starts, nstarts * 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
@@ -2124,3 +2191,5 @@ int phj_host_free(void* p) {
 }
 
 }  // extern "C"
+
+#include "phj_dist.inl"

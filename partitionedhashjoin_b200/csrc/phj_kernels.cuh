@@ -99,6 +99,19 @@ __device__ __forceinline__ ulonglong2 ld_stream_v2(const ulonglong2* p) {
                  : "l"(p));
     return v;
 }
+// One 32-byte bucket (four keys) with ONE 256-bit load (LDG.E.256, sm_100): a divergent bucket read then
+// costs the L1 one sector access instead of the two of a pair of 128-bit loads -- ncu showed the
+// table probes bound by exactly that (l1tex throughput 96 %, DRAM and L2 half idle).
+struct __align__(32) Bucket4 {
+    unsigned long long k0, k1, k2, k3;
+};
+__device__ __forceinline__ Bucket4 ld_bucket4(const uint64_t* p) {
+    Bucket4 b;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(b.k0), "=l"(b.k1), "=l"(b.k2), "=l"(b.k3)
+                 : "l"(p));
+    return b;
+}
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -1432,40 +1445,41 @@ __device__ __forceinline__ uint32_t partition_of(const uint64_t* __restrict__ bo
     return a;
 }
 
-// Equal share of [first, first + n) for this CTA.
-__device__ __forceinline__ void cta_slice(uint64_t first, uint64_t n, uint64_t& lo, uint64_t& hi) {
-    const uint64_t len = n / gridDim.x, rem = n % gridDim.x;
-    lo = first + len * blockIdx.x + min((uint64_t)blockIdx.x, rem);
-    hi = lo + len + (blockIdx.x < rem ? 1 : 0);
-}
-
+// Both kernels walk their relation in TILES dealt round-robin to the CTAs (tile t goes to CTA t mod grid),
+// so that all resident CTAs work on neighbouring tiles: at any moment only the one or two partitions
+// under that moving front have their tables touched, and those stay in L2 whatever the total size of
+// all tables is. (First version: one contiguous slice per CTA -- every partition's table was live at
+// once, 268 MB of them at 10 M build keys, and two thirds of the lookups went to DRAM at 64 bytes each.)
 template <int TPB>
 __global__ void __launch_bounds__(TPB) pt_build(PtParams p) {
-    uint64_t lo, hi;
-    cta_slice(p.bounds_build[0], p.bounds_build[p.npart] - p.bounds_build[0], lo, hi);
-    if (lo >= hi) return;
+    constexpr int U = 2;
+    constexpr uint64_t TILE = (uint64_t)TPB * U;
+    const uint64_t first = p.bounds_build[0], end = p.bounds_build[p.npart];
     const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
     const uint32_t bmask = p.region_buckets - 1;
-    for (uint32_t part = partition_of(p.bounds_build, p.npart, lo); part < p.npart; ++part) {
-        const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
-        if (r0 >= hi) break;
-        if (r1 - r0 > p.max_keys) continue;  // oversize: left to the global-table fallback
-        const uint64_t s0 = max(lo, r0), s1 = min(hi, r1);
-        uint64_t* __restrict__ region = p.table + (uint64_t)part * p.region_buckets * 4;
-        const bool careful = part == p.sentinel_part;
-        // warp-converged insert loop (see cta_sync()): first free slot of the home bucket, then the next bucket
-        for (uint64_t i0 = s0; i0 < s1; i0 += TPB) {
-            const uint64_t i = i0 + threadIdx.x;
+    for (uint64_t t0 = first + (uint64_t)blockIdx.x * TILE; t0 < end; t0 += (uint64_t)gridDim.x * TILE) {
+        const uint32_t part0 = partition_of(p.bounds_build, p.npart, t0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = t0 + (uint64_t)u * TPB + threadIdx.x;
+            bool pending = i < end;
+            uint32_t part = part0;
+            while (pending && i >= p.bounds_build[part + 1]) ++part;  // a tile may straddle (empty) partitions
             uint64_t key = 0;
-            bool pending = i < s1;
             if (pending) {
-                key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.build + i));
-                if (careful && key == kEmptyKey) {
-                    p.flags[0] = 1;
-                    pending = false;
+                if (p.bounds_build[part + 1] - p.bounds_build[part] > p.max_keys) {
+                    pending = false;  // oversize: counted by the caller, joined elsewhere
+                } else {
+                    key = ld_stream_u64(reinterpret_cast<const uint64_t*>(p.build + i));
+                    if (part == p.sentinel_part && key == kEmptyKey) {
+                        p.flags[0] = 1;
+                        pending = false;
+                    }
                 }
             }
+            uint64_t* __restrict__ region = p.table + (uint64_t)part * p.region_buckets * 4;
             uint32_t bucket = table_bucket32(key, mul_lo, mul_hi, p.region_shift32) & bmask, s = 0;
+            // warp-converged insert loop (see cta_sync()): first free slot of the home bucket, then the next bucket
             while (__any_sync(0xffffffffu, pending)) {
                 if (pending) {
                     unsigned long long* slot = reinterpret_cast<unsigned long long*>(region + (uint64_t)bucket * 4 + s);
@@ -1483,61 +1497,63 @@ __global__ void __launch_bounds__(TPB) pt_build(PtParams p) {
     }
 }
 
+// (A/B, ncu r02d: one contiguous slice per CTA instead -- all 64 tables live at once -- had an L2 hit
+// rate of 12 % and read 19.4 GB from DRAM, 3.34 ms; the round-robin tiles read 3.6 GB, 1.44 ms.)
 template <int TPB>
 __global__ void __launch_bounds__(TPB) pt_probe(PtParams p) {
     __shared__ unsigned long long block_count;
     if (threadIdx.x == 0) block_count = 0;
-    uint64_t lo, hi;
-    cta_slice(p.bounds_probe[0], p.bounds_probe[p.npart] - p.bounds_probe[0], lo, hi);
+    constexpr int U = 4;
+    constexpr uint64_t TILE = (uint64_t)TPB * U;
+    const uint64_t first = p.bounds_probe[0], end = p.bounds_probe[p.npart];
     const uint32_t mul_lo = (uint32_t)p.table_mul, mul_hi = (uint32_t)(p.table_mul >> 32);
     const uint32_t bmask = p.region_buckets - 1;
     const uint32_t sentinel_hit = p.flags[0];
     uint32_t count = 0;
-    constexpr int U = 4;
-    if (lo < hi) {
-        for (uint32_t part = partition_of(p.bounds_probe, p.npart, lo); part < p.npart; ++part) {
-            const uint64_t ps0 = p.bounds_probe[part];
-            if (ps0 >= hi) break;
-            const uint64_t s0 = max(lo, ps0), s1 = min(hi, p.bounds_probe[part + 1]);
-            if (s0 >= s1) continue;
-            const uint64_t r0 = p.bounds_build[part], r1 = p.bounds_build[part + 1];
-            if (r1 == r0 || r1 - r0 > p.max_keys) continue;
-            const uint64_t* __restrict__ region = p.table + (uint64_t)part * p.region_buckets * 4;
-            const bool careful = part == p.sentinel_part;
-            for (uint64_t i0 = s0; i0 < s1; i0 += (uint64_t)TPB * U) {
-                uint64_t key[U];
-                uint32_t bucket[U];
-                bool pending[U];
+    const uint64_t lo = first + (uint64_t)blockIdx.x * TILE;
+    uint32_t part0 = lo < end ? partition_of(p.bounds_probe, p.npart, lo) : 0;
+    for (uint64_t t0 = lo; t0 < end; t0 += (uint64_t)gridDim.x * TILE) {
+        uint64_t key[U];
+        bool pending[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint64_t i = i0 + (uint64_t)u * TPB + threadIdx.x;
-                    pending[u] = i < s1;
-                    key[u] = pending[u] ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
-                }
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = t0 + (uint64_t)u * TPB + threadIdx.x;
+            pending[u] = i < end;
+            key[u] = pending[u] ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.probe + i)) : 0;
+        }
+        // the tile's partition(s): the front only moves forward; nearly always the tile lies in one
+        // partition, a tile that straddles a boundary resolves per tuple
+        while (t0 >= p.bounds_probe[part0 + 1]) ++part0;
+        const bool uniform = min(t0 + TILE, end) <= p.bounds_probe[part0 + 1];
+        uint32_t part[U], bucket[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (careful && pending[u] && key[u] == kEmptyKey) {
-                        count += sentinel_hit;
+        for (int u = 0; u < U; ++u) {
+            part[u] = part0;
+            if (!uniform) {
+                const uint64_t i = t0 + (uint64_t)u * TPB + threadIdx.x;
+                while (pending[u] && i >= p.bounds_probe[part[u] + 1]) ++part[u];
+            }
+            const uint64_t nb = p.bounds_build[part[u] + 1] - p.bounds_build[part[u]];
+            if (nb == 0 || nb > p.max_keys) pending[u] = false;  // src/RadixCluster/HashJoin.hpp:273-276 / oversize
+            if (part[u] == p.sentinel_part && pending[u] && key[u] == kEmptyKey) {
+                count += sentinel_hit;
+                pending[u] = false;
+            }
+            bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, p.region_shift32) & bmask;
+        }
+        // one 32-byte bucket per step; a bucket whose last slot is free ends the search
+        while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (pending[u]) {
+                    const Bucket4 b = ld_bucket4(p.table + ((uint64_t)part[u] * p.region_buckets + bucket[u]) * 4);
+                    if (b.k0 == key[u] || b.k1 == key[u] || b.k2 == key[u] || b.k3 == key[u]) {
+                        ++count;
                         pending[u] = false;
-                    }
-                    bucket[u] = table_bucket32(key[u], mul_lo, mul_hi, p.region_shift32) & bmask;
-                }
-                // one 32-byte bucket per step; a bucket whose last slot is free ends the search
-                while (__any_sync(0xffffffffu, pending[0] | pending[1] | pending[2] | pending[3])) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (pending[u]) {
-                            const ulonglong2* b = reinterpret_cast<const ulonglong2*>(region + (uint64_t)bucket[u] * 4);
-                            const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
-                            if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
-                                ++count;
-                                pending[u] = false;
-                            } else if (k23.y == kEmptyKey) {
-                                pending[u] = false;
-                            } else {
-                                bucket[u] = (bucket[u] + 1) & bmask;
-                            }
-                        }
+                    } else if (b.k3 == kEmptyKey) {
+                        pending[u] = false;
+                    } else {
+                        bucket[u] = (bucket[u] + 1) & bmask;
                     }
                 }
             }
@@ -1673,12 +1689,11 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (pending[u]) {
-                    const ulonglong2* b = reinterpret_cast<const ulonglong2*>(p.table + bucket[u] * 4);
-                    const ulonglong2 k01 = __ldg(b), k23 = __ldg(b + 1);
-                    if (k01.x == key[u] || k01.y == key[u] || k23.x == key[u] || k23.y == key[u]) {
+                    const Bucket4 b = ld_bucket4(p.table + bucket[u] * 4);
+                    if (b.k0 == key[u] || b.k1 == key[u] || b.k2 == key[u] || b.k3 == key[u]) {
                         ++count;
                         pending[u] = false;
-                    } else if (k23.y == kEmptyKey) {
+                    } else if (b.k3 == kEmptyKey) {
                         pending[u] = false;  // slots fill in order: last one free => bucket not full
                     } else {
                         bucket[u] = (bucket[u] + 1) & p.bucket_mask;

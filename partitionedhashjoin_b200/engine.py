@@ -172,7 +172,7 @@ class Engine:
     def __init__(self, algo="radix-partitioning", partitions: int = 0, radix_bits=(0, 0), hash="xxh3",
                  hash_seed: int = 0x9E3779B97F4A7C15, table_seed: int = 1, device: int = 0,
                  flags: int = 0, shard_shift: int = 0, split_ctas: int = 0, reserve=(0, 0),
-                 split_chunks: int = 0, upload_chunks: int = 0):
+                 split_chunks: int = 0, upload_chunks: int = 0, num_gpus: int = 0):
         cfg = PhjConfig()
         if isinstance(algo, str):
             if algo not in self.ALGOS:
@@ -191,6 +191,9 @@ class Engine:
         cfg.split_chunks = split_chunks
         cfg.upload_chunks = upload_chunks  # join_host: 0 = automatic, 1 = upload then join, k = k probe chunks
         cfg.reserve_build, cfg.reserve_probe = reserve
+        # num_gpus > 1: this process drives GPUs device .. device + num_gpus - 1 (the sharded join of
+        # csrc/phj_dist.inl); partitions then = GPUs x local partitions (<= 256), split_chunks = probe chunks
+        cfg.num_gpus = num_gpus
         self._h = C.c_void_p()
         check(lib.phj_create(C.byref(cfg), C.byref(self._h)))
         self._keep = []

@@ -830,6 +830,109 @@ class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
         return self.last
 
 
+class ShardedJoin:
+    """One rank of the sharded radix join that lives INSIDE libphj_b200.so (phj_dist_*, csrc/phj_dist.inl):
+    count -> NCCL all-gather of the piece sizes -> device-side layout -> the radix scatter stores R and then S,
+    chunk by chunk, straight into the owners' windows over NVLink while the local L2-table probe of the previous
+    chunk runs -> NCCL all-reduce of the count. The host enqueues the join and waits once; Python only bootstraps
+    (the NCCL unique id travels over torch.distributed) and calls phj_dist_join. `dist` = torch.distributed
+    (initialised) or None for a single rank."""
+
+    def __init__(self, dist, rank, world, device, partitions=0, chunks=0, hash="xxh3",
+                 hash_seed=0x9E3779B97F4A7C15, table_seed=1, flags=0):
+        import ctypes as C
+
+        import torch  # noqa: F401  (first: the library then binds the NCCL torch has loaded)
+
+        from . import _lib
+        self._C, self._lib, self._check = C, _lib.lib, _lib.check
+        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self._lib.phj_nccl_unique_id(ident))
+        if world > 1:
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        cfg = _lib.PhjConfig()
+        cfg.algo = _lib.ALGO_RADIX_PARTITIONING
+        cfg.hash = _lib.HASH_NAMES[hash] if isinstance(hash, str) else hash
+        cfg.partitions = partitions
+        cfg.hash_seed = hash_seed & (2**64 - 1)
+        cfg.table_seed = table_seed & (2**64 - 1)
+        cfg.device = device
+        cfg.flags = flags
+        cfg.split_chunks = chunks
+        self._h = C.c_void_p()
+        self._check(self._lib.phj_dist_create(C.byref(cfg), rank, world, ident, C.byref(self._h)))
+        self._keep = None
+        self.launches = 0
+        self.last = {}
+
+    def upload(self, R_shard, S_shard):
+        from .engine import as_tuples
+        R, S = as_tuples(R_shard), as_tuples(S_shard)
+        self._check(self._lib.phj_dist_upload(self._h, R.ctypes.data, R.shape[0], S.ctypes.data, S.shape[0]))
+
+    def bind_device(self, d_build, n_build, d_probe, n_probe, keepalive=None):
+        C = self._C
+        self._check(self._lib.phj_dist_bind_device(self._h, C.c_void_p(d_build), n_build, C.c_void_p(d_probe), n_probe))
+        self._keep = keepalive
+
+    def join(self) -> dict:
+        from ._lib import PhjResult
+        res = PhjResult()
+        self._check(self._lib.phj_dist_join(self._h, self._C.byref(res)))
+        self.last = res.as_dict()
+        self.launches += self.last["kernel_launches"]
+        return self.last
+
+    def info(self) -> dict:
+        from ._lib import PhjDistLayout
+        lay = PhjDistLayout()
+        self._check(self._lib.phj_dist_info(self._h, self._C.byref(lay)))
+        return {"world": lay.world, "rank": lay.rank, "digits": lay.digits, "local_partitions": lay.local_partitions,
+                "chunks": lay.chunks, "region_buckets": lay.region_buckets,
+                "window_tuples": [int(lay.window_tuples[0]), int(lay.window_tuples[1])], "resizes": lay.resizes,
+                "sent_remote_bytes": int(lay.sent_remote_bytes)}
+
+    def kernel_times(self):
+        C = self._C
+        names, ns = (C.c_char_p * 64)(), (C.c_uint64 * 64)()
+        n = self._lib.phj_dist_kernel_times(self._h, names, ns, 64)
+        return [(names[i].decode(), int(ns[i])) for i in range(n)]
+
+    def kernel_trace(self):
+        """[(kernel, begin ns, end ns)] of the last join relative to its first event (PHJ_KERNEL_TIMES=1)."""
+        C = self._C
+        names, b, e = (C.c_char_p * 64)(), (C.c_uint64 * 64)(), (C.c_uint64 * 64)()
+        n = self._lib.phj_dist_kernel_trace(self._h, names, b, e, 64)
+        return [(names[i].decode(), int(b[i]), int(e[i])) for i in range(n)]
+
+    def read_window(self, which):
+        """(tuples in this rank's window, boundaries): build -> [local_partitions + 1]; probe ->
+        [chunks][local_partitions + 1], absolute positions (test read-back)."""
+        from ._lib import TUPLE_DTYPE
+        lay = self.info()
+        nb = lay["local_partitions"] + 1
+        bounds = np.zeros(nb if which == 0 else lay["chunks"] * nb, dtype=np.uint64)
+        self._check(self._lib.phj_dist_read_window(self._h, which, None, 0, bounds.ctypes.data))
+        out = np.empty(int(bounds[-1]), dtype=TUPLE_DTYPE)
+        self._check(self._lib.phj_dist_read_window(self._h, which, out.ctypes.data, out.shape[0], bounds.ctypes.data))
+        return out, (bounds if which == 0 else bounds.reshape(lay["chunks"], nb)).astype(np.int64)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.phj_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_inputs(phj, rank, world, n_build, n_probe, skew, base_seed, batches):
     """Weak-scaling shards: R = keys 1..world*n_build cut by rank, S = Zipf over the whole key range."""
     Rp, Sp = phj.PinnedTuples(n_build), phj.PinnedTuples(n_probe)

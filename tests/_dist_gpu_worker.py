@@ -17,6 +17,67 @@ import _oracle  # noqa: E402
 from partitionedhashjoin_b200 import multigpu  # noqa: E402
 
 
+def check_window(job, oracle, rel_global, which, rank, hash_seed=0x9E3779B97F4A7C15, hash_id=0):
+    """What landed in this rank's window is exactly the tuples whose split digit it owns: per (chunk, local
+    partition) region every tuple carries that digit and the payloads (= global row numbers) increase, i.e.
+    pieces in source-rank order with input order inside a piece (the reference's stable partition order);
+    over all chunks a partition holds exactly the relation's tuples of its digit."""
+    lay = job.info()
+    got, bounds = job.read_window(which)
+    dl, ndig = lay["local_partitions"], lay["digits"]
+    digit = (oracle.hash_batch(hash_id, hash_seed, rel_global["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+    regions = bounds[None] if which == 0 else bounds
+    for l in range(dl):
+        d = rank * dl + l
+        pieces = []
+        for c in range(regions.shape[0]):
+            piece = got[regions[c][l]:regions[c][l + 1]]
+            dg = (oracle.hash_batch(hash_id, hash_seed, piece["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+            assert (dg == d).all(), (which, c, l)
+            assert (np.diff(piece["payload"]) > 0).all(), (which, c, l, "order inside a region")
+            pieces.append(piece)
+        allp = np.concatenate(pieces)
+        allp = allp[np.argsort(allp["payload"], kind="stable")]
+        expect = rel_global[digit == d]
+        assert allp.shape[0] == expect.shape[0], (which, l, allp.shape, expect.shape)
+        assert (allp["id"] == expect["id"]).all() and (allp["payload"] == expect["payload"]).all()
+
+
+def check_library_join(rank, world, local, oracle, R, S, want, shard, mode):
+    dist_mod = dist if world > 1 else None
+    for partitions, chunks in ((0, 0), (world * 4, 3), (256, 1), (world, 5)):
+        if partitions and partitions < world:
+            continue
+        job = multigpu.ShardedJoin(dist_mod, rank, world, local, partitions=partitions, chunks=chunks)
+        job.upload(shard(R), shard(S))
+        for _ in range(3):
+            res = job.join()
+            assert res["matches"] == want, (res["matches"], want, partitions, chunks)
+        assert job.info()["resizes"] == 1, job.info()
+        check_window(job, oracle, R, 0, rank)
+        check_window(job, oracle, S, 1, rank)
+        # bigger shards: the device-side overflow flag sends every rank through a collective re-size
+        job.upload(shard(R), np.concatenate([shard(S)] * 2))
+        res = job.join()
+        assert res["matches"] == 2 * want, (res["matches"], 2 * want)
+        res = job.join()
+        assert res["matches"] == 2 * want and res["gpus"] == world
+        # smaller again: the windows are kept
+        job.upload(shard(R), shard(S)[: shard(S).shape[0] // 2])
+        n_resizes = job.info()["resizes"]
+        r1 = job.join()
+        part = np.concatenate([shard_of(S, q, world)[: shard_of(S, q, world).shape[0] // 2] for q in range(world)])
+        assert r1["matches"] == oracle.count_by_sort(R, part) and job.info()["resizes"] == n_resizes
+        job.close()
+    if rank == 0:
+        print(json.dumps({"mode": mode, "world": world, "matches": res["matches"] // 2, "want": want}))
+
+
+def shard_of(rel, q, world):
+    per = rel.shape[0] // world
+    return rel[q * per:(rel.shape[0] if q == world - 1 else (q + 1) * per)]
+
+
 def main():
     mode = sys.argv[1]  # pipelined | pass1 | fused | nccl
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -36,6 +97,11 @@ def main():
         lo, hi = rank * per, (rel.shape[0] if rank == world - 1 else (rank + 1) * per)
         return rel[lo:hi]
 
+    if mode.startswith("lib"):  # the sharded join inside libphj_b200.so (phj_dist_*): ShardedJoin
+        check_library_join(rank, world, local, oracle, R, S, want, shard, mode)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     fused = mode in ("pass1", "fused")
     if mode == "npj":  # no-partitioning join, build side gathered on every rank (not yet in the pytest matrix)
         job = multigpu.ReplicatedNoPartitioningJoin(dist, rank, world, multigpu.NpjGpuBackend(world, local))

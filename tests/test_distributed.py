@@ -243,6 +243,50 @@ def test_fused_shuffle_single_gpu(phj, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("hash", ["xxh3", "murmur3", "city"])
+def test_library_sharded_join_single_rank(phj, oracle, hash):
+    """The sharded join inside the library (phj_dist_*) with ONE rank on one GPU: the whole pipeline -- count, NCCL
+    all-gather, device-side layout, scatter into the (own) window chunk by chunk with stream-ordered barriers, L2
+    tables, all-reduce -- against the oracle's count, on the adversarial cases, with the window contents checked."""
+    import numpy as np
+
+    import _cases
+    import _dist_gpu_worker as worker
+    from partitionedhashjoin_b200 import multigpu
+    hash_id = {"xxh3": 0, "murmur3": 1, "city": 2}[hash]
+    cases = dict(_cases.adversarial_cases())
+    cases["big_random"] = (_cases.tuples(_cases.splitmix64(300_000, 51).astype(np.int64) % 200_003),
+                           _cases.tuples(_cases.splitmix64(2_000_000, 52).astype(np.int64) % 300_007))
+    for partitions, chunks in ((0, 0), (8, 3), (256, 16), (1, 1)):
+        job = multigpu.ShardedJoin(None, 0, 1, 0, partitions=partitions, chunks=chunks, hash=hash)
+        for name, (R, S) in cases.items():
+            R, S = R.copy(), S.copy()
+            R["payload"], S["payload"] = np.arange(R.shape[0]), np.arange(S.shape[0])
+            job.upload(R, S)
+            want = oracle.count_by_sort(R, S)
+            for _ in range(2):
+                res = job.join()
+                assert res["matches"] == want, (name, partitions, chunks, res["matches"], want)
+            if R.shape[0] and S.shape[0]:
+                worker.check_window(job, oracle, R, 0, 0, hash_id=hash_id)
+                worker.check_window(job, oracle, S, 1, 0, hash_id=hash_id)
+        job.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_library_sharded_join_on_gpus(phj, world):
+    """One rank per GPU: the library's sharded join (NVLink peer stores + NCCL) against the oracle's count with the
+    contents of every rank's windows checked; skipped when the box has fewer GPUs."""
+    if phj.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = torchrun(world, os.path.join(HERE, "_dist_gpu_worker.py"), "lib", timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["world"] == world and line["matches"] == line["want"] and line["want"] > 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pipelined-sm"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"),
                                         (8, "pass1"), (8, "pipelined")])
 def test_sharded_join_on_gpus(phj, world, mode):

@@ -1,0 +1,32 @@
+"""Profiling driver for one radix-join configuration: 10 M x 200 M keys generated on the device, a few joins,
+nothing else -- short enough to run under `ncu --set full`.
+
+    python tools/ncu_join.py [partitions] [flags] [alpha] [joins]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("PHJ_KERNEL_TIMES", "1")
+import partitionedhashjoin_b200 as phj  # noqa: E402
+
+
+def main():
+    parts = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 0
+    alpha = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+    joins = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    nr, ns = 10_000_000, 200_000_000
+    dR = phj.DeviceTuples(nr, 0).fill_sequential(1)
+    dS = phj.DeviceTuples(ns, 0).fill_zipf(alpha, 1, nr, 12345, 1 << 14)
+    with phj.Engine("radix-partitioning", partitions=parts, flags=flags) as e:
+        e.bind_device(dR.ptr, nr, dS.ptr, ns, keepalive=(dR, dS))
+        for _ in range(joins):
+            res = e.join()
+            assert res["matches"] == ns, res
+            print(f"partitions={parts} flags={flags:#x} alpha={alpha}: {res['total_ns'] / 1e6:.3f} ms",
+                  [(n, round(t / 1e3, 1)) for n, t in e.kernel_times()], flush=True)
+
+
+if __name__ == "__main__":
+    main()
