@@ -244,7 +244,7 @@ def gpu_arm(args):
     if phj.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
 
-    if world > 1:
+    if world > 1 or args.workload == "scaled":
         from partitionedhashjoin_b200 import multigpu
         return multigpu.bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSampler,
                               METRIC, UNIT, measured_hbm_peak)
@@ -362,6 +362,19 @@ def gpu_arm(args):
 
     cpu = cpu_baseline_leg(args, R, S) if not args.no_cpu_baseline else None
     eng.close()
+    if not args.quick:
+        # BASELINE.json configs[4] on ONE GPU (the N = 1 point of its strong scaling): 160 M x 3.2 B through the
+        # library's sharded join with a single rank -- 54 GB of input + 60 GB of windows fit one B200's HBM
+        import torch
+
+        from partitionedhashjoin_b200 import multigpu
+        del keep, R, S
+        torch.cuda.set_device(local)
+        free, _ = torch.cuda.mem_get_info(local)
+        if free > 140e9:
+            others["scaled_160Mx3200M"] = multigpu.scaled_other_config(phj, multigpu.SingleRank, torch, 0, 1, local, args)
+        else:
+            others["scaled_160Mx3200M"] = {"skipped": f"only {free / 1e9:.0f} GB of HBM free"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -400,17 +413,16 @@ def main():
     ap.add_argument("--workload", default="default", choices=["default", "scaled"],
                     help="N > 1 only: scaled = BASELINE.json configs[4], 160M x 3.2B in total sharded over the ranks "
                          "(strong scaling), generated on the device; use --partitions 8192")
-    ap.add_argument("--sm-shuffle", action="store_true",
-                    help="N > 1, pipelined shuffle: NVLink stores from the split scatter instead of copy-engine pushes")
-    ap.add_argument("--chunks", type=int, default=4, help="N > 1, pipelined shuffle: probe chunks")
-    ap.add_argument("--split-ctas", type=int, default=96,
-                    help="N > 1, pipelined shuffle: CTAs of the NVLink-bound split scatter (0 = all)")
-    ap.add_argument("--shuffle", default="pass1", choices=["pass1", "pipelined", "fused", "nccl", "npj"],
-                    help="N > 1: pipelined = pass1 cut into probe chunks, shuffle of chunk c+1 overlapping the local "
-                         "join of chunk c; pass1 = the split scatter writes (owner : pass-1 digit) pieces into the owners' "
-                         "windows over NVLink and the local join starts at pass 2; fused = same stores, split by "
-                         "owner only; nccl = local split + NCCL all-to-all; npj = the no-partitioning join instead: build shards "
-                         "gathered on every rank, probe shards stay (no shuffle)")
+    ap.add_argument("--chunks", type=int, default=0, help="N > 1: probe chunks of the shuffle (0 = the library's default, 4)")
+    ap.add_argument("--dist-partitions", type=int, default=0,
+                    help="N > 1: split digits = GPUs x local partitions (a power of two <= 256; 0 = the library's default, 64)")
+    ap.add_argument("--shuffle", default="library", choices=["library", "pass1", "fused", "nccl", "npj"],
+                    help="N > 1: library = the sharded join inside libphj_b200.so (phj_dist_*: device-side layout, NVLink "
+                         "peer stores, probe chunks overlapping the shuffle, L2-table local join); the host-driven paths "
+                         "of round 1: pass1 = the split scatter writes (owner : pass-1 digit) pieces into the owners' "
+                         "windows and the local join starts at pass 2 (keeps heavy-hitter digits local); fused = same "
+                         "stores, split by owner only; nccl = local split + NCCL all-to-all; npj = the no-partitioning "
+                         "join: build shards gathered on every rank, probe shards stay (no shuffle)")
     ap.add_argument("--quick", action="store_true", help="skip the informational extra configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",

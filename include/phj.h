@@ -310,6 +310,11 @@ int phj_dist_kernel_times(phj_dist* d, const char** names, uint64_t* ns, uint32_
  * PHJ_KERNEL_TIMES=1): shows which kernels of the two streams ran side by side. */
 int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, uint64_t* end_ns, uint32_t cap);
 
+/* NVLink reference measured in place: every rank copies `bytes` of its probe window into the next rank's
+ * window with a plain cudaMemcpyAsync (one per repeat), all ranks at once -- the per-direction bandwidth the
+ * shuffle is compared with (bench.py: shuffle.nvlink_peak_GBps). Collective; overwrites the windows. */
+int phj_dist_measure_peer_copy(phj_dist* d, uint64_t bytes, uint32_t repeats, uint64_t* ns_per_copy);
+
 /* How the last join laid this rank's data out, and test read-back of its windows: `which` 0 = build
  * (bounds: local_partitions + 1), 1 = probe (bounds: chunks x (local_partitions + 1), absolute positions:
  * chunk c's tuples of local partition l lie at [bounds[c][l], bounds[c][l + 1]), ordered by source rank,

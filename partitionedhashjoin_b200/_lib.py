@@ -155,6 +155,7 @@ SIGNATURES = {
     "phj_dist_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
     "phj_dist_kernel_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.c_uint32]),
+    "phj_dist_measure_peer_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "phj_dist_info": (C.c_int, [C.c_void_p, C.POINTER(PhjDistLayout)]),
     "phj_dist_read_window": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "phj_shared_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),

@@ -401,9 +401,19 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
     // ---- stream B: clear the tables while stream A still scatters R ----
     PHJ_CUDA(cudaEventRecord(D->ev_t[2], sa));
     PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the layout (boundaries) is ready, the flags are zero
-    uint32_t grid_l = (uint32_t)h->sm_count * 8, scatter_cap = D->cfg.split_ctas;
-    if (const char* x = getenv("PHJ_DIST_PROBE_CTAS")) grid_l = (uint32_t)std::max(1, atoi(x));      // experiment
-    if (const char* x = getenv("PHJ_DIST_SCATTER_CTAS")) scatter_cap = (uint32_t)std::max(0, atoi(x));  // experiment
+    // The two legs must CO-RESIDE to overlap: a scatter CTA (1024 threads x 64 registers) owns a whole SM's
+    // register file, as do six probe CTAs, so left to themselves the two kernels only take turns on the SMs
+    // (measured at 2 GPUs: 5.4 ms with 4 chunks against 4.5 ms without any overlap). So the SMs are split:
+    // the NVLink-bound scatter gets the share of SMs its instruction work needs next to the probe's (1.3 ms
+    // against 1.1 ms of a whole GPU: 54 %), the probe -- whose tiles are dealt round-robin to however many
+    // CTAs there are -- the rest. 80 / 68 SMs: 4.07 ms; 100 / 48: 4.28; 110 / 38: 4.75; 120 / 28: 5.42.
+    // With one chunk nothing overlaps and both kernels get the whole GPU.
+    uint32_t grid_l = (uint32_t)h->sm_count * 8, scatter_cap = 0;
+    if (K > 1) {
+        scatter_cap = D->cfg.split_ctas ? D->cfg.split_ctas : (uint32_t)(h->sm_count * 54 / 100);
+        scatter_cap = std::min<uint32_t>(std::max<uint32_t>(scatter_cap, 1), (uint32_t)h->sm_count - 1);
+        grid_l = ((uint32_t)h->sm_count - scatter_cap) * 6;  // pt_probe: 256 threads x 40 registers = 6 CTAs per SM
+    }
     {
         KernelScope ks(h, "pt_clear", 1, sb);
         gt_clear<<<grid_l, 256, 0, sb>>>(D->d_pt, (uint64_t)dl * D->region_buckets * 4);
@@ -464,8 +474,10 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
         PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
         q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
         {
+            // the last chunk's probe runs after the last scatter: it gets the whole GPU
+            const uint32_t grid_p = c + 1 == K ? (uint32_t)h->sm_count * 8 : grid_l;
             KernelScope ks(h, "pt_probe", 1, sb);
-            pt_probe<256><<<grid_l, 256, 0, sb>>>(q);
+            pt_probe<256><<<grid_p, 256, 0, sb>>>(q);
         }
     }
     PHJ_CUDA(cudaEventRecord(D->ev_t[3], sa));  // the shuffle is complete
@@ -867,6 +879,26 @@ int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, u
         ++n;
     }
     return (int)n;
+}
+
+int phj_dist_measure_peer_copy(phj_dist* d, uint64_t bytes, uint32_t repeats, uint64_t* ns_per_copy) {
+    if (!d || !ns_per_copy) return fail(PHJ_ERR_INVALID, "null argument");
+    if (!d->sized) return fail(PHJ_ERR_STATE, "the windows exist after the first join");
+    PHJ_CUDA(cudaSetDevice(d->device));
+    *ns_per_copy = 0;
+    if (d->world < 2) return PHJ_OK;
+    const int next = (d->rank + 1) % d->world;
+    bytes = std::min<uint64_t>(bytes, 16 * std::min(d->caps[1][d->rank], d->caps[1][next]));
+    cudaStream_t sa = d->split->stream;
+    int rc = dist_host_barrier(d);  // everybody copies at the same time: every GPU sends and receives
+    if (rc != PHJ_OK) return rc;
+    PHJ_CUDA(cudaEventRecord(d->ev_t[6], sa));
+    for (uint32_t i = 0; i < std::max<uint32_t>(repeats, 1); ++i)
+        PHJ_CUDA(cudaMemcpyAsync(d->peer[1][next], d->win[1], bytes, cudaMemcpyDeviceToDevice, sa));
+    PHJ_CUDA(cudaEventRecord(d->ev_t[7], sa));
+    PHJ_CUDA(cudaStreamSynchronize(sa));
+    *ns_per_copy = (uint64_t)(ev_ms(d->ev_t[6], d->ev_t[7]) * 1e6 / std::max<uint32_t>(repeats, 1));
+    return dist_host_barrier(d);
 }
 
 int phj_dist_info(phj_dist* d, phj_dist_layout* out) {

@@ -91,6 +91,7 @@ enum Scalar : int {  // device-resident uint32 scalars
     kNsegs2,
     kNcounts2,
     kOversize,
+    kPlanTruncated,  // plan_pass2 ran out of segment slots (must never happen: the join fails if it does)
     kGtFlags,
     kCtCursor,
     kNumScalars = 8
@@ -562,6 +563,11 @@ int build_plan(phj_handle* h) {
             nseg_plan[rel] = len ? (uint32_t)((pn + len - 1) / len) : 0;
             nseg[rel] = len ? (uint32_t)((h->n[rel] + len - 1) / len) : 0;
             h->seg_len[rel] = len ? len : kScatTile;
+            // radix_histogram_lanes keeps lane-private 16-bit counters for a whole segment: a thread must see
+            // fewer than 65536 tuples per segment whatever their digits are
+            if (len / PHJ_HIST_TPB >= 65536)
+                return fail(PHJ_ERR_INVALID, "internal: segments of %llu tuples overflow the histogram's 16-bit lane counters",
+                            (unsigned long long)len);
             h->nseg1_rel[rel] = nseg[rel];
             h->cnt_base1_rel[rel] = cnt_base;
             for (uint32_t s = 0; s < nseg[rel]; ++s) {
@@ -977,6 +983,7 @@ int join_radix(phj_handle* h, phj_result* out) {
         pl.nsegs = h->d_scalars + kNsegs2;
         pl.ncounts = h->d_scalars + kNcounts2;
         pl.max_segs = h->max_segs2;
+        pl.truncated = h->d_scalars + kPlanTruncated;
         p2.segs = h->d_segs2;
         p2.nsegs = h->d_scalars + kNsegs2;
         p2.counts = h->d_counts;
@@ -1186,7 +1193,7 @@ int join_radix(phj_handle* h, phj_result* out) {
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
-    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 4, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_cta_times, h->d_cta_times, (size_t)h->join_grid * 16,
                              cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
@@ -1194,6 +1201,8 @@ int join_radix(phj_handle* h, phj_result* out) {
     PHJ_CUDA(cudaGetLastError());
 
     const uint32_t oversize = (uint32_t)(h->h_out[1] & 0xffffffffu);
+    if (h->h_out[1] >> 32)  // kPlanTruncated sits right behind kOversize
+        return fail(PHJ_ERR_INVALID, "internal: the pass-2 plan needed more than %u segments", h->max_segs2);
     float extra_ms = 0;
     if (oversize && h->prepart && !h->parent_digits.empty())
         return fail(PHJ_ERR_INVALID, "%u build partitions exceed the shared-memory table; with explicitly numbered "

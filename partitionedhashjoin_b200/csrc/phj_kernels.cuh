@@ -812,6 +812,7 @@ struct Plan2Params {
     uint32_t* nsegs;      // out: total segments
     uint32_t* ncounts;    // out: total counters = d2 * nsegs
     uint32_t max_segs;
+    uint32_t* truncated;  // set when the parents need more than max_segs segments
 };
 
 __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
@@ -863,6 +864,7 @@ __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
     if (threadIdx.x == 0) {
         *p.nsegs = min(seg_base, p.max_segs);
         *p.ncounts = min(seg_base, p.max_segs) * p.d2;
+        if (seg_base > p.max_segs) *p.truncated = 1;
     }
 }
 

@@ -909,6 +909,14 @@ class ShardedJoin:
         n = self._lib.phj_dist_kernel_trace(self._h, names, b, e, 64)
         return [(names[i].decode(), int(b[i]), int(e[i])) for i in range(n)]
 
+    def measure_peer_copy(self, nbytes=1 << 30, repeats=3):
+        """GB/s of a plain peer cudaMemcpyAsync of this rank's window into the next rank's, all ranks at once."""
+        ns = self._C.c_uint64()
+        self._check(self._lib.phj_dist_measure_peer_copy(self._h, nbytes, repeats, self._C.byref(ns)))
+        lay = self.info()
+        moved = min(nbytes, 16 * lay["window_tuples"][1])
+        return moved / ns.value if ns.value else 0.0
+
     def read_window(self, which):
         """(tuples in this rank's window, boundaries): build -> [local_partitions + 1]; probe ->
         [chunks][local_partitions + 1], absolute positions (test read-back)."""
@@ -942,52 +950,161 @@ def shard_inputs(phj, rank, world, n_build, n_probe, skew, base_seed, batches):
     return Rp, Sp
 
 
+class SingleRank:
+    """Stand-in for torch.distributed when there is one rank (bench.py --gpus 1 --workload scaled)."""
+
+    class ReduceOp:
+        SUM, MAX, MIN = "sum", "max", "min"
+
+    @staticmethod
+    def all_reduce(t, op=None):
+        return t
+
+    @staticmethod
+    def all_gather(out, t):
+        out[0].copy_(t)
+
+    @staticmethod
+    def barrier():
+        pass
+
+    @staticmethod
+    def destroy_process_group():
+        pass
+
+
+def scaled_inputs(phj, dist, torch, rank, world, local, skew):
+    """BASELINE.json configs[4]: 160 M x 3.2 B in total, row-sharded over the ranks (strong scaling), generated ON
+    the device (the host generator would need minutes and a 51 GB upload). Probe keys are drawn over twice the
+    build key range, so the count is not |S|; the independent count (chunk-wise) brings
+    the probe keys back to the host 100 M at a time and lets numpy count those inside [1, |R|]."""
+    total_build, total_probe = 160_000_000, 3_200_000_000
+    n_build, n_probe = total_build // world, total_probe // world
+    dR = phj.DeviceTuples(n_build, local).fill_sequential(1 + rank * n_build)
+    dS = phj.DeviceTuples(n_probe, local).fill_zipf(skew, 1, 2 * total_build, 12345 + 100_003 * rank, 1 << 16)
+    mine, step = 0, 100_000_000
+    for first in range(0, n_probe, step):
+        ids = dS.download(first, min(step, n_probe - first))["id"]
+        mine += int(((ids >= 1) & (ids <= total_build)).sum())
+    want = int(round(_allreduce(dist, torch, local, [float(mine)])[0]))
+    return dR, dS, n_build, n_probe, want
+
+
+def scaled_other_config(phj, dist, torch, rank, world, local, args, joins=3):
+    """The scaled configuration as an `other_configs` entry of the default run: a few joins, count checked."""
+    dR, dS, n_build, n_probe, want = scaled_inputs(phj, dist, torch, rank, world, local, 1.05)
+    job = ShardedJoin(dist if world > 1 else None, rank, world, local, hash=args.hash)
+    job.bind_device(dR.ptr, n_build, dS.ptr, n_probe, keepalive=(dR, dS))
+    got = [job.join()["matches"] for _ in range(2)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(joins):
+        res = job.join()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = _allreduce(dist, torch, local, [time.perf_counter() - t0], dist.ReduceOp.MAX)[0] / joins
+    lay = job.info()
+    job.close()
+    dR.close()
+    dS.close()
+    return {"workload": "160M x 3200M in total over the ranks (strong scaling), device-generated, Zipf 1.05 over 2x the "
+                        "build key range", "ms_per_join": dt * 1e3, "Gtuples_s": round(3.36e9 / dt / 1e9, 2),
+            "matches": res["matches"], "want": want, "ok": all(g == want for g in got) and res["matches"] == want,
+            "want_how": "numpy count of the probe keys inside [1, |R|], read back from the device 100 M at a time, "
+                        "summed over the ranks", "shuffle_ms": res["shuffle_ns"] / 1e6, "count_ms": res["count_ns"] / 1e6,
+            "digits": lay["digits"], "chunks": lay["chunks"]}
+
+
+def _allreduce(dist, torch, local, values, op=None):
+    t = torch.tensor(values, dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+def parity_check(phj, dist, torch, rank, world, local, make_job, skew, n_build=1_000_000, n_probe=20_000_000):
+    """A join whose answer is NOT |S|: probe keys drawn over twice the build key range, one
+    build key duplicated on every rank, INT64_MIN on both sides. The all-reduced count of the product is compared
+    with an independent one: every rank gathers ALL build keys (torch all_gather) and counts its own probe keys with
+    numpy isin; the counts are summed. Also: what landed in the windows is as many tuples as were sent."""
+    int64_min = -(2 ** 63)
+    R = np.empty(n_build, dtype=phj.TUPLE_DTYPE)
+    S = np.empty(n_probe, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1 + rank * n_build)
+    phj.fill_zipf(S, skew, 1, 2 * world * n_build, 4242 + 31 * rank, 16)
+    R["id"][-1] = 7                      # the same build key once more on every rank (duplicates collapse)
+    R["id"][-2] = int64_min if rank == 0 else R["id"][-2]
+    S["id"][::1_000_003] = int64_min     # the reserved table marker as a probe key: matches rank 0's build tuple
+    S["payload"] += rank * n_probe
+    job = make_job()
+    job.upload(R, S)
+    got = [job.join()["matches"] for _ in range(2)]
+    keys = torch.from_numpy(np.ascontiguousarray(R["id"])).to(f"cuda:{local}")
+    everyone = [torch.empty_like(keys) for _ in range(world)]
+    dist.all_gather(everyone, keys)
+    build_keys = np.unique(torch.cat(everyone).cpu().numpy())
+    mine = int(np.isin(S["id"], build_keys).sum())
+    want = int(round(_allreduce(dist, torch, local, [float(mine)])[0]))
+    out = {"count": got[-1], "want": want, "ok": got[0] == want and got[1] == want, "skew": skew,
+           "build_per_rank": n_build, "probe_per_rank": n_probe,
+           "how": "probe keys over 2x the build key range, a duplicated build key, INT64_MIN on both sides; "
+                  "want = sum over ranks of numpy isin(own probe keys, all-gathered build keys)"}
+    if hasattr(job, "read_window"):
+        landed = sum(int(job.read_window(w)[1].reshape(-1)[-1]) for w in (0, 1))
+        tot = _allreduce(dist, torch, local, [float(landed)])[0]
+        out["window_tuples"] = int(tot)
+        out["ok"] = out["ok"] and int(tot) == world * (n_build + n_probe)
+    job.close()
+    return out
+
+
 def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSampler, metric, unit, measured_hbm_peak):
-    """bench.py --gpus N (N > 1): every rank brings a 10 M x 200 M shard (weak scaling)."""
+    """bench.py --gpus N (N > 1). Default workload: every rank brings a 10 M x 200 M shard (weak scaling) and the
+    library's sharded join (ShardedJoin -> phj_dist_*) joins them; --workload scaled: BASELINE.json configs[4],
+    160 M x 3.2 B in total (strong scaling). Before anything is timed a join with a non-trivial answer is checked
+    against an independent count (`parity`)."""
     import json
 
     import torch
 
     import partitionedhashjoin_b200 as phj
     scaled = getattr(args, "workload", "default") == "scaled"
+    mode = getattr(args, "shuffle", "library")
+    dev = f"cuda:{local}"
+
+    def make_job(kind=None):
+        kind = kind or mode
+        if kind == "library":
+            return ShardedJoin(dist if world > 1 else None, rank, world, local, partitions=args.dist_partitions, chunks=args.chunks, hash=args.hash)
+        if kind in ("pass1", "fused"):
+            return FusedShardedRadixJoin(dist, rank, world, FusedGpuBackend(
+                world, local, partitions_local=args.partitions, hash=args.hash, pass1_in_shuffle=(kind == "pass1")))
+        if kind == "npj":
+            return ReplicatedNoPartitioningJoin(dist, rank, world, NpjGpuBackend(world, local, hash=args.hash))
+        return ShardedRadixJoin(dist, rank, world, GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash))
+
+    if world == 1:
+        dist = SingleRank
+    # ---- parity first: a non-trivial count on uniform and on heavy-hitter keys; the legacy host-driven path with
+    # ---- heavy-hitter digits kept local (layout_hot) on the same Zipf 1.25 data
+    parity = parity_check(phj, dist, torch, rank, world, local, make_job, 0.01)
+    parity_skew = parity_check(phj, dist, torch, rank, world, local, make_job, 1.25)
+    parity_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("pass1"), 1.25) if world > 1 else None
+    assert parity["ok"] and parity_skew["ok"] and (parity_hot is None or parity_hot["ok"]), (parity, parity_skew, parity_hot)
+
     if scaled:
-        # BASELINE.json configs[4]: 160 M x 3.2 B in total, row-sharded over the ranks (strong scaling),
-        # generated ON the device (the host generator would need minutes and a 51 GB upload)
-        total_build, total_probe = 160_000_000, 3_200_000_000
-        n_build, n_probe = total_build // world, total_probe // world
-        dR = phj.DeviceTuples(n_build, local).fill_sequential(1 + rank * n_build)
-        dS = phj.DeviceTuples(n_probe, local).fill_zipf(args.skew, 1, total_build, 12345 + 100_003 * rank, 1 << 16)
-        # local fan-out for build partitions of ~2.4 K keys, like the single-GPU default
-        args.partitions = 1 << max(2, (n_build // 1800).bit_length() - 1)
+        dR, dS, n_build, n_probe, want = scaled_inputs(phj, dist, torch, rank, world, local, args.skew)
     else:
         n_build, n_probe = 10_000_000, 200_000_000
         Rp, Sp = shard_inputs(phj, rank, world, n_build, n_probe, args.skew, 12345, 64)
-    mode = getattr(args, "shuffle", "pass1")
-    fused = mode in ("fused", "pass1", "pipelined")
-    if mode == "pipelined":  # chunked: the NVLink shuffle of chunk c + 1 overlaps the local join of chunk c
-        backend = PipelinedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
-                                      chunks=args.chunks, split_ctas=args.split_ctas,
-                                      copy_engines=not getattr(args, "sm_shuffle", False))
-        job = PipelinedShardedRadixJoin(dist, rank, world, backend)
-    elif fused:  # the shuffle is the split scatter's own NVLink stores into the owners' windows
-        backend = FusedGpuBackend(world, local, partitions_local=args.partitions, hash=args.hash,
-                                  pass1_in_shuffle=(mode == "pass1"))
-        job = FusedShardedRadixJoin(dist, rank, world, backend)
-    elif mode == "npj":  # no-partitioning join: build shards gathered on every rank, probe shards stay
-        if scaled:
-            raise SystemExit("--shuffle npj joins the uploaded default workload only")
-        backend = NpjGpuBackend(world, local, hash=args.hash)
-        job = ReplicatedNoPartitioningJoin(dist, rank, world, backend)
-    else:      # split locally, then one NCCL all-to-all per relation
-        backend = GpuBackend(world, local, partitions_local=args.partitions, hash=args.hash)
-        job = ShardedRadixJoin(dist, rank, world, backend)
+        want = world * n_probe  # generator data over R's own key range: every probe key has a build match
+    job = make_job()
     if scaled:
-        backend.bind_device(dR.ptr, n_build, dS.ptr, n_probe, keepalive=(dR, dS))
+        job.bind_device(dR.ptr, n_build, dS.ptr, n_probe, keepalive=(dR, dS))
     else:
         job.upload(Rp.array, Sp.array)
     for _ in range(args.warmup):
         res = job.join()
-    want = world * n_probe
     assert res["matches"] == want, (res["matches"], want)
 
     def sync():
@@ -996,32 +1113,39 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
         torch.cuda.synchronize()
 
     # Timed on the device: a CUDA event pair brackets the K joins (every join returns with its streams
-    # synchronised, so the closing event's timestamp lies after the last kernel), barrier +
-    # synchronize on both sides, max over ranks. The wall clock is kept beside it.
+    # synchronised, so the closing event's timestamp lies after the last kernel), barrier + synchronize on both
+    # sides, max over ranks. The wall clock is kept beside it.
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = backend.launches
+    launches0 = job.launches if hasattr(job, "launches") else job.backend.launches
+    keys = ("count_ns", "shuffle_ns", "build_ns", "probe_ns", "total_ns")
+    sums, ktimes = {k: 0 for k in keys}, {}
     with ClockSampler(local) as clocks:
         sync()
         ev0.record()
         t0 = time.perf_counter()
-        parts = {"split_s": 0.0, "exchange_s": 0.0, "local_s": 0.0, "reduce_s": 0.0}
         for _ in range(args.steps):
             res = job.join()
-            for k in parts:
-                parts[k] += res[k]
+            for k in keys:
+                sums[k] += res.get(k, 0)
+            if hasattr(job, "kernel_times"):
+                for name, ns in job.kernel_times():
+                    ktimes.setdefault(name, []).append(ns)
         ev1.record()
         sync()
         wall = time.perf_counter() - t0
-    elapsed = ev0.elapsed_time(ev1) / 1e3
-    t = torch.tensor([elapsed, wall], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed, wall = float(t[0].item()), float(t[1].item())
     assert res["matches"] == want
+    elapsed, wall = _allreduce(dist, torch, local, [ev0.elapsed_time(ev1) / 1e3, wall], dist.ReduceOp.MAX)
+    launches1 = job.launches if hasattr(job, "launches") else job.backend.launches
+    launches = int(_allreduce(dist, torch, local, [float(launches1 - launches0)])[0])
 
-    # e2e: the host shards are uploaded inside the timed region (the scaled workload is generated on
-    # the device and has no host copy, hence no end-to-end number)
-    e2e_steps = max(3, min(args.steps, 5))
-    te = torch.tensor([0.0], dtype=torch.float64, device=f"cuda:{local}")
+    # NVLink reference, measured in this run: a plain peer copy, every rank into its neighbour's window at once
+    peer_gbps = job.measure_peer_copy() if hasattr(job, "measure_peer_copy") else 0.0
+    peer_gbps = _allreduce(dist, torch, local, [peer_gbps], dist.ReduceOp.MIN)[0]
+    sent = _allreduce(dist, torch, local, [float(res.get("shuffle_bytes", 0))], dist.ReduceOp.MAX)[0]
+
+    # e2e: the host shards are uploaded inside the timed region (the scaled workload is generated on the device
+    # and has no host copy, hence no end-to-end number)
+    e2e_steps, e2e_s = max(3, min(args.steps, 5)), 0.0
     if not scaled:
         sync()
         t0 = time.perf_counter()
@@ -1029,36 +1153,62 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             job.upload(Rp.array, Sp.array)
             r2 = job.join()
         sync()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = _allreduce(dist, torch, local, [time.perf_counter() - t0], dist.ReduceOp.MAX)[0]
         assert r2["matches"] == want
-    launches = torch.tensor([backend.launches - launches0], dtype=torch.int64, device=f"cuda:{local}")
-    dist.all_reduce(launches)
+    lay = job.info() if hasattr(job, "info") else {}
+    job.close()
+
+    # ---- the other multi-GPU configurations, a few joins each ----
+    others = {}
+    if not scaled and not args.quick:
+        def few(j, n=3, expect=want):
+            j.upload(Rp.array, Sp.array)
+            runs = [j.join() for _ in range(n + 1)][1:]
+            for r in runs:
+                assert r["matches"] == expect, (r["matches"], expect)
+            sync()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                j.join()
+            sync()
+            dt = _allreduce(dist, torch, local, [time.perf_counter() - t0], dist.ReduceOp.MAX)[0] / n
+            j.close()
+            return round(world * (n_build + n_probe) / dt / 1e9, 2)
+        if world > 1:
+            others["no_partitioning_replicated_build_Gtuples_s"] = few(make_job("npj"))
+            others["legacy_host_driven_pass1_Gtuples_s"] = few(make_job("pass1"))
+        others["library_1_chunk_no_overlap_Gtuples_s"] = few(ShardedJoin(dist, rank, world, local, chunks=1, hash=args.hash))
+        for skew in (1.05, 1.25):
+            phj.fill_zipf(Sp.array, skew, 1, world * n_build, 12345 + 7919 * rank, 64)
+            others[f"library_zipf{skew}_Gtuples_s"] = few(make_job("library"))
+            if skew == 1.25 and world > 1:
+                others["legacy_pass1_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("pass1"))
+        Rp.close()
+        Sp.close()
+        others["scaled_160Mx3200M"] = scaled_other_config(phj, dist, torch, rank, world, local, args)
 
     if rank == 0:
         n_tuples = world * (n_build + n_probe)
         ms = elapsed / args.steps * 1e3
         peak, peak_src = measured_hbm_peak()
-        lr = res["local_result"]
         cfg = workload_config(args)
         cfg["primary"], cfg["secondary"] = world * n_build, world * n_probe
-        if scaled:
-            cfg["l2_flush"] = f"inputs ({16 * (n_build + n_probe) / 1e9:.1f} GB per GPU) are larger than L2"
-        if mode == "npj":
-            cfg["workload"] = (f"no-partitioning join over {world} B200: build shards ({n_build // 10**6}M each) "
-                               f"gathered on every rank (NCCL broadcasts), probe shards ({n_probe // 10**6}M each) "
-                               f"stay, {args.hash}, Zipf skew {args.skew}")
-        else:
+        cfg["partitions"] = lay.get("digits", args.partitions)
+        cfg["l2_flush"] = f"inputs ({16 * (n_build + n_probe) / 1e9:.2f} GB per GPU) are larger than L2"
+        if mode == "library":
             cfg["workload"] = (
-                f"radix join sharded over {world} B200: {world} x ({n_build // 10**6}M x {n_probe // 10**6}M) "
-                f"row shards = {world * n_build // 10**6}M x {world * n_probe // 10**6}M"
-                f"{' (device-generated)' if scaled else ''}, partition shuffle "
-                f"{'fused into the split scatter (NVLink peer stores)' if fused else 'by NCCL all-to-all'}"
-                f"{' and doubling as radix pass 1' if fused and backend.b1 else ''}"
-                f"{f', pipelined over {args.chunks} probe chunks' if mode == 'pipelined' else ''}, then local "
-                f"2-pass radix join ({args.partitions} partitions/GPU), {args.hash}, Zipf skew {args.skew}")
-        cfg["parallelism"] = f"build side replicated x{world}" if mode == "npj" else f"partition-sharded x{world}"
-        exch_bytes = res["send_bytes_remote"]
+                f"radix join sharded over {world} B200: {world} x ({n_build // 10**6}M x {n_probe // 10**6}M) row shards = "
+                f"{world * n_build // 10**6}M x {world * n_probe // 10**6}M{' (device-generated, keys over 2x the build range)' if scaled else ''}; "
+                f"ONE partitioning pass = the shuffle ({lay.get('digits')} digits = {world} GPUs x {lay.get('local_partitions')} local "
+                f"partitions, NVLink peer stores from the scatter kernel, {lay.get('chunks')} probe chunks overlapping the local "
+                f"L2-table probes), NCCL for sizes / barriers / count, {args.hash}, Zipf skew {args.skew}")
+        else:
+            cfg["workload"] = f"radix join sharded over {world} B200, shuffle mode {mode}, {args.hash}, Zipf skew {args.skew}"
+        cfg["parallelism"] = f"partition-sharded x{world}"
+        scat = [ns for name, v in ktimes.items() if name.startswith("radix_scatter") for ns in v]
+        scat_ms = sum(scat) / max(args.steps, 1) / 1e6  # all scatter launches of one join, this rank
+        alg_bytes = 32.0 * (n_build + n_probe)
+        shuffle_ms = sums["shuffle_ns"] / args.steps / 1e6
         line = {
             "metric": metric, "value": n_tuples / (elapsed / args.steps), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -1066,19 +1216,28 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             "scaling": "strong" if scaled else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": cfg,
             "e2e": None if scaled else {
-                "value": n_tuples / (float(te.item()) / e2e_steps), "unit": unit, "h2d_bytes_per_step": 16 * n_tuples,
-                "d2h_bytes_per_step": int(lr["d2h_bytes"] + 8 * (2 * world + 2)) * world, "steps": e2e_steps},
-            "gpu_launches": int(launches.item()),
-            "roofline": {"bound": "hbm", "kernel": "local join (per GPU)", "unit": "GB/s", "peak": peak,
-                         "peak_source": peak_src, "achieved": lr["hbm_bytes_alg"] / lr["total_ns"],
-                         "frac": lr["hbm_bytes_alg"] / lr["total_ns"] / peak, "traffic": None},
-            "phases_ms_rank0": {k[:-2]: v / args.steps * 1e3 for k, v in parts.items()},
-            "shuffle": {"bytes_sent_remote_rank0": exch_bytes,
-                        "GBps_rank0": exch_bytes / max(parts["exchange_s"] / args.steps, 1e-9) / 1e9,
-                        "nvlink_peak_GBps": 770.0},
-            "clocks": clocks.summary(), "matches": res["matches"], "cpu_baseline": None,
+                "value": n_tuples / (e2e_s / e2e_steps), "unit": unit, "h2d_bytes_per_step": 16 * n_tuples,
+                "d2h_bytes_per_step": world * (64 + 8 * world * 2 * lay.get("digits", 64) * (lay.get("chunks", 1) + 1)),
+                "steps": e2e_steps, "host_memory": "pinned (phj_host_alloc)"},
+            "gpu_launches": launches,
+            "parity": parity, "parity_zipf1.25": parity_skew, "parity_zipf1.25_legacy_hot_digits": parity_hot,
+            "roofline": {"bound": "hbm", "kernel": "radix_scatter[shuffle] (rank 0, all launches of a join; NVLink-bound "
+                                                   "for N > 1: see `shuffle`)", "unit": "GB/s", "peak": peak,
+                         "peak_source": peak_src, "achieved": alg_bytes / max(scat_ms, 1e-9) / 1e6,
+                         "frac": alg_bytes / max(scat_ms, 1e-9) / 1e6 / peak, "traffic": None,
+                         "algorithmic_bytes_per_join_per_gpu": alg_bytes, "ms_per_join": scat_ms},
+            "phases_ms_rank0": {k[:-3]: v / args.steps / 1e6 for k, v in sums.items()},
+            "kernel_us_rank0": {name: round(sum(v) / len(v) / 1e3, 1) for name, v in ktimes.items()},
+            "shuffle": {"bytes_sent_remote_per_gpu": sent, "ms": shuffle_ms,
+                        "GBps_per_gpu": sent / max(shuffle_ms, 1e-9) / 1e6,
+                        "nvlink_peak_GBps": peer_gbps,
+                        "nvlink_peak_source": "plain peer cudaMemcpyAsync of 1 GiB into the next rank's window, all "
+                                              "ranks at once, measured in this run",
+                        "nvlink_frac": (sent / max(shuffle_ms, 1e-9) / 1e6) / peer_gbps if peer_gbps else None,
+                        "nvlink_nominal_GBps": 900.0},
+            "layout": lay, "clocks": clocks.summary(), "matches": res["matches"], "want": want,
+            "cpu_baseline": None, "other_configs": others,
         }
         print(json.dumps(line), flush=True)
-    job.close()
     dist.barrier()
     dist.destroy_process_group()
