@@ -126,6 +126,10 @@ typedef struct {
                                      partitions: one radix pass (partitions = 32 .. 256) then needs no second
                                      partitioning pass at all -- 3.41 ms against 3.95 ms for two passes + shared
                                      memory at 10 M x 200 M. The multi-GPU path always joins this way. */
+#define PHJ_FLAG_COOP_PROBE 0x200u /* global-table probes (NO_PARTITIONING, oversize fallback) by groups of four
+                                      lanes per key (shuffle broadcast + one 8-byte slot per lane + ballot) instead
+                                      of one thread per key reading the 32-byte bucket with one 256-bit load.
+                                      Kept for the A/B in DESIGN.md section 4; the per-thread probe is faster. */
 #define PHJ_FLAG_NO_HIST12 0x100u /* two-pass plans: do not take both passes' histograms from one read
                                      (radix_histogram_full); the pass-1 scatter counts for pass 2 instead */
 

@@ -403,16 +403,22 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
     PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the layout (boundaries) is ready, the flags are zero
     // The two legs must CO-RESIDE to overlap: a scatter CTA (1024 threads x 64 registers) owns a whole SM's
     // register file, as do six probe CTAs, so left to themselves the two kernels only take turns on the SMs
-    // (measured at 2 GPUs: 5.4 ms with 4 chunks against 4.5 ms without any overlap). So the SMs are split:
-    // the NVLink-bound scatter gets the share of SMs its instruction work needs next to the probe's (1.3 ms
-    // against 1.1 ms of a whole GPU: 54 %), the probe -- whose tiles are dealt round-robin to however many
-    // CTAs there are -- the rest. 80 / 68 SMs: 4.07 ms; 100 / 48: 4.28; 110 / 38: 4.75; 120 / 28: 5.42.
-    // With one chunk nothing overlaps and both kernels get the whole GPU.
+    // (measured at 2 GPUs: 5.4 ms with 4 chunks against 4.5 ms without any overlap). So the SMs are split. The
+    // probe -- whose tiles are dealt round-robin to however many CTAs there are -- gets as many SMs as it needs
+    // to finish a chunk while the next chunk's scatter is bound by NVLink ((W - 1) / W of the chunk at ~0.6 TB/s
+    // against ~0.3 ms of a whole GPU for the probe), the scatter the rest: more scatter CTAs mean more stores in
+    // flight (2 GPUs, whole GPU: 660 GB/s; 80 CTAs: 560 GB/s). Measured at 2 GPUs, scatter / probe SMs:
+    // 80 / 68: 4.07 ms; 100 / 48: 4.28; 110 / 38: 4.75; 120 / 28: 5.42. With one chunk nothing overlaps and
+    // both kernels get the whole GPU.
     uint32_t grid_l = (uint32_t)h->sm_count * 8, scatter_cap = 0;
     if (K > 1) {
-        scatter_cap = D->cfg.split_ctas ? D->cfg.split_ctas : (uint32_t)(h->sm_count * 54 / 100);
-        scatter_cap = std::min<uint32_t>(std::max<uint32_t>(scatter_cap, 1), (uint32_t)h->sm_count - 1);
-        grid_l = ((uint32_t)h->sm_count - scatter_cap) * 6;  // pt_probe: 256 threads x 40 registers = 6 CTAs per SM
+        const uint32_t sms = (uint32_t)h->sm_count;
+        const double remote = (double)(D->world - 1) / D->world;
+        uint32_t probe_sms = remote > 0 ? (uint32_t)(sms * 0.30 / (1.29 * remote) + 0.5) : sms / 2;
+        probe_sms = std::min(std::max(probe_sms, sms / 5), sms / 2);
+        scatter_cap = D->cfg.split_ctas ? std::min<uint32_t>(D->cfg.split_ctas, sms - 1) : sms - probe_sms;
+        scatter_cap = std::max<uint32_t>(scatter_cap, 1);
+        grid_l = (sms - scatter_cap) * 6;  // pt_probe: 256 threads x <= 40 registers = 6 CTAs per SM
     }
     {
         KernelScope ks(h, "pt_clear", 1, sb);

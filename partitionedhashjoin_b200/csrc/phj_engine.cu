@@ -432,6 +432,11 @@ cudaError_t launch_join(phj_handle* h, const JoinParams& jp, uint32_t grid, size
 
 template <int HASH>
 void launch_gt_t(phj_handle* h, bool build, const GtParams& gp, uint32_t grid) {
+    if (!build && (h->cfg.flags & PHJ_FLAG_COOP_PROBE)) {  // A/B: four lanes per probe
+        if (h->pow2) gt_probe_coop<HASH, true><<<grid, 256, 0, h->stream>>>(gp);
+        else gt_probe_coop<HASH, false><<<grid, 256, 0, h->stream>>>(gp);
+        return;
+    }
     if (h->pow2) {
         if (build) gt_build<HASH, true><<<grid, 256, 0, h->stream>>>(gp);
         else gt_probe<HASH, true><<<grid, 256, 0, h->stream>>>(gp);

@@ -26,6 +26,7 @@
 #define PHJ_SCAT_MINB 1
 #endif
 
+
 namespace phj {
 
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN marks a free table slot
@@ -452,6 +453,9 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         __syncwarp();
 
         // ---- rank (stable within the warp's 32*IPT consecutive tuples) ----
+        // (Tried in round 2: first the IPT hash chains and votes as pure register work, then the counter updates as
+        // one short LDS -> STS chain per round. Slower: 1.39 / 1.47 ms per pass against 1.29 / 1.36 ms -- the
+        // interleaved rounds already overlap across the CTA's 16 warps, and the split costs registers.)
         uint32_t dr[IPT];  // digit (9 bits) | pass-2 digit << 9 (FUSE2, 7 bits) | rank << 16
         auto rank_round = [&](int i, auto is_full) {
             constexpr bool kFull = decltype(is_full)::value;
@@ -1501,6 +1505,15 @@ __global__ void __launch_bounds__(TPB) pt_build(PtParams p) {
 
 // (A/B, ncu r02d: one contiguous slice per CTA instead -- all 64 tables live at once -- had an L2 hit
 // rate of 12 % and read 19.4 GB from DRAM, 3.34 ms; the round-robin tiles read 3.6 GB, 1.44 ms.)
+// (Tried in round 2, ncu r02l: the probe tuples streamed into shared memory by TMA bulk loads -- double buffer,
+// one mbarrier per buffer, cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes -- so that only the
+// bucket reads go through the L1: l1tex sectors 518 M -> 216 M as intended, but 3.66 ms instead of 1.13 ms. The
+// block-wide barrier that hands a buffer back to the loader makes every tile wait for the slowest of its 1024
+// bucket reads (long_scoreboard 70 %, issue slots 21 % busy), and half of those miss the L2 at uniform keys.
+// It needs per-warp "empty" barriers and a deeper ring, at which point shared memory caps the CTAs per SM
+// below what hides the lookup latency. The register-staged stream below stays.)
+// (A/B, ncu r02d: one contiguous slice per CTA instead -- all 64 tables live at once -- had an L2 hit
+// rate of 12 % and read 19.4 GB from DRAM, 3.34 ms; the round-robin tiles read 3.6 GB, 1.44 ms.)
 template <int TPB>
 __global__ void __launch_bounds__(TPB) pt_probe(PtParams p) {
     __shared__ unsigned long long block_count;
@@ -1699,6 +1712,62 @@ __global__ void __launch_bounds__(256) gt_probe(GtParams p) {
                         pending[u] = false;  // slots fill in order: last one free => bucket not full
                     } else {
                         bucket[u] = (bucket[u] + 1) & p.bucket_mask;
+                    }
+                }
+            }
+        }
+    }
+    __shared__ unsigned long long block_count;
+    if (threadIdx.x == 0) block_count = 0;
+    cta_sync();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(&block_count, (unsigned long long)count);
+    cta_sync();
+    if (threadIdx.x == 0 && block_count) atomicAdd(p.matches, block_count);
+}
+
+// A/B for the north star's "probed by cooperative warps using ballot and match primitives": four lanes
+// share one probe -- the owner lane's key and bucket are broadcast with shuffles, every lane of the group
+// reads ONE 8-byte slot of the 32-byte bucket (the group's four loads coalesce into one sector), hit and
+// "last slot free" are found with a ballot over the group. Same sectors as the per-thread probe, four
+// times the load instructions plus shuffles and a vote per step. PHJ_FLAG_COOP_PROBE selects it.
+template <int HASH, bool POW2>
+__global__ void __launch_bounds__(256) gt_probe_coop(GtParams p) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t sentinel_hit = p.flags[0];
+    const int lane = threadIdx.x & 31, sub = lane & 3, gbase = lane & ~3;
+    uint32_t count = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        bool mine = i < p.n;
+        const uint64_t key = mine ? ld_stream_u64(reinterpret_cast<const uint64_t*>(p.rel + i)) : 0;
+        const uint64_t h = hash_key<HASH>(key, p.hp);
+        if (mine && !gt_selected<POW2>(p, h)) mine = false;
+        if (mine && key == kEmptyKey) {
+            count += sentinel_hit;
+            mine = false;
+        }
+        const uint64_t my_bucket = gt_bucket<POW2>(p, h);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {  // the group's four probes, one after the other
+            const uint64_t k = __shfl_sync(0xffffffffu, key, gbase + r);
+            uint64_t bucket = __shfl_sync(0xffffffffu, my_bucket, gbase + r);
+            bool pending = __shfl_sync(0xffffffffu, (int)mine, gbase + r) != 0;
+            while (__any_sync(0xffffffffu, pending)) {
+                uint64_t slot = kEmptyKey;
+                if (pending) slot = __ldg(reinterpret_cast<const unsigned long long*>(p.table + bucket * 4 + sub));
+                const uint32_t hits = __ballot_sync(0xffffffffu, pending && slot == k);
+                const uint32_t frees = __ballot_sync(0xffffffffu, pending && sub == 3 && slot == kEmptyKey);
+                if (pending) {
+                    const uint32_t gmask = 0xfu << gbase;
+                    if (hits & gmask) {
+                        if (sub == r) ++count;  // counted once, by the lane that owns the key
+                        pending = false;
+                    } else if (frees & gmask) {
+                        pending = false;
+                    } else {
+                        bucket = (bucket + 1) & p.bucket_mask;
                     }
                 }
             }

@@ -111,6 +111,35 @@ def test_cli_stream_upload(phjoin, tmp_path, join, extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_cli_several_gpus(phjoin, tmp_path, gpus):
+    """--gpus N: ONE process drives N GPUs through phj_config.num_gpus (the reference's caller is one Run(tableA,
+    tableB, timer), src/main.cpp:110-139); -p = GPUs x partitions per GPU. Skipped when the box has fewer GPUs."""
+    import partitionedhashjoin_b200 as phj
+    if phj.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    out = tmp_path / "result.txt"
+    r = run(phjoin, "--join", "radix-partitioning", "--primary", "2000000", "--secondary", "30000000", "--skew", "1.05",
+            "--gpus", str(gpus), "-p", "64", "--repeat", "3", "--log", "debug", "-u", "us", "-f", str(out))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Joined 30000000 tuples." in r.stderr
+    d = json.load(open(out))
+    assert d["parameters"]["Type"] == "RadixParitioning" and d["parameters"]["NumberOfPartitions"] == "64"
+    assert int(d["results"]["partition"]) > 0 and int(d["results"]["probe"]) > 0
+    # partitions must be GPUs x partitions per GPU
+    r = run(phjoin, "--join", "radix-partitioning", "--primary", "1000", "--secondary", "1000", "--gpus", str(gpus), "-p", "1")
+    assert r.returncode == 1 and "GPUs x local partitions" in r.stderr
+
+
+def test_cli_several_gpus_argument_errors(phjoin):
+    for args, message in ((("--join", "no-partitioning", "--gpus", "2"), "--gpus > 1: the join sharded over several GPUs"),
+                          (("--join", "radix-partitioning", "--gpus", "0"), "--gpus must be at least 1"),
+                          (("--join", "radix-partitioning", "--gpus", "2", "--materialize"), "--gpus > 1 counts only")):
+        r = run(phjoin, *args)
+        assert r.returncode == 1 and message in r.stdout
+
+
+@pytest.mark.gpu
 def test_cli_materialize(phjoin, tmp_path):
     """--materialize: Run() returns the filled Table<JoinedTuple>; generator data joins 1:1."""
     out = tmp_path / "result.txt"

@@ -274,6 +274,36 @@ def test_library_sharded_join_single_rank(phj, oracle, hash):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_one_process_several_gpus(phj, oracle, gpus):
+    """phj_config.num_gpus: one process, one host thread per GPU, the same sharded join (phj_upload shards the rows,
+    phj_join returns the global count) -- against the oracle on adversarial and larger inputs, incl. re-uploads that
+    grow the windows. Skipped when the box has fewer GPUs."""
+    import numpy as np
+
+    import _cases
+    if phj.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    cases = dict(_cases.adversarial_cases())
+    cases["big_random"] = (_cases.tuples(_cases.splitmix64(300_000, 51).astype(np.int64) % 200_003),
+                           _cases.tuples(_cases.splitmix64(2_000_000, 52).astype(np.int64) % 300_007))
+    for partitions, chunks in ((0, 0), (gpus, 3), (256, 1)):
+        with phj.Engine("radix-partitioning", partitions=partitions, split_chunks=chunks, num_gpus=gpus) as e:
+            for name, (R, S) in cases.items():
+                want = oracle.count_by_sort(R, S)
+                e.upload(R, S)
+                for _ in range(2):
+                    res = e.join()
+                    assert res["matches"] == want and res["gpus"] == gpus, (name, partitions, chunks, res, want)
+                res = e.join_host(R, S)
+                assert res["matches"] == want and res["h2d_bytes"] == 16 * (R.shape[0] + S.shape[0])
+    with pytest.raises(phj.PhjError):
+        phj.Engine("no-partitioning", num_gpus=gpus)
+    with pytest.raises(phj.PhjError):
+        phj.Engine("radix-partitioning", partitions=gpus // 2 or 3, num_gpus=gpus)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_library_sharded_join_on_gpus(phj, world):
     """One rank per GPU: the library's sharded join (NVLink peer stores + NCCL) against the oracle's count with the

@@ -86,6 +86,7 @@ def test_counts_match_reference_golden(phj, oracle, name):
     want = GOLDEN["joins"][name]["matches"]
     assert oracle.count_by_sort(R, S) == want
     assert run(phj, R, S, "no-partitioning")["matches"] == want
+    assert run(phj, R, S, "no-partitioning", flags=phj.FLAG_COOP_PROBE)["matches"] == want  # four lanes per probe
     for P in (0, 1, 2, 3, 32, 64, 100, 1000, 2048, 4096, 65536):
         res = run(phj, R, S, "radix-partitioning", partitions=P)
         assert res["matches"] == want, (name, P, res)

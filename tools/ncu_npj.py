@@ -18,6 +18,7 @@ def main():
     dR = phj.DeviceTuples(nr, 0).fill_sequential(1)
     dS = phj.DeviceTuples(ns, 0).fill_zipf(alpha, 1, nr, 12345, 1 << 14)
     flags = phj.FLAG_CHAINED_TABLE if os.environ.get("CHAINED") == "1" else 0
+    flags |= phj.FLAG_COOP_PROBE if os.environ.get("COOP") == "1" else 0
     with phj.Engine("no-partitioning", flags=flags) as e:
         e.bind_device(dR.ptr, nr, dS.ptr, ns, keepalive=(dR, dS))
         for _ in range(joins):
