@@ -275,20 +275,11 @@ int phj_device_partitions(phj_handle* h, int32_t which, const void** d_data, con
  * typically a peer GPU's receive window mapped with phj_shared_open, i.e. the partition shuffle
  * happens as NVLink stores from the scatter kernel (TMA bulk stores) instead of a separate
  * all-to-all. A null dst array keeps that relation local (split into the handle's own buffer); a
- * null ENTRY keeps that digit local (phj_shard_push sends it later). Call order per join: phj_shard_count, exchange the counts, then per chunk:
+ * null ENTRY keeps that digit in that buffer too. Call order per join: phj_shard_count, exchange the counts, then per chunk:
  * phj_shard_scatter + a barrier across ranks. */
 int phj_shard_count(phj_handle* h, uint64_t* counts);
 int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
                       void* const* dst_probe, const uint64_t* off_probe, phj_result* out);
-
-/* The same shuffle on the copy engines: after a LOCAL phj_shard_scatter of `chunk` (both dst null:
- * the pieces sit in the handle's split buffer), phj_shard_push enqueues one device-to-device copy
- * per (relation, digit) piece to dst[rel][d] + off[rel][d] on the handle's copy stream and returns;
- * phj_shard_push_wait blocks until they have landed. The SMs stay free meanwhile -- for the split of
- * the next chunk and the local join of the previous one (multigpu.PipelinedShardedRadixJoin). */
-int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
-                   void* const* dst_probe, const uint64_t* off_probe, uint64_t* bytes);
-int phj_shard_push_wait(phj_handle* h);
 
 /* ---- the sharded radix join, one process per GPU ---------------------------------------
  * What RadixClustering::HashJoiner::Run (src/RadixCluster/HashJoin.hpp:190-241) becomes when R and S are

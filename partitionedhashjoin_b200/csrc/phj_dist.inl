@@ -481,7 +481,7 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
         q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
         {
             // the last chunk's probe runs after the last scatter: it gets the whole GPU
-            const uint32_t grid_p = c + 1 == K ? (uint32_t)h->sm_count * 8 : grid_l;
+            const uint32_t grid_p = c + 1 == K ? (uint32_t)h->sm_count * 6 : grid_l;  // one wave: six CTAs per SM
             KernelScope ks(h, "pt_probe", 1, sb);
             pt_probe<256><<<grid_p, 256, 0, sb>>>(q);
         }

@@ -81,7 +81,6 @@ constexpr int kMaxBitsPerPass = 8;
 constexpr int kMaxKernelTimes = 48;
 constexpr int kMaxSplitDigits = 256;  // PHJ_ALGO_SHARD_SPLIT: owner ranks x local pass-1 digits
 constexpr int kMaxSplitChunks = 16;
-constexpr int kCopyStreams = 4;
 constexpr int kMaxUploadChunks = 32;                     // streamed phj_join_host
 constexpr size_t kUploadChunkBytes = (size_t)256 << 20;  // ... automatic chunking: ~256 MB of probe tuples
 
@@ -120,7 +119,6 @@ struct phj_handle {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_streams[kCopyStreams] = {};  // phj_shard_push: device-to-device copies on the copy engines
 
     // relations: 0 = build (R), 1 = probe (S)
     ulonglong2* d_in[2] = {nullptr, nullptr};
@@ -1184,8 +1182,10 @@ int join_radix(phj_handle* h, phj_result* out) {
         }
         PHJ_CUDA(cudaEventRecord(h->ev[2], h->stream));
         {
+            // exactly the CTAs that are resident at once (256 threads x 40 registers: six per SM): the tiles are
+            // dealt round-robin, so a second wave would walk the whole probe side again behind the first
             KernelScope ks(h, "pt_probe");
-            pt_probe<256><<<grid, 256, 0, h->stream>>>(q);
+            pt_probe<256><<<(uint32_t)h->sm_count * 6, 256, 0, h->stream>>>(q);
         }
     } else {
         KernelScope ks(h, "join_partitions");
@@ -1429,8 +1429,6 @@ void phj_destroy(phj_handle* h) {
         if (k.begin) cudaEventDestroy(k.begin);
         if (k.end) cudaEventDestroy(k.end);
     }
-    for (auto& cs : h->copy_streams)
-        if (cs) cudaStreamDestroy(cs);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1748,33 +1746,47 @@ static int join_host_streamed(phj_handle* h, const phj_tuple* build, size_t n_bu
     }
 
     memset(out, 0, sizeof(*out));
-    for (uint32_t c = 0; c < chunks; ++c) {
-        const size_t first = std::min(n_probe, (size_t)c * chunk_len);
-        const size_t len = std::min(n_probe - first, chunk_len);
-        // plan for this chunk while it is still on its way
-        if ((rc = phj_bind_device(child, h->d_in[0], n_build, h->d_in[1] + first, len)) != PHJ_OK) return rc;
-        while (up.published.load(std::memory_order_acquire) <= (int)c && !up.failed.load()) std::this_thread::yield();
-        if (up.failed.load()) break;
-        PHJ_CUDA(cudaStreamWaitEvent(child->stream, h->upload_ev[2 + c], 0));
-        phj_result r;
-        if ((rc = phj_join(child, &r)) != PHJ_OK) return rc;
-        out->matches += r.matches;
-        out->partition_ns += r.partition_ns;
-        out->build_ns += r.build_ns;
-        out->probe_ns += r.probe_ns;
-        out->join_ns += r.join_ns;
-        out->total_ns += r.total_ns;
-        out->hbm_bytes_alg += r.hbm_bytes_alg;
-        out->kernel_launches += r.kernel_launches;
-        out->d2h_bytes += r.d2h_bytes;
-        out->fallback_partitions = std::max(out->fallback_partitions, r.fallback_partitions);
-        out->passes = r.passes;
-        out->partitions = r.partitions;
-    }
+    auto join_chunks = [&]() -> int {
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const size_t first = std::min(n_probe, (size_t)c * chunk_len);
+            const size_t len = std::min(n_probe - first, chunk_len);
+            // plan for this chunk while it is still on its way
+            int rc2 = phj_bind_device(child, h->d_in[0], n_build, h->d_in[1] + first, len);
+            if (rc2 != PHJ_OK) return rc2;
+            while (up.published.load(std::memory_order_acquire) <= (int)c && !up.failed.load()) std::this_thread::yield();
+            if (up.failed.load()) return PHJ_OK;  // reported below, with the uploader's message
+            PHJ_CUDA(cudaStreamWaitEvent(child->stream, h->upload_ev[2 + c], 0));
+            phj_result r;
+            if ((rc2 = phj_join(child, &r)) != PHJ_OK) return rc2;
+            out->matches += r.matches;
+            out->partition_ns += r.partition_ns;
+            out->build_ns += r.build_ns;
+            out->probe_ns += r.probe_ns;
+            out->join_ns += r.join_ns;
+            out->total_ns += r.total_ns;
+            out->hbm_bytes_alg += r.hbm_bytes_alg;
+            out->kernel_launches += r.kernel_launches;
+            out->d2h_bytes += r.d2h_bytes;
+            out->fallback_partitions = std::max(out->fallback_partitions, r.fallback_partitions);
+            out->passes = r.passes;
+            out->partitions = r.partitions;
+        }
+        return PHJ_OK;
+    };
+    rc = join_chunks();
+    // Every exit goes through here: the uploader has issued all it will issue, and its copies -- which read the
+    // CALLER's buffers -- have drained before the caller gets control back, error or not.
+    const std::string join_error = g_error;
     if (up.thread.joinable()) up.thread.join();
+    cudaStreamSynchronize(h->upload_stream);
+    cudaStreamSynchronize(child->stream);
+    if (rc != PHJ_OK) {
+        g_error = join_error;
+        return rc;
+    }
     if (up.failed.load()) return fail(PHJ_ERR_CUDA, "%s", up.error.c_str());
+    PHJ_CUDA(cudaGetLastError());
     PHJ_CUDA(cudaEventRecord(h->ev[4], child->stream));
-    PHJ_CUDA(cudaStreamSynchronize(h->upload_stream));
     PHJ_CUDA(cudaEventSynchronize(h->ev[4]));
     out->h2d_ns = (uint64_t)(ev_ms(h->upload_ev[0], h->upload_ev[1 + chunks]) * 1e6);
     out->e2e_ns = (uint64_t)(ev_ms(h->upload_ev[0], h->ev[4]) * 1e6);
@@ -1957,7 +1969,7 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
         bool any_local = false;
         for (uint32_t d = 0; d < w; ++d) {
             // this chunk's run of digit d starts at cursor == starts[rel][d][chunk]: rebase it to off[d];
-            // a null destination keeps that digit in the handle's own split buffer (for phj_shard_push)
+            // a null destination keeps that digit in the handle's own split buffer
             const uint64_t start = h->h_shard_starts[((size_t)rel * w + d) * (K + 1) + chunk];
             if (dst[rel][d]) {
                 host_ptrs[rel][d] = reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0) - start;
@@ -2008,47 +2020,6 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
     h->launches = 0;
     if (chunk + 1 == K) h->shard_counted = false;
     h->joined_radix = K == 1 && (!dst_build || !dst_probe);
-    return PHJ_OK;
-}
-
-int phj_shard_push(phj_handle* h, uint32_t chunk, void* const* dst_build, const uint64_t* off_build,
-                   void* const* dst_probe, const uint64_t* off_probe, uint64_t* bytes_out) {
-    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
-    if (h->cfg.algo != PHJ_ALGO_SHARD_SPLIT) return fail(PHJ_ERR_STATE, "not a shard-split handle");
-    if (chunk >= h->nchunks) return fail(PHJ_ERR_INVALID, "chunk %u out of range [0, %u)", chunk, h->nchunks);
-    if (!h->h_shard_starts || !h->d_buf_a[0] || !h->d_buf_a[1])
-        return fail(PHJ_ERR_STATE, "phj_shard_push needs a phj_shard_scatter of this chunk with local digits first");
-    PHJ_CUDA(cudaSetDevice(h->device));
-    for (auto& cs : h->copy_streams)
-        if (!cs) PHJ_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    const uint32_t w = h->d1, K = h->nchunks;
-    uint32_t next = 0;
-    void* const* dst[2] = {dst_build, dst_probe};
-    const uint64_t* off[2] = {off_build, off_probe};
-    uint64_t bytes = 0;
-    for (int rel = 0; rel < 2; ++rel) {
-        if (!dst[rel]) continue;
-        for (uint32_t d = 0; d < w; ++d) {
-            // piece (digit d, this chunk) of the local split output: [starts[d][chunk], starts[d][chunk + 1])
-            const uint64_t* st = h->h_shard_starts + ((size_t)rel * w + d) * (K + 1);
-            const uint64_t len = st[chunk + 1] - st[chunk];
-            if (!len || !dst[rel][d]) continue;  // null: that digit was scattered straight to its window
-            // round-robin over a few streams: the copies spread over the device's copy engines
-            PHJ_CUDA(cudaMemcpyAsync(reinterpret_cast<ulonglong2*>(dst[rel][d]) + (off[rel] ? off[rel][d] : 0),
-                                     h->d_buf_a[rel] + st[chunk], len * 16, cudaMemcpyDeviceToDevice,
-                                     h->copy_streams[next++ % kCopyStreams]));
-            bytes += len * 16;
-        }
-    }
-    if (bytes_out) *bytes_out = bytes;
-    return PHJ_OK;
-}
-
-int phj_shard_push_wait(phj_handle* h) {
-    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
-    PHJ_CUDA(cudaSetDevice(h->device));
-    for (auto& cs : h->copy_streams)
-        if (cs) PHJ_CUDA(cudaStreamSynchronize(cs));
     return PHJ_OK;
 }
 

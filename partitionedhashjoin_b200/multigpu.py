@@ -591,245 +591,6 @@ class FusedShardedRadixJoin:
         be.close()
 
 
-class PipelinedGpuBackend(FusedGpuBackend):
-    """FusedGpuBackend with the probe shard cut into row chunks, so that the NVLink shuffle of chunk
-    c + 1 (a split scatter capped to `split_ctas` CTAs on a high-priority stream) overlaps the local
-    pass 2 + join of chunk c (the match count is additive over a partition of S). One histogram
-    pass counts all chunks at once. Windows: 0 = build side (travels with chunk 0), 1 / 2 = probe
-    chunks, double-buffered."""
-
-    def __init__(self, world, device, partitions_local=4096, hash="xxh3", hash_seed=0x9E3779B97F4A7C15,
-                 chunks=4, split_ctas=0, copy_engines=True):
-        import ctypes
-        import torch
-
-        from . import _lib, engine
-        self.torch, self.world, self.device, self.chunks = torch, world, device, chunks
-        # copy_engines: every chunk is split LOCALLY at HBM speed and its pieces travel as device-to-
-        # device copies on the copy engines, so the SMs never wait on NVLink; otherwise the split
-        # scatter stores into the peers' windows itself (and shares the SMs with the local join)
-        self.copy_engines = copy_engines
-        self.b1, self.b2, self.ndig = split_plan(world, partitions_local, True)
-        if not self.b1:
-            raise ValueError("the pipelined shuffle needs a power-of-two local fan-out >= 4 (two-level digit)")
-        self.d1 = self.ndig // world
-        self._mk_local = lambda reserve: engine.Engine(
-            "radix-partitioning", partitions=partitions_local, radix_bits=(self.b1, self.b2), hash=hash,
-            hash_seed=hash_seed, device=device, reserve=reserve)
-        self.split_engine = engine.Engine("shard-split", partitions=self.ndig, hash=hash, hash_seed=hash_seed,
-                                          device=device, shard_shift=self.b2,
-                                          flags=_lib.FLAG_SPLIT_LOCAL_TILES if copy_engines else _lib.FLAG_SPLIT_REMOTE_ONLY,
-                                          split_ctas=0 if copy_engines else split_ctas, split_chunks=chunks)
-        self.locals = [None, None]
-        self.local_reserve = (0, 0)
-        self.trace = None   # set to [] to record per-call host times and per-kernel device times
-        self.launches = 0
-        self._C, self._lib, self._check = ctypes, _lib.lib, _lib.check
-        self.win = [None] * 3
-        self.peer = [[None] * world for _ in range(3)]
-
-    def thread_init(self):
-        self.torch.cuda.set_device(self.device)
-
-    def reserve_local(self, rows_build, rows_probe):
-        """Window capacities changed: the local joins plan for that many tuples, so that every chunk
-        (they differ by a few tuples) re-binds without re-planning."""
-        if (rows_build, rows_probe) != self.local_reserve:
-            for e in self.locals:
-                if e is not None:
-                    e.close()
-            self.locals = [self._mk_local((rows_build, rows_probe)) for _ in range(2)]
-            self.local_reserve = (rows_build, rows_probe)
-
-    def count(self):
-        """counts[chunk][rel][digit] of this rank's shard, one histogram pass for all chunks."""
-        counts = np.zeros((self.chunks, 2, self.ndig), dtype=np.uint64)
-        self._check(self._lib.phj_shard_count(self.split_engine._h, counts.ctypes.data))
-        return counts.astype(np.int64)
-
-    def scatter(self, c, offsets, owner_of):
-        from ._lib import PhjResult
-        C = self._C
-        arrs = []
-        for which, w in ((0, 0), (1, 1 + c % 2)):
-            ptrs = (C.c_void_p * self.ndig)(*[C.c_void_p(self.peer[w][int(owner_of[d])]) for d in range(self.ndig)])
-            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
-        res = PhjResult()
-        t0 = time.perf_counter()
-        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
-                                                arrs[3].ctypes.data, C.byref(res)))
-        self.launches += res.kernel_launches
-        if self.trace is not None:
-            self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
-        return int(res.total_ns)
-
-    def _dst_arrays(self, c, offsets, owner_of, own):
-        """Per-digit destination pointers of chunk c: this rank's own digits (own=True) or the other
-        ranks' digits (own=False); the rest are null."""
-        C = self._C
-        arrs = []
-        for which, w in ((0, 0), (1, 1 + c % 2)):
-            ptrs = (C.c_void_p * self.ndig)(*[
-                C.c_void_p(self.peer[w][int(owner_of[d])]) if (int(owner_of[d]) == self.rank) == own else C.c_void_p(None)
-                for d in range(self.ndig)])
-            arrs += [ptrs, np.ascontiguousarray(offsets[which], dtype=np.uint64)]
-        return arrs
-
-    def scatter_local(self, c, offsets, owner_of):
-        """Split chunk c at HBM speed: this rank's own digits go straight into its window, the others
-        into the handle's split buffer, from where push() sends them."""
-        from ._lib import PhjResult
-        res = PhjResult()
-        t0 = time.perf_counter()
-        arrs = self._dst_arrays(c, offsets, owner_of, own=True)
-        self._check(self._lib.phj_shard_scatter(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
-                                                arrs[3].ctypes.data, self._C.byref(res)))
-        self.launches += res.kernel_launches
-        if self.trace is not None:
-            self.trace.append(("scatter", c, t0, time.perf_counter(), self.split_engine.kernel_times()))
-        return int(res.total_ns)
-
-    def push(self, c, offsets, owner_of):
-        """Enqueue the copies of chunk c's pieces into their owners' windows (copy engines)."""
-        C = self._C
-        arrs = self._dst_arrays(c, offsets, owner_of, own=False)
-        nbytes = C.c_uint64()
-        self._check(self._lib.phj_shard_push(self.split_engine._h, c, arrs[0], arrs[1].ctypes.data, arrs[2],
-                                             arrs[3].ctypes.data, C.byref(nbytes)))
-        return int(nbytes.value)
-
-    def push_wait(self):
-        self._check(self._lib.phj_shard_push_wait(self.split_engine._h))
-
-    def local_join(self, c, rows, bounds, first_digit=0):
-        w = 1 + c % 2
-        eng = self.locals[c % 2]
-        t0 = time.perf_counter()
-        if len(bounds[0]) < 2:
-            return 0, {"kernel_launches": 0, "hbm_bytes_alg": 0, "total_ns": 1, "d2h_bytes": 0}  # owns no digit
-        eng.bind_device_partitioned(self.win[0] if rows[0] else 0, rows[0], self.win[w] if rows[1] else 0, rows[1],
-                                    bounds[0], bounds[1], first_parent=first_digit, parent_space=self.ndig)
-        t1 = time.perf_counter()
-        res = eng.join()
-        self.launches += res["kernel_launches"]
-        if self.trace is not None:
-            self.trace.append(("local", c, t0, t1, time.perf_counter(), eng.kernel_times()))
-        return res["matches"], res
-
-    def close(self):
-        for e in [self.split_engine] + self.locals:
-            if e is not None:
-                e.close()
-
-
-class PipelinedShardedRadixJoin(FusedShardedRadixJoin):
-    """The fused shuffle, software-pipelined over row chunks of the probe shard: after ONE count +
-    sizes all-gather for all chunks, a producer thread runs NVLink scatter -> barrier for chunk
-    c + 1 while the caller's thread runs the local pass 2 + join of chunk c. The two legs use
-    different resources (NVLink vs HBM), so the join costs about max(shuffle, local), not the sum."""
-
-    def join(self) -> dict:
-        import queue
-        import threading
-        be, world, rank, K = self.backend, self.world, self.rank, self.backend.chunks
-        t0 = time.perf_counter()
-        counts = be.count()                                    # [chunk][rel][digit]
-        t1 = time.perf_counter()
-        M = self._gather_counts(counts)                        # [source][chunk * 2 + rel][digit]
-        M = M.reshape(world, K, 2, -1)
-        first = self.ownership(M.sum(axis=1), world, self.balance)      # one cut for all chunks
-        plans = [self.layout(M[:, c], world, rank, first) for c in range(K)]  # (need, offsets, bounds, owner) per chunk
-        want = {0: plans[0][0][0]}
-        for slot in (0, 1):
-            needs = [plans[c][0][1] for c in range(slot, K, 2)]
-            if needs:
-                want[1 + slot] = np.max(needs, axis=0)
-        regrown = self._ensure_windows(want)
-        if hasattr(be, "reserve_local"):
-            be.reserve_local(int(self.caps[0][rank]), int(max(self.caps[1][rank], self.caps[2][rank])))
-        build_rows, build_bounds = int(plans[0][0][0][rank]), plans[0][2][0]
-        t2 = time.perf_counter()
-
-        free = [threading.Semaphore(1), threading.Semaphore(1)]
-        ready = queue.Queue()
-        abort = threading.Event()
-        stats = {"scatter_s": 0.0, "scatter_device_ns": 0}
-
-        def acquire(slot):
-            while not free[slot].acquire(timeout=0.05):
-                if abort.is_set():
-                    raise RuntimeError("aborted")
-
-        def producer():
-            # Chunk c goes into window slot c % 2 of EVERY rank, so that slot must be free everywhere
-            # before anyone writes: each rank waits for its own consumer to release the slot of chunk
-            # c + 1 before entering the barrier that ends chunk c.
-            try:
-                if hasattr(be, "thread_init"):
-                    be.thread_init()
-                ce = getattr(be, "copy_engines", False)
-                acquire(0)
-                if ce:
-                    stats["scatter_device_ns"] += be.scatter_local(0, plans[0][1], plans[0][3])
-                for c in range(K):
-                    ts = time.perf_counter()
-                    need, offsets, bounds, owner_of = plans[c]
-                    if ce:
-                        be.push(c, offsets, owner_of)              # copy engines, asynchronous
-                        if c + 1 < K:
-                            acquire((c + 1) % 2)                   # the split writes this rank's own digits there
-                            stats["scatter_device_ns"] += be.scatter_local(c + 1, plans[c + 1][1], plans[c + 1][3])
-                        be.push_wait()
-                    else:
-                        stats["scatter_device_ns"] += be.scatter(c, offsets, owner_of)
-                        if c + 1 < K:
-                            acquire((c + 1) % 2)
-                    if world > 1:
-                        self.dist.barrier()    # chunk c has landed everywhere; slot (c + 1) % 2 is free everywhere
-                    stats["scatter_s"] += time.perf_counter() - ts
-                    ready.put((c, [build_rows, int(need[1][rank])], [build_bounds, bounds[1]]))
-            except BaseException as e:  # hand the failure to the consumer
-                ready.put(e)
-
-        th = threading.Thread(target=producer, name="phj-shuffle", daemon=True)
-        th.start()
-        local_matches, local_s, wait_s, res, recv_rows = 0, 0.0, 0.0, None, [build_rows, 0]
-        try:
-            for _ in range(K):
-                tw = time.perf_counter()
-                item = ready.get()
-                if isinstance(item, BaseException):
-                    raise item
-                c, rows, bounds = item
-                tj = time.perf_counter()
-                m, res = be.local_join(c, rows, bounds, int(first[rank]))
-                local_matches += m
-                free[c % 2].release()
-                local_s += time.perf_counter() - tj
-                wait_s += tj - tw
-                recv_rows[1] += rows[1]
-        except BaseException:
-            abort.set()
-            raise
-        finally:
-            th.join(timeout=60)
-        t4 = time.perf_counter()
-        total = be.count_tensor(local_matches)
-        if world > 1:
-            self.dist.all_reduce(total)
-        matches = int(total.item())
-        t5 = time.perf_counter()
-        mine = counts[:, :, int(first[rank]):int(first[rank + 1])].sum()
-        self.last = {"matches": matches, "local_matches": int(local_matches), "split_s": t1 - t0,
-                     "exchange_s": (t2 - t1) + stats["scatter_s"], "sizes_s": t2 - t1,
-                     "scatter_s": stats["scatter_s"], "local_s": local_s, "wait_s": wait_s, "reduce_s": t5 - t4,
-                     "pipeline_s": t4 - t2, "total_s": t5 - t0, "recv_rows": recv_rows, "regrown": regrown,
-                     "send_bytes_remote": int(16 * (counts.sum() - mine)) if world > 1 else 0, "local_result": res,
-                     "split_device_ns": stats["scatter_device_ns"], "scatter_device_ns": stats["scatter_device_ns"],
-                     "chunks": K}
-        return self.last
-
-
 class ShardedJoin:
     """One rank of the sharded radix join that lives INSIDE libphj_b200.so (phj_dist_*, csrc/phj_dist.inl):
     count -> NCCL all-gather of the piece sizes -> device-side layout -> the radix scatter stores R and then S,

@@ -79,7 +79,7 @@ def shard_of(rel, q, world):
 
 
 def main():
-    mode = sys.argv[1]  # pipelined | pass1 | fused | nccl
+    mode = sys.argv[1]  # lib | pass1 | fused | nccl | npj
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -115,10 +115,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         return
-    if mode.startswith("pipelined"):
-        job = multigpu.PipelinedShardedRadixJoin(dist, rank, world, multigpu.PipelinedGpuBackend(
-            world, local, partitions_local=256, chunks=3, split_ctas=64, copy_engines=(mode == "pipelined")))
-    elif fused:
+    if fused:
         job = multigpu.FusedShardedRadixJoin(dist, rank, world, multigpu.FusedGpuBackend(
             world, local, partitions_local=256, pass1_in_shuffle=(mode == "pass1")))
     else:
@@ -163,13 +160,6 @@ def main():
         job.upload(shard(R), np.concatenate([shard(S)] * 2))
         res = job.join()
         assert res["matches"] == 2 * want and res["regrown"]
-    if mode.startswith("pipelined"):
-        assert not res["regrown"] and res["chunks"] == 3
-        job.upload(shard(R), np.concatenate([shard(S)] * 2))
-        res = job.join()
-        assert res["matches"] == 2 * want and res["regrown"]
-        res = job.join()
-        assert res["matches"] == 2 * want and not res["regrown"]
     if rank == 0:
         print(json.dumps({"mode": mode, "world": world, "matches": first, "want": want}))
     job.close()

@@ -180,86 +180,10 @@ class OracleFusedBackend(OracleBackend):
         return self.oracle.count_by_sort(*got), {"kernel_launches": 0}
 
 
-class OraclePipelinedBackend(OracleFusedBackend):
-    """CPU stand-in for multigpu.PipelinedGpuBackend: the probe shard travels in row chunks through
-    two alternating windows, the build shard with chunk 0 into window 0."""
-
-    def __init__(self, world, oracle, partitions_local, chunks, copy_engines=False):
-        super().__init__(world, oracle, partitions_local, True)
-        self.chunks = chunks
-        self.copy_engines = copy_engines
-        self.joined = []
-        self.split_done = set()
-
-    # copy-engine flavour: a local split per chunk, then the pieces are pushed
-    def _write(self, c, offsets, owner_of, own):
-        self.owner_of = np.asarray(owner_of)
-        for which, w in ((0, 0), (1, 1 + c % 2)):
-            for d in range(self.ndig):
-                piece = self.chunk_pieces[c][which][d]
-                if piece.shape[0] and (int(owner_of[d]) == self.rank) == own:
-                    shm = self.peer[w][int(owner_of[d])]
-                    win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
-                    o = int(offsets[which][d])
-                    win[o:o + piece.shape[0]] = piece
-                    del win
-
-    def scatter_local(self, c, offsets, owner_of):
-        self._write(c, offsets, owner_of, own=True)  # own digits straight into the own window
-        self.split_done.add(c)
-        return 0
-
-    def push(self, c, offsets, owner_of):
-        assert c in self.split_done  # a chunk is pushed only after its local split
-        self._write(c, offsets, owner_of, own=False)
-        return 0
-
-    def push_wait(self):
-        pass
-
-    def upload(self, R, S):
-        super().upload(R, S)
-        n = self.rel[1].shape[0]
-        per = -(-n // self.chunks) if n else 0
-        self.lo = [min(c * per, n) for c in range(self.chunks + 1)]
-
-    def count(self):
-        self.chunk_pieces, counts = [], []
-        for c in range(self.chunks):
-            rels = [self.rel[0] if c == 0 else self.rel[0][:0], self.rel[1][self.lo[c]:self.lo[c + 1]]]
-            pieces, cc = [], []
-            for rel in rels:
-                dig = self.digit(rel["id"]) if rel.shape[0] else np.empty(0, np.int64)
-                pieces.append([rel[dig == d] for d in range(self.ndig)])
-                cc.append(np.bincount(dig, minlength=self.ndig))
-            self.chunk_pieces.append(pieces)
-            counts.append(np.stack(cc))
-        return np.stack(counts).astype(np.int64)
-
-    def scatter(self, c, offsets, owner_of):
-        self.owner_of = np.asarray(owner_of)
-        for which, w in ((0, 0), (1, 1 + c % 2)):
-            for d in range(self.ndig):
-                piece = self.chunk_pieces[c][which][d]
-                if piece.shape[0]:
-                    shm = self.peer[w][int(owner_of[d])]
-                    win = np.ndarray((shm.size // 16,), dtype=_cases.TUPLE, buffer=shm.buf)
-                    o = int(offsets[which][d])
-                    win[o:o + piece.shape[0]] = piece
-                    del win
-        return 0
-
-    def local_join(self, c, rows, bounds, first_digit=0):
-        m, res = self.local_join_window(rows, bounds, first_digit, None, windows=(0, 1 + c % 2))
-        self.joined.append(self.received)
-        return m, res
-
-
 def main():
     case = sys.argv[1]
-    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1", "pipelined", "pipelined-ce")
-    pass1 = fused and sys.argv[2] in ("pass1", "pipelined", "pipelined-ce")
-    pipelined = fused and sys.argv[2] in ("pipelined", "pipelined-ce")
+    fused = len(sys.argv) > 2 and sys.argv[2] in ("fused", "pass1")
+    pass1 = fused and sys.argv[2] == "pass1"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     oracle = _oracle.Oracle()
@@ -302,11 +226,7 @@ def main():
             dist.barrier()
         dist.destroy_process_group()
         return
-    if pipelined:
-        backend = OraclePipelinedBackend(world, oracle, 256, chunks=3, copy_engines=sys.argv[2] == "pipelined-ce")
-        backend.rank = rank
-        job = multigpu.PipelinedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
-    elif fused:
+    if fused:
         backend = OracleFusedBackend(world, oracle, 256, pass1)
         assert (backend.b1 > 0) == pass1
         job = multigpu.FusedShardedRadixJoin(dist if world > 1 else None, rank, world, backend)
@@ -316,12 +236,7 @@ def main():
     job.upload(shard(R), shard(S))
     res = job.join()
     # every received tuple belongs to this rank, and nothing was lost or duplicated
-    if pipelined:
-        got_R = backend.joined[0][0]
-        got_S = np.concatenate([j[1] for j in backend.joined])
-        backend.joined = []
-    else:
-        got_R, got_S = backend.received
+    got_R, got_S = backend.received
     for rel in (got_R, got_S):
         if rel.shape[0]:
             if fused and res.get("hot_digits"):
@@ -335,7 +250,7 @@ def main():
     if world > 1:
         dist.all_reduce(rows)
     assert rows.tolist() == [R.shape[0], S.shape[0]], rows.tolist()  # nothing lost; only replicas added
-    if case == "skewed" and pass1 and not pipelined and world > 1:
+    if case == "skewed" and pass1 and world > 1:
         assert res["hot_digits"], "the 70 % key must be recognised as a heavy hitter"
     assert res["matches"] == want, (res["matches"], want)
     res2 = job.join()  # the job is reusable

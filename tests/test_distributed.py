@@ -35,11 +35,7 @@ def test_sharded_join_over_gloo(world, case):
 
 
 @pytest.mark.parametrize("world,case,mode", [(2, "random", "pass1"), (2, "skewed", "pass1"), (2, "tiny", "pass1"),
-                                             (4, "random", "pass1"), (4, "skewed", "pass1"), (1, "random", "pass1"), (2, "random", "fused"),
-                                             (2, "random", "pipelined"), (2, "skewed", "pipelined"),
-                                             (2, "tiny", "pipelined"), (4, "random", "pipelined"),
-                                             (1, "random", "pipelined"), (2, "skewed", "pipelined-ce"),
-                                             (4, "random", "pipelined-ce")])
+                                             (4, "random", "pass1"), (4, "skewed", "pass1"), (1, "random", "pass1"), (2, "random", "fused")])
 def test_fused_shuffle_over_gloo(world, case, mode):
     """FusedShardedRadixJoin: sizes all-gather -> window offsets -> every rank writes its pieces into
     the owners' windows (shared memory stands in for the CUDA-IPC-mapped NVLink windows). pass1:
@@ -317,8 +313,7 @@ def test_library_sharded_join_on_gpus(phj, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,mode", [(2, "pipelined"), (2, "pipelined-sm"), (2, "pass1"), (2, "fused"), (2, "nccl"), (4, "pass1"),
-                                        (8, "pass1"), (8, "pipelined")])
+@pytest.mark.parametrize("world,mode", [(2, "pass1"), (2, "fused"), (2, "nccl"), (2, "npj"), (4, "pass1"), (8, "pass1")])
 def test_sharded_join_on_gpus(phj, world, mode):
     """One rank per GPU over NCCL: the fused NVLink-store shuffle (and the all-to-all variant)
     against the oracle's count; skipped when the box has fewer GPUs."""

@@ -452,6 +452,31 @@ def test_full_size_partition_properties(phj, oracle, full_relations):
     check_full_size_partitioning(oracle, S, got, bounds, P, stable=True)
 
 
+@pytest.mark.parametrize("alpha", [0.01, 1.25])
+def test_full_size_counts_other_skews(phj, alpha):
+    """BASELINE.json configs[1] ("uniform" = the reference generator's minimum skew 0.01) and configs[3] (Zipf 1.25,
+    key 1 = 22 % of S) at the full 10 M x 200 M: |S| on the whole build side, and on half of it exactly the number
+    of probe keys <= |R| / 2 (numpy), through the two-pass plan, the one-pass plan with L2-resident tables and the
+    no-partitioning join."""
+    nr, ns = FULL[0]
+    R = np.empty(nr, dtype=phj.TUPLE_DTYPE)
+    S = np.empty(ns, dtype=phj.TUPLE_DTYPE)
+    phj.fill_sequential(R, 1)
+    phj.fill_zipf(S, alpha, 1, nr, 12345, 64)
+    half = nr // 2
+    want_half = int((S["id"] <= half).sum())
+    assert 0 < want_half < ns
+    for algo, kw in (("radix-partitioning", {"partitions": 4096}),
+                     ("radix-partitioning", {"partitions": 64, "flags": phj.FLAG_L2_TABLES}),
+                     ("radix-partitioning", {"partitions": 8, "flags": phj.FLAG_L2_TABLES}),
+                     ("no-partitioning", {})):
+        with phj.Engine(algo, **kw) as e:
+            e.upload(R, S)
+            assert e.join()["matches"] == ns, (algo, kw)
+            e.upload(R[:half], S)
+            assert e.join()["matches"] == want_half, (algo, kw)
+
+
 def check_full_size_partitioning(oracle, S, got, bounds, P, stable):
     assert int(bounds[0]) == 0 and int(bounds[-1]) == S.shape[0] and (np.diff(bounds.astype(np.int64)) >= 0).all()
     # permutation: payload is the input index, so the sorted payloads are 0..n-1 and ids follow
