@@ -351,6 +351,10 @@ int phj_memcpy_h2d(int32_t device, void* d_dst, const void* h_src, size_t bytes)
 int phj_memcpy_d2h(int32_t device, void* h_dst, const void* d_src, size_t bytes);
 int phj_memcpy_d2d(int32_t device, void* d_dst, const void* d_src, size_t bytes); /* incl. mapped peer memory */
 
+/* Which kernels of the following joins get CUDA events around them: null = none, "" = all, else those whose
+ * name contains `filter` (what PHJ_KERNEL_TIMES = 1 / a name selects at phj_create). */
+int phj_kernel_timing(phj_handle* h, const char* filter);
+
 /* Per-kernel device times of the last phj_join: up to `cap` entries; returns the number written.
  * names[i] points to a static string. */
 int phj_kernel_times(phj_handle* h, const char** names, uint64_t* ns, uint32_t cap);

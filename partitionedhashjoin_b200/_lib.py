@@ -167,6 +167,7 @@ SIGNATURES = {
     "phj_memcpy_d2h": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "phj_memcpy_d2d": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "phj_set_parent_digits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "phj_kernel_timing": (C.c_int, [C.c_void_p, C.c_char_p]),
     "phj_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
     "phj_get_device_info": (C.c_int, [C.c_int32, C.POINTER(PhjDeviceInfo)]),
     "phj_device_count": (C.c_int, []),

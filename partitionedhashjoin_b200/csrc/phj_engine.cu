@@ -39,8 +39,22 @@
 #ifndef PHJ_SCAT_MINB
 #define PHJ_SCAT_MINB 2  // two 512-thread CTAs per SM: caps the scatter at 64 registers (no spills)
 #endif
+#ifndef PHJ_SCAT_PSCAN
+#define PHJ_SCAT_PSCAN 1  // all-warp counter scan in radix_scatter (0: the two-warp scan of round 1, for the A/B)
+#endif
+#ifndef PHJ_SEGS_PER_SM
+#define PHJ_SEGS_PER_SM 16  // segments (= CTAs of the partitioning kernels) per SM for the large relation: 8 -> 16
+                            // shortens every kernel's tail (histogram 524 -> 485 us, join 3.92 -> 3.84 ms)
+#endif
+#ifndef PHJ_SCAT_ALLWRITE
+#define PHJ_SCAT_ALLWRITE 1  // all lanes of a digit group store the warp counter (0: an elected leader; measured
+                             // 1299 / 1380 -> 1284 / 1362 us per pass, tools/ab_scatter.py)
+#endif
 #ifndef PHJ_SCAT_MINB_PLAIN
 #define PHJ_SCAT_MINB_PLAIN PHJ_SCAT_MINB  // CTAs per SM of the scatter without the fused pass-2 histogram
+#endif
+#ifndef PHJ_JOIN_WAVES
+#define PHJ_JOIN_WAVES 4  // probe slices (CTAs) of join_partitions per resident CTA slot
 #endif
 #ifndef PHJ_JOIN_TPB
 #define PHJ_JOIN_TPB 512
@@ -170,8 +184,9 @@ struct phj_handle {
     uint32_t* d_scalars = nullptr;
     uint32_t* d_counts = nullptr;
     uint64_t* d_cursors = nullptr;
-    uint64_t* d_chunk_sums = nullptr;
-    size_t cap_counts = 0, cap_cursors = 0, cap_chunk_sums = 0;
+    phj::ScanState* d_scan_state = nullptr;  // scan_lookback: chunk sums + epochs + ticket
+    uint32_t scan_epoch = 0;
+    size_t cap_counts = 0, cap_cursors = 0;
     uint64_t* d_bounds1[2] = {nullptr, nullptr};
     uint64_t* d_bounds2[2] = {nullptr, nullptr};
     size_t cap_bounds1 = 0, cap_bounds2 = 0;
@@ -212,6 +227,7 @@ struct phj_handle {
     KernelTime ktimes[kMaxKernelTimes] = {};
     int n_ktimes = 0;
     bool time_kernels = false;
+    std::string ktime_filter;  // non-empty: only kernels whose scope name contains it are timed
     bool use_match = false;   // PHJ_RANK=match: match.any instead of ballots in the stable kernels
     bool use_lanes = true;
     bool lanes_scatter = false;    // PHJ_RANK=stable|match disables the lane-private kernels
@@ -251,7 +267,8 @@ struct KernelScope {
     KernelScope(phj_handle* h_, const char* name, uint32_t kernels = 1, cudaStream_t on = nullptr)
         : h(h_), idx(-1), name_(name), stream(on ? on : h_->stream) {
         h->launches += kernels;  // kernels launched inside this scope (phj_result.kernel_launches)
-        if (h->time_kernels && h->n_ktimes < kMaxKernelTimes) {
+        if (h->time_kernels && h->n_ktimes < kMaxKernelTimes &&
+            (h->ktime_filter.empty() || strstr(name, h->ktime_filter.c_str()))) {
             idx = h->n_ktimes++;
             h->ktimes[idx].name = name;
             h->ktimes[idx].used = true;
@@ -526,7 +543,7 @@ DigitFn digit_fn(const phj_handle* h, int pass) {
 uint32_t segments_for(const phj_handle* h, size_t n, int tile) {
     if (n == 0) return 0;
     // ~8 segments per SM for the big relation; never shorter than 4 tiles
-    uint64_t target = (uint64_t)h->sm_count * 8;
+    uint64_t target = (uint64_t)h->sm_count * PHJ_SEGS_PER_SM;
     uint64_t by_len = (n + (uint64_t)tile * 4 - 1) / ((uint64_t)tile * 4);
     return (uint32_t)std::max<uint64_t>(1, std::min(target, by_len));
 }
@@ -640,7 +657,10 @@ int build_plan(phj_handle* h) {
             return fail(PHJ_ERR_INVALID, "internal: %zu counters exceed the scan capacity", ncounts_max);
         if ((rc = dev_reserve(&h->d_counts, &h->cap_counts, ncounts_max)) != PHJ_OK) return rc;
         if ((rc = dev_reserve(&h->d_cursors, &h->cap_cursors, ncounts_max)) != PHJ_OK) return rc;
-        if ((rc = dev_reserve(&h->d_chunk_sums, &h->cap_chunk_sums, 1024)) != PHJ_OK) return rc;
+        if (!h->d_scan_state) {
+            PHJ_CUDA(cudaMalloc(&h->d_scan_state, sizeof(ScanState)));
+            PHJ_CUDA(cudaMemset(h->d_scan_state, 0, sizeof(ScanState)));
+        }
         // ---- boundaries ----
         const size_t nb1 = (size_t)h->d1 + 1, nb2 = (size_t)h->nparts + 1;
         if (nb1 > h->cap_bounds1 || !h->d_bounds1[0]) {
@@ -693,7 +713,7 @@ int build_plan(phj_handle* h) {
         h->join_max_keys = slots / 4 * 3;
         const size_t smem = (size_t)slots * 8;
         uint32_t resident = (uint32_t)std::max<size_t>(1, std::min<size_t>((h->smem_optin) / (smem + 1024), 2048 / PHJ_JOIN_TPB));
-        h->join_grid = (uint32_t)h->sm_count * resident * 4;
+        h->join_grid = (uint32_t)h->sm_count * resident * PHJ_JOIN_WAVES;
         {
             // PHJ_FLAG_L2_TABLES: L2-resident partition tables instead of shared-memory ones. A region of
             // 32-byte buckets per partition, load <= 0.4 at the mean partition size; partitions beyond 75 % of
@@ -783,14 +803,9 @@ uint32_t table_hash_shift(const phj_handle* h) {
 int run_scan(phj_handle* h, int ncounts_scalar, size_t ncounts_max) {
     uint32_t chunks = (uint32_t)std::max<size_t>(1, (ncounts_max + kScanChunk - 1) / kScanChunk);
     {
-        KernelScope ks(h, "scan_reduce");
-        scan_reduce<<<chunks, kScanTpb, 0, h->stream>>>(h->d_counts, h->d_scalars + ncounts_scalar,
-                                                        h->d_chunk_sums);
-    }
-    {
-        KernelScope ks(h, "scan_write");
-        scan_write<<<chunks, kScanTpb, 0, h->stream>>>(h->d_counts, h->d_scalars + ncounts_scalar,
-                                                       h->d_chunk_sums, h->d_cursors);
+        KernelScope ks(h, "scan");
+        scan_lookback<<<chunks, kScanTpb, 0, h->stream>>>(h->d_counts, h->d_scalars + ncounts_scalar, h->d_cursors,
+                                                          h->d_scan_state, ++h->scan_epoch);
     }
     return PHJ_OK;
 }
@@ -958,7 +973,6 @@ int join_radix(phj_handle* h, phj_result* out) {
     p1.df = digit_fn(h, 1);
     // pass-2 bookkeeping (needed before scatter 1 when the pass-2 histogram is fused into it)
     Plan2Params pl{};
-    FillEmptyParams fe{};
     PassParams p2{};
     if (two) {
         for (int rel = 0; rel < 2; ++rel) {
@@ -969,9 +983,6 @@ int join_radix(phj_handle* h, phj_result* out) {
             pl.seg_len[rel] = h->seg_len2[rel];
             pl.n[rel] = h->n[rel];
             pl.target_segs[rel] = h->target_segs2[rel];
-            fe.bounds1[rel] = h->d_bounds1[rel];
-            fe.bounds2[rel] = h->d_bounds2[rel];
-            fe.n[rel] = h->n[rel];
             p2.in[rel] = h->d_buf_a[rel];
             p2.out[rel] = h->d_buf_b[rel];
             p2.bounds[rel] = h->d_bounds2[rel];
@@ -979,14 +990,16 @@ int join_radix(phj_handle* h, phj_result* out) {
         pl.cursors = h->d_cursors;
         pl.bias[0] = 0;
         pl.bias[1] = h->n[0];
-        pl.d1 = fe.d1 = h->d1;
-        pl.d2 = fe.d2 = h->d2;
+        pl.d1 = h->d1;
+        pl.d2 = h->d2;
         pl.tile = kScatTile;
         pl.segs = h->d_segs2;
         pl.nsegs = h->d_scalars + kNsegs2;
         pl.ncounts = h->d_scalars + kNcounts2;
         pl.max_segs = h->max_segs2;
-        pl.truncated = h->d_scalars + kPlanTruncated;
+        pl.truncated = reinterpret_cast<uint32_t*>(h->d_matches + 1) + 1;
+        pl.zero_words = h->d_matches;  // the plan kernel also clears the join's result words
+        for (int rel = 0; rel < 2; ++rel) pl.bounds2[rel] = h->d_bounds2[rel];
         p2.segs = h->d_segs2;
         p2.nsegs = h->d_scalars + kNsegs2;
         p2.counts = h->d_counts;
@@ -998,10 +1011,11 @@ int join_radix(phj_handle* h, phj_result* out) {
         p2.hp = hp;
         p2.df = digit_fn(h, 2);
     }
+    bool results_cleared = false;
     auto run_plan2 = [&]() {
-        KernelScope ks(h, "plan_pass2", 2);
+        KernelScope ks(h, "plan_pass2");
         plan_pass2<<<1, 1024, 0, h->stream>>>(pl);
-        fill_empty_parent_bounds<<<(2 * h->d1 + 255) / 256, 256, 0, h->stream>>>(fe);
+        results_cleared = true;
     };
     const bool hist12 = two && h->hist12 && !h->prepart && h->nsegs1 > 0;
     const bool fuse2 = two && h->fuse2 && !h->prepart && !hist12;
@@ -1039,32 +1053,26 @@ int join_radix(phj_handle* h, phj_result* out) {
             // its segments to the runs and sum the (segment, digit pair) counts into pass 2's counters
             // -- all before the pass-1 cursors are overwritten by pass 2's scan.
             run_plan2();
-            Align2Params ap{};
-            Counts2Params cp{};
-            ap.cursors = cp.cursors = h->d_cursors;
+            AlignCounts2Params ap{};
+            ap.cursors = h->d_cursors;
             for (int rel = 0; rel < 2; ++rel) {
-                ap.cnt_base1[rel] = cp.cnt_base1[rel] = h->cnt_base1_rel[rel];
-                ap.nseg1[rel] = cp.nseg1[rel] = h->nseg1_rel[rel];
-                ap.bias[rel] = cp.bias[rel] = pl.bias[rel];
+                ap.cnt_base1[rel] = h->cnt_base1_rel[rel];
+                ap.nseg1[rel] = h->nseg1_rel[rel];
+                ap.bias[rel] = pl.bias[rel];
                 ap.bounds1[rel] = h->d_bounds1[rel];
-                ap.parents2[rel] = cp.parents2[rel] = h->d_parents2[rel];
-                ap.seg_len[rel] = cp.seg_len[rel] = h->seg_len2[rel];
+                ap.parents2[rel] = h->d_parents2[rel];
+                ap.seg_len[rel] = h->seg_len2[rel];
             }
-            cp.seg_first1[0] = 0;
-            cp.seg_first1[1] = h->nseg1_rel[0];
+            ap.seg_first1[0] = 0;
+            ap.seg_first1[1] = h->nseg1_rel[0];
             ap.segs = h->d_segs2;
             ap.nsegs = h->d_scalars + kNsegs2;
-            cp.hist12 = h->d_hist12;
-            cp.d1 = h->d1;
-            cp.d2 = h->d2;
-            cp.counts2 = h->d_counts;
-            PHJ_CUDA(cudaMemsetAsync(h->d_counts, 0, (size_t)h->max_segs2 * h->d2 * sizeof(uint32_t), h->stream));
+            ap.hist12 = h->d_hist12;
+            ap.d2 = h->d2;
+            ap.counts2 = h->d_counts;
             {
-                KernelScope ks(h, "pass2_counts", 2);
-                align_pass2_segments<<<(h->max_segs2 + 255) / 256, 256, 0, h->stream>>>(ap);
-                const uint32_t max_nseg1 = std::max(h->nseg1_rel[0], h->nseg1_rel[1]);
-                const dim3 grid(2 * h->d1, std::max<uint32_t>(1, std::min<uint32_t>(8, (max_nseg1 + 63) / 64)));
-                pass2_counts_from_hist12<<<grid, 1024, 0, h->stream>>>(cp);
+                KernelScope ks(h, "pass2_counts");
+                pass2_align_counts<<<(h->max_segs2 + 3) / 4, 256, 0, h->stream>>>(ap);
             }
         } else if (fuse2) {
             // the scanned cursors already hold the pass-1 boundaries: plan pass 2 now, and let the
@@ -1116,8 +1124,8 @@ int join_radix(phj_handle* h, phj_result* out) {
     // ---- build + probe per partition ----
     const ulonglong2* part_build = two ? h->d_buf_b[0] : h->prepart ? h->d_in[0] : h->d_buf_a[0];
     const ulonglong2* part_probe = two ? h->d_buf_b[1] : h->prepart ? h->d_in[1] : h->d_buf_a[1];
-    PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 8, h->stream));
-    PHJ_CUDA(cudaMemsetAsync(h->d_scalars + kOversize, 0, 4, h->stream));
+    if (!results_cleared) PHJ_CUDA(cudaMemsetAsync(h->d_matches, 0, 16, h->stream));  // else: plan_pass2 did
+    uint32_t* d_oversize = reinterpret_cast<uint32_t*>(h->d_matches + 1);
     JoinParams jp{};
     jp.build = part_build;
     jp.probe = part_probe;
@@ -1187,26 +1195,25 @@ int join_radix(phj_handle* h, phj_result* out) {
             KernelScope ks(h, "pt_probe");
             pt_probe<256><<<(uint32_t)h->sm_count * 6, 256, 0, h->stream>>>(q);
         }
-    } else {
-        KernelScope ks(h, "join_partitions");
-        PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
-    }
-    {
         KernelScope ks(h, "count_oversize");
         count_oversize<<<(uint32_t)((h->nparts + 255) / 256), 256, 0, h->stream>>>(
-            h->d_bounds2[0], (uint32_t)h->nparts, h->join_max_keys, h->d_scalars + kOversize);
+            h->d_bounds2[0], (uint32_t)h->nparts, h->join_max_keys, d_oversize);
+    } else {
+        KernelScope ks(h, "join_partitions");
+        jp.oversize = d_oversize;  // the join kernel also counts the partitions it has to leave to the global table
+        PHJ_CUDA(launch_join(h, jp, h->join_grid, (size_t)h->join_slots * 8));
     }
     PHJ_CUDA(cudaEventRecord(h->ev[3], h->stream));
-    PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 8, cudaMemcpyDeviceToHost, h->stream));
-    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 1, h->d_scalars + kOversize, 8, cudaMemcpyDeviceToHost, h->stream));
+    // {matches, oversize | truncated << 32} in one copy; the per-CTA phase times (diagnostics) follow it
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out, h->d_matches, 16, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
     PHJ_CUDA(cudaMemcpyAsync(h->h_cta_times, h->d_cta_times, (size_t)h->join_grid * 16,
                              cudaMemcpyDeviceToHost, h->stream));
-    PHJ_CUDA(cudaEventRecord(h->ev[4], h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
 
     const uint32_t oversize = (uint32_t)(h->h_out[1] & 0xffffffffu);
-    if (h->h_out[1] >> 32)  // kPlanTruncated sits right behind kOversize
+    if (h->h_out[1] >> 32)  // plan_pass2's truncation flag shares the word
         return fail(PHJ_ERR_INVALID, "internal: the pass-2 plan needed more than %u segments", h->max_segs2);
     float extra_ms = 0;
     if (oversize && h->prepart && !h->parent_digits.empty())
@@ -1359,8 +1366,11 @@ int phj_create(const phj_config* config, phj_handle** out) {
     h->device = config->device;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    // PHJ_KERNEL_TIMES=1: CUDA events around every kernel; any other non-empty value: only around kernels whose
+    // name contains it (every pair of events costs the stream about a microsecond)
     const char* kt = getenv("PHJ_KERNEL_TIMES");
-    h->time_kernels = kt && kt[0] == '1';
+    h->time_kernels = kt && kt[0] && kt[0] != '0';
+    if (h->time_kernels && strcmp(kt, "1")) h->ktime_filter = kt;
     if (const char* rk = getenv("PHJ_RANK")) {
         h->use_match = !strcmp(rk, "match");
         h->use_lanes = strcmp(rk, "match") && strcmp(rk, "stable");
@@ -1384,7 +1394,7 @@ int phj_create(const phj_config* config, phj_handle** out) {
         cudaEventCreate(&k.end);
     }
     if (cudaMalloc(&h->d_scalars, kNumScalars * 4) != cudaSuccess ||
-        cudaMalloc(&h->d_matches, 16) != cudaSuccess ||
+        cudaMalloc(&h->d_matches, 32) != cudaSuccess ||
         cudaMallocHost(&h->h_out, 64) != cudaSuccess)
         return cleanup(fail(PHJ_ERR_NOMEM, "allocation of engine scalars failed"));
     cudaMemset(h->d_scalars, 0, kNumScalars * 4);
@@ -1417,7 +1427,7 @@ void phj_destroy(phj_handle* h) {
         if (h->d_parents2[rel]) cudaFree(h->d_parents2[rel]);
     }
     void* ptrs[] = {h->d_segs1, h->d_segs2, h->d_scalars, h->d_counts, h->d_cursors,
-                    h->d_chunk_sums, h->d_matches, h->d_cta_times, h->d_gt, h->d_hist12, h->d_pt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows, h->d_ct_heads, h->d_ct_buckets};
+                    h->d_scan_state, h->d_matches, h->d_cta_times, h->d_gt, h->d_hist12, h->d_pt, h->d_outd[0], h->d_outd[1], h->d_pre_bounds, h->d_shard_starts, h->d_joined, h->d_cta_rows, h->d_ct_heads, h->d_ct_buckets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1619,7 +1629,7 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->sm_count * 2 * 4, 8192);
     mp.slice_len = h->n[1] / grid;
     mp.slice_rem = h->n[1] % grid;
-    mp.cursor = h->d_matches + 1;
+    mp.cursor = h->d_matches + 2;
     if (!h->d_cta_rows) PHJ_CUDA(cudaMalloc(&h->d_cta_rows, 8192 * sizeof(unsigned long long)));
     mp.cta_rows = h->d_cta_rows;
     const size_t smem = (size_t)mp.cap_tuples * 16 + (size_t)slots * 4;
@@ -1628,12 +1638,12 @@ int phj_join_materialize(phj_handle* h, phj_result* out) {
     PHJ_CUDA(cudaFuncSetAttribute(count_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PHJ_CUDA(cudaFuncSetAttribute(write_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PHJ_CUDA(cudaEventRecord(h->ev[5], h->stream));
-    PHJ_CUDA(cudaMemsetAsync(h->d_matches + 1, 0, 8, h->stream));
+    PHJ_CUDA(cudaMemsetAsync(h->d_matches + 2, 0, 8, h->stream));
     {
         KernelScope ks(h, "join_materialize[count]");
         count_kern<<<grid, kTpb, smem, h->stream>>>(mp);
     }
-    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 2, h->d_matches + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    PHJ_CUDA(cudaMemcpyAsync(h->h_out + 2, h->d_matches + 2, 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
     const uint64_t rows = h->h_out[2];
@@ -2111,6 +2121,13 @@ int phj_memcpy_d2h(int32_t device, void* h_dst, const void* d_src, size_t bytes)
     if (bytes && (!h_dst || !d_src)) return fail(PHJ_ERR_INVALID, "null argument");
     PHJ_CUDA(cudaSetDevice(device));
     if (bytes) PHJ_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return PHJ_OK;
+}
+
+int phj_kernel_timing(phj_handle* h, const char* filter) {
+    if (!h) return fail(PHJ_ERR_INVALID, "handle is null");
+    h->time_kernels = filter != nullptr;
+    h->ktime_filter = filter ? filter : "";
     return PHJ_OK;
 }
 

@@ -225,9 +225,8 @@ __global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
 }
 
 // =================================================================================================
-// K2  flat exclusive scan of the counters (uint32 counts -> uint64 cursors), two launches:
-// scan_reduce (per-chunk sums) and scan_write (every CTA re-scans the <= 1024 chunk sums with
-// warp shuffles for its carry-in, then scans its own chunk).
+// K2  flat exclusive scan of the counters (uint32 counts -> uint64 cursors) in ONE launch (round 1 used two:
+// per-chunk sums, then every CTA re-scanned the <= 1024 chunk sums for its carry-in and scanned its chunk).
 // =================================================================================================
 constexpr int kScanTpb = 1024;
 constexpr int kScanIpt = 4;
@@ -262,38 +261,29 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* sh
     return excl;
 }
 
-__global__ void __launch_bounds__(kScanTpb) scan_reduce(const uint32_t* __restrict__ counts,
-                                                        const uint32_t* __restrict__ n_ptr,
-                                                        uint64_t* __restrict__ chunk_sums) {
-    __shared__ uint64_t sh[33];
-    const uint32_t n = *n_ptr;
-    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk;
-    if (base >= n) return;
-    uint64_t s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanIpt; ++i) {
-        uint64_t idx = base + (uint64_t)i * kScanTpb + threadIdx.x;
-        if (idx < n) s += counts[idx];
-    }
-    uint64_t total;
-    block_excl_scan_u64(s, sh, &total);
-    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
-}
+// scan_lookback: a CTA takes the next chunk (ticket), publishes
+// the chunk's sum under this launch's epoch, adds up the sums of all earlier chunks as they appear (at most 1024,
+// one per thread -- chunks are handed out in order, so every chunk a CTA waits for belongs to a CTA that is
+// already running) and scans its own chunk. Saves a launch, a launch gap and a second read of the counters:
+// 15 + 3 us -> 8 us per radix pass at 114 K counters (measured).
+struct ScanState {
+    unsigned long long sum[1024];  // chunk sums of the current launch
+    uint32_t epoch[1024];          // launch that wrote sum[i]
+    uint32_t ticket;               // next chunk; wraps to 0 with the last CTA of a launch
+};
 
-__global__ void __launch_bounds__(kScanTpb) scan_write(const uint32_t* __restrict__ counts,
-                                                       const uint32_t* __restrict__ n_ptr,
-                                                       const uint64_t* __restrict__ chunk_sums,
-                                                       uint64_t* __restrict__ cursors) {
+__global__ void __launch_bounds__(kScanTpb) scan_lookback(const uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ n_ptr,
+                                                          uint64_t* __restrict__ cursors, ScanState* st,
+                                                          uint32_t epoch) {
     __shared__ uint64_t sh[33];
     __shared__ uint64_t carry_sh;
+    __shared__ uint32_t chunk_sh;
+    if (threadIdx.x == 0) chunk_sh = atomicInc(&st->ticket, gridDim.x - 1);
+    __syncthreads();
+    const uint32_t chunk = chunk_sh;
     const uint32_t n = *n_ptr;
-    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk;
-    if (base >= n) return;
-    // carry-in = sum of the chunk sums before this CTA's chunk (<= 1024 chunks by construction)
-    uint64_t c = threadIdx.x < blockIdx.x ? chunk_sums[threadIdx.x] : 0;
-    uint64_t carry;
-    block_excl_scan_u64(c, sh, &carry);
-    if (threadIdx.x == 0) carry_sh = carry;
+    const uint64_t base = (uint64_t)chunk * kScanChunk;
     // each thread owns kScanIpt consecutive counters
     const uint64_t first = base + (uint64_t)threadIdx.x * kScanIpt;
     uint32_t v[kScanIpt];
@@ -303,7 +293,30 @@ __global__ void __launch_bounds__(kScanTpb) scan_write(const uint32_t* __restric
         v[i] = first + i < n ? counts[first + i] : 0;
         s += v[i];
     }
-    uint64_t excl = block_excl_scan_u64(s, sh, nullptr) + carry_sh;
+    uint64_t total;
+    const uint64_t excl_in_chunk = block_excl_scan_u64(s, sh, &total);
+    if (threadIdx.x == 0) {
+        st->sum[chunk] = total;
+        __threadfence();
+        reinterpret_cast<volatile uint32_t*>(st->epoch)[chunk] = epoch;
+    }
+    if (base >= n) return;  // nothing to write (its sum, 0, is published for the chunks behind it)
+    // carry-in: the sums of the chunks before this one
+    uint64_t c = 0;
+    {
+        // warp-converged spin (see cta_sync()): every lane leaves the loop in the same trip
+        const bool mine = threadIdx.x < chunk;
+        bool ready = !mine;
+        while (!__all_sync(0xffffffffu, ready))
+            if (!ready) ready = reinterpret_cast<volatile uint32_t*>(st->epoch)[threadIdx.x] == epoch;
+        __threadfence();
+        if (mine) c = reinterpret_cast<volatile unsigned long long*>(st->sum)[threadIdx.x];
+    }
+    uint64_t carry;
+    block_excl_scan_u64(c, sh, &carry);
+    if (threadIdx.x == 0) carry_sh = carry;
+    __syncthreads();
+    uint64_t excl = excl_in_chunk + carry_sh;
 #pragma unroll
     for (int i = 0; i < kScanIpt; ++i) {
         if (first + i < n) cursors[first + i] = excl;
@@ -334,9 +347,10 @@ struct ScatterSmem {
     static constexpr size_t gbase_bytes = (size_t)D * 8;
     static constexpr size_t wc_bytes = (size_t)NW * (D + 1) * 4;
     static constexpr size_t dbase_bytes = (size_t)(D + 4) * 4;
+    static constexpr size_t dtot_bytes = 64 * 4;  // PSCAN: per-digit tile totals (D <= 64), read in pairs
     static constexpr size_t sdig_bytes = (size_t)T * 2;
     static constexpr size_t total_tma =  // TMA bulk stores flush whole runs: no per-slot digit array
-        (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + 16 * 4 + 64 + 15) / 16 * 16;
+        (stage_bytes + gcur_bytes + gbase_bytes + wc_bytes + dbase_bytes + dtot_bytes + 16 * 4 + 64 + 15) / 16 * 16;
     static constexpr size_t total = total_tma + sdig_bytes;
     static constexpr size_t bytes(bool tma_store) { return tma_store ? total_tma : total; }
     // extra shared memory of the fused pass-2 histogram: counters + split positions + counter indices
@@ -356,8 +370,14 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     uint64_t* gcur = reinterpret_cast<uint64_t*>(smem_raw + L::stage_bytes);
     uint64_t* gbase = gcur + D;
     uint32_t* wtot_sh = reinterpret_cast<uint32_t*>(gbase + D);  // 16 entries: digit-scan warp totals
-    uint32_t* wc = wtot_sh + 16;
+    uint32_t* dtot = wtot_sh + 16;                                // 64 entries, 8-byte aligned: PSCAN digit totals
+    uint32_t* wc = dtot + 64;
     uint32_t* dbase = wc + NW * (D + 1);
+    // PSCAN: a tile's counters are scanned by ALL warps (shuffles over the source-warp index, 32 / NW digits per
+    // warp instruction) and every warp folds the digit bases into its own counter row: three CTA barriers per
+    // tile instead of four, and no phase in which two warps work while the others wait.
+    constexpr bool PSCAN = PHJ_SCAT_PSCAN && !FUSE2 && D <= 64 && (NW == 8 || NW == 16 || NW == 32);
+    static_assert(T <= 0xffff, "tile slots fit 16 bits");
     uint16_t* sdig = reinterpret_cast<uint16_t*>(smem_raw + L::total_tma);  // only without TMA stores
     // FUSE2: [2][D][d2] pass-2 counters of this segment + per-digit split position / first segment
     uint32_t* h2 = reinterpret_cast<uint32_t*>(smem_raw + (TMA_STORE ? L::total_tma : L::total));
@@ -372,6 +392,7 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
     uint32_t* wcw = wc + warp * (D + 1);
     const uint32_t lt = lanemask_lt();
     const uint32_t nsegs = p.seg_count ? p.seg_count : *p.nsegs;
+    if (PSCAN && tid < 64) dtot[tid] = 0;  // entries >= D are never written again
 
     // One CTA per segment by default; a smaller grid (the multi-GPU split, which leaves SMs to the
     // local join running beside it) makes every CTA walk several segments.
@@ -465,7 +486,11 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
             const uint32_t peers = warp_peers<kFull ? BITS : BITS + 1, BALLOT>(d);
             const uint32_t prev = wcw[d];
             __syncwarp();
+#if PHJ_SCAT_ALLWRITE
+            wcw[d] = prev + __popc(peers);  // every peer stores the same word: no leader election (BREV + FLO + ISETP)
+#else
             if (lane == __ffs(peers) - 1) wcw[d] = prev + __popc(peers);
+#endif
             __syncwarp();
             dr[i] = d | ((prev + __popc(peers & lt)) << 16);
             if (FUSE2) dr[i] |= digit_of<POW2>(h, p.df2) << 9;
@@ -479,6 +504,58 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
         }
         cta_sync();
 
+        if constexpr (PSCAN) {
+            // ---- scan across warps: lane = (digit slot q, source warp w_src) ----
+            {
+                const int w_src = lane % NW, q = lane / NW;
+#pragma unroll
+                for (int r = 0; r < (D + 31) / 32; ++r) {
+                    const int d = r * 32 + warp + NW * q;  // shared-memory banks (w_src + d) % 32: no conflicts
+                    const bool act = d < D && d < r * 32 + 32;
+                    uint32_t* cell = wc + w_src * (D + 1) + (act ? d : 0);
+                    const uint32_t c = act ? *cell : 0;
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int o = 1; o < NW; o <<= 1) {
+                        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (w_src >= o) incl += n;
+                    }
+                    if (act) {
+                        *cell = incl - c;  // tuples of digit d in the warps before w_src
+                        if (w_src == NW - 1) dtot[d] = incl;
+                    }
+                }
+            }
+            if (TMA_STORE) bulk_wait_read0();  // previous tile's bulk stores have read `stage`
+            cta_sync();
+            // ---- scan across digits, redundantly in every warp (two digits per lane), folded into the warp's
+            //      own counter row: wcw[d] = tile slot of this warp's first tuple of digit d ----
+            {
+                const uint2 t = reinterpret_cast<const uint2*>(dtot)[lane];
+                const uint32_t s2 = t.x + t.y;
+                uint32_t incl = s2;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                const uint32_t ex0 = incl - s2, ex1 = ex0 + t.x;
+                if (2 * lane < D) wcw[2 * lane] += ex0;
+                if (2 * lane + 1 < D) wcw[2 * lane + 1] += ex1;
+                if (warp < 2) {  // bookkeeping of the flush: warp 0 takes the even digits, warp 1 the odd ones
+                    const int d = 2 * lane + warp;
+                    if (d < D) {
+                        const uint32_t ex = warp ? ex1 : ex0;
+                        dbase[d] = ex;
+                        if (d == D - 1) dbase[D] = n_valid;
+                        const uint64_t g = gcur[d];
+                        gbase[d] = g - ex;  // out index of tile slot j of this digit = gbase + j
+                        gcur[d] = g + (warp ? t.y : t.x);
+                    }
+                }
+                __syncwarp();
+            }
+        } else {
         // ---- per-digit scan across warps, then across digits (32-bit, two barriers) ----
         uint32_t tot = 0, incl = 0;
         if (tid < D) {
@@ -517,17 +594,19 @@ __global__ void __launch_bounds__(TPB, MINB) radix_scatter(PassParams p) {
             gcur[tid] += tot;
         }
         cta_sync();
+        }  // !PSCAN
 
         // ---- stage ----
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = dr[i] & 0x1ffu;
             if (full || d < D) {
-                const uint32_t db = FUSE2 ? dthr[d] : dbase[d];
+                uint32_t db = 0;  // PSCAN: the digit's base is already inside wcw[d]
+                if constexpr (!PSCAN) db = FUSE2 ? dthr[d] : dbase[d];
                 const uint32_t pos = (FUSE2 ? db & 0xffffu : db) + wcw[d] + (dr[i] >> 16);
                 stage[pos] = v[i];
                 if (!TMA_STORE) sdig[pos] = (uint16_t)d;
-                if (FUSE2) {
+                if constexpr (FUSE2) {
                     const uint32_t slot = pos >= (db >> 16);
                     const uint32_t c2 = (slot * D + d) * kFuse2MaxD2 + ((dr[i] >> 9) & 0x7fu);
                     atomicAdd(&h2[c2 >> 1], 1u << ((c2 & 1) * 16));
@@ -817,12 +896,15 @@ struct Plan2Params {
     uint32_t* ncounts;    // out: total counters = d2 * nsegs
     uint32_t max_segs;
     uint32_t* truncated;  // set when the parents need more than max_segs segments
+    uint64_t* bounds2[2];  // pass-2 boundaries: those of EMPTY parents are written here (no segment ever does)
+    unsigned long long* zero_words;  // the join's match counter and its oversize / truncated word: cleared here
 };
 
 __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
     __shared__ uint64_t sh[33];
     __shared__ uint32_t rel_base_sh;
     uint32_t seg_base = 0;  // segments emitted by previous relations
+    if (threadIdx.x == 0 && p.zero_words) p.zero_words[0] = p.zero_words[1] = 0;
     for (int rel = 0; rel < 2; ++rel) {
         const uint64_t n = p.n[rel];
         const uint64_t seg_len = p.seg_len[rel];
@@ -838,6 +920,8 @@ __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
             len = hi - lo;
             ns = (uint32_t)((len + seg_len - 1) / seg_len);
             p.bounds1[rel][threadIdx.x] = lo;
+            if (len == 0 && p.bounds2[rel])  // no segment of this parent will write its boundaries
+                for (uint32_t d = 0; d < p.d2; ++d) p.bounds2[rel][(uint64_t)threadIdx.x * p.d2 + d] = lo;
         }
         uint64_t total;
         const uint32_t first = (uint32_t)block_excl_scan_u64(ns, sh, &total);
@@ -877,22 +961,29 @@ __global__ void __launch_bounds__(1024) plan_pass2(Plan2Params p) {
 // = the tuples of pass-1 digit d that pass-1 segment s wrote, starting at its scanned cursor.
 // Segment j of parent d keeps plan_pass2's nominal window [lo + j L, lo + (j + 1) L) but holds exactly
 // the runs that START inside it, so its pass-2 digit counts are sums of hist12 rows.
-// align_pass2_segments moves every segment's begin / end to those run starts (binary search over
-// the parent's cursors); pass2_counts_from_hist12 adds the rows up into the pass-2 counters.
+// pass2_align_counts moves every segment's begin / end to those run starts (binary search over the parent's
+// cursors) and adds the rows up into the pass-2 counters (round 1: two launches, a memset and atomics).
 // =================================================================================================
-struct Align2Params {
+// 64 threads per pass-2 segment. All of them find the runs that
+// start inside the segment's window ([a0, a1) by binary search over the parent's cursors, the loads are
+// broadcasts), thread 0 writes the aligned segment, and thread d2 adds up hist12[s][d][d2] over those runs:
+// every pass-2 counter is written exactly once, so no memset and no atomic. 11 + 33 us -> see DESIGN.md.
+struct AlignCounts2Params {
     const uint64_t* cursors;  // scanned pass-1 cursors (as in Plan2Params)
-    uint32_t cnt_base1[2], nseg1[2];
+    uint32_t cnt_base1[2], nseg1[2], seg_first1[2];
     uint64_t bias[2];
     const uint64_t* bounds1[2];  // d1 + 1 per relation
     const Parent2* parents2[2];
     uint64_t seg_len[2];
     Segment* segs;
     const uint32_t* nsegs;
+    const uint32_t* hist12;  // [pass-1 segment][kFullD1][kFullD2]
+    uint32_t d2;
+    uint32_t* counts2;
 };
 
-__global__ void align_pass2_segments(Align2Params p) {
-    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) pass2_align_counts(AlignCounts2Params p) {
+    const uint32_t gi = blockIdx.x * (256 / kFullD2) + threadIdx.x / kFullD2, d2 = threadIdx.x % kFullD2;
     if (gi >= *p.nsegs) return;
     Segment sg = p.segs[gi];
     const uint32_t rel = sg.rel, d = sg.parent_first & 0x7fffffffu;
@@ -900,9 +991,7 @@ __global__ void align_pass2_segments(Align2Params p) {
     const uint32_t j = sg.cnt_index - par.cnt_base, n1 = p.nseg1[rel];
     const uint64_t lo = par.lo, hi = p.bounds1[rel][d + 1], bias = p.bias[rel];
     const uint64_t* __restrict__ cur = p.cursors + p.cnt_base1[rel] + (uint64_t)d * n1;
-    // Start of the first run that begins at or after a target position (the parent's end if there is
-    // none); the searches for this segment's begin and end advance together, so their dependent
-    // loads overlap.
+    // first run that starts at or after a target position; the two searches advance together
     const uint64_t t0 = lo + (uint64_t)j * p.seg_len[rel], t1 = t0 + p.seg_len[rel];
     uint32_t a0 = 0, b0 = n1, a1 = 0, b1 = n1;
     while (a0 < b0 || a1 < b1) {
@@ -917,79 +1006,27 @@ __global__ void align_pass2_segments(Align2Params p) {
             else a1 = m1 + 1;
         }
     }
-    sg.begin = j == 0 ? lo : a0 == n1 ? hi : cur[a0] - bias;
-    sg.end = j + 1 == par.nseg ? hi : a1 == n1 ? hi : cur[a1] - bias;
-    p.segs[gi] = sg;
-}
-
-struct Counts2Params {
-    const uint32_t* hist12;   // [pass-1 segment][kFullD1][kFullD2]
-    const uint64_t* cursors;  // scanned pass-1 cursors
-    uint32_t cnt_base1[2], nseg1[2], seg_first1[2];  // seg_first1: index of the relation's first pass-1 segment
-    uint64_t bias[2];
-    const Parent2* parents2[2];
-    uint64_t seg_len[2];
-    uint32_t d1, d2;
-    uint32_t* counts2;  // zeroed before the launch
-};
-
-// grid (2 * d1 parents, s-chunks), 1024 threads = 16 segment lanes x 64 pass-2 digits: a thread walks
-// a few consecutive pass-1 segments of its parent, adds up hist12[s][d][d2] while the runs stay in
-// one pass-2 segment and flushes the sum with one atomic when it changes.
-__global__ void __launch_bounds__(1024) pass2_counts_from_hist12(Counts2Params p) {
-    const uint32_t rel = blockIdx.x / p.d1, d = blockIdx.x % p.d1;
-    const uint32_t d2 = threadIdx.x & (kFullD2 - 1), sl = threadIdx.x / kFullD2;
-    const uint32_t n1 = p.nseg1[rel];
-    const uint32_t lanes = gridDim.y * (1024 / kFullD2);
-    const uint32_t chunk = (n1 + lanes - 1) / lanes;
-    const uint32_t s0 = (blockIdx.y * (1024 / kFullD2) + sl) * chunk, s1 = min(n1, s0 + chunk);
-    if (d2 >= p.d2 || s0 >= s1) return;
-    const Parent2 par = p.parents2[rel][d];
-    if (par.nseg == 0) return;  // empty parent: nothing was counted
-    const uint64_t* __restrict__ cur = p.cursors + p.cnt_base1[rel] + (uint64_t)d * n1;
-    const uint32_t* __restrict__ hrow =
-        p.hist12 + ((uint64_t)p.seg_first1[rel] + s0) * (kFullD1 * kFullD2) + d * kFullD2 + d2;
-    const uint64_t base = p.bias[rel] + par.lo, len = p.seg_len[rel];
-    // pass-2 segment of the first run (one division per thread), then only comparisons: run starts
-    // grow with s, so the segment index moves forward
-    const uint64_t pos0 = cur[s0] - base;
-    uint32_t jcur = (uint32_t)min(((pos0 | len) >> 32) ? pos0 / len : (uint64_t)((uint32_t)pos0 / (uint32_t)len),
-                                  (uint64_t)(par.nseg - 1));
-    uint64_t next = (uint64_t)(jcur + 1) * len;  // first position of the next segment's window
-    uint32_t acc = 0;
-    for (uint32_t s = s0; s < s1; ++s, hrow += kFullD1 * kFullD2) {
-        const uint32_t c = *hrow;
-        const uint64_t pos = cur[s] - base;
-        if (pos >= next && jcur + 1 < par.nseg) {
-            if (acc) atomicAdd(&p.counts2[par.cnt_base + d2 * par.nseg + jcur], acc);
-            acc = 0;
-            do {
-                ++jcur;
-                next += len;
-            } while (pos >= next && jcur + 1 < par.nseg);
-        }
-        acc += c;
+    const bool last = j + 1 == par.nseg;
+    if (j == 0) a0 = 0;
+    if (last) a1 = n1;
+    if (d2 == 0) {
+        sg.begin = j == 0 ? lo : a0 == n1 ? hi : cur[a0] - bias;
+        sg.end = last ? hi : a1 == n1 ? hi : cur[a1] - bias;
+        p.segs[gi] = sg;
     }
-    if (acc) atomicAdd(&p.counts2[par.cnt_base + d2 * par.nseg + jcur], acc);
-}
-
-// Boundaries of parents that received no segment (empty parents) are never written by
-// radix_scatter: fill them from their parent's start. One thread per (rel, parent).
-struct FillEmptyParams {
-    const uint64_t* bounds1[2];
-    uint64_t* bounds2[2];
-    uint64_t n[2];
-    uint32_t d1, d2;
-};
-__global__ void fill_empty_parent_bounds(FillEmptyParams p) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * p.d1) return;
-    const int rel = i / p.d1;
-    const uint32_t parent = i % p.d1;
-    const uint64_t lo = p.bounds1[rel][parent];
-    const uint64_t hi = (parent + 1 == p.d1) ? p.n[rel] : p.bounds1[rel][parent + 1];
-    if (hi == lo)
-        for (uint32_t d = 0; d < p.d2; ++d) p.bounds2[rel][(uint64_t)parent * p.d2 + d] = lo;
+    if (d2 >= p.d2) return;
+    const uint32_t* __restrict__ hrow =
+        p.hist12 + ((uint64_t)p.seg_first1[rel] + a0) * (kFullD1 * kFullD2) + d * kFullD2 + d2;
+    uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    uint32_t s = a0;
+    for (; s + 4 <= a1; s += 4, hrow += 4 * kFullD1 * kFullD2) {
+        acc0 += hrow[0];
+        acc1 += hrow[kFullD1 * kFullD2];
+        acc2 += hrow[2 * kFullD1 * kFullD2];
+        acc3 += hrow[3 * kFullD1 * kFullD2];
+    }
+    for (; s < a1; ++s, hrow += kFullD1 * kFullD2) acc0 += hrow[0];
+    p.counts2[par.cnt_base + d2 * par.nseg + j] = acc0 + acc1 + acc2 + acc3;
 }
 
 // =================================================================================================
@@ -1020,6 +1057,7 @@ struct JoinParams {
                             // free-slot marker, every other partition runs without that check
     unsigned long long* matches;
     uint64_t* cta_times;  // 2 per CTA: build ns, probe ns
+    uint32_t* oversize;   // optional: += the partitions skipped because their build side exceeds max_keys
 };
 
 // Hash of a key inside one partition's table. All keys of a partition share the partitioning hash's
@@ -1050,6 +1088,9 @@ __global__ void __launch_bounds__(TPB) join_partitions(JoinParams p) {
     if (tid == 0) block_count = 0;
     uint64_t build_ns = 0, probe_ns = 0;
     uint32_t count = 0;
+    if (p.oversize)  // what count_oversize did in a launch of its own
+        for (uint32_t i = blockIdx.x * TPB + tid; i < p.npart; i += gridDim.x * TPB)
+            if (p.bounds_build[i + 1] - p.bounds_build[i] > p.max_keys) atomicAdd(p.oversize, 1u);
 
     if (lo < hi) {
         // last partition whose start is <= lo

@@ -294,6 +294,10 @@ class Engine:
         check(lib.phj_device_partitions(self._h, which, C.byref(d_data), C.byref(d_bounds), C.byref(n)))
         return d_data.value or 0, d_bounds.value or 0, int(n.value)
 
+    def kernel_timing(self, filter) -> None:
+        """CUDA events around the kernels of the following joins: None = none, "" = all, else names containing it."""
+        check(lib.phj_kernel_timing(self._h, None if filter is None else filter.encode()))
+
     def kernel_times(self) -> list:
         names = (C.c_char_p * 32)()
         ns = (C.c_uint64 * 32)()
