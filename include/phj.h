@@ -328,6 +328,10 @@ typedef struct {
 int phj_dist_info(phj_dist* d, phj_dist_layout* out);
 int phj_dist_read_window(phj_dist* d, int32_t which, phj_tuple* out, uint64_t cap_tuples, uint64_t* bounds);
 
+/* Inside ONE process a window of another GPU needs no IPC handle: enable peer access from `device` to `peer`
+ * once and use the pointer phj_shared_alloc returned (what phj_config.num_gpus does internally). */
+int phj_enable_peer_access(int32_t device, int32_t peer);
+
 /* Device memory that other processes on the node can map (CUDA IPC): the receive buffers of the
  * fused shuffle. `ipc_handle` is 64 opaque bytes to hand to the peers (any transport). */
 int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* ipc_handle);

@@ -144,6 +144,7 @@ SIGNATURES = {
     "phj_shard_count": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phj_shard_scatter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(PhjResult)]),
+    "phj_enable_peer_access": (C.c_int, [C.c_int32, C.c_int32]),
     "phj_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "phj_dist_create": (C.c_int, [C.POINTER(PhjConfig), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phj_dist_destroy": (None, [C.c_void_p]),

@@ -4,16 +4,19 @@
 // partitions are independent join units, so the join shards by partition with ONE exchange step, and
 // that exchange doubles as the (only) partitioning pass:
 //
-//   count     every rank histograms its row shard of R and S by the split digit
-//             (owner rank : local partition) = the low log2(world) + b bits of the partitioning hash,
-//             once for all row chunks of S                                      [stream A]
-//   sizes     NCCL all-gather of the chunk starts, device to device; a one-CTA kernel turns them into
-//             where each of this rank's pieces lands inside its owner's window (digit-major, then
-//             source rank: the reference's stable partition order, src/RadixCluster/HashJoin.hpp:394-412),
-//             into the boundaries of this rank's own partitions, and into an overflow flag    [A]
+//   count     every rank histograms its row shard by the split digit (owner rank : local partition) = the
+//             low log2(world) + b bits of the partitioning hash, PIECE BY PIECE: R and the first probe
+//             chunk on stream A, every later chunk on stream C while the pieces before it travel
+//             (chunk_scan: 0-based scatter cursors per (digit, piece) + the running chunk starts)
+//   sizes     NCCL all-gather of the chunk starts, device to device, once per piece -- the gather that
+//             brings the counts of chunk c + 1 is at the same time the barrier behind chunk c; a one-CTA
+//             kernel turns them into where each of this rank's runs lands inside its owner's window
+//             (digit-major, then source rank: the reference's stable partition order,
+//             src/RadixCluster/HashJoin.hpp:394-412), the boundaries of this rank's own partitions, and
+//             an overflow flag                                                                [A]
 //   scatter   the radix scatter kernel writes every digit run STRAIGHT INTO THE OWNER'S WINDOW over
 //             NVLink with its TMA bulk stores -- first R, then S chunk by chunk, each followed by a
-//             stream-ordered NCCL barrier ("everybody's chunk c has landed")                 [A]
+//             stream-ordered NCCL collective ("everybody's chunk c has landed")              [A]
 //   local     per-partition tables in global memory, hot in L2 (pt_build after R's barrier, pt_probe
 //             of chunk c after chunk c's barrier): it runs on stream B WHILE stream A scatters the
 //             next chunk -- NVLink-bound stores on one side, L2 / HBM-bound probes on the other
@@ -90,15 +93,18 @@ NcclApi* nccl_api() {
     } while (0)
 
 // ---- the device-side layout ------------------------------------------------------------------------
-// all_starts[src][rel][digit][K + 1] (what every rank's split_starts produced, all-gathered). Thread d
-// owns split digit d = owner * d_local + local partition.
+// all_starts[src][rel][digit][K + 1] (every rank's running chunk starts, chunk_scan, all-gathered): entry c + 1
+// minus entry c = that rank's tuples of (digit, chunk c); the build relation counts as chunk 0. Thread d owns split
+// digit d = owner * d_local + local partition. One launch per piece that travels (`which` = 0: R; 1 + c: chunk c of
+// S), as soon as every rank's counts of that piece have arrived -- later chunks are still being counted then.
 struct LayoutParams {
     const uint64_t* all_starts;
     uint32_t world, rank, ndig, d_local, K;
+    uint32_t which;
     ulonglong2* const* peer_build;  // [world]: base of every rank's build window, as mapped HERE
     ulonglong2* const* peer_probe;
     ulonglong2** outd;    // out [(1 + K)][ndig]: destination base of digit d for the R launch (0) and the
-                          // S launch of chunk c (1 + c), rebased so that base + scatter cursor is the slot
+                          // S launch of chunk c (1 + c): base + the scatter's (chunk-local) cursor is the slot
     uint64_t* lb_build;   // out [d_local + 1]: boundaries of this rank's partitions in its build window
     uint64_t* lb_probe;   // out [K][d_local + 1]: ... of chunk c's region of its probe window (absolute)
     uint64_t cap_build, cap_probe;  // this rank's windows, tuples
@@ -107,62 +113,57 @@ struct LayoutParams {
 };
 
 __global__ void __launch_bounds__(256) dist_layout(LayoutParams p) {
-    __shared__ uint64_t tot_r[256];
-    __shared__ uint64_t tot_s[kMaxSplitChunks][256];
+    __shared__ uint64_t tot[256];     // tuples of digit d in this piece, over all source ranks
+    __shared__ uint64_t earlier[256]; // probe: tuples of digit d in the chunks before this one
     const uint32_t d = threadIdx.x, K = p.K, stride = K + 1;
-    uint64_t before_r = 0, before_s[kMaxSplitChunks];
+    const bool probe = p.which > 0;
+    const uint32_t c = probe ? p.which - 1 : 0;
+    uint64_t before = 0;  // ... of the source ranks before this one
     if (d < p.ndig) {
-        uint64_t tr = 0;
-        uint64_t ts[kMaxSplitChunks];
-        for (uint32_t c = 0; c < K; ++c) ts[c] = before_s[c] = 0;
+        uint64_t t = 0, e = 0;
         for (uint32_t src = 0; src < p.world; ++src) {
-            const uint64_t* r = p.all_starts + ((uint64_t)(src * 2 + 0) * p.ndig + d) * stride;
-            const uint64_t* s = p.all_starts + ((uint64_t)(src * 2 + 1) * p.ndig + d) * stride;
-            const uint64_t cr = r[K] - r[0];
-            tr += cr;
-            if (src < p.rank) before_r += cr;
-            for (uint32_t c = 0; c < K; ++c) {
-                const uint64_t cs = s[c + 1] - s[c];
-                ts[c] += cs;
-                if (src < p.rank) before_s[c] += cs;
-            }
+            const uint64_t* st = p.all_starts + ((uint64_t)(src * 2 + (probe ? 1 : 0)) * p.ndig + d) * stride;
+            const uint64_t n = probe ? st[c + 1] - st[c] : st[K] - st[0];
+            t += n;
+            if (src < p.rank) before += n;
+            if (probe) e += st[c] - st[0];
         }
-        tot_r[d] = tr;
-        for (uint32_t c = 0; c < K; ++c) tot_s[c][d] = ts[c];
+        tot[d] = t;
+        earlier[d] = e;
     }
     __syncthreads();
     if (d >= p.ndig) return;
     const uint32_t owner = d / p.d_local, first = owner * p.d_local, l = d - first;
-    const uint64_t* my_r = p.all_starts + ((uint64_t)(p.rank * 2 + 0) * p.ndig + d) * stride;
-    const uint64_t* my_s = p.all_starts + ((uint64_t)(p.rank * 2 + 1) * p.ndig + d) * stride;
-    uint64_t base_r = 0;
-    for (uint32_t e = first; e < d; ++e) base_r += tot_r[e];
-    p.outd[d] = p.peer_build[owner] + base_r + before_r - my_r[0];
     const bool mine = owner == p.rank, last = l + 1 == p.d_local;
-    if (mine) {
-        p.lb_build[l] = base_r;
-        if (last) {
-            p.lb_build[p.d_local] = base_r + tot_r[d];
-            if (base_r + tot_r[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
-        }
-        if (tot_r[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
-    }
-    uint64_t region = 0;  // start of chunk c's region in the owner's probe window
-    for (uint32_t c = 0; c < K; ++c) {
-        uint64_t pre = 0, size = 0;
-        for (uint32_t e = first; e < first + p.d_local; ++e) {
-            if (e < d) pre += tot_s[c][e];
-            size += tot_s[c][e];
-        }
-        const uint64_t base_s = region + pre;
-        p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base_s + before_s[c] - my_s[c];
+    if (!probe) {
+        uint64_t base = 0;
+        for (uint32_t e = first; e < d; ++e) base += tot[e];
+        p.outd[d] = p.peer_build[owner] + base + before;
         if (mine) {
-            p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base_s;
-            if (last) p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base_s + tot_s[c][d];
+            p.lb_build[l] = base;
+            if (last) {
+                p.lb_build[p.d_local] = base + tot[d];
+                if (base + tot[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
+            }
+            if (tot[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
         }
-        region += size;
+        return;
     }
-    if (mine && last && region > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+    // chunk c's region of the owner's probe window starts behind the regions of the chunks before it
+    uint64_t region = 0, pre = 0;
+    for (uint32_t e = first; e < first + p.d_local; ++e) {
+        region += earlier[e];
+        if (e < d) pre += tot[e];
+    }
+    const uint64_t base = region + pre;
+    p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base + before;
+    if (mine) {
+        p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base;
+        if (last) {
+            p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base + tot[d];
+            if (c + 1 == K && base + tot[d] > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+        }
+    }
 }
 
 }  // namespace
@@ -178,6 +179,7 @@ struct phj_dist {
     bool own_comm = false;
     phj_handle* split = nullptr;  // PHJ_ALGO_SHARD_SPLIT handle: stream A, histogram, scan, scatter
     cudaStream_t sb = nullptr;    // stream B: the local join
+    cudaStream_t sc = nullptr;    // stream C: the counts of the probe chunks behind the first
     uint32_t b_local = 0, d_local = 1, ndig = 1, K = 1;
     // windows: 0 = build, 1 = probe
     void* win[2] = {nullptr, nullptr};
@@ -199,7 +201,7 @@ struct phj_dist {
     size_t cap_pt = 0;
     uint32_t region_buckets = 0, max_keys = 0;
     uint32_t* d_ptflags = nullptr;
-    cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
+    cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_cnt[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
     bool sized = false, have_data = false;
     size_t n[2] = {0, 0};
     uint64_t sent_remote_bytes = 0;  // this rank's tuples that leave the GPU, from the last sizing pass
@@ -282,16 +284,72 @@ int dist_close_peers(phj_dist* D) {
     return PHJ_OK;
 }
 
-// The count phase on stream A: histogram, scan, chunk starts, all-gather of the starts.
-int dist_enqueue_count(phj_dist* D) {
+// Counting one piece of the row shard (`which` = 0: R; 1 + c: chunk c of S) on `stream`: histogram of the piece's
+// segments by split digit, then chunk_scan: the piece's 0-based scatter cursors and its entry of the chunk starts.
+int dist_enqueue_count_piece(phj_dist* D, uint32_t which, cudaStream_t stream) {
+    phj_handle* h = D->split;
+    const uint32_t K = D->K;
+    if (!h->d_shard_starts) {
+        const size_t cap = (size_t)2 * kMaxSplitDigits * (kMaxSplitChunks + 1);
+        PHJ_CUDA(cudaMalloc(&h->d_shard_starts, cap * 8));
+        PHJ_CUDA(cudaMallocHost(&h->h_shard_starts, cap * 8));
+    }
+    const int rel = which ? 1 : 0;
+    const uint32_t c = which ? which - 1 : 0;
+    const uint32_t nseg0 = h->nseg1_rel[0];
+    const uint32_t first = which ? h->chunk_first_seg[1][c] : 0;
+    const uint32_t count = which ? h->chunk_first_seg[1][c + 1] - first : nseg0;
+    cudaStream_t keep = h->stream;
+    h->stream = stream;  // launch_pass and KernelScope follow the handle's stream
+    cudaError_t e = cudaSuccess;
+    if (count) {
+        PassParams p1{};
+        fill_pass1_params(h, p1);
+        p1.seg_first = (which ? nseg0 : 0) + first;
+        p1.seg_count = count;
+        KernelScope ks(h, "radix_histogram[split]");
+        e = launch_pass(h, false, h->b1, p1, count);
+    }
+    if (e == cudaSuccess) {
+        ChunkScanParams cs{};
+        cs.counts = h->d_counts;
+        cs.cursors = h->d_cursors;
+        cs.starts = h->d_shard_starts;
+        cs.cnt_base = h->cnt_base1_rel[rel];
+        cs.nseg_rel = h->nseg1_rel[rel];
+        cs.first_seg = first;
+        cs.nseg_chunk = count;
+        cs.ndig = D->ndig;
+        cs.K = K;
+        cs.rel = (uint32_t)rel;
+        cs.chunk = c;
+        KernelScope ks(h, "chunk_scan");
+        chunk_scan<<<D->ndig, 256, 0, stream>>>(cs);
+        e = cudaGetLastError();
+    }
+    h->stream = keep;
+    PHJ_CUDA(e);
+    return PHJ_OK;
+}
+
+// All-gather of the chunk starts on stream A (5 KB per rank; entries of chunks that are still being counted are in
+// flux and not read by anybody yet). Stream-ordered, so it is also a barrier: when it completes HERE, every rank
+// has finished what it had enqueued before it.
+int dist_enqueue_gather(phj_dist* D) {
     NcclApi* nc = nccl_api();
     phj_handle* h = D->split;
-    int rc = shard_count_enqueue(h);
-    if (rc != PHJ_OK) return rc;
     const size_t per_rank = (size_t)2 * D->ndig * (D->K + 1);
     PHJ_NCCL(nc->AllGather(h->d_shard_starts, D->d_all_starts, per_rank, ncclUint64, D->comm, h->stream));
     h->launches += 1;
     return PHJ_OK;
+}
+
+// The whole count at once on stream A (the sizing pass).
+int dist_enqueue_count(phj_dist* D) {
+    int rc;
+    for (uint32_t which = 0; which <= D->K; ++which)
+        if ((rc = dist_enqueue_count_piece(D, which, D->split->stream)) != PHJ_OK) return rc;
+    return dist_enqueue_gather(D);
 }
 
 // Host-synchronous sizing pass (first join, new relations, or after an overflow): counts as the join
@@ -366,41 +424,54 @@ int dist_size(phj_dist* D) {
     return PHJ_OK;
 }
 
-// The whole join, enqueued; `counted`: dist_size has just produced d_all_starts for these relations.
-int dist_enqueue_join(phj_dist* D, bool counted) {
+// The whole join, enqueued.
+int dist_enqueue_join(phj_dist* D) {
     NcclApi* nc = nccl_api();
     phj_handle* h = D->split;
-    cudaStream_t sa = h->stream, sb = D->sb;
+    cudaStream_t sa = h->stream, sb = D->sb, sc = D->sc;
     const uint32_t K = D->K, ndig = D->ndig, dl = D->d_local;
     int rc;
     PHJ_CUDA(cudaEventRecord(D->ev_t[0], sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_flags, 0, 4 * sizeof(unsigned long long), sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_ptflags, 0, 4, sa));
-    if (!counted && (rc = dist_enqueue_count(D)) != PHJ_OK) return rc;
+    // ---- count: R and the first probe chunk on stream A; the other chunks on stream C, behind them, while R and
+    //      the chunks before them travel (the scatter is bound by NVLink, HBM is nearly idle then) ----
+    if ((rc = dist_enqueue_count_piece(D, 0, sa)) != PHJ_OK) return rc;
+    if ((rc = dist_enqueue_count_piece(D, 1, sa)) != PHJ_OK) return rc;
+    PHJ_CUDA(cudaEventRecord(D->ev_cnt[0], sa));
+    PHJ_CUDA(cudaStreamWaitEvent(sc, D->ev_cnt[0], 0));
+    for (uint32_t c = 1; c < K; ++c) {
+        if ((rc = dist_enqueue_count_piece(D, 1 + c, sc)) != PHJ_OK) return rc;
+        PHJ_CUDA(cudaEventRecord(D->ev_cnt[c], sc));
+    }
+    if ((rc = dist_enqueue_gather(D)) != PHJ_OK) return rc;
     PHJ_CUDA(cudaEventRecord(D->ev_t[1], sa));
-    {
-        LayoutParams lp{};
-        lp.all_starts = D->d_all_starts;
-        lp.world = (uint32_t)D->world;
-        lp.rank = (uint32_t)D->rank;
-        lp.ndig = ndig;
-        lp.d_local = dl;
-        lp.K = K;
-        lp.peer_build = D->d_peer;
-        lp.peer_probe = D->d_peer + kMaxRanks;
-        lp.outd = D->d_outd;
-        lp.lb_build = D->d_lb;
-        lp.lb_probe = D->d_lb + (dl + 1);
-        lp.cap_build = D->caps[0][D->rank];
-        lp.cap_probe = D->caps[1][D->rank];
-        lp.max_keys = D->max_keys;
-        lp.flags = D->d_flags;
+    LayoutParams lp{};
+    lp.all_starts = D->d_all_starts;
+    lp.world = (uint32_t)D->world;
+    lp.rank = (uint32_t)D->rank;
+    lp.ndig = ndig;
+    lp.d_local = dl;
+    lp.K = K;
+    lp.peer_build = D->d_peer;
+    lp.peer_probe = D->d_peer + kMaxRanks;
+    lp.outd = D->d_outd;
+    lp.lb_build = D->d_lb;
+    lp.lb_probe = D->d_lb + (dl + 1);
+    lp.cap_build = D->caps[0][D->rank];
+    lp.cap_probe = D->caps[1][D->rank];
+    lp.max_keys = D->max_keys;
+    lp.flags = D->d_flags;
+    auto layout = [&](uint32_t which) {
+        lp.which = which;
         KernelScope ks(h, "dist_layout");
         dist_layout<<<1, 256, 0, sa>>>(lp);
-    }
+    };
+    layout(0);
+    layout(1);
     // ---- stream B: clear the tables while stream A still scatters R ----
     PHJ_CUDA(cudaEventRecord(D->ev_t[2], sa));
-    PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the layout (boundaries) is ready, the flags are zero
+    PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the build boundaries are ready, the flags are zero
     // The two legs must CO-RESIDE to overlap: a scatter CTA (1024 threads x 64 registers) owns a whole SM's
     // register file, as do six probe CTAs, so left to themselves the two kernels only take turns on the SMs
     // (measured at 2 GPUs: 5.4 ms with 4 chunks against 4.5 ms without any overlap). So the SMs are split. The
@@ -425,9 +496,10 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
         gt_clear<<<grid_l, 256, 0, sb>>>(D->d_pt, (uint64_t)dl * D->region_buckets * 4);
     }
 
-    // ---- stream A: R, then S chunk by chunk, into the owners' windows; a barrier after each ----
+    // ---- stream A: R, then S chunk by chunk, into the owners' windows ----
     PassParams p1{};
     fill_pass1_params(h, p1);
+    p1.cursor_bias[0] = p1.cursor_bias[1] = 0;  // chunk_scan's cursors are 0-based per (digit, piece)
     const uint32_t nseg0 = h->nseg1_rel[0];
     auto scatter = [&](uint32_t first, uint32_t count, uint32_t table) -> int {
         PassParams pp = p1;
@@ -438,12 +510,16 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
             KernelScope ks(h, table == 0 ? "radix_scatter[shuffle R]" : "radix_scatter[shuffle S]");
             PHJ_CUDA(launch_split_scatter(h, h->b1, pp, scatter_cap ? std::min(count, scatter_cap) : count));
         }
-        // stream-ordered barrier: when it completes HERE, every rank's scatter of this piece has completed
+        return PHJ_OK;
+    };
+    // stream-ordered barrier: when it completes HERE, every rank's scatter of this piece has completed
+    auto barrier = [&]() -> int {
         PHJ_NCCL(nc->AllReduce(D->d_flags + 8, D->d_flags + 8, 1, ncclUint64, ncclSum, D->comm, sa));
         h->launches += 1;
         return PHJ_OK;
     };
     if ((rc = scatter(0, nseg0, 0)) != PHJ_OK) return rc;
+    if ((rc = barrier()) != PHJ_OK) return rc;
     PHJ_CUDA(cudaEventRecord(D->ev_r, sa));
 
     PtParams q{};
@@ -476,7 +552,15 @@ int dist_enqueue_join(phj_dist* D, bool counted) {
     for (uint32_t c = 0; c < K; ++c) {
         const uint32_t first = nseg0 + h->chunk_first_seg[1][c], last = nseg0 + h->chunk_first_seg[1][c + 1];
         if ((rc = scatter(first, last - first, 1 + c)) != PHJ_OK) return rc;
+        if (c + 1 < K) {
+            // the all-gather that brings everybody's counts of chunk c + 1 is also the barrier behind chunk c
+            PHJ_CUDA(cudaStreamWaitEvent(sa, D->ev_cnt[c + 1], 0));
+            if ((rc = dist_enqueue_gather(D)) != PHJ_OK) return rc;
+        } else if ((rc = barrier()) != PHJ_OK) {
+            return rc;
+        }
         PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
+        if (c + 1 < K) layout(2 + c);
         PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
         q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
         {
@@ -511,9 +595,10 @@ int dist_join_rank(phj_dist* D, phj_result* out) {
         // times -- the same work
         if (!D->sized && (rc = dist_size(D)) != PHJ_OK) return rc;
         h->n_ktimes = 0;
-        if ((rc = dist_enqueue_join(D, false)) != PHJ_OK) return rc;
+        if ((rc = dist_enqueue_join(D)) != PHJ_OK) return rc;
         PHJ_CUDA(cudaStreamSynchronize(h->stream));
         PHJ_CUDA(cudaStreamSynchronize(D->sb));
+        PHJ_CUDA(cudaStreamSynchronize(D->sc));
         PHJ_CUDA(cudaGetLastError());
         if (D->h_flags[5] == 0 && D->h_flags[6] == 0) break;  // no window / table anywhere was too small
         if (attempt == 1)
@@ -556,6 +641,8 @@ int dist_alloc(phj_dist* D) {
     PHJ_CUDA(cudaMallocHost(&D->h_xchg, (size_t)128 * (1 + D->world)));
     PHJ_CUDA(cudaMalloc(&D->d_ptflags, 16));
     PHJ_CUDA(cudaStreamCreateWithFlags(&D->sb, cudaStreamNonBlocking));
+    PHJ_CUDA(cudaStreamCreateWithFlags(&D->sc, cudaStreamNonBlocking));
+    for (auto& e : D->ev_cnt) PHJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     PHJ_CUDA(cudaEventCreate(&D->ev_r));
     PHJ_CUDA(cudaEventCreate(&D->ev_local));
     for (auto& e : D->ev_c) PHJ_CUDA(cudaEventCreate(&e));
@@ -605,6 +692,7 @@ void dist_free(phj_dist* D) {
     cudaSetDevice(D->device);
     if (D->split && D->split->stream) cudaStreamSynchronize(D->split->stream);
     if (D->sb) cudaStreamSynchronize(D->sb);
+    if (D->sc) cudaStreamSynchronize(D->sc);
     for (int w = 0; w < 2; ++w)
         for (int r = 0; r < D->world; ++r)
             if (D->peer[w][r] && r != D->rank && !D->group) cudaIpcCloseMemHandle(D->peer[w][r]);
@@ -618,6 +706,9 @@ void dist_free(phj_dist* D) {
     if (D->h_flags) cudaFreeHost(D->h_flags);
     if (D->h_xchg) cudaFreeHost(D->h_xchg);
     if (D->sb) cudaStreamDestroy(D->sb);
+    if (D->sc) cudaStreamDestroy(D->sc);
+    for (auto& e : D->ev_cnt)
+        if (e) cudaEventDestroy(e);
     if (D->ev_r) cudaEventDestroy(D->ev_r);
     if (D->ev_local) cudaEventDestroy(D->ev_local);
     for (auto& e : D->ev_c)

@@ -2049,6 +2049,18 @@ int phj_shared_alloc(int32_t device, size_t bytes, void** d_ptr, unsigned char* 
     return PHJ_OK;
 }
 
+int phj_enable_peer_access(int32_t device, int32_t peer) {
+    PHJ_CUDA(cudaSetDevice(device));
+    int can = 0;
+    PHJ_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(PHJ_ERR_CUDA, "GPU %d cannot access GPU %d's memory", device, peer);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(PHJ_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", device, peer, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PHJ_OK;
+}
+
 int phj_shared_open(int32_t device, const unsigned char* ipc_handle, void** d_ptr) {
     if (!d_ptr || !ipc_handle) return fail(PHJ_ERR_INVALID, "null argument");
     PHJ_CUDA(cudaSetDevice(device));

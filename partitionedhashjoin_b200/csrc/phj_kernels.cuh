@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(TPB) radix_histogram(PassParams p) {
     constexpr int T = TPB * IPT;
     __shared__ uint32_t wc[NW][D + 1];  // [..][D] swallows the out-of-range lanes of a tail tile
 
-    if (blockIdx.x >= *p.nsegs) return;
-    const Segment seg = p.segs[blockIdx.x];
+    if (blockIdx.x >= (p.seg_count ? p.seg_count : *p.nsegs)) return;  // seg_count: one row chunk's segments
+    const Segment seg = p.segs[p.seg_first + blockIdx.x];
     const ulonglong2* __restrict__ in = p.in[seg.rel];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* wcw = wc[warp];
@@ -675,8 +675,8 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes(PassParams p) {
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);      // [NW][WARP_WORDS]
     uint32_t* total = cnt + NW * WARP_WORDS;                    // [D]
 
-    if (blockIdx.x >= *p.nsegs) return;
-    const Segment seg = p.segs[blockIdx.x];
+    if (blockIdx.x >= (p.seg_count ? p.seg_count : *p.nsegs)) return;  // seg_count: one row chunk's segments
+    const Segment seg = p.segs[p.seg_first + blockIdx.x];
     const ulonglong2* __restrict__ in = p.in[seg.rel];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* mine = reinterpret_cast<unsigned char*>(cnt + warp * WARP_WORDS);
@@ -751,8 +751,8 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes8(PassParams p) {
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);  // [NW][WARP_WORDS]
     uint32_t* total = cnt + NW * WARP_WORDS;                // [D]
 
-    if (blockIdx.x >= *p.nsegs) return;
-    const Segment seg = p.segs[blockIdx.x];
+    if (blockIdx.x >= (p.seg_count ? p.seg_count : *p.nsegs)) return;  // seg_count: one row chunk's segments
+    const Segment seg = p.segs[p.seg_first + blockIdx.x];
     const ulonglong2* __restrict__ in = p.in[seg.rel];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* mine_w = cnt + warp * WARP_WORDS;
@@ -832,8 +832,8 @@ __global__ void __launch_bounds__(TPB) radix_histogram_full(PassParams p) {
     constexpr int NB = kFullD1 * kFullD2;
     __shared__ uint32_t cnt[NB];
 
-    if (blockIdx.x >= *p.nsegs) return;
-    const Segment seg = p.segs[blockIdx.x];
+    if (blockIdx.x >= (p.seg_count ? p.seg_count : *p.nsegs)) return;  // seg_count: one row chunk's segments
+    const Segment seg = p.segs[p.seg_first + blockIdx.x];
     const ulonglong2* __restrict__ in = p.in[seg.rel];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -1957,6 +1957,45 @@ __global__ void __launch_bounds__(256) ct_probe(CtParams p) {
 // Multi-GPU split in K row chunks: where chunk c's tuples of digit d start in the (virtual) split
 // output, starts[(rel * ndigits + d) * (K + 1) + c]; entry K is the end of the digit. Chunk c of a
 // relation is the segment range [first_seg[rel][c], first_seg[rel][c + 1]).
+// The sharded join counts its row shard chunk by chunk (the count of chunk c + 1 runs while chunk c travels): one
+// CTA per split digit scans the digit's counters over THIS chunk's segments only, so the scatter cursors of a
+// chunk are 0-based per (digit, chunk), and appends the digit's total to the running chunk starts
+// starts[(rel * ndig + d) * (K + 1) + c] (same array the host-driven path fills with split_starts).
+struct ChunkScanParams {
+    const uint32_t* counts;
+    uint64_t* cursors;
+    uint64_t* starts;
+    uint32_t cnt_base, nseg_rel;     // the relation's counter block: [digit][segment]
+    uint32_t first_seg, nseg_chunk;  // this chunk's segments inside the relation
+    uint32_t ndig, K, rel;
+    uint32_t chunk;                  // probe relation: writes starts[chunk + 1] (and [0] for chunk 0); the build
+                                     // relation travels whole with chunk 0: all of starts[1 .. K] = its total
+};
+__global__ void __launch_bounds__(256) chunk_scan(ChunkScanParams p) {
+    __shared__ uint64_t sh[33];
+    const uint32_t d = blockIdx.x;
+    const uint64_t idx0 = p.cnt_base + (uint64_t)d * p.nseg_rel + p.first_seg;
+    uint64_t carry = 0;
+    for (uint32_t i0 = 0; i0 < p.nseg_chunk; i0 += 256) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint64_t v = i < p.nseg_chunk ? p.counts[idx0 + i] : 0;
+        uint64_t total;
+        const uint64_t excl = block_excl_scan_u64(v, sh, &total);
+        if (i < p.nseg_chunk) p.cursors[idx0 + i] = carry + excl;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        uint64_t* st = p.starts + ((uint64_t)p.rel * p.ndig + d) * (p.K + 1);
+        if (p.rel == 0) {
+            st[0] = 0;
+            for (uint32_t c = 1; c <= p.K; ++c) st[c] = carry;
+        } else {
+            if (p.chunk == 0) st[0] = 0;
+            st[p.chunk + 1] = (p.chunk == 0 ? 0 : st[p.chunk]) + carry;
+        }
+    }
+}
+
 struct SplitStartsParams {
     const uint64_t* cursors;
     uint64_t* starts;
