@@ -35,6 +35,8 @@ FLAG_SPLIT_LOCAL_TILES = 0x40
 FLAG_L2_TABLES = 0x80
 FLAG_NO_HIST12 = 0x100
 FLAG_COOP_PROBE = 0x200
+FLAG_COUNT_UPFRONT = 0x400
+FLAG_COUNT_PIECEWISE = 0x800
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

@@ -93,18 +93,18 @@ NcclApi* nccl_api() {
     } while (0)
 
 // ---- the device-side layout ------------------------------------------------------------------------
-// all_starts[src][rel][digit][K + 1] (every rank's running chunk starts, chunk_scan, all-gathered): entry c + 1
-// minus entry c = that rank's tuples of (digit, chunk c); the build relation counts as chunk 0. Thread d owns split
-// digit d = owner * d_local + local partition. One launch per piece that travels (`which` = 0: R; 1 + c: chunk c of
-// S), as soon as every rank's counts of that piece have arrived -- later chunks are still being counted then.
+// all_sizes[src][rel][digit][K + 1] (every rank's chunk_scan totals, all-gathered): entry c = that rank's tuples of
+// (digit, chunk c); the build relation counts as chunk 0. Thread d owns split digit d = owner * d_local + local
+// partition. The kernel lays out pieces [which_first, which_last] (0: R; 1 + c: chunk c of S): all of them at once
+// when the shard was counted up front, one per launch when the counts arrive piece by piece.
 struct LayoutParams {
-    const uint64_t* all_starts;
+    const uint64_t* all_sizes;
     uint32_t world, rank, ndig, d_local, K;
-    uint32_t which;
+    uint32_t which_first, which_last;
     ulonglong2* const* peer_build;  // [world]: base of every rank's build window, as mapped HERE
     ulonglong2* const* peer_probe;
     ulonglong2** outd;    // out [(1 + K)][ndig]: destination base of digit d for the R launch (0) and the
-                          // S launch of chunk c (1 + c): base + the scatter's (chunk-local) cursor is the slot
+                          // S launch of chunk c (1 + c): base + the scatter's (piece-local) cursor is the slot
     uint64_t* lb_build;   // out [d_local + 1]: boundaries of this rank's partitions in its build window
     uint64_t* lb_probe;   // out [K][d_local + 1]: ... of chunk c's region of its probe window (absolute)
     uint64_t cap_build, cap_probe;  // this rank's windows, tuples
@@ -116,52 +116,54 @@ __global__ void __launch_bounds__(256) dist_layout(LayoutParams p) {
     __shared__ uint64_t tot[256];     // tuples of digit d in this piece, over all source ranks
     __shared__ uint64_t earlier[256]; // probe: tuples of digit d in the chunks before this one
     const uint32_t d = threadIdx.x, K = p.K, stride = K + 1;
-    const bool probe = p.which > 0;
-    const uint32_t c = probe ? p.which - 1 : 0;
-    uint64_t before = 0;  // ... of the source ranks before this one
-    if (d < p.ndig) {
-        uint64_t t = 0, e = 0;
-        for (uint32_t src = 0; src < p.world; ++src) {
-            const uint64_t* st = p.all_starts + ((uint64_t)(src * 2 + (probe ? 1 : 0)) * p.ndig + d) * stride;
-            const uint64_t n = probe ? st[c + 1] - st[c] : st[K] - st[0];
-            t += n;
-            if (src < p.rank) before += n;
-            if (probe) e += st[c] - st[0];
-        }
-        tot[d] = t;
-        earlier[d] = e;
-    }
-    __syncthreads();
-    if (d >= p.ndig) return;
     const uint32_t owner = d / p.d_local, first = owner * p.d_local, l = d - first;
     const bool mine = owner == p.rank, last = l + 1 == p.d_local;
-    if (!probe) {
-        uint64_t base = 0;
-        for (uint32_t e = first; e < d; ++e) base += tot[e];
-        p.outd[d] = p.peer_build[owner] + base + before;
-        if (mine) {
-            p.lb_build[l] = base;
-            if (last) {
-                p.lb_build[p.d_local] = base + tot[d];
-                if (base + tot[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
+    for (uint32_t which = p.which_first; which <= p.which_last; ++which) {
+        const bool probe = which > 0;
+        const uint32_t c = probe ? which - 1 : 0;
+        uint64_t before = 0;  // ... of the source ranks before this one
+        if (which != p.which_first) __syncthreads();
+        if (d < p.ndig) {
+            uint64_t t = 0, e = 0;
+            for (uint32_t src = 0; src < p.world; ++src) {
+                const uint64_t* sz = p.all_sizes + ((uint64_t)(src * 2 + (probe ? 1 : 0)) * p.ndig + d) * stride;
+                t += sz[c];
+                if (src < p.rank) before += sz[c];
+                for (uint32_t cc = 0; cc < c; ++cc) e += sz[cc];
             }
-            if (tot[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
+            tot[d] = t;
+            earlier[d] = e;
         }
-        return;
-    }
-    // chunk c's region of the owner's probe window starts behind the regions of the chunks before it
-    uint64_t region = 0, pre = 0;
-    for (uint32_t e = first; e < first + p.d_local; ++e) {
-        region += earlier[e];
-        if (e < d) pre += tot[e];
-    }
-    const uint64_t base = region + pre;
-    p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base + before;
-    if (mine) {
-        p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base;
-        if (last) {
-            p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base + tot[d];
-            if (c + 1 == K && base + tot[d] > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+        __syncthreads();
+        if (d >= p.ndig) continue;
+        if (!probe) {
+            uint64_t base = 0;
+            for (uint32_t e = first; e < d; ++e) base += tot[e];
+            p.outd[d] = p.peer_build[owner] + base + before;
+            if (mine) {
+                p.lb_build[l] = base;
+                if (last) {
+                    p.lb_build[p.d_local] = base + tot[d];
+                    if (base + tot[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
+                }
+                if (tot[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
+            }
+            continue;
+        }
+        // chunk c's region of the owner's probe window starts behind the regions of the chunks before it
+        uint64_t region = 0, pre = 0;
+        for (uint32_t e = first; e < first + p.d_local; ++e) {
+            region += earlier[e];
+            if (e < d) pre += tot[e];
+        }
+        const uint64_t base = region + pre;
+        p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base + before;
+        if (mine) {
+            p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base;
+            if (last) {
+                p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base + tot[d];
+                if (c + 1 == K && base + tot[d] > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+            }
         }
     }
 }
@@ -203,6 +205,7 @@ struct phj_dist {
     uint32_t* d_ptflags = nullptr;
     cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_cnt[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
     bool sized = false, have_data = false;
+    bool piecewise = false;  // count the probe chunks behind the first while the pieces before them travel
     size_t n[2] = {0, 0};
     uint64_t sent_remote_bytes = 0;  // this rank's tuples that leave the GPU, from the last sizing pass
     uint32_t resizes = 0;
@@ -284,47 +287,53 @@ int dist_close_peers(phj_dist* D) {
     return PHJ_OK;
 }
 
-// Counting one piece of the row shard (`which` = 0: R; 1 + c: chunk c of S) on `stream`: histogram of the piece's
-// segments by split digit, then chunk_scan: the piece's 0-based scatter cursors and its entry of the chunk starts.
-int dist_enqueue_count_piece(phj_dist* D, uint32_t which, cudaStream_t stream) {
+// Counting pieces [first, last] of the row shard (0: R; 1 + c: chunk c of S) on `stream`: ONE histogram launch
+// over their segments by split digit (the pieces of a relation are consecutive segments; R and S are adjacent too),
+// then chunk_scan: every piece's 0-based scatter cursors and its per-digit sizes.
+int dist_enqueue_count_pieces(phj_dist* D, uint32_t first, uint32_t last, cudaStream_t stream) {
     phj_handle* h = D->split;
     const uint32_t K = D->K;
     if (!h->d_shard_starts) {
         const size_t cap = (size_t)2 * kMaxSplitDigits * (kMaxSplitChunks + 1);
         PHJ_CUDA(cudaMalloc(&h->d_shard_starts, cap * 8));
+        PHJ_CUDA(cudaMemset(h->d_shard_starts, 0, cap * 8));
         PHJ_CUDA(cudaMallocHost(&h->h_shard_starts, cap * 8));
     }
-    const int rel = which ? 1 : 0;
-    const uint32_t c = which ? which - 1 : 0;
     const uint32_t nseg0 = h->nseg1_rel[0];
-    const uint32_t first = which ? h->chunk_first_seg[1][c] : 0;
-    const uint32_t count = which ? h->chunk_first_seg[1][c + 1] - first : nseg0;
+    ChunkScanParams cs{};
+    cs.counts = h->d_counts;
+    cs.cursors = h->d_cursors;
+    cs.sizes = h->d_shard_starts;
+    for (int rel = 0; rel < 2; ++rel) {
+        cs.cnt_base[rel] = h->cnt_base1_rel[rel];
+        cs.nseg_rel[rel] = h->nseg1_rel[rel];
+    }
+    cs.ndig = D->ndig;
+    cs.K = K;
+    cs.piece_first = first;
+    cs.seg_first[0] = 0;
+    cs.seg_count[0] = nseg0;
+    for (uint32_t c = 0; c < K; ++c) {
+        cs.seg_first[1 + c] = h->chunk_first_seg[1][c];
+        cs.seg_count[1 + c] = h->chunk_first_seg[1][c + 1] - h->chunk_first_seg[1][c];
+    }
+    // segments of the pieces in the handle's segment list: R's, then S's
+    const uint32_t seg_lo = first ? nseg0 + cs.seg_first[first] : 0;
+    const uint32_t seg_hi = last ? nseg0 + cs.seg_first[last] + cs.seg_count[last] : nseg0;
     cudaStream_t keep = h->stream;
     h->stream = stream;  // launch_pass and KernelScope follow the handle's stream
     cudaError_t e = cudaSuccess;
-    if (count) {
+    if (seg_hi > seg_lo) {
         PassParams p1{};
         fill_pass1_params(h, p1);
-        p1.seg_first = (which ? nseg0 : 0) + first;
-        p1.seg_count = count;
+        p1.seg_first = seg_lo;
+        p1.seg_count = seg_hi - seg_lo;
         KernelScope ks(h, "radix_histogram[split]");
-        e = launch_pass(h, false, h->b1, p1, count);
+        e = launch_pass(h, false, h->b1, p1, seg_hi - seg_lo);
     }
     if (e == cudaSuccess) {
-        ChunkScanParams cs{};
-        cs.counts = h->d_counts;
-        cs.cursors = h->d_cursors;
-        cs.starts = h->d_shard_starts;
-        cs.cnt_base = h->cnt_base1_rel[rel];
-        cs.nseg_rel = h->nseg1_rel[rel];
-        cs.first_seg = first;
-        cs.nseg_chunk = count;
-        cs.ndig = D->ndig;
-        cs.K = K;
-        cs.rel = (uint32_t)rel;
-        cs.chunk = c;
         KernelScope ks(h, "chunk_scan");
-        chunk_scan<<<D->ndig, 256, 0, stream>>>(cs);
+        chunk_scan<<<dim3(D->ndig, last - first + 1), 256, 0, stream>>>(cs);
         e = cudaGetLastError();
     }
     h->stream = keep;
@@ -332,8 +341,8 @@ int dist_enqueue_count_piece(phj_dist* D, uint32_t which, cudaStream_t stream) {
     return PHJ_OK;
 }
 
-// All-gather of the chunk starts on stream A (5 KB per rank; entries of chunks that are still being counted are in
-// flux and not read by anybody yet). Stream-ordered, so it is also a barrier: when it completes HERE, every rank
+// All-gather of the per-piece sizes on stream A (5 KB per rank; entries of pieces that are still being counted are
+// in flux and not read by anybody yet). Stream-ordered, so it is also a barrier: when it completes HERE, every rank
 // has finished what it had enqueued before it.
 int dist_enqueue_gather(phj_dist* D) {
     NcclApi* nc = nccl_api();
@@ -344,11 +353,10 @@ int dist_enqueue_gather(phj_dist* D) {
     return PHJ_OK;
 }
 
-// The whole count at once on stream A (the sizing pass).
+// The whole count at once on stream A.
 int dist_enqueue_count(phj_dist* D) {
-    int rc;
-    for (uint32_t which = 0; which <= D->K; ++which)
-        if ((rc = dist_enqueue_count_piece(D, which, D->split->stream)) != PHJ_OK) return rc;
+    int rc = dist_enqueue_count_pieces(D, 0, D->K, D->split->stream);
+    if (rc != PHJ_OK) return rc;
     return dist_enqueue_gather(D);
 }
 
@@ -373,8 +381,10 @@ int dist_size(phj_dist* D) {
         for (int src = 0; src < W; ++src)
             for (int rel = 0; rel < 2; ++rel) {
                 const uint64_t* st = D->h_all_starts + (((size_t)src * 2 + rel) * ndig + d) * (K + 1);
-                tot[rel] += st[K] - st[0];
-                if (src == D->rank && (int)(d / dl) != D->rank) mine_remote += st[K] - st[0];
+                uint64_t n = 0;  // per-piece sizes: R has one piece (entry 0), S one per chunk
+                for (uint32_t c = 0; c < (rel ? K : 1); ++c) n += st[c];
+                tot[rel] += n;
+                if (src == D->rank && (int)(d / dl) != D->rank) mine_remote += n;
             }
         need[0][d / dl] += tot[0];
         need[1][d / dl] += tot[1];
@@ -434,20 +444,24 @@ int dist_enqueue_join(phj_dist* D) {
     PHJ_CUDA(cudaEventRecord(D->ev_t[0], sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_flags, 0, 4 * sizeof(unsigned long long), sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_ptflags, 0, 4, sa));
-    // ---- count: R and the first probe chunk on stream A; the other chunks on stream C, behind them, while R and
-    //      the chunks before them travel (the scatter is bound by NVLink, HBM is nearly idle then) ----
-    if ((rc = dist_enqueue_count_piece(D, 0, sa)) != PHJ_OK) return rc;
-    if ((rc = dist_enqueue_count_piece(D, 1, sa)) != PHJ_OK) return rc;
-    PHJ_CUDA(cudaEventRecord(D->ev_cnt[0], sa));
-    PHJ_CUDA(cudaStreamWaitEvent(sc, D->ev_cnt[0], 0));
-    for (uint32_t c = 1; c < K; ++c) {
-        if ((rc = dist_enqueue_count_piece(D, 1 + c, sc)) != PHJ_OK) return rc;
-        PHJ_CUDA(cudaEventRecord(D->ev_cnt[c], sc));
+    // ---- count. Piece-wise (4 GPUs and more: the scatter is bound by NVLink there and leaves SMs and HBM idle):
+    //      R and the first probe chunk on stream A, the other chunks on stream C, behind them, while the pieces
+    //      before them travel. Up front (1-2 GPUs: the GPU is busy throughout, measured 4.50 against 4.07 ms at
+    //      2 GPUs when the later histograms compete with the table build): everything on stream A, one gather ----
+    const bool piecewise = D->piecewise && K > 1;
+    if ((rc = dist_enqueue_count_pieces(D, 0, piecewise ? 1 : K, sa)) != PHJ_OK) return rc;
+    if (piecewise) {
+        PHJ_CUDA(cudaEventRecord(D->ev_cnt[0], sa));
+        PHJ_CUDA(cudaStreamWaitEvent(sc, D->ev_cnt[0], 0));
+        for (uint32_t c = 1; c < K; ++c) {
+            if ((rc = dist_enqueue_count_pieces(D, 1 + c, 1 + c, sc)) != PHJ_OK) return rc;
+            PHJ_CUDA(cudaEventRecord(D->ev_cnt[c], sc));
+        }
     }
     if ((rc = dist_enqueue_gather(D)) != PHJ_OK) return rc;
     PHJ_CUDA(cudaEventRecord(D->ev_t[1], sa));
     LayoutParams lp{};
-    lp.all_starts = D->d_all_starts;
+    lp.all_sizes = D->d_all_starts;
     lp.world = (uint32_t)D->world;
     lp.rank = (uint32_t)D->rank;
     lp.ndig = ndig;
@@ -462,13 +476,13 @@ int dist_enqueue_join(phj_dist* D) {
     lp.cap_probe = D->caps[1][D->rank];
     lp.max_keys = D->max_keys;
     lp.flags = D->d_flags;
-    auto layout = [&](uint32_t which) {
-        lp.which = which;
+    auto layout = [&](uint32_t first, uint32_t last) {
+        lp.which_first = first;
+        lp.which_last = last;
         KernelScope ks(h, "dist_layout");
         dist_layout<<<1, 256, 0, sa>>>(lp);
     };
-    layout(0);
-    layout(1);
+    layout(0, piecewise ? 1 : K);
     // ---- stream B: clear the tables while stream A still scatters R ----
     PHJ_CUDA(cudaEventRecord(D->ev_t[2], sa));
     PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_t[2], 0));  // the build boundaries are ready, the flags are zero
@@ -552,7 +566,7 @@ int dist_enqueue_join(phj_dist* D) {
     for (uint32_t c = 0; c < K; ++c) {
         const uint32_t first = nseg0 + h->chunk_first_seg[1][c], last = nseg0 + h->chunk_first_seg[1][c + 1];
         if ((rc = scatter(first, last - first, 1 + c)) != PHJ_OK) return rc;
-        if (c + 1 < K) {
+        if (piecewise && c + 1 < K) {
             // the all-gather that brings everybody's counts of chunk c + 1 is also the barrier behind chunk c
             PHJ_CUDA(cudaStreamWaitEvent(sa, D->ev_cnt[c + 1], 0));
             if ((rc = dist_enqueue_gather(D)) != PHJ_OK) return rc;
@@ -560,7 +574,7 @@ int dist_enqueue_join(phj_dist* D) {
             return rc;
         }
         PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
-        if (c + 1 < K) layout(2 + c);
+        if (piecewise && c + 1 < K) layout(2 + c, 2 + c);
         PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
         q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
         {
@@ -640,8 +654,12 @@ int dist_alloc(phj_dist* D) {
     PHJ_CUDA(cudaMalloc(&D->d_xchg, (size_t)128 * (1 + D->world)));
     PHJ_CUDA(cudaMallocHost(&D->h_xchg, (size_t)128 * (1 + D->world)));
     PHJ_CUDA(cudaMalloc(&D->d_ptflags, 16));
-    PHJ_CUDA(cudaStreamCreateWithFlags(&D->sb, cudaStreamNonBlocking));
-    PHJ_CUDA(cudaStreamCreateWithFlags(&D->sc, cudaStreamNonBlocking));
+    // CTAs of stream A (the scatter, highest priority) go first whenever an SM slot frees up, then the histograms
+    // of the later chunks (C: a late count would stall the NVLink scatter behind it), then the local join (B)
+    int prio_lo = 0, prio_hi = 0;
+    PHJ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PHJ_CUDA(cudaStreamCreateWithPriority(&D->sb, cudaStreamNonBlocking, prio_lo));
+    PHJ_CUDA(cudaStreamCreateWithPriority(&D->sc, cudaStreamNonBlocking, (prio_lo + prio_hi) / 2));
     for (auto& e : D->ev_cnt) PHJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     PHJ_CUDA(cudaEventCreate(&D->ev_r));
     PHJ_CUDA(cudaEventCreate(&D->ev_local));
@@ -670,6 +688,8 @@ int dist_plan(phj_dist* D) {
     D->b_local = (uint32_t)ilog2_ceil(D->d_local);
     D->K = D->cfg.split_chunks ? D->cfg.split_chunks : 4;
     if (D->K > (uint32_t)kMaxSplitChunks) return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
+    // the later chunks' counts hide behind the exchange only where the exchange leaves the GPU idle (see the join)
+    D->piecewise = (D->cfg.flags & PHJ_FLAG_COUNT_PIECEWISE) || (W >= 4 && !(D->cfg.flags & PHJ_FLAG_COUNT_UPFRONT));
     return PHJ_OK;
 }
 

@@ -32,6 +32,7 @@ namespace phj {
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN marks a free table slot
 constexpr uint32_t kFuse2MaxD2 = 64;  // fused pass-2 histogram: pass 2 of at most 6 bits (with a 6-bit pass 1)
 constexpr uint32_t kFullD1 = 64, kFullD2 = 64;  // radix_histogram_full: two passes of at most 6 bits
+constexpr uint32_t kMaxPieces = 18;  // sharded join: the build relation + up to 16 probe chunks
 
 struct __align__(16) Segment {
     uint64_t begin, end;  // tuple range inside the relation's input array
@@ -1957,43 +1958,34 @@ __global__ void __launch_bounds__(256) ct_probe(CtParams p) {
 // Multi-GPU split in K row chunks: where chunk c's tuples of digit d start in the (virtual) split
 // output, starts[(rel * ndigits + d) * (K + 1) + c]; entry K is the end of the digit. Chunk c of a
 // relation is the segment range [first_seg[rel][c], first_seg[rel][c + 1]).
-// The sharded join counts its row shard chunk by chunk (the count of chunk c + 1 runs while chunk c travels): one
-// CTA per split digit scans the digit's counters over THIS chunk's segments only, so the scatter cursors of a
-// chunk are 0-based per (digit, chunk), and appends the digit's total to the running chunk starts
-// starts[(rel * ndig + d) * (K + 1) + c] (same array the host-driven path fills with split_starts).
+// The sharded join counts its row shard piece by piece (piece 0 = the build relation, piece 1 + c = chunk c of the
+// probe relation; with enough GPUs the count of chunk c + 1 runs while chunk c travels). One CTA per (split digit,
+// piece) scans the digit's counters over THAT piece's segments only, so the scatter cursors of a piece are 0-based
+// per digit, and writes the digit's total to sizes[(rel * ndig + d) * (K + 1) + c] (the build relation: c = 0).
 struct ChunkScanParams {
     const uint32_t* counts;
     uint64_t* cursors;
-    uint64_t* starts;
-    uint32_t cnt_base, nseg_rel;     // the relation's counter block: [digit][segment]
-    uint32_t first_seg, nseg_chunk;  // this chunk's segments inside the relation
-    uint32_t ndig, K, rel;
-    uint32_t chunk;                  // probe relation: writes starts[chunk + 1] (and [0] for chunk 0); the build
-                                     // relation travels whole with chunk 0: all of starts[1 .. K] = its total
+    uint64_t* sizes;
+    uint32_t cnt_base[2], nseg_rel[2];  // a relation's counter block: [digit][segment]
+    uint32_t ndig, K;
+    uint32_t piece_first;               // blockIdx.y = 0 is this piece
+    uint32_t seg_first[kMaxPieces], seg_count[kMaxPieces];  // per piece: its segments inside its relation
 };
 __global__ void __launch_bounds__(256) chunk_scan(ChunkScanParams p) {
     __shared__ uint64_t sh[33];
-    const uint32_t d = blockIdx.x;
-    const uint64_t idx0 = p.cnt_base + (uint64_t)d * p.nseg_rel + p.first_seg;
+    const uint32_t d = blockIdx.x, piece = p.piece_first + blockIdx.y;
+    const uint32_t rel = piece ? 1 : 0, c = piece ? piece - 1 : 0, n = p.seg_count[piece];
+    const uint64_t idx0 = p.cnt_base[rel] + (uint64_t)d * p.nseg_rel[rel] + p.seg_first[piece];
     uint64_t carry = 0;
-    for (uint32_t i0 = 0; i0 < p.nseg_chunk; i0 += 256) {
+    for (uint32_t i0 = 0; i0 < n; i0 += 256) {
         const uint32_t i = i0 + threadIdx.x;
-        const uint64_t v = i < p.nseg_chunk ? p.counts[idx0 + i] : 0;
+        const uint64_t v = i < n ? p.counts[idx0 + i] : 0;
         uint64_t total;
         const uint64_t excl = block_excl_scan_u64(v, sh, &total);
-        if (i < p.nseg_chunk) p.cursors[idx0 + i] = carry + excl;
+        if (i < n) p.cursors[idx0 + i] = carry + excl;
         carry += total;
     }
-    if (threadIdx.x == 0) {
-        uint64_t* st = p.starts + ((uint64_t)p.rel * p.ndig + d) * (p.K + 1);
-        if (p.rel == 0) {
-            st[0] = 0;
-            for (uint32_t c = 1; c <= p.K; ++c) st[c] = carry;
-        } else {
-            if (p.chunk == 0) st[0] = 0;
-            st[p.chunk + 1] = (p.chunk == 0 ? 0 : st[p.chunk]) + carry;
-        }
-    }
+    if (threadIdx.x == 0) p.sizes[((uint64_t)rel * p.ndig + d) * (p.K + 1) + c] = carry;
 }
 
 struct SplitStartsParams {

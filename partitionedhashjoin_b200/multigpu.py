@@ -600,7 +600,7 @@ class ShardedJoin:
     (initialised) or None for a single rank."""
 
     def __init__(self, dist, rank, world, device, partitions=0, chunks=0, hash="xxh3",
-                 hash_seed=0x9E3779B97F4A7C15, table_seed=1, flags=0):
+                 hash_seed=0x9E3779B97F4A7C15, table_seed=1, flags=0, split_ctas=0):
         import ctypes as C
 
         import torch  # noqa: F401  (first: the library then binds the NCCL torch has loaded)
@@ -624,6 +624,7 @@ class ShardedJoin:
         cfg.device = device
         cfg.flags = flags
         cfg.split_chunks = chunks
+        cfg.split_ctas = split_ctas  # SMs of the NVLink scatter while it overlaps the local join (0 = choose)
         self._h = C.c_void_p()
         self._check(self._lib.phj_dist_create(C.byref(cfg), rank, world, ident, C.byref(self._h)))
         self._keep = None

@@ -45,10 +45,14 @@ def check_window(job, oracle, rel_global, which, rank, hash_seed=0x9E3779B97F4A7
 
 def check_library_join(rank, world, local, oracle, R, S, want, shard, mode):
     dist_mod = dist if world > 1 else None
-    for partitions, chunks in ((0, 0), (world * 4, 3), (256, 1), (world, 5)):
+    # both count modes at every world size: piece-wise (later probe chunks counted while the earlier ones travel)
+    # is the default from 4 GPUs on, up front below that
+    from partitionedhashjoin_b200 import _lib
+    for partitions, chunks, flags in ((0, 0, 0), (world * 4, 3, _lib.FLAG_COUNT_PIECEWISE), (256, 1, 0),
+                                      (world, 5, _lib.FLAG_COUNT_UPFRONT), (0, 4, _lib.FLAG_COUNT_PIECEWISE)):
         if partitions and partitions < world:
             continue
-        job = multigpu.ShardedJoin(dist_mod, rank, world, local, partitions=partitions, chunks=chunks)
+        job = multigpu.ShardedJoin(dist_mod, rank, world, local, partitions=partitions, chunks=chunks, flags=flags)
         job.upload(shard(R), shard(S))
         for _ in range(3):
             res = job.join()

@@ -58,7 +58,10 @@ def main():
             args += [ptrs, np.ascontiguousarray(off)]
         remote = int(counts[:, ~own].sum()) * 16
         res = _lib.PhjResult()
-        for _ in range(reps):
+        for it in range(reps):
+            if it:  # a scatter consumes its count
+                again = np.zeros((2, ndig), dtype=np.uint64)
+                check(lib.phj_shard_count(e._h, again.ctypes.data))
             check(lib.phj_shard_scatter(e._h, 0, args[0], args[1].ctypes.data, args[2], args[3].ctypes.data, C.byref(res)))
             kt = dict(e.kernel_times())
             ns_scatter = sum(t for n, t in e.kernel_times() if "scatter" in n)

@@ -3,7 +3,7 @@
     python tools/probe_dist.py                               one rank on GPU 0
     torchrun --nproc-per-node N tools/probe_dist.py          one rank per GPU
 
-Env: NR / NS tuples per rank, ALPHA, PARTS (GPUs x local partitions, 0 = default), CHUNKS, JOINS.
+Env: NR / NS tuples per rank, ALPHA, CONFIGS (partitions:chunks,...), JOINS, FLAGS (phj_config.flags, e.g. 0x800).
 """
 import json
 import os
@@ -30,11 +30,14 @@ def main():
     joins = int(os.environ.get("JOINS", 6))
     dR = phj.DeviceTuples(nr, local).fill_sequential(1 + rank * nr)
     dS = phj.DeviceTuples(ns, local).fill_zipf(alpha, 1, world * nr, 12345 + 7919 * rank, 1 << 14)
-    for parts, chunks in [tuple(int(x) for x in pc.split(":")) for pc in
-                          os.environ.get("CONFIGS", "0:4,0:1,0:8,128:4,256:4").split(",")]:
+    for cfg in os.environ.get("CONFIGS", "0:4,0:1,0:8,128:4,256:4").split(","):
+        # partitions : chunks [: flags [: scatter SMs]]
+        f = [int(x, 0) for x in cfg.split(":")] + [0, 0]
+        parts, chunks, flags, split_ctas = f[0], f[1], f[2] or int(os.environ.get("FLAGS", "0"), 0), f[3]
         if parts and parts < world:
             continue
-        job = multigpu.ShardedJoin(dist, rank, world, local, partitions=parts, chunks=chunks)
+        job = multigpu.ShardedJoin(dist, rank, world, local, partitions=parts, chunks=chunks, flags=flags,
+                                   split_ctas=split_ctas)
         job.bind_device(dR.ptr, nr, dS.ptr, ns, keepalive=(dR, dS))
         best = None
         for _ in range(joins):
@@ -50,7 +53,8 @@ def main():
             worst = best["total_ns"]
         if rank == 0:
             lay = job.info()
-            print(f"== world {world} partitions {lay['digits']} ({lay['local_partitions']}/GPU) chunks {lay['chunks']}: "
+            print(f"== world {world} partitions {lay['digits']} ({lay['local_partitions']}/GPU) chunks {lay['chunks']} "
+                  f"flags {flags:#x} scatter SMs {split_ctas or 'auto'}: "
                   f"total {worst / 1e6:.3f} ms (rank 0: {best['total_ns'] / 1e6:.3f}) count {best['count_ns'] / 1e6:.3f} "
                   f"shuffle {best['shuffle_ns'] / 1e6:.3f} build {best['build_ns'] / 1e6:.3f} probe {best['probe_ns'] / 1e6:.3f} "
                   f"-> {world * (nr + ns) / (worst / 1e9) / 1e9:.2f} G tuples/s; sent {best['shuffle_bytes'] / 1e9:.2f} GB "
