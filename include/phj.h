@@ -130,10 +130,10 @@ typedef struct {
                                       lanes per key (shuffle broadcast + one 8-byte slot per lane + ballot) instead
                                       of one thread per key reading the 32-byte bucket with one 256-bit load.
                                       Kept for the A/B in DESIGN.md section 4; the per-thread probe is faster. */
-#define PHJ_FLAG_COUNT_UPFRONT 0x400u   /* sharded join: histogram the whole row shard before anything travels */
-#define PHJ_FLAG_COUNT_PIECEWISE 0x800u /* sharded join: count probe chunk c + 1 while chunk c travels (default from
-                                         * 4 GPUs on, where the exchange is bound by NVLink; with 1-2 GPUs the later
-                                         * histograms compete with the table build: 4.50 against 4.07 ms at 2 GPUs) */
+#define PHJ_FLAG_COUNT_UPFRONT 0x400u   /* sharded join: histogram the whole row shard before anything travels (default) */
+#define PHJ_FLAG_COUNT_PIECEWISE 0x800u /* sharded join: count probe chunk c + 1 while chunk c travels. Hides 0.3 ms of
+                                         * counting and gives it back through a slower shuffle: 5.81 against 5.87 ms at
+                                         * 8 GPUs, slower at 2 (profiles/r02_multigpu.md). Opt-in, tested. */
 #define PHJ_FLAG_NO_HIST12 0x100u /* two-pass plans: do not take both passes' histograms from one read
                                      (radix_histogram_full); the pass-1 scatter counts for pass 2 instead */
 

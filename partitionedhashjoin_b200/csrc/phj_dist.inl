@@ -444,10 +444,12 @@ int dist_enqueue_join(phj_dist* D) {
     PHJ_CUDA(cudaEventRecord(D->ev_t[0], sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_flags, 0, 4 * sizeof(unsigned long long), sa));
     PHJ_CUDA(cudaMemsetAsync(D->d_ptflags, 0, 4, sa));
-    // ---- count. Piece-wise (4 GPUs and more: the scatter is bound by NVLink there and leaves SMs and HBM idle):
-    //      R and the first probe chunk on stream A, the other chunks on stream C, behind them, while the pieces
-    //      before them travel. Up front (1-2 GPUs: the GPU is busy throughout, measured 4.50 against 4.07 ms at
-    //      2 GPUs when the later histograms compete with the table build): everything on stream A, one gather ----
+    // ---- count. Up front (the default): the whole row shard on stream A, one gather, one layout launch.
+    //      Piece-wise (PHJ_FLAG_COUNT_PIECEWISE): R and the first probe chunk on stream A, the other chunks on
+    //      stream C while the pieces before them travel, the gather of chunk c + 1's sizes doubling as the barrier
+    //      behind chunk c: 0.3 ms less exposed counting, paid back by a slower shuffle (the histograms take SMs
+    //      and HBM from the scatter: 569 instead of 590 GB/s) and 70 us more per chunk boundary -- 5.81 against
+    //      5.87 ms at 8 GPUs; at 2 GPUs the GPU is busy throughout and it loses (profiles/r02_multigpu.md). ----
     const bool piecewise = D->piecewise && K > 1;
     if ((rc = dist_enqueue_count_pieces(D, 0, piecewise ? 1 : K, sa)) != PHJ_OK) return rc;
     if (piecewise) {
@@ -573,8 +575,11 @@ int dist_enqueue_join(phj_dist* D) {
         } else if ((rc = barrier()) != PHJ_OK) {
             return rc;
         }
-        PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
+        // The probe of chunk c is released right in front of the launch of the next scatter, never earlier: its
+        // CTAs spread over every free SM, and a scatter CTA needs a whole one (measured at 8 GPUs with the layout
+        // kernel in between: 1.76 instead of 1.16 ms per chunk).
         if (piecewise && c + 1 < K) layout(2 + c, 2 + c);
+        PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
         PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
         q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
         {
@@ -688,8 +693,8 @@ int dist_plan(phj_dist* D) {
     D->b_local = (uint32_t)ilog2_ceil(D->d_local);
     D->K = D->cfg.split_chunks ? D->cfg.split_chunks : 4;
     if (D->K > (uint32_t)kMaxSplitChunks) return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
-    // the later chunks' counts hide behind the exchange only where the exchange leaves the GPU idle (see the join)
-    D->piecewise = (D->cfg.flags & PHJ_FLAG_COUNT_PIECEWISE) || (W >= 4 && !(D->cfg.flags & PHJ_FLAG_COUNT_UPFRONT));
+    // counting the later chunks behind the exchange is opt-in: a wash at 8 GPUs, slower at 2 (see the join)
+    D->piecewise = (D->cfg.flags & PHJ_FLAG_COUNT_PIECEWISE) && !(D->cfg.flags & PHJ_FLAG_COUNT_UPFRONT);
     return PHJ_OK;
 }
 

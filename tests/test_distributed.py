@@ -21,9 +21,14 @@ def free_port():
 
 
 def torchrun(world, script, *args, timeout=300):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), script, *args]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    for attempt in range(3):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), script, *args]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        # the probed port can be taken again (an NCCL bootstrap socket of the run before) by the time torchrun binds it
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
+    return r
 
 
 @pytest.mark.parametrize("world,case", [(2, "random"), (2, "skewed"), (2, "tiny"), (4, "random"), (1, "random")])
