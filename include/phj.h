@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PHJ_ABI_VERSION 4
+#define PHJ_ABI_VERSION 5
 
 /* Common::Tuple (src/Common/Table.hpp:20-25): alignas(16) {int64 id; int64 payload}. */
 typedef struct {
@@ -134,6 +134,9 @@ typedef struct {
 #define PHJ_FLAG_COUNT_PIECEWISE 0x800u /* sharded join: count probe chunk c + 1 while chunk c travels. Hides 0.3 ms of
                                          * counting and gives it back through a slower shuffle: 5.81 against 5.87 ms at
                                          * 8 GPUs, slower at 2 (profiles/r02_multigpu.md). Opt-in, tested. */
+#define PHJ_FLAG_HOT_DIGITS 0x1000u /* sharded join: split digits whose probe side alone outweighs a quarter of one
+                                     * rank's fair share (Zipf heavy hitters) keep their probe tuples where they
+                                     * are; their build partition is replicated to every rank */
 #define PHJ_FLAG_NO_HIST12 0x100u /* two-pass plans: do not take both passes' histograms from one read
                                      (radix_histogram_full); the pass-1 scatter counts for pass 2 instead */
 
@@ -315,9 +318,11 @@ int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, u
 int phj_dist_measure_peer_copy(phj_dist* d, uint64_t bytes, uint32_t repeats, uint64_t* ns_per_copy);
 
 /* How the last join laid this rank's data out, and test read-back of its windows: `which` 0 = build
- * (bounds: local_partitions + 1), 1 = probe (bounds: chunks x (local_partitions + 1), absolute positions:
+ * (bounds: partitions_here + 1), 1 = probe (bounds: chunks x (partitions_here + 1), absolute positions:
  * chunk c's tuples of local partition l lie at [bounds[c][l], bounds[c][l + 1]), ordered by source rank,
- * then input order). The window's used prefix (bounds' last entry) is copied to `out` when it is given. */
+ * then input order). Partitions [local_partitions, partitions_here) are the hot digits of other owners in digit
+ * order: the whole build partition (copied from its owner), this rank's own probe tuples. The window's used
+ * prefix (bounds' last entry) is copied to `out` when it is given. */
 typedef struct {
     uint32_t world, rank;
     uint32_t digits;            /* split digits = world x local_partitions; owner = digit / local_partitions */
@@ -326,8 +331,11 @@ typedef struct {
     uint32_t region_buckets;    /* 32-byte buckets per local partition's table */
     uint64_t window_tuples[2];  /* capacity of this rank's build / probe window */
     uint32_t resizes;           /* host-synchronous sizing passes that re-allocated a window so far */
-    uint32_t reserved;
+    uint32_t partitions_here;   /* partitions in this rank's windows: local_partitions + the hot digits of other owners */
     uint64_t sent_remote_bytes;
+    uint32_t hot_count;         /* PHJ_FLAG_HOT_DIGITS: split digits kept local / replicated, ascending */
+    uint32_t hot_digits[32];
+    uint32_t reserved;
 } phj_dist_layout;
 int phj_dist_info(phj_dist* d, phj_dist_layout* out);
 int phj_dist_read_window(phj_dist* d, int32_t which, phj_tuple* out, uint64_t cap_tuples, uint64_t* bounds);

@@ -37,6 +37,7 @@ FLAG_NO_HIST12 = 0x100
 FLAG_COOP_PROBE = 0x200
 FLAG_COUNT_UPFRONT = 0x400
 FLAG_COUNT_PIECEWISE = 0x800
+FLAG_HOT_DIGITS = 0x1000
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 
@@ -102,8 +103,11 @@ class PhjDistLayout(C.Structure):
         ("region_buckets", C.c_uint32),
         ("window_tuples", C.c_uint64 * 2),
         ("resizes", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("partitions_here", C.c_uint32),
         ("sent_remote_bytes", C.c_uint64),
+        ("hot_count", C.c_uint32),
+        ("hot_digits", C.c_uint32 * 32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -97,6 +97,21 @@ NcclApi* nccl_api() {
 // (digit, chunk c); the build relation counts as chunk 0. Thread d owns split digit d = owner * d_local + local
 // partition. The kernel lays out pieces [which_first, which_last] (0: R; 1 + c: chunk c of S): all of them at once
 // when the shard was counted up front, one per launch when the counts arrive piece by piece.
+//
+// Heavy hitters (PHJ_FLAG_HOT_DIGITS, SURVEY.md 8e "skew caveat"): the sizing pass marks the split digits whose
+// probe side alone outweighs a quarter of one rank's fair share (key 1 at Zipf 1.25 is 22 % of S) as HOT. Their
+// probe tuples do not travel -- every rank keeps its own in an extra partition behind the partitions it owns --
+// and their (small, never skewed) build partition is copied from the owner's window to every other rank after
+// R has landed (dist_pull). A rank's window: its d_local owned partitions (a hot one holds only the rank's own
+// probe tuples), then one partition per hot digit of another owner, in digit order.
+constexpr int kMaxHot = 32;
+
+struct PullDesc {
+    const ulonglong2* src;  // a hot digit's build partition in its owner's window, as mapped here
+    ulonglong2* dst;        // its place in this rank's build window
+    unsigned long long n;
+};
+
 struct LayoutParams {
     const uint64_t* all_sizes;
     uint32_t world, rank, ndig, d_local, K;
@@ -105,34 +120,57 @@ struct LayoutParams {
     ulonglong2* const* peer_probe;
     ulonglong2** outd;    // out [(1 + K)][ndig]: destination base of digit d for the R launch (0) and the
                           // S launch of chunk c (1 + c): base + the scatter's (piece-local) cursor is the slot
-    uint64_t* lb_build;   // out [d_local + 1]: boundaries of this rank's partitions in its build window
-    uint64_t* lb_probe;   // out [K][d_local + 1]: ... of chunk c's region of its probe window (absolute)
+    uint64_t* lb_build;   // out [np + 1]: boundaries of this rank's partitions in its build window
+    uint64_t* lb_probe;   // out [K][np + 1]: ... of chunk c's region of its probe window (absolute)
     uint64_t cap_build, cap_probe;  // this rank's windows, tuples
     uint32_t max_keys;              // largest build partition the tables accept
     unsigned long long* flags;      // [1] += 1 if a window is too small, [2] += oversize partitions
+    uint32_t np;                    // partitions of this rank: d_local + the hot digits of other owners
+    uint32_t n_hot;
+    uint32_t hot[kMaxHot];          // ascending
+    PullDesc* pulls;                // out [np - d_local]
 };
 
 __global__ void __launch_bounds__(256) dist_layout(LayoutParams p) {
-    __shared__ uint64_t tot[256];     // tuples of digit d in this piece, over all source ranks
-    __shared__ uint64_t earlier[256]; // probe: tuples of digit d in the chunks before this one
-    const uint32_t d = threadIdx.x, K = p.K, stride = K + 1;
-    const uint32_t owner = d / p.d_local, first = owner * p.d_local, l = d - first;
-    const bool mine = owner == p.rank, last = l + 1 == p.d_local;
+    __shared__ uint64_t tot[256];      // tuples of digit d in this piece that land in its OWNER's window
+    __shared__ uint64_t earlier[256];  // probe: the same over the chunks before this one
+    __shared__ uint64_t own[256];      // probe: this rank's own tuples of digit d in this piece
+    __shared__ uint32_t is_hot[256];
+    const uint32_t d = threadIdx.x, K = p.K, stride = K + 1, dl = p.d_local;
+    const uint32_t owner = d / dl, first = owner * dl, l = d - first, my_first = p.rank * dl;
+    const bool mine = owner == p.rank, last = l + 1 == dl;
+    is_hot[d] = 0;
+    __syncthreads();
+    if (d < p.n_hot) is_hot[p.hot[d]] = 1;
+    __syncthreads();
+    // this rank's extra partitions: the hot digits of other owners, in digit order
+    uint32_t j = 0, n_foreign = 0;
+    for (uint32_t i = 0; i < p.n_hot; ++i) {
+        const uint32_t e = p.hot[i];
+        if (e / dl == p.rank) continue;
+        ++n_foreign;
+        if (e < d) ++j;
+    }
+    const bool foreign_hot = d < p.ndig && is_hot[d] && !mine;           // extra partition j of this rank
+    const bool final_part = n_foreign ? (foreign_hot && j + 1 == n_foreign) : (mine && last);
     for (uint32_t which = p.which_first; which <= p.which_last; ++which) {
         const bool probe = which > 0;
         const uint32_t c = probe ? which - 1 : 0;
-        uint64_t before = 0;  // ... of the source ranks before this one
+        uint64_t before = 0;  // ... of the source ranks before this one, in the owner's window
         if (which != p.which_first) __syncthreads();
         if (d < p.ndig) {
+            const bool stays = probe && is_hot[d];  // a hot digit's probe tuples stay where they are
             uint64_t t = 0, e = 0;
             for (uint32_t src = 0; src < p.world; ++src) {
+                if (stays && src != owner) continue;
                 const uint64_t* sz = p.all_sizes + ((uint64_t)(src * 2 + (probe ? 1 : 0)) * p.ndig + d) * stride;
                 t += sz[c];
-                if (src < p.rank) before += sz[c];
+                if (src < p.rank && !stays) before += sz[c];
                 for (uint32_t cc = 0; cc < c; ++cc) e += sz[cc];
             }
             tot[d] = t;
             earlier[d] = e;
+            own[d] = p.all_sizes[((uint64_t)(p.rank * 2 + (probe ? 1 : 0)) * p.ndig + d) * stride + c];
         }
         __syncthreads();
         if (d >= p.ndig) continue;
@@ -142,30 +180,69 @@ __global__ void __launch_bounds__(256) dist_layout(LayoutParams p) {
             p.outd[d] = p.peer_build[owner] + base + before;
             if (mine) {
                 p.lb_build[l] = base;
-                if (last) {
-                    p.lb_build[p.d_local] = base + tot[d];
-                    if (base + tot[d] > p.cap_build) atomicAdd(&p.flags[1], 1ull);
-                }
-                if (tot[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
+                if (last) p.lb_build[dl] = base + tot[d];
             }
+            uint64_t end = base + tot[d];
+            if (foreign_hot) {
+                uint64_t eb = 0;  // behind the owned partitions and the extra partitions before this one
+                for (uint32_t e = my_first; e < my_first + dl; ++e) eb += tot[e];
+                for (uint32_t i = 0; i < p.n_hot; ++i)
+                    if (p.hot[i] < d && p.hot[i] / dl != p.rank) eb += tot[p.hot[i]];
+                end = eb + tot[d];
+                p.lb_build[dl + j + 1] = end;
+                PullDesc pd;
+                pd.src = p.peer_build[owner] + base;
+                pd.dst = p.peer_build[p.rank] + eb;
+                pd.n = tot[d];
+                p.pulls[j] = pd;
+            }
+            if ((mine || foreign_hot) && tot[d] > p.max_keys) atomicAdd(&p.flags[2], 1ull);
+            if (final_part && end > p.cap_build) atomicAdd(&p.flags[1], 1ull);
             continue;
         }
-        // chunk c's region of the owner's probe window starts behind the regions of the chunks before it
-        uint64_t region = 0, pre = 0;
-        for (uint32_t e = first; e < first + p.d_local; ++e) {
+        // The window this digit's tuples go to: the owner's, or -- hot digit -- this rank's own. Chunk c's region of
+        // rank w's probe window starts behind the regions of the chunks before it: w's owned partitions plus w's own
+        // tuples of the hot digits it does not own.
+        const bool stays = is_hot[d] != 0;
+        const uint32_t w = stays ? p.rank : owner, wfirst = w * dl;
+        uint64_t region = 0, owned = 0;
+        for (uint32_t e = wfirst; e < wfirst + dl; ++e) {
             region += earlier[e];
-            if (e < d) pre += tot[e];
+            owned += tot[e];
         }
-        const uint64_t base = region + pre;
-        p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[owner] + base + before;
-        if (mine) {
-            p.lb_probe[(uint64_t)c * (p.d_local + 1) + l] = base;
-            if (last) {
-                p.lb_probe[(uint64_t)c * (p.d_local + 1) + p.d_local] = base + tot[d];
-                if (c + 1 == K && base + tot[d] > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
+        for (uint32_t i = 0; i < p.n_hot; ++i) {
+            const uint32_t h = p.hot[i];
+            if (h / dl == w) continue;
+            const uint64_t* sz = p.all_sizes + ((uint64_t)(w * 2 + 1) * p.ndig + h) * stride;
+            for (uint32_t cc = 0; cc < c; ++cc) region += sz[cc];
+        }
+        uint64_t base, end;
+        if (!foreign_hot) {  // among w's owned partitions
+            uint64_t pre = 0;
+            for (uint32_t e = wfirst; e < d; ++e) pre += tot[e];
+            base = region + pre;
+            end = base + tot[d];
+            if (mine) {
+                p.lb_probe[(uint64_t)c * (p.np + 1) + l] = base;
+                if (last) p.lb_probe[(uint64_t)c * (p.np + 1) + dl] = end;
             }
+        } else {             // extra partition j of this rank: its own tuples of a hot digit
+            base = region + owned;
+            for (uint32_t i = 0; i < p.n_hot; ++i)
+                if (p.hot[i] < d && p.hot[i] / dl != p.rank) base += own[p.hot[i]];
+            end = base + own[d];
+            p.lb_probe[(uint64_t)c * (p.np + 1) + dl + j + 1] = end;
         }
+        p.outd[(uint64_t)(1 + c) * p.ndig + d] = p.peer_probe[w] + base + before;
+        if (c + 1 == K && final_part && end > p.cap_probe) atomicAdd(&p.flags[1], 1ull);
     }
+}
+
+// Copies the build partitions of the hot digits of other owners into this rank's window (after R's barrier).
+__global__ void __launch_bounds__(256) dist_pull(const PullDesc* __restrict__ pulls) {
+    const PullDesc pd = pulls[blockIdx.y];
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < pd.n; i += (uint64_t)gridDim.x * 256)
+        pd.dst[i] = pd.src[i];
 }
 
 }  // namespace
@@ -206,6 +283,10 @@ struct phj_dist {
     cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_cnt[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
     bool sized = false, have_data = false;
     bool piecewise = false;  // count the probe chunks behind the first while the pieces before them travel
+    // heavy hitters (PHJ_FLAG_HOT_DIGITS): decided by the sizing pass, identically on every rank
+    uint32_t n_hot = 0, hot[kMaxHot] = {};
+    uint32_t np = 1;               // partitions of this rank: d_local + the hot digits of other owners
+    PullDesc* d_pulls = nullptr;
     size_t n[2] = {0, 0};
     uint64_t sent_remote_bytes = 0;  // this rank's tuples that leave the GPU, from the last sizing pass
     uint32_t resizes = 0;
@@ -374,22 +455,49 @@ int dist_size(phj_dist* D) {
     PHJ_CUDA(cudaMemcpyAsync(D->h_all_starts, D->d_all_starts, total * 8, cudaMemcpyDeviceToHost, h->stream));
     PHJ_CUDA(cudaStreamSynchronize(h->stream));
     PHJ_CUDA(cudaGetLastError());
+    // per (source, relation, digit): tuples over all pieces (R has one piece, entry 0; S one per chunk)
+    auto size_of = [&](int src, int rel, uint32_t d) {
+        const uint64_t* st = D->h_all_starts + (((size_t)src * 2 + rel) * ndig + d) * (K + 1);
+        uint64_t n = 0;
+        for (uint32_t c = 0; c < (rel ? K : 1); ++c) n += st[c];
+        return n;
+    };
+    std::vector<uint64_t> tot_r(ndig, 0), tot_s(ndig, 0);
+    uint64_t total_s = 0;
+    for (uint32_t d = 0; d < ndig; ++d)
+        for (int src = 0; src < W; ++src) {
+            tot_r[d] += size_of(src, 0, d);
+            tot_s[d] += size_of(src, 1, d);
+        }
+    for (uint32_t d = 0; d < ndig; ++d) total_s += tot_s[d];
+    // Heavy hitters: split digits whose probe side alone outweighs a quarter of one rank's fair share. Never the case
+    // for uniform keys (a digit is world / digits of a share); key 1 at Zipf 1.25 is 22 % of S. Every rank derives the
+    // same set from the same all-gathered sizes.
+    D->n_hot = 0;
+    if ((D->cfg.flags & PHJ_FLAG_HOT_DIGITS) && W > 1 && ndig > (uint32_t)W)
+        for (uint32_t d = 0; d < ndig && D->n_hot < (uint32_t)kMaxHot; ++d)
+            if (tot_s[d] * (uint64_t)W * 4 > std::max<uint64_t>(total_s, 1)) D->hot[D->n_hot++] = d;
+    std::vector<bool> is_hot(ndig, false);
+    for (uint32_t i = 0; i < D->n_hot; ++i) is_hot[D->hot[i]] = true;
     uint64_t need[2][kMaxRanks] = {};
     uint64_t max_part = 0, mine_remote = 0;
     for (uint32_t d = 0; d < ndig; ++d) {
-        uint64_t tot[2] = {0, 0};
-        for (int src = 0; src < W; ++src)
-            for (int rel = 0; rel < 2; ++rel) {
-                const uint64_t* st = D->h_all_starts + (((size_t)src * 2 + rel) * ndig + d) * (K + 1);
-                uint64_t n = 0;  // per-piece sizes: R has one piece (entry 0), S one per chunk
-                for (uint32_t c = 0; c < (rel ? K : 1); ++c) n += st[c];
-                tot[rel] += n;
-                if (src == D->rank && (int)(d / dl) != D->rank) mine_remote += n;
+        const int owner = (int)(d / dl);
+        max_part = std::max(max_part, tot_r[d]);
+        if (owner != D->rank) mine_remote += size_of(D->rank, 0, d) + (is_hot[d] ? 0 : size_of(D->rank, 1, d));
+        for (int r = 0; r < W; ++r) {
+            if (r == owner) {
+                need[0][r] += tot_r[d];
+                need[1][r] += is_hot[d] ? size_of(r, 1, d) : tot_s[d];
+            } else if (is_hot[d]) {  // an extra partition: the build side pulled from the owner, the own probe tuples
+                need[0][r] += tot_r[d];
+                need[1][r] += size_of(r, 1, d);
             }
-        need[0][d / dl] += tot[0];
-        need[1][d / dl] += tot[1];
-        max_part = std::max(max_part, tot[0]);
+        }
     }
+    D->np = dl;
+    for (uint32_t i = 0; i < D->n_hot; ++i)
+        if ((int)(D->hot[i] / dl) != D->rank) ++D->np;
     D->sent_remote_bytes = 16 * mine_remote;
     bool grow_any = false, grow_mine[2] = {false, false};
     for (int w = 0; w < 2; ++w)
@@ -419,9 +527,9 @@ int dist_size(phj_dist* D) {
     // tables: load <= 0.5 at the largest build partition seen (duplicates only lower it), 10 % to spare
     uint32_t rb = 64;
     while ((uint64_t)rb * 2 < max_part + max_part / 10) rb <<= 1;
-    if (rb != D->region_buckets || !D->d_pt) {
-        const size_t want = (size_t)dl * rb * 4;
-        if (want > D->cap_pt) {
+    {
+        const size_t want = (size_t)D->np * rb * 4;  // one region per partition of this rank
+        if (want > D->cap_pt || !D->d_pt) {
             if (D->d_pt) PHJ_CUDA(cudaFree(D->d_pt));
             D->d_pt = nullptr;
             PHJ_CUDA(cudaMalloc(&D->d_pt, want * 8));
@@ -472,8 +580,13 @@ int dist_enqueue_join(phj_dist* D) {
     lp.peer_build = D->d_peer;
     lp.peer_probe = D->d_peer + kMaxRanks;
     lp.outd = D->d_outd;
+    const uint32_t np = D->np;  // this rank's partitions: the owned ones + the hot digits of other owners
     lp.lb_build = D->d_lb;
-    lp.lb_probe = D->d_lb + (dl + 1);
+    lp.lb_probe = D->d_lb + (np + 1);
+    lp.np = np;
+    lp.n_hot = D->n_hot;
+    for (uint32_t i = 0; i < D->n_hot; ++i) lp.hot[i] = D->hot[i];
+    lp.pulls = D->d_pulls;
     lp.cap_build = D->caps[0][D->rank];
     lp.cap_probe = D->caps[1][D->rank];
     lp.max_keys = D->max_keys;
@@ -509,7 +622,7 @@ int dist_enqueue_join(phj_dist* D) {
     }
     {
         KernelScope ks(h, "pt_clear", 1, sb);
-        gt_clear<<<grid_l, 256, 0, sb>>>(D->d_pt, (uint64_t)dl * D->region_buckets * 4);
+        gt_clear<<<grid_l, 256, 0, sb>>>(D->d_pt, (uint64_t)np * D->region_buckets * 4);
     }
 
     // ---- stream A: R, then S chunk by chunk, into the owners' windows ----
@@ -536,13 +649,18 @@ int dist_enqueue_join(phj_dist* D) {
     };
     if ((rc = scatter(0, nseg0, 0)) != PHJ_OK) return rc;
     if ((rc = barrier()) != PHJ_OK) return rc;
+    if (np > dl) {
+        // heavy hitters: their build partitions, complete in the owners' windows now, are copied here
+        KernelScope ks(h, "dist_pull");
+        dist_pull<<<dim3(64, np - dl), 256, 0, sa>>>(D->d_pulls);
+    }
     PHJ_CUDA(cudaEventRecord(D->ev_r, sa));
 
     PtParams q{};
     q.build = reinterpret_cast<const ulonglong2*>(D->win[0]);
     q.probe = reinterpret_cast<const ulonglong2*>(D->win[1]);
     q.bounds_build = D->d_lb;
-    q.npart = dl;
+    q.npart = np;
     q.max_keys = D->max_keys;
     q.table_mul = (h->cfg.table_seed * 0x9E3779B97F4A7C15ULL) | 1ULL;
     if (h->cfg.table_seed == 0) q.table_mul = 0xBF58476D1CE4E5B9ULL;
@@ -551,6 +669,12 @@ int dist_enqueue_join(phj_dist* D) {
         const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
         const uint64_t digit = hash_key_dyn(h->cfg.hash, kEmptyKey, hp) & (ndig - 1);
         q.sentinel_part = digit / dl == (uint64_t)D->rank ? (uint32_t)(digit % dl) : 0xffffffffu;
+        uint32_t extra = dl;  // ... or one of the hot digits of other owners kept here
+        for (uint32_t i = 0; i < D->n_hot; ++i) {
+            if (D->hot[i] / dl == (uint32_t)D->rank) continue;
+            if (D->hot[i] == digit) q.sentinel_part = extra;
+            ++extra;
+        }
     }
     q.table = D->d_pt;
     q.region_buckets = D->region_buckets;
@@ -558,7 +682,7 @@ int dist_enqueue_join(phj_dist* D) {
     q.flags = D->d_ptflags;
     q.matches = D->d_flags;
     PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_r, 0));
-    q.bounds_probe = D->d_lb + (dl + 1);
+    q.bounds_probe = D->d_lb + (np + 1);
     {
         KernelScope ks(h, "pt_build", 1, sb);
         pt_build<256><<<grid_l, 256, 0, sb>>>(q);
@@ -581,7 +705,7 @@ int dist_enqueue_join(phj_dist* D) {
         if (piecewise && c + 1 < K) layout(2 + c, 2 + c);
         PHJ_CUDA(cudaEventRecord(D->ev_c[c], sa));
         PHJ_CUDA(cudaStreamWaitEvent(sb, D->ev_c[c], 0));
-        q.bounds_probe = D->d_lb + (dl + 1) + (size_t)c * (dl + 1);
+        q.bounds_probe = D->d_lb + (np + 1) + (size_t)c * (np + 1);
         {
             // the last chunk's probe runs after the last scatter: it gets the whole GPU
             const uint32_t grid_p = c + 1 == K ? (uint32_t)h->sm_count * 6 : grid_l;  // one wave: six CTAs per SM
@@ -652,7 +776,8 @@ int dist_alloc(phj_dist* D) {
     PHJ_CUDA(cudaMallocHost(&D->h_all_starts, total * 8));
     PHJ_CUDA(cudaMalloc(&D->d_peer, sizeof(ulonglong2*) * 2 * kMaxRanks));
     PHJ_CUDA(cudaMalloc(&D->d_outd, sizeof(ulonglong2*) * (size_t)(1 + D->K) * D->ndig));
-    PHJ_CUDA(cudaMalloc(&D->d_lb, 8 * (size_t)(1 + D->K) * (D->d_local + 1)));
+    PHJ_CUDA(cudaMalloc(&D->d_lb, 8 * (size_t)(1 + D->K) * (D->d_local + kMaxHot + 1)));
+    PHJ_CUDA(cudaMalloc(&D->d_pulls, sizeof(PullDesc) * kMaxHot));
     PHJ_CUDA(cudaMalloc(&D->d_flags, 16 * sizeof(unsigned long long)));
     PHJ_CUDA(cudaMemset(D->d_flags, 0, 16 * sizeof(unsigned long long)));
     PHJ_CUDA(cudaMallocHost(&D->h_flags, 8 * sizeof(unsigned long long)));
@@ -724,7 +849,7 @@ void dist_free(phj_dist* D) {
     if (D->comm && D->own_comm && nccl_api()) nccl_api()->CommDestroy(D->comm);
     for (int w = 0; w < 2; ++w)
         if (D->win[w]) cudaFree(D->win[w]);
-    void* dev[] = {D->d_all_starts, D->d_peer, D->d_outd, D->d_lb, D->d_flags, D->d_xchg, D->d_pt, D->d_ptflags};
+    void* dev[] = {D->d_all_starts, D->d_peer, D->d_outd, D->d_lb, D->d_flags, D->d_xchg, D->d_pt, D->d_ptflags, D->d_pulls};
     for (void* p : dev)
         if (p) cudaFree(p);
     if (D->h_all_starts) cudaFreeHost(D->h_all_starts);
@@ -1036,6 +1161,9 @@ int phj_dist_info(phj_dist* d, phj_dist_layout* out) {
     out->window_tuples[1] = d->caps[1][d->rank];
     out->resizes = d->resizes;
     out->sent_remote_bytes = d->sent_remote_bytes;
+    out->partitions_here = d->np;
+    out->hot_count = d->n_hot;
+    for (uint32_t i = 0; i < d->n_hot; ++i) out->hot_digits[i] = d->hot[i];
     return PHJ_OK;
 }
 
@@ -1044,10 +1172,10 @@ int phj_dist_read_window(phj_dist* d, int32_t which, phj_tuple* out, uint64_t ca
     if (which < 0 || which > 1) return fail(PHJ_ERR_INVALID, "which must be 0 (build) or 1 (probe)");
     if (!d->sized) return fail(PHJ_ERR_STATE, "no join has run yet");
     PHJ_CUDA(cudaSetDevice(d->device));
-    const uint32_t dl = d->d_local;
-    const size_t nb = which == 0 ? dl + 1 : (size_t)d->K * (dl + 1);
+    const uint32_t np = d->np;
+    const size_t nb = which == 0 ? np + 1 : (size_t)d->K * (np + 1);
     std::vector<uint64_t> b(nb);
-    PHJ_CUDA(cudaMemcpy(b.data(), d->d_lb + (which == 0 ? 0 : dl + 1), nb * 8, cudaMemcpyDeviceToHost));
+    PHJ_CUDA(cudaMemcpy(b.data(), d->d_lb + (which == 0 ? 0 : np + 1), nb * 8, cudaMemcpyDeviceToHost));
     if (bounds) memcpy(bounds, b.data(), nb * 8);
     const uint64_t used = b[nb - 1];
     if (out) {

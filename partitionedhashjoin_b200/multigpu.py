@@ -656,7 +656,8 @@ class ShardedJoin:
         return {"world": lay.world, "rank": lay.rank, "digits": lay.digits, "local_partitions": lay.local_partitions,
                 "chunks": lay.chunks, "region_buckets": lay.region_buckets,
                 "window_tuples": [int(lay.window_tuples[0]), int(lay.window_tuples[1])], "resizes": lay.resizes,
-                "sent_remote_bytes": int(lay.sent_remote_bytes)}
+                "sent_remote_bytes": int(lay.sent_remote_bytes), "partitions_here": lay.partitions_here,
+                "hot_digits": [int(lay.hot_digits[i]) for i in range(lay.hot_count)]}
 
     def kernel_times(self):
         C = self._C
@@ -680,11 +681,11 @@ class ShardedJoin:
         return moved / ns.value if ns.value else 0.0
 
     def read_window(self, which):
-        """(tuples in this rank's window, boundaries): build -> [local_partitions + 1]; probe ->
-        [chunks][local_partitions + 1], absolute positions (test read-back)."""
+        """(tuples in this rank's window, boundaries): build -> [partitions_here + 1]; probe ->
+        [chunks][partitions_here + 1], absolute positions (test read-back)."""
         from ._lib import TUPLE_DTYPE
         lay = self.info()
-        nb = lay["local_partitions"] + 1
+        nb = lay["partitions_here"] + 1
         bounds = np.zeros(nb if which == 0 else lay["chunks"] * nb, dtype=np.uint64)
         self._check(self._lib.phj_dist_read_window(self._h, which, None, 0, bounds.ctypes.data))
         out = np.empty(int(bounds[-1]), dtype=TUPLE_DTYPE)
@@ -812,10 +813,15 @@ def parity_check(phj, dist, torch, rank, world, local, make_job, skew, n_build=1
            "how": "probe keys over 2x the build key range, a duplicated build key, INT64_MIN on both sides; "
                   "want = sum over ranks of numpy isin(own probe keys, all-gathered build keys)"}
     if hasattr(job, "read_window"):
-        landed = sum(int(job.read_window(w)[1].reshape(-1)[-1]) for w in (0, 1))
-        tot = _allreduce(dist, torch, local, [float(landed)])[0]
-        out["window_tuples"] = int(tot)
-        out["ok"] = out["ok"] and int(tot) == world * (n_build + n_probe)
+        landed = [int(job.read_window(w)[1].reshape(-1)[-1]) for w in (0, 1)]
+        tot_b, tot_p = (int(v) for v in _allreduce(dist, torch, local, [float(landed[0]), float(landed[1])]))
+        hot = job.info().get("hot_digits", [])
+        out["window_tuples"] = tot_b + tot_p
+        # every probe tuple lands exactly once; so does every build tuple, unless heavy-hitter digits are replicated
+        out["ok"] = out["ok"] and tot_p == world * n_probe and \
+            (tot_b > world * n_build if hot else tot_b == world * n_build)
+        if hot:
+            out["hot_digits"] = hot
     job.close()
     return out
 
@@ -836,8 +842,10 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
 
     def make_job(kind=None):
         kind = kind or mode
-        if kind == "library":
-            return ShardedJoin(dist if world > 1 else None, rank, world, local, partitions=args.dist_partitions, chunks=args.chunks, hash=args.hash)
+        if kind in ("library", "library_hot"):
+            from ._lib import FLAG_HOT_DIGITS
+            return ShardedJoin(dist if world > 1 else None, rank, world, local, partitions=args.dist_partitions,
+                               chunks=args.chunks, hash=args.hash, flags=FLAG_HOT_DIGITS if kind == "library_hot" else 0)
         if kind in ("pass1", "fused"):
             return FusedShardedRadixJoin(dist, rank, world, FusedGpuBackend(
                 world, local, partitions_local=args.partitions, hash=args.hash, pass1_in_shuffle=(kind == "pass1")))
@@ -852,7 +860,11 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     parity = parity_check(phj, dist, torch, rank, world, local, make_job, 0.01)
     parity_skew = parity_check(phj, dist, torch, rank, world, local, make_job, 1.25)
     parity_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("pass1"), 1.25) if world > 1 else None
-    assert parity["ok"] and parity_skew["ok"] and (parity_hot is None or parity_hot["ok"]), (parity, parity_skew, parity_hot)
+    # ... and the library path with PHJ_FLAG_HOT_DIGITS (heavy-hitter digits kept local, their build side replicated)
+    parity_lib_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("library_hot"), 1.25) \
+        if world > 1 else None
+    assert parity["ok"] and parity_skew["ok"] and (parity_hot is None or parity_hot["ok"]) and \
+        (parity_lib_hot is None or parity_lib_hot["ok"]), (parity, parity_skew, parity_hot, parity_lib_hot)
 
     if scaled:
         dR, dS, n_build, n_probe, want = scaled_inputs(phj, dist, torch, rank, world, local, args.skew)
@@ -944,6 +956,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             phj.fill_zipf(Sp.array, skew, 1, world * n_build, 12345 + 7919 * rank, 64)
             others[f"library_zipf{skew}_Gtuples_s"] = few(make_job("library"))
             if skew == 1.25 and world > 1:
+                others["library_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("library_hot"))
                 others["legacy_pass1_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("pass1"))
         Rp.close()
         Sp.close()
@@ -983,6 +996,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
                 "steps": e2e_steps, "host_memory": "pinned (phj_host_alloc)"},
             "gpu_launches": launches,
             "parity": parity, "parity_zipf1.25": parity_skew, "parity_zipf1.25_legacy_hot_digits": parity_hot,
+            "parity_zipf1.25_library_hot_digits": parity_lib_hot,
             "roofline": {"bound": "hbm", "kernel": "radix_scatter[shuffle] (rank 0, all launches of a join; NVLink-bound "
                                                    "for N > 1: see `shuffle`)", "unit": "GB/s", "peak": peak,
                          "peak_source": peak_src, "achieved": alg_bytes / max(scat_ms, 1e-9) / 1e6,

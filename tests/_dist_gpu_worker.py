@@ -43,6 +43,38 @@ def check_window(job, oracle, rel_global, which, rank, hash_seed=0x9E3779B97F4A7
         assert (allp["id"] == expect["id"]).all() and (allp["payload"] == expect["payload"]).all()
 
 
+def check_window_hot(job, oracle, rel_global, which, rank, world, hash_seed=0x9E3779B97F4A7C15, hash_id=0):
+    """PHJ_FLAG_HOT_DIGITS: this rank's partitions are the digits it owns, then the hot digits of other owners. A build
+    partition holds ALL tuples of its digit (a foreign hot one was copied from its owner); a probe partition of a hot
+    digit holds this rank's OWN tuples only (they never travelled), any other one everybody's."""
+    lay = job.info()
+    got, bounds = job.read_window(which)
+    dl, ndig, hot = lay["local_partitions"], lay["digits"], lay["hot_digits"]
+    parts = list(range(rank * dl, rank * dl + dl)) + [h for h in hot if h // dl != rank]
+    assert lay["partitions_here"] == len(parts)
+    digit = (oracle.hash_batch(hash_id, hash_seed, rel_global["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+    per = rel_global.shape[0] // world
+    in_my_shard = np.zeros(rel_global.shape[0], dtype=bool)
+    in_my_shard[rank * per:(rel_global.shape[0] if rank == world - 1 else (rank + 1) * per)] = True
+    regions = bounds[None] if which == 0 else bounds
+    for idx, d in enumerate(parts):
+        pieces = []
+        for c in range(regions.shape[0]):
+            piece = got[regions[c][idx]:regions[c][idx + 1]]
+            dg = (oracle.hash_batch(hash_id, hash_seed, piece["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+            assert (dg == d).all(), (which, c, idx, d)
+            assert (np.diff(piece["payload"]) > 0).all(), (which, c, idx, "order inside a region")
+            pieces.append(piece)
+        allp = np.concatenate(pieces)
+        allp = allp[np.argsort(allp["payload"], kind="stable")]
+        sel = digit == d
+        if which == 1 and d in hot:
+            sel &= in_my_shard
+        expect = rel_global[sel]
+        assert allp.shape[0] == expect.shape[0], (which, idx, d, allp.shape, expect.shape)
+        assert (allp["id"] == expect["id"]).all() and (allp["payload"] == expect["payload"]).all()
+
+
 def check_library_join(rank, world, local, oracle, R, S, want, shard, mode):
     dist_mod = dist if world > 1 else None
     # both count modes at every world size: piece-wise (later probe chunks counted while the earlier ones travel)
@@ -72,6 +104,26 @@ def check_library_join(rank, world, local, oracle, R, S, want, shard, mode):
         r1 = job.join()
         part = np.concatenate([shard_of(S, q, world)[: shard_of(S, q, world).shape[0] // 2] for q in range(world)])
         assert r1["matches"] == oracle.count_by_sort(R, part) and job.info()["resizes"] == n_resizes
+        job.close()
+    # heavy hitters kept local (30 % of the probe keys are one key): the probe tuples of its split digit do not
+    # travel, its build partition is copied to every rank; both count modes
+    for flags in (_lib.FLAG_HOT_DIGITS, _lib.FLAG_HOT_DIGITS | _lib.FLAG_COUNT_PIECEWISE):
+        job = multigpu.ShardedJoin(dist_mod, rank, world, local, chunks=3, flags=flags)
+        job.upload(shard(R), shard(S))
+        for _ in range(3):
+            res_hot = job.join()
+            assert res_hot["matches"] == want, (res_hot["matches"], want, flags)
+        lay = job.info()
+        if world > 1:
+            assert lay["hot_digits"], lay
+            # what no longer crosses NVLink: this rank's probe tuples of the hot digits it does not own
+            plain = multigpu.ShardedJoin(dist_mod, rank, world, local, chunks=3)
+            plain.upload(shard(R), shard(S))
+            plain.join()
+            assert lay["sent_remote_bytes"] <= plain.info()["sent_remote_bytes"]
+            plain.close()
+        check_window_hot(job, oracle, R, 0, rank, world)
+        check_window_hot(job, oracle, S, 1, rank, world)
         job.close()
     if rank == 0:
         print(json.dumps({"mode": mode, "world": world, "matches": res["matches"] // 2, "want": want}))

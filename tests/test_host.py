@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(phj):
     for name in names:
         assert hasattr(raw, name), f"{name} is declared in include/phj.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert phj._lib.lib.phj_abi_version() == 4
+    assert phj._lib.lib.phj_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header(phj, tmp_path):
