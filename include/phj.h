@@ -134,9 +134,12 @@ typedef struct {
 #define PHJ_FLAG_COUNT_PIECEWISE 0x800u /* sharded join: count probe chunk c + 1 while chunk c travels. Hides 0.3 ms of
                                          * counting and gives it back through a slower shuffle: 5.81 against 5.87 ms at
                                          * 8 GPUs, slower at 2 (profiles/r02_multigpu.md). Opt-in, tested. */
-#define PHJ_FLAG_HOT_DIGITS 0x1000u /* sharded join: split digits whose probe side alone outweighs a quarter of one
-                                     * rank's fair share (Zipf heavy hitters) keep their probe tuples where they
-                                     * are; their build partition is replicated to every rank */
+#define PHJ_FLAG_HOT_DIGITS 0x1000u /* accepted for compatibility: heavy-hitter handling is the default */
+#define PHJ_FLAG_NO_HOT_DIGITS 0x2000u /* sharded join: by default the split digits whose probe side alone outweighs a
+                                     * quarter of one rank's fair share (Zipf heavy hitters; never the case for
+                                     * uniform keys) keep their probe tuples where they are, and their build partition
+                                     * is replicated to every rank: 5.84 against 10.07 ms at 8 GPUs and
+                                     * Zipf 1.25. This flag sends every digit to its owner regardless. */
 #define PHJ_FLAG_NO_HIST12 0x100u /* two-pass plans: do not take both passes' histograms from one read
                                      (radix_histogram_full); the pass-1 scatter counts for pass 2 instead */
 

@@ -38,6 +38,7 @@ FLAG_COOP_PROBE = 0x200
 FLAG_COUNT_UPFRONT = 0x400
 FLAG_COUNT_PIECEWISE = 0x800
 FLAG_HOT_DIGITS = 0x1000
+FLAG_NO_HOT_DIGITS = 0x2000
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 

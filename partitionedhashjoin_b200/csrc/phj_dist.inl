@@ -98,7 +98,7 @@ NcclApi* nccl_api() {
 // partition. The kernel lays out pieces [which_first, which_last] (0: R; 1 + c: chunk c of S): all of them at once
 // when the shard was counted up front, one per launch when the counts arrive piece by piece.
 //
-// Heavy hitters (PHJ_FLAG_HOT_DIGITS, SURVEY.md 8e "skew caveat"): the sizing pass marks the split digits whose
+// Heavy hitters (default; PHJ_FLAG_NO_HOT_DIGITS turns it off; SURVEY.md 8e "skew caveat"): the sizing pass marks the split digits whose
 // probe side alone outweighs a quarter of one rank's fair share (key 1 at Zipf 1.25 is 22 % of S) as HOT. Their
 // probe tuples do not travel -- every rank keeps its own in an extra partition behind the partitions it owns --
 // and their (small, never skewed) build partition is copied from the owner's window to every other rank after
@@ -283,7 +283,7 @@ struct phj_dist {
     cudaEvent_t ev_r = nullptr, ev_c[kMaxSplitChunks] = {}, ev_cnt[kMaxSplitChunks] = {}, ev_local = nullptr, ev_t[8] = {};
     bool sized = false, have_data = false;
     bool piecewise = false;  // count the probe chunks behind the first while the pieces before them travel
-    // heavy hitters (PHJ_FLAG_HOT_DIGITS): decided by the sizing pass, identically on every rank
+    // heavy hitters: decided by the sizing pass, identically on every rank
     uint32_t n_hot = 0, hot[kMaxHot] = {};
     uint32_t np = 1;               // partitions of this rank: d_local + the hot digits of other owners
     PullDesc* d_pulls = nullptr;
@@ -474,7 +474,7 @@ int dist_size(phj_dist* D) {
     // for uniform keys (a digit is world / digits of a share); key 1 at Zipf 1.25 is 22 % of S. Every rank derives the
     // same set from the same all-gathered sizes.
     D->n_hot = 0;
-    if ((D->cfg.flags & PHJ_FLAG_HOT_DIGITS) && W > 1 && ndig > (uint32_t)W)
+    if (!(D->cfg.flags & PHJ_FLAG_NO_HOT_DIGITS) && W > 1 && ndig > (uint32_t)W)
         for (uint32_t d = 0; d < ndig && D->n_hot < (uint32_t)kMaxHot; ++d)
             if (tot_s[d] * (uint64_t)W * 4 > std::max<uint64_t>(total_s, 1)) D->hot[D->n_hot++] = d;
     std::vector<bool> is_hot(ndig, false);

@@ -842,10 +842,11 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
 
     def make_job(kind=None):
         kind = kind or mode
-        if kind in ("library", "library_hot"):
-            from ._lib import FLAG_HOT_DIGITS
+        if kind in ("library", "library_no_hot"):
+            from ._lib import FLAG_NO_HOT_DIGITS
             return ShardedJoin(dist if world > 1 else None, rank, world, local, partitions=args.dist_partitions,
-                               chunks=args.chunks, hash=args.hash, flags=FLAG_HOT_DIGITS if kind == "library_hot" else 0)
+                               chunks=args.chunks, hash=args.hash,
+                               flags=FLAG_NO_HOT_DIGITS if kind == "library_no_hot" else 0)
         if kind in ("pass1", "fused"):
             return FusedShardedRadixJoin(dist, rank, world, FusedGpuBackend(
                 world, local, partitions_local=args.partitions, hash=args.hash, pass1_in_shuffle=(kind == "pass1")))
@@ -860,8 +861,9 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     parity = parity_check(phj, dist, torch, rank, world, local, make_job, 0.01)
     parity_skew = parity_check(phj, dist, torch, rank, world, local, make_job, 1.25)
     parity_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("pass1"), 1.25) if world > 1 else None
-    # ... and the library path with PHJ_FLAG_HOT_DIGITS (heavy-hitter digits kept local, their build side replicated)
-    parity_lib_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("library_hot"), 1.25) \
+    # ... and the library path with PHJ_FLAG_NO_HOT_DIGITS (by default it keeps heavy-hitter digits local and replicates
+    # their build side: `parity_zipf1.25` went that way, see its `hot_digits`)
+    parity_lib_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("library_no_hot"), 1.25) \
         if world > 1 else None
     assert parity["ok"] and parity_skew["ok"] and (parity_hot is None or parity_hot["ok"]) and \
         (parity_lib_hot is None or parity_lib_hot["ok"]), (parity, parity_skew, parity_hot, parity_lib_hot)
@@ -956,7 +958,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             phj.fill_zipf(Sp.array, skew, 1, world * n_build, 12345 + 7919 * rank, 64)
             others[f"library_zipf{skew}_Gtuples_s"] = few(make_job("library"))
             if skew == 1.25 and world > 1:
-                others["library_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("library_hot"))
+                others["library_no_hot_digits_zipf1.25_Gtuples_s"] = few(make_job("library_no_hot"))
                 others["legacy_pass1_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("pass1"))
         Rp.close()
         Sp.close()
@@ -996,7 +998,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
                 "steps": e2e_steps, "host_memory": "pinned (phj_host_alloc)"},
             "gpu_launches": launches,
             "parity": parity, "parity_zipf1.25": parity_skew, "parity_zipf1.25_legacy_hot_digits": parity_hot,
-            "parity_zipf1.25_library_hot_digits": parity_lib_hot,
+            "parity_zipf1.25_library_no_hot_digits": parity_lib_hot,
             "roofline": {"bound": "hbm", "kernel": "radix_scatter[shuffle] (rank 0, all launches of a join; NVLink-bound "
                                                    "for N > 1: see `shuffle`)", "unit": "GB/s", "peak": peak,
                          "peak_source": peak_src, "achieved": alg_bytes / max(scat_ms, 1e-9) / 1e6,

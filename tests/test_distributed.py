@@ -269,8 +269,8 @@ def test_library_sharded_join_single_rank(phj, oracle, hash):
                 res = job.join()
                 assert res["matches"] == want, (name, partitions, chunks, res["matches"], want)
             if R.shape[0] and S.shape[0]:
-                worker.check_window(job, oracle, R, 0, 0, hash_id=hash_id)
-                worker.check_window(job, oracle, S, 1, 0, hash_id=hash_id)
+                worker.check_window(job, oracle, R, 0, 0, 1, hash_id=hash_id)
+                worker.check_window(job, oracle, S, 1, 0, 1, hash_id=hash_id)
         job.close()
 
 
