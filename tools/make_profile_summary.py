@@ -41,7 +41,12 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM r
         ("smsp__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"), ("launch__registers_per_thread", "registers/thread"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
-        ("lts__t_sector_hit_rate.pct", "L2 hit rate %")]
+        ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+        ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe active % of peak"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe active % of peak"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe % of peak"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU data-pipe wavefronts % of peak"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "warps stalled on a barrier per issue")]
 out += [f"## `--set full` capture of the top kernels (`{rep.split('/')[-1]}`, not tracked: binary)", ""]
 seen = set()
 for r in data:
