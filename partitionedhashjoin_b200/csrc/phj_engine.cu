@@ -796,7 +796,13 @@ int ensure_gt_for_fallback(phj_handle* h) {
 
 uint32_t table_hash_shift(const phj_handle* h) {
     // the table takes hash bits above the ones the partitioning consumed
-    return h->cfg.algo != PHJ_ALGO_NO_PARTITIONING ? (uint32_t)std::min(h->bits_total, 24) : 0u;
+    if (h->cfg.algo == PHJ_ALGO_NO_PARTITIONING) return 0u;
+    int bits = h->bits_total;
+    // Relations that arrived partitioned by a WIDER pass-1 digit than this handle's own (the owner-rank bits of the
+    // multi-GPU split sit right above it) are nearly constant in those bits too: skip them, or only 1 / world of the
+    // buckets would be home buckets and the rest would fill by overflow alone.
+    if (h->prepart && h->prepart_space > ((uint64_t)1 << h->b1)) bits += ilog2_ceil(h->prepart_space) - h->b1;
+    return (uint32_t)std::min(bits, 24);
 }
 
 // ---- the joins ----------------------------------------------------------------------------------

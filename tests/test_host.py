@@ -35,13 +35,25 @@ def test_library_exports_every_declared_symbol(phj):
     assert phj._lib.lib.phj_abi_version() == 5
 
 
+def test_flag_values_match_the_header(phj):
+    """Every PHJ_FLAG_* of include/phj.h has a ctypes-side constant of the same value, and no two flags share a bit."""
+    from partitionedhashjoin_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "phj.h")).read()
+    flags = {name: int(value, 16) for name, value in re.findall(r"#define\s+PHJ_(FLAG_[A-Z0-9_]+)\s+0x([0-9a-fA-F]+)u", text)}
+    assert len(flags) >= 12
+    for name, value in flags.items():
+        assert getattr(_lib, name) == value, name
+    assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())
+
+
 def test_struct_layouts_match_the_header(phj, tmp_path):
     """sizeof/offsetof as the C compiler sees include/phj.h == the ctypes mirrors."""
     from partitionedhashjoin_b200 import _lib
     src = tmp_path / "layout.c"
     fields = {"phj_config": [f for f, _ in _lib.PhjConfig._fields_],
               "phj_result": [f for f, _ in _lib.PhjResult._fields_],
-              "phj_device_info": [f for f, _ in _lib.PhjDeviceInfo._fields_]}
+              "phj_device_info": [f for f, _ in _lib.PhjDeviceInfo._fields_],
+              "phj_dist_layout": [f for f, _ in _lib.PhjDistLayout._fields_]}
     body = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/phj.h"', "int main(void){"]
     for st, fs in fields.items():
         body.append(f'printf("{st} %zu\\n", sizeof({st}));')
@@ -52,7 +64,8 @@ def test_struct_layouts_match_the_header(phj, tmp_path):
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
     out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
-    mirrors = {"phj_config": _lib.PhjConfig, "phj_result": _lib.PhjResult, "phj_device_info": _lib.PhjDeviceInfo}
+    mirrors = {"phj_config": _lib.PhjConfig, "phj_result": _lib.PhjResult, "phj_device_info": _lib.PhjDeviceInfo,
+               "phj_dist_layout": _lib.PhjDistLayout}
     for st, cls in mirrors.items():
         assert int(out[st]) == C.sizeof(cls)
         for f, _ in cls._fields_:
