@@ -103,8 +103,8 @@ enum Scalar : int {  // device-resident uint32 scalars
     kNcounts1,
     kNsegs2,
     kNcounts2,
-    kOversize,
-    kPlanTruncated,  // plan_pass2 ran out of segment slots (must never happen: the join fails if it does)
+    kUnused4,  // (the oversize count and plan_pass2's truncation flag now share a word behind the match counter)
+    kUnused5,
     kGtFlags,
     kCtCursor,
     kNumScalars = 8

@@ -2,7 +2,7 @@
 //
 // Reference loops these kernels replace (file:line under /root/reference/):
 //   radix_histogram   scanTable                 src/RadixCluster/HashJoin.hpp:343-357
-//   scan_*            createPrefixSumTable      src/RadixCluster/HashJoin.hpp:363-390
+//   scan_lookback     createPrefixSumTable      src/RadixCluster/HashJoin.hpp:363-390
 //                     + ComputePartitionsBoundaries                         :18-25
 //   radix_scatter     partitionTable            src/RadixCluster/HashJoin.hpp:394-412
 //   join_partitions   Join lambda               src/RadixCluster/HashJoin.hpp:258-323
@@ -24,6 +24,12 @@
 
 #ifndef PHJ_SCAT_MINB
 #define PHJ_SCAT_MINB 1
+#endif
+#ifndef PHJ_SCAT_PSCAN
+#define PHJ_SCAT_PSCAN 1  // all-warp counter scan in radix_scatter
+#endif
+#ifndef PHJ_SCAT_ALLWRITE
+#define PHJ_SCAT_ALLWRITE 1  // every lane of a digit group stores the warp counter
 #endif
 
 
@@ -823,7 +829,7 @@ __global__ void __launch_bounds__(TPB) radix_histogram_lanes8(PassParams p) {
 // radix_histogram_lanes does, and (b) the table itself to hist12[segment]. The pass-1 scatter is
 // stable and segments are input slices, so in the pass-1 output partition d1 is the concatenation
 // over segments s of run (s, d1), whose pass-2 digit counts are exactly hist12[s][d1][*]: pass 2
-// gets its counters by summing rows (pass2_counts_from_hist12) instead of reading its input again
+// gets its counters by summing rows (pass2_align_counts) instead of reading its input again
 // or having the pass-1 scatter count (FUSE2). The kernel stays HBM-bound: the atomics hide behind
 // the loads. HBM: reads 16 B/tuple (8 used), writes 16 KB per segment.
 // =================================================================================================
