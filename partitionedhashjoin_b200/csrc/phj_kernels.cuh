@@ -31,6 +31,9 @@
 #ifndef PHJ_SCAT_ALLWRITE
 #define PHJ_SCAT_ALLWRITE 1  // every lane of a digit group stores the warp counter
 #endif
+#ifndef PHJ_SCAT_PEERS4
+#define PHJ_SCAT_PEERS4 1  // warp_peers in three ALU instructions per digit bit (inline PTX; 0: the C++ form, six)
+#endif
 
 
 namespace phj {
@@ -173,6 +176,32 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 template <int NBITS, bool BALLOT>
 __device__ __forceinline__ uint32_t warp_peers(uint32_t d) {
     if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+#if PHJ_SCAT_PEERS4
+    // Spelled out in PTX so that ptxas sees six independent bit tests of one register: it then moves all of them into
+    // predicates with ONE R2P and spends three ALU-pipe instructions per digit bit (VOTE, a predicated NOT for this
+    // lane's polarity, an OR of `lanes that differ from me in this bit`). The C++ form below compiled to six per bit
+    // (SHF + LOP3 + a second ISETP for the negated predicate + SEL + VOTE + LOP3), and the scatter's rank phase is
+    // bound by exactly this pipe: measured 1275 / 1350 -> 1178 / 1228 us per pass at
+    // 10 M x 200 M, partitions bit-identical (tools/ab_scatter.py peers4 check).
+    uint32_t differ = 0;
+#pragma unroll
+    for (int b = 0; b < NBITS; ++b) {
+        uint32_t m, pol;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t;\n\t"
+            "and.b32 t, %2, %3;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+            "selp.b32 %1, 0xffffffff, 0, p;\n\t"
+            "}"
+            : "=r"(m), "=r"(pol)
+            : "r"(d), "r"(1u << b));
+        differ |= m ^ pol;  // bit set: the lanes where it is clear (~m); bit clear: the lanes where it is set (m)
+    }
+    return ~differ;
+#endif
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < NBITS; ++b) {

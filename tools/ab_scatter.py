@@ -13,6 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARDIR = os.path.join(ROOT, "partitionedhashjoin_b200", "variants")
 VARIANTS = {
+    "peers6": "-DPHJ_SCAT_PEERS4=0",                        # warp_peers as plain C++: six ALU instructions per digit bit
     "base": "",                                             # the default build: 16 segments per SM, leader-free store
     "segs8": "-DPHJ_SEGS_PER_SM=8",                         # round 1's segment length
     "segs24": "-DPHJ_SEGS_PER_SM=24",
