@@ -124,8 +124,8 @@ typedef struct {
                                      memory that stay hot in the 126 MB L2 (all CTAs walk the probe side in
                                      partition order) instead of shared-memory tables. Made for FEW, LARGE
                                      partitions: one radix pass (partitions = 32 .. 256) then needs no second
-                                     partitioning pass at all -- 3.41 ms against 3.95 ms for two passes + shared
-                                     memory at 10 M x 200 M. The multi-GPU path always joins this way. */
+                                     partitioning pass at all -- 3.03-3.07 ms against 3.6-3.8 ms for two passes +
+                                     shared memory at 10 M x 200 M. The multi-GPU path always joins this way. */
 #define PHJ_FLAG_COOP_PROBE 0x200u /* global-table probes (NO_PARTITIONING, oversize fallback) by groups of four
                                       lanes per key (shuffle broadcast + one 8-byte slot per lane + ballot) instead
                                       of one thread per key reading the 32-byte bucket with one 256-bit load.
