@@ -1,5 +1,5 @@
 # round-2 evidence on ONE B200 (final build): tests, the bench line, ncu launch list + full capture of the top kernels
-# (the reference arm and the L2-table / no-partitioning captures of the same round: gpurun_out/r02m_*, tools/gpu_r02*.sh)
+# (the reference arm and the L2-table / no-partitioning captures of the same round: gpurun_out/r02m_*, tools/runs/gpu_r02*.sh)
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02x_gputests.log 2>&1; echo "gpu tests rc=$?"; tail -n 4 gpurun_out/r02x_gputests.log
 timeout 600 python bench.py > gpurun_out/r02x_bench1.json 2> gpurun_out/r02x_bench1.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02x_bench1.json
