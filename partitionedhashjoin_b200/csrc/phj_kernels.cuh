@@ -103,6 +103,9 @@ struct __align__(16) Parent2 {
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------
+// (tests/emu compiles this file for the host and brings host versions of exactly this block: every line of
+// inline PTX of the kernels, except warp_peers' ballot below, is between this guard and its #endif)
+#ifndef PHJ_PTX_HELPERS_PROVIDED
 __device__ __forceinline__ ulonglong2 ld_stream_v2(const ulonglong2* p) {
     ulonglong2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
@@ -169,6 +172,7 @@ __device__ __forceinline__ void bulk_wait_all0() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+#endif  // PHJ_PTX_HELPERS_PROVIDED
 
 // Lanes of the warp whose digit equals this lane's. BALLOT = false: one match.any (a long-latency
 // instruction on B200, tens of cycles of a per-SM unit); BALLOT = true: one vote per digit bit
