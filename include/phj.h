@@ -44,8 +44,8 @@ enum {
     PHJ_ALGO_RADIX_PARTITIONING = 1,
     /* Multi-GPU exchange step (no counterpart in the single-process reference): phj_join only
      * splits the uploaded relations by the digit (hash >> shard_shift) % partitions, `partitions`
-     * a power of two <= 256. Either partitions = number of ranks (digit = owner rank; shard_shift
-     * beyond the local join's hash bits) and every rank then runs an ordinary RADIX_PARTITIONING
+     * a power of two <= 256 (any value <= 256 when shard_shift is 0: the digit then is hash % partitions).
+     * Either partitions = number of ranks (digit = owner rank; shard_shift beyond the local join's hash bits) and every rank then runs an ordinary RADIX_PARTITIONING
      * join on what it received; or partitions = ranks x local pass-1 digits with shard_shift =
      * the local join's radix_bits[1] (digit = owner rank : local pass-1 digit), in which case what
      * a rank receives is already pass-1 partitioned (phj_bind_device_partitioned). */
@@ -95,13 +95,15 @@ typedef struct {
     uint32_t upload_chunks; /* phj_join_host: row chunks the probe relation is uploaded in, each joined
                                as soon as it has landed (1 = upload everything, then join; 0 = choose:
                                ~256 MB chunks when the probe relation is large, else 1; <= 32) */
-    int32_t num_gpus;       /* RADIX_PARTITIONING, 0 or 1 = one GPU. N > 1 (a power of two): this process drives
+    int32_t num_gpus;       /* RADIX_PARTITIONING, 0 or 1 = one GPU. N > 1 (at most 16): this process drives
                                GPUs device .. device + N - 1 -- phj_upload gives GPU g the rows [g n / N,
                                (g + 1) n / N) of both relations, phj_join runs the sharded join below (one host
                                thread per GPU, NCCL for sizes / barriers / the count, NVLink peer stores for the
                                tuples) and returns the global count. `partitions` then is GPUs x local
-                               partitions (a power of two <= 256; 0 = 64) and split_chunks the number of probe
-                               chunks whose shuffle overlaps the local probe of the previous one (0 = 4). */
+                               partitions (<= 256, a multiple of N, a power of two when N is one; 0 = 64, or the
+                               largest multiple of N below it) and split_chunks the number of probe chunks whose
+                               shuffle overlaps the local probe of the previous one (0 = 4). For N = 2, 4, 8, 16
+                               the split digit is a bit field of the hash, for any other N it is hash % partitions. */
     uint32_t reserved0;
 } phj_config;
 
@@ -299,7 +301,7 @@ int phj_shard_scatter(phj_handle* h, uint32_t chunk, void* const* dst_build, con
  * same way, :210-216), NCCL carries the piece sizes, the barriers and the count. All ranks call the same
  * functions in the same order (they are collectives). phj_nccl_unique_id: rank 0 obtains 128 opaque bytes
  * and hands them to the others over any transport (torch.distributed, MPI, a file). config as for
- * phj_create (algo RADIX_PARTITIONING; partitions = GPUs x local partitions, a power of two <= 256, 0 = 64;
+ * phj_create (algo RADIX_PARTITIONING; partitions = GPUs x local partitions as for num_gpus, 0 = choose;
  * split_chunks = probe chunks, 0 = 4; device = this rank's GPU). phj_dist_join returns the GLOBAL count on
  * every rank. The same join inside ONE process: phj_config.num_gpus. */
 typedef struct phj_dist phj_dist;
@@ -328,7 +330,8 @@ int phj_dist_measure_peer_copy(phj_dist* d, uint64_t bytes, uint32_t repeats, ui
  * prefix (bounds' last entry) is copied to `out` when it is given. */
 typedef struct {
     uint32_t world, rank;
-    uint32_t digits;            /* split digits = world x local_partitions; owner = digit / local_partitions */
+    uint32_t digits;            /* split digits = world x local_partitions; owner = digit / local_partitions; digit =
+                                   hash & (digits - 1), or hash % digits when digits is not a power of two */
     uint32_t local_partitions;
     uint32_t chunks;
     uint32_t region_buckets;    /* 32-byte buckets per local partition's table */

@@ -520,7 +520,8 @@ int dist_enqueue_join(phj_dist* D) {
     q.table_mul |= 1ULL << 32;
     {
         const HashParams hp = make_hash_params(h->cfg.hash, h->cfg.hash_seed);
-        const uint64_t digit = hash_key_dyn(h->cfg.hash, kEmptyKey, hp) & (ndig - 1);
+        const uint64_t hs = hash_key_dyn(h->cfg.hash, kEmptyKey, hp);
+        const uint64_t digit = (ndig & (ndig - 1)) ? hs % ndig : hs & (ndig - 1);
         q.sentinel_part = digit / dl == (uint64_t)D->rank ? (uint32_t)(digit % dl) : 0xffffffffu;
         uint32_t extra = dl;  // ... or one of the hot digits of other owners kept here
         for (uint32_t i = 0; i < D->n_hot; ++i) {
@@ -656,13 +657,18 @@ int dist_alloc(phj_dist* D) {
 // NVLink (tile / digits tuples) against the size of one table.
 int dist_plan(phj_dist* D) {
     const int W = D->world;
-    if (W < 1 || W > kMaxRanks || (W & (W - 1))) return fail(PHJ_ERR_INVALID, "the number of GPUs must be a power of two <= %d", kMaxRanks);
-    uint32_t ndig = 64;
+    if (W < 1 || W > kMaxRanks) return fail(PHJ_ERR_INVALID, "the number of GPUs must be in [1, %d]", kMaxRanks);
+    // Every GPU owns the same number of split digits. For 2, 4, 8, 16 GPUs the digit is a bit field of the hash
+    // (64 digits by default); for any other count it is hash % digits with digits = GPUs x floor(64 / GPUs)
+    // (63, 60, 60, 63 for 3, 5, 6, 7 GPUs), the kernels' `%` path.
+    uint32_t ndig = (64u / (uint32_t)W) * (uint32_t)W;
     if (D->cfg.partitions) {
         const uint64_t P = D->cfg.partitions;
-        if ((P & (P - 1)) || P < (uint64_t)W || P > (uint64_t)kMaxSplitDigits)
-            return fail(PHJ_ERR_INVALID, "sharded join: partitions = GPUs x local partitions must be a power of two "
-                                         "in [%d, %d] (0 = choose)", W, kMaxSplitDigits);
+        const bool pow2_world = (W & (W - 1)) == 0;
+        if (P < (uint64_t)W || P > (uint64_t)kMaxSplitDigits || P % (uint64_t)W || (pow2_world && (P & (P - 1))))
+            return fail(PHJ_ERR_INVALID, "sharded join: partitions = GPUs x local partitions must be a multiple of the "
+                                         "%d GPUs in [%d, %d]%s (0 = choose)", W, W, kMaxSplitDigits,
+                        pow2_world ? " and a power of two" : "");
         ndig = (uint32_t)P;
     }
     ndig = std::max<uint32_t>(ndig, (uint32_t)W);

@@ -404,11 +404,11 @@ cudaError_t launch_pass_b(phj_handle* h, bool scatter, const PassParams& pp, uin
 // The multi-GPU split scatter: tiles of 8192 tuples (1024 threads, one CTA per SM). It is bound by
 // NVLink, not by HBM, and NVLink efficiency grows with the length of the per-digit runs a tile
 // yields (measured at 2 GPUs, 128 digits: exchange 3.95 / 3.32 / 3.02 ms for 2048 / 4096 / 8192).
-template <int BITS, int HASH>
+template <int BITS, int HASH, bool POW2 = true>
 cudaError_t launch_split_scatter_t(phj_handle* h, const PassParams& pp, uint32_t grid) {
     constexpr int kTpb = 1024, kIpt = 8;
     using L = ScatterSmem<BITS, kTpb, kIpt>;
-    auto kern = radix_scatter<BITS, HASH, true, kTpb, kIpt, true, true, false, 1>;
+    auto kern = radix_scatter<BITS, HASH, POW2, kTpb, kIpt, true, true, false, 1>;
     static bool configured[16] = {};
     if (!configured[h->device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total_tma);
@@ -421,6 +421,19 @@ cudaError_t launch_split_scatter_t(phj_handle* h, const PassParams& pp, uint32_t
 
 cudaError_t launch_split_scatter(phj_handle* h, int bits, const PassParams& pp, uint32_t grid) {
     const bool wide = bits > 6;
+    if (!h->pow2) {  // ranks x local partitions is not a power of two (3, 5, 6, 7 ... GPUs): digit = hash % digits
+        switch (h->cfg.hash) {
+            case PHJ_HASH_MURMUR3:
+                return wide ? launch_split_scatter_t<8, kMurmur3, false>(h, pp, grid)
+                            : launch_split_scatter_t<6, kMurmur3, false>(h, pp, grid);
+            case PHJ_HASH_CITY:
+                return wide ? launch_split_scatter_t<8, kCity, false>(h, pp, grid)
+                            : launch_split_scatter_t<6, kCity, false>(h, pp, grid);
+            default:
+                return wide ? launch_split_scatter_t<8, kXXH3, false>(h, pp, grid)
+                            : launch_split_scatter_t<6, kXXH3, false>(h, pp, grid);
+        }
+    }
     switch (h->cfg.hash) {
         case PHJ_HASH_MURMUR3:
             return wide ? launch_split_scatter_t<8, kMurmur3>(h, pp, grid) : launch_split_scatter_t<6, kMurmur3>(h, pp, grid);
@@ -527,6 +540,10 @@ DigitFn digit_fn(const phj_handle* h, int pass) {
         f.pmask = ~0ull;
         f.shift = h->cfg.shard_shift;
         f.mask = (uint32_t)(h->P - 1);
+        if (!h->pow2) {  // digit = hash % P (the kernels' POW2 = false path; shard_shift is 0 then)
+            f.shift = 0;
+            f.mask = ~0u;
+        }
         return f;
     }
     if (pass == 1) {
@@ -1274,10 +1291,12 @@ int validate_config(const phj_config* c) {
         return fail(PHJ_ERR_INVALID, "Unrecognized join algorithm: %d.", c->algo);
     if (c->algo == PHJ_ALGO_SHARD_SPLIT) {
         const uint64_t w = c->partitions;
-        if (w == 0 || w > kMaxSplitDigits || (w & (w - 1)) || c->shard_shift > 56 || c->radix_bits[0] ||
-            c->radix_bits[1])
-            return fail(PHJ_ERR_INVALID, "shard split needs partitions = ranks x local pass-1 digits (a power of "
-                                         "two <= 256), shard_shift <= 56 and no radix_bits");
+        // a digit count that is not a power of two (ranks x local partitions for 3, 5, 6, 7 ... ranks) is taken
+        // as hash % partitions, which has no bit field to shift
+        if (w == 0 || w > kMaxSplitDigits || ((w & (w - 1)) && c->shard_shift != 0) || c->shard_shift > 56 ||
+            c->radix_bits[0] || c->radix_bits[1])
+            return fail(PHJ_ERR_INVALID, "shard split needs partitions = ranks x local pass-1 digits (<= 256; a power "
+                                         "of two unless shard_shift is 0), shard_shift <= 56 and no radix_bits");
         if (c->split_chunks > (uint32_t)kMaxSplitChunks)
             return fail(PHJ_ERR_INVALID, "split_chunks must be <= %d", kMaxSplitChunks);
     }

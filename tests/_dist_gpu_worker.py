@@ -26,7 +26,11 @@ def check_window(job, oracle, rel_global, which, rank, world, hash_seed=0x9E3779
     dl, ndig, hot = lay["local_partitions"], lay["digits"], lay["hot_digits"]
     parts = list(range(rank * dl, rank * dl + dl)) + [h for h in hot if h // dl != rank]
     assert lay["partitions_here"] == len(parts)
-    digit = (oracle.hash_batch(hash_id, hash_seed, rel_global["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+    def digits_of(keys):  # a bit field of the hash for 2 / 4 / 8 ... ranks, hash % digits for any other count
+        h = oracle.hash_batch(hash_id, hash_seed, keys)
+        return (h % np.uint64(ndig) if ndig & (ndig - 1) else h & np.uint64(ndig - 1)).astype(np.int64)
+
+    digit = digits_of(rel_global["id"])
     per = rel_global.shape[0] // world
     in_my_shard = np.zeros(rel_global.shape[0], dtype=bool)
     in_my_shard[rank * per:(rel_global.shape[0] if rank == world - 1 else (rank + 1) * per)] = True
@@ -35,7 +39,7 @@ def check_window(job, oracle, rel_global, which, rank, world, hash_seed=0x9E3779
         pieces = []
         for c in range(regions.shape[0]):
             piece = got[regions[c][idx]:regions[c][idx + 1]]
-            dg = (oracle.hash_batch(hash_id, hash_seed, piece["id"]) & np.uint64(ndig - 1)).astype(np.int64)
+            dg = digits_of(piece["id"])
             assert (dg == d).all(), (which, c, idx, d)
             assert (np.diff(piece["payload"]) > 0).all(), (which, c, idx, "order inside a region")
             pieces.append(piece)
@@ -54,7 +58,7 @@ def check_library_join(rank, world, local, oracle, R, S, want, shard, mode):
     # both count modes at every world size: piece-wise (later probe chunks counted while the earlier ones travel)
     # is the default from 4 GPUs on, up front below that
     from partitionedhashjoin_b200 import _lib
-    for partitions, chunks, flags in ((0, 0, 0), (world * 4, 3, _lib.FLAG_COUNT_PIECEWISE), (256, 1, 0),
+    for partitions, chunks, flags in ((0, 0, 0), (world * 4, 3, _lib.FLAG_COUNT_PIECEWISE), (256 // world * world, 1, 0),
                                       (world, 5, _lib.FLAG_COUNT_UPFRONT), (0, 4, _lib.FLAG_COUNT_PIECEWISE)):
         if partitions and partitions < world:
             continue

@@ -128,7 +128,7 @@ def check_single():
 
 
 def check_group():
-    """phj_config.num_gpus on 2 / 4 / 8 emulated GPUs (one process, the engine's own host thread per GPU, peer
+    """phj_config.num_gpus on 2 / 3 / 4 / 6 / 8 emulated GPUs (one process, the engine's own host thread per GPU, peer
     stores into the other threads' windows, collectives between the threads): the global count against the oracle,
     on uniform and heavy-hitter keys, re-uploads that grow the windows, the one-call host join."""
     import _cases
@@ -141,8 +141,9 @@ def check_group():
     cases["random_larger"] = (_cases.tuples(_cases.splitmix64(30_000, 51).astype(np.int64) % 20_011),
                               _cases.tuples(_cases.splitmix64(90_000, 52).astype(np.int64) % 30_011))
     done, n = [], 0
-    for gpus in (2, 4, 8):
-        for partitions, chunks, flags in ((0, 0, 0), (gpus, 3, phj.FLAG_COUNT_PIECEWISE), (256, 1, phj.FLAG_NO_HOT_DIGITS)):
+    for gpus in (2, 3, 4, 6, 8):  # 3 and 6: the split digit is hash % digits instead of a bit field
+        for partitions, chunks, flags in ((0, 0, 0), (gpus, 3, phj.FLAG_COUNT_PIECEWISE),
+                                          (256 // gpus * gpus, 1, phj.FLAG_NO_HOT_DIGITS)):
             with phj.Engine("radix-partitioning", partitions=partitions, split_chunks=chunks, num_gpus=gpus,
                             flags=flags) as e:
                 for name, (Rc, Sc) in cases.items():

@@ -275,7 +275,7 @@ def test_library_sharded_join_single_rank(phj, oracle, hash):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gpus", [2, 4, 8])
+@pytest.mark.parametrize("gpus", [2, 4, 8, 3, 6])
 def test_one_process_several_gpus(phj, oracle, gpus):
     """phj_config.num_gpus: one process, one host thread per GPU, the same sharded join (phj_upload shards the rows,
     phj_join returns the global count) -- against the oracle on adversarial and larger inputs, incl. re-uploads that
@@ -288,7 +288,7 @@ def test_one_process_several_gpus(phj, oracle, gpus):
     cases = dict(_cases.adversarial_cases())
     cases["big_random"] = (_cases.tuples(_cases.splitmix64(300_000, 51).astype(np.int64) % 200_003),
                            _cases.tuples(_cases.splitmix64(2_000_000, 52).astype(np.int64) % 300_007))
-    for partitions, chunks in ((0, 0), (gpus, 3), (256, 1)):
+    for partitions, chunks in ((0, 0), (gpus, 3), (256 // gpus * gpus, 1)):
         with phj.Engine("radix-partitioning", partitions=partitions, split_chunks=chunks, num_gpus=gpus) as e:
             for name, (R, S) in cases.items():
                 want = oracle.count_by_sort(R, S)
@@ -305,7 +305,7 @@ def test_one_process_several_gpus(phj, oracle, gpus):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 4, 8, 3, 6])
 def test_library_sharded_join_on_gpus(phj, world):
     """One rank per GPU: the library's sharded join (NVLink peer stores + NCCL) against the oracle's count with the
     contents of every rank's windows checked; skipped when the box has fewer GPUs."""

@@ -1,6 +1,6 @@
 """The product's engine and kernel SOURCE, executed on the CPU (tests/emu) and held to the oracle -- so that the
 CPU test run also covers what otherwise only the `-m gpu` tests on the B200 see: every join plan, the partition
-layout bit for bit, and the sharded join at 2 / 4 / 8 ranks (which the driver's single-GPU box skips).
+layout bit for bit, and the sharded join at 2 / 3 / 4 / 6 / 8 ranks (which the driver's single-GPU box skips).
 
 tests/emu compiles the UNMODIFIED phj_engine.cu against a host stand-in for the CUDA runtime and NCCL, and the
 kernel headers with g++ through a device-language shim whose launcher runs every CUDA thread as a fiber. It is test
@@ -18,8 +18,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 BUILD = os.path.join(EMU, "_build")
-CHECKS = {"single": ["single"], "group": ["group"], "ranks2": ["ranks", "2"], "ranks4": ["ranks", "4"],
-          "ranks8": ["ranks", "8"]}
+WORLDS = [2, 3, 4, 6, 8]
+CHECKS = {"single": ["single"], "group": ["group"], **{f"ranks{w}": ["ranks", str(w)] for w in WORLDS}}
 
 
 @pytest.fixture(scope="module")
@@ -72,12 +72,13 @@ def test_single_gpu_engine_on_emulated_kernels(emulated_runs):
 
 
 def test_one_process_sharded_join_on_emulated_gpus(emulated_runs):
-    """phj_config.num_gpus = 2 / 4 / 8: the same calls as a single GPU, the global count against the oracle."""
+    """phj_config.num_gpus = 2 / 3 / 4 / 6 / 8: the same calls as a single GPU, the global count against the oracle
+    (3 and 6 GPUs: the split digit is hash % digits, not a bit field of the hash)."""
     line = finished(emulated_runs, "group")
-    assert {"2 GPUs ok", "4 GPUs ok", "8 GPUs ok"} <= set(line["done"])
+    assert {f"{w} GPUs ok" for w in WORLDS} <= set(line["done"])
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", WORLDS)
 def test_sharded_join_ranks_on_emulated_gpus(emulated_runs, world):
     """phj_dist_* with one rank per thread: tests/_dist_gpu_worker.py::check_library_join, the very function the
     `-m gpu` multi-rank tests run on real GPUs (window contents tuple by tuple, both count modes, a collective
