@@ -41,7 +41,7 @@ inline std::string HelpText() {
          "  --data-seed arg (=12345)              Base seed of the Zipf generator (batch b uses seed + b).\n"
          "  --radix-bits arg                      b1,b2: bits of partitioning pass 1 and 2.\n"
          "  --device arg (=0)                     CUDA device.\n"
-         "  --gpus arg (=1)                       Number of GPUs (1 .. 16): the radix join sharded by partition,      \n"
+         "  --gpus arg (=1)                       Number of GPUs (1 .. 16): the radix join sharded by partition,\n"
          "                                        --partitions then = GPUs x partitions per GPU (<= 256).\n"
          "  --repeat arg (=1)                     Joins per run; the fastest is reported.\n"
          "  --no-tma-store                        Flush scatter tiles with st.global instead of TMA bulk stores.\n"
