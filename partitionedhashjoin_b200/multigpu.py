@@ -860,7 +860,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
     # ---- heavy-hitter digits kept local (layout_hot) on the same Zipf 1.25 data
     parity = parity_check(phj, dist, torch, rank, world, local, make_job, 0.01)
     parity_skew = parity_check(phj, dist, torch, rank, world, local, make_job, 1.25)
-    parity_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("pass1"), 1.25) if world > 1 else None
+    legacy = world > 1 and not world & (world - 1)  # the round-1 host-driven paths want a power of two
+    parity_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("pass1"), 1.25) if legacy else None
     # ... and the library path with PHJ_FLAG_NO_HOT_DIGITS (by default it keeps heavy-hitter digits local and replicates
     # their build side: `parity_zipf1.25` went that way, see its `hot_digits`)
     parity_lib_hot = parity_check(phj, dist, torch, rank, world, local, lambda: make_job("library_no_hot"), 1.25) \
@@ -952,6 +953,7 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             return round(world * (n_build + n_probe) / dt / 1e9, 2)
         if world > 1:
             others["no_partitioning_replicated_build_Gtuples_s"] = few(make_job("npj"))
+        if legacy:
             others["legacy_host_driven_pass1_Gtuples_s"] = few(make_job("pass1"))
         others["library_1_chunk_no_overlap_Gtuples_s"] = few(ShardedJoin(dist, rank, world, local, chunks=1, hash=args.hash))
         for skew in (1.05, 1.25):
@@ -959,7 +961,8 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             others[f"library_zipf{skew}_Gtuples_s"] = few(make_job("library"))
             if skew == 1.25 and world > 1:
                 others["library_no_hot_digits_zipf1.25_Gtuples_s"] = few(make_job("library_no_hot"))
-                others["legacy_pass1_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("pass1"))
+                if legacy:
+                    others["legacy_pass1_hot_digits_local_zipf1.25_Gtuples_s"] = few(make_job("pass1"))
         Rp.close()
         Sp.close()
         others["scaled_160Mx3200M"] = scaled_other_config(phj, dist, torch, rank, world, local, args)
