@@ -243,6 +243,8 @@ def gpu_arm(args):
     import partitionedhashjoin_b200 as phj
     if phj.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    if "emulated" in phj.device_info(0)["name"]:  # PHJ_LIB pointing at tests/emu's build: logic tests only
+        raise SystemExit("bench.py measures the B200: the emulated test build (tests/emu) is not a device")
 
     if world > 1 or args.workload == "scaled":
         from partitionedhashjoin_b200 import multigpu

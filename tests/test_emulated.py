@@ -84,3 +84,14 @@ def test_sharded_join_ranks_on_emulated_gpus(emulated_runs, world):
     `-m gpu` multi-rank tests run on real GPUs (window contents tuple by tuple, both count modes, a collective
     re-size, heavy-hitter digits kept local against the plain exchange)."""
     finished(emulated_runs, f"ranks{world}")
+
+
+def test_bench_refuses_the_emulated_build(emulated_runs):
+    """No number may come from the emulator: bench.py stops when PHJ_LIB points at it."""
+    env = dict(os.environ)
+    env["PHJ_LIB"] = os.path.join(BUILD, "libphj_emu_engine.so")
+    env["LD_LIBRARY_PATH"] = BUILD + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--quick", "--steps", "1"], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "emulated test build" in r.stderr + r.stdout, (r.returncode, r.stderr[-500:])
+    assert not any(line.startswith("{") for line in r.stdout.splitlines())
