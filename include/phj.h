@@ -95,7 +95,7 @@ typedef struct {
     uint32_t upload_chunks; /* phj_join_host: row chunks the probe relation is uploaded in, each joined
                                as soon as it has landed (1 = upload everything, then join; 0 = choose:
                                ~256 MB chunks when the probe relation is large, else 1; <= 32) */
-    int32_t num_gpus;       /* RADIX_PARTITIONING, 0 or 1 = one GPU. N > 1 (at most 16): this process drives
+    int32_t num_gpus;       /* 0 or 1 = one GPU. N > 1 (at most 16), RADIX_PARTITIONING: this process drives
                                GPUs device .. device + N - 1 -- phj_upload gives GPU g the rows [g n / N,
                                (g + 1) n / N) of both relations, phj_join runs the sharded join below (one host
                                thread per GPU, NCCL for sizes / barriers / the count, NVLink peer stores for the
@@ -103,7 +103,10 @@ typedef struct {
                                partitions (<= 256, a multiple of N, a power of two when N is one; 0 = 64, or the
                                largest multiple of N below it) and split_chunks the number of probe chunks whose
                                shuffle overlaps the local probe of the previous one (0 = 4). For N = 2, 4, 8, 16
-                               the split digit is a bit field of the hash, for any other N it is hash % partitions. */
+                               the split digit is a bit field of the hash, for any other N it is hash % partitions.
+                               NO_PARTITIONING with N > 1 needs no exchange: every GPU receives the
+                               whole build relation and rows [g n / N, (g + 1) n / N) of the probe relation, builds
+                               its own table and probes its share; phj_join returns the sum of the counts. */
     uint32_t reserved0;
 } phj_config;
 

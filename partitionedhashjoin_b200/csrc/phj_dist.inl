@@ -163,6 +163,10 @@ struct phj_group {
     std::vector<Worker*> workers;
     // sharding of the host relations given to phj_upload
     std::vector<ncclComm_t> comms;
+    // NO_PARTITIONING over several GPUs needs no exchange: every GPU gets the whole build relation
+    // and a row shard of the probe relation, builds its own table and probes its shard; the counts add up.
+    // One ordinary single-GPU handle per device, no NCCL, no peer access.
+    std::vector<phj_handle*> replicas;
 };
 
 namespace {
@@ -798,7 +802,8 @@ void group_destroy(phj_group* g) {
         delete w;
     }
     for (phj_dist* D : g->ranks) dist_free(D);
-    if (nccl_api())
+    for (phj_handle* h : g->replicas) phj_destroy(h);
+    if (!g->comms.empty() && nccl_api())
         for (ncclComm_t c : g->comms)
             if (c) nccl_api()->CommDestroy(c);
     if (g->bar_ok) pthread_barrier_destroy(&g->bar);
@@ -807,20 +812,41 @@ void group_destroy(phj_group* g) {
 
 int group_create(const phj_config* cfg, phj_group** out) {
     *out = nullptr;
-    if (cfg->algo != PHJ_ALGO_RADIX_PARTITIONING)
-        return fail(PHJ_ERR_INVALID, "num_gpus > 1 serves the radix-partitioning join");
-    NcclApi* nc = nccl_api();
-    if (!nc) return fail(PHJ_ERR_CUDA, "num_gpus > 1 needs NCCL");
+    if (cfg->algo != PHJ_ALGO_RADIX_PARTITIONING && cfg->algo != PHJ_ALGO_NO_PARTITIONING)
+        return fail(PHJ_ERR_INVALID, "num_gpus > 1 serves the radix-partitioning and the no-partitioning join");
     const int W = cfg->num_gpus;
     int ndev = 0;
     PHJ_CUDA(cudaGetDeviceCount(&ndev));
+    if (W > kMaxRanks) return fail(PHJ_ERR_INVALID, "the number of GPUs must be in [1, %d]", kMaxRanks);
     if (W > ndev) return fail(PHJ_ERR_INVALID, "num_gpus = %d but only %d CUDA devices are visible", W, ndev);
+    if (cfg->device < 0 || cfg->device + W > ndev)
+        return fail(PHJ_ERR_INVALID, "devices %d .. %d are not all visible", cfg->device, cfg->device + W - 1);
     phj_group* g = new phj_group;
     g->world = W;
     auto cleanup = [&](int code) {
         group_destroy(g);
         return code;
     };
+    if (cfg->algo == PHJ_ALGO_NO_PARTITIONING) {  // replicas of the build side: one plain handle per GPU
+        for (int r = 0; r < W; ++r) {
+            phj_config c = *cfg;
+            c.num_gpus = 0;
+            c.device = cfg->device + r;
+            phj_handle* h = nullptr;
+            const int rc = phj_create(&c, &h);
+            if (rc != PHJ_OK) return cleanup(rc);
+            g->replicas.push_back(h);
+        }
+        for (int r = 0; r < W; ++r) {
+            auto* w = new phj_group::Worker;
+            g->workers.push_back(w);
+            w->thread = std::thread(worker_main, w);
+        }
+        *out = g;
+        return PHJ_OK;
+    }
+    NcclApi* nc = nccl_api();
+    if (!nc) return cleanup(fail(PHJ_ERR_CUDA, "num_gpus > 1 needs NCCL"));
     if (pthread_barrier_init(&g->bar, nullptr, (unsigned)W) != 0) return cleanup(fail(PHJ_ERR_NOMEM, "pthread_barrier_init failed"));
     g->bar_ok = true;
     int devs[kMaxRanks];
@@ -873,6 +899,12 @@ int group_set_relations(phj_group* g, const void* build, size_t n_build, const v
     if (device_resident)
         return fail(PHJ_ERR_INVALID, "num_gpus > 1: relations come from host memory (phj_upload / phj_join_host)");
     const int W = g->world;
+    if (!g->replicas.empty())  // no-partitioning: the whole build relation on every GPU, a row shard of the probe side
+        return group_run(g, [&](int r) {
+            const size_t p0 = n_probe * r / W, p1 = n_probe * (r + 1) / W;
+            return phj_upload(g->replicas[r], reinterpret_cast<const phj_tuple*>(build), n_build,
+                              reinterpret_cast<const phj_tuple*>(probe) + p0, p1 - p0);
+        });
     return group_run(g, [&](int r) {
         const size_t b0 = n_build * r / W, b1 = n_build * (r + 1) / W;
         const size_t p0 = n_probe * r / W, p1 = n_probe * (r + 1) / W;
@@ -883,9 +915,20 @@ int group_set_relations(phj_group* g, const void* build, size_t n_build, const v
 
 int group_join(phj_group* g, phj_result* out) {
     std::vector<phj_result> res(g->world);
-    int rc = group_run(g, [&](int r) { return dist_join_rank(g->ranks[r], &res[r]); });
+    const bool replicas = !g->replicas.empty();
+    int rc = group_run(g, [&](int r) {
+        return replicas ? phj_join(g->replicas[r], &res[r]) : dist_join_rank(g->ranks[r], &res[r]);
+    });
     if (rc != PHJ_OK) return rc;
     *out = res[0];
+    if (replicas) {  // every GPU counted its probe shard against the whole build relation
+        out->gpus = (uint32_t)g->world;
+        for (int r = 1; r < g->world; ++r) {
+            out->matches += res[r].matches;
+            out->build_ns = std::max(out->build_ns, res[r].build_ns);
+            out->probe_ns = std::max(out->probe_ns, res[r].probe_ns);
+        }
+    }
     for (int r = 1; r < g->world; ++r) {  // the slowest rank defines the join's times
         out->total_ns = std::max(out->total_ns, res[r].total_ns);
         out->partition_ns = std::max(out->partition_ns, res[r].partition_ns);

@@ -41,8 +41,10 @@ inline std::string HelpText() {
          "  --data-seed arg (=12345)              Base seed of the Zipf generator (batch b uses seed + b).\n"
          "  --radix-bits arg                      b1,b2: bits of partitioning pass 1 and 2.\n"
          "  --device arg (=0)                     CUDA device.\n"
-         "  --gpus arg (=1)                       Number of GPUs (1 .. 16): the radix join sharded by partition,\n"
+         "  --gpus arg (=1)                       Number of GPUs (1 .. 16). Radix join: sharded by partition,\n"
          "                                        --partitions then = GPUs x partitions per GPU (<= 256).\n"
+         "                                        No-partitioning join: every GPU builds the whole table and\n"
+         "                                        probes its share of the secondary relation.\n"
          "  --repeat arg (=1)                     Joins per run; the fastest is reported.\n"
          "  --no-tma-store                        Flush scatter tiles with st.global instead of TMA bulk stores.\n"
          "  --table arg (=linear-probing)         Hash table of the no-partitioning join: linear-probing or\n"
@@ -172,8 +174,6 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     if (c.Gpu.StreamUpload && (c.Gpu.Materialize || c.Gpu.Repeat > 1))
         throw std::invalid_argument("--stream-upload joins once and count-only: not with --materialize or --repeat.");
     if (c.Gpu.Gpus < 1) throw std::invalid_argument("--gpus must be at least 1");
-    if (c.Gpu.Gpus > 1 && c.JoinType != Common::JoinAlgorithmType::RadixParitioning)
-        throw std::invalid_argument("--gpus > 1: the join sharded over several GPUs is the RadixParitioning join.");
     if (c.Gpu.Gpus > 1 && c.Gpu.Materialize)
         throw std::invalid_argument("--gpus > 1 counts only: --materialize needs one GPU.");
     return c;

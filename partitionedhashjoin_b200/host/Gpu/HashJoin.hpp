@@ -51,7 +51,7 @@ class Engine {
         if (gpu.ChainedTable && algo == PHJ_ALGO_NO_PARTITIONING) cfg.flags |= PHJ_FLAG_CHAINED_TABLE;
         // --gpus N: this process drives N GPUs; the library shards both relations by row range, shuffles the
         // partitions over NVLink and returns the global count (include/phj.h: phj_config.num_gpus)
-        if (gpu.Gpus > 1 && algo == PHJ_ALGO_RADIX_PARTITIONING) cfg.num_gpus = gpu.Gpus;
+        if (gpu.Gpus > 1) cfg.num_gpus = gpu.Gpus;  // radix: sharded by partition; no-partitioning: build side replicated
         Check(phj_create(&cfg, &m_handle));
     }
     ~Engine() { phj_destroy(m_handle); }

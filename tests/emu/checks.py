@@ -154,8 +154,17 @@ def check_group():
                     n += 1
                 res = e.join_host(R, S)
                 assert res["matches"] == oracle.count_by_sort(R, S)
+        # the no-partitioning joiner over the same GPUs: whole build relation everywhere, probe rows sharded
+        for flags in (0, phj.FLAG_CHAINED_TABLE):
+            with phj.Engine("no-partitioning", num_gpus=gpus, flags=flags) as e:
+                for name, (Rc, Sc) in cases.items():
+                    e.upload(Rc, Sc)
+                    res = e.join()
+                    assert res["matches"] == oracle.count_by_sort(Rc, Sc) and res["gpus"] == gpus, (gpus, name, flags, res)
+                    n += 1
+                assert e.join_host(R, S)["matches"] == oracle.count_by_sort(R, S)
         done.append(f"{gpus} GPUs ok")
-    done.append(f"{n} sharded joins == oracle")
+    done.append(f"{n} joins over several GPUs == oracle")
     return done
 
 

@@ -129,10 +129,15 @@ def test_cli_several_gpus(phjoin, tmp_path, gpus):
     # partitions must be GPUs x partitions per GPU
     r = run(phjoin, "--join", "radix-partitioning", "--primary", "1000", "--secondary", "1000", "--gpus", str(gpus), "-p", "1")
     assert r.returncode == 1 and "GPUs x local partitions" in r.stderr
+    # the no-partitioning joiner on the same GPUs: every GPU builds the whole table, probes its share of tableB
+    r = run(phjoin, "--join", "no-partitioning", "--primary", "1500000", "--secondary", "30000000", "--skew", "1.05",
+            "--gpus", str(gpus), "--log", "debug", "-f", str(out))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Joined 30000000 tuples." in r.stderr
 
 
 def test_cli_several_gpus_argument_errors(phjoin):
-    for args, message in ((("--join", "no-partitioning", "--gpus", "2"), "--gpus > 1: the join sharded over several GPUs"),
+    for args, message in ((("--join", "no-partitioning", "--gpus", "2", "-p", "64"), "only for RadixParitioning"),
                           (("--join", "radix-partitioning", "--gpus", "0"), "--gpus must be at least 1"),
                           (("--join", "radix-partitioning", "--gpus", "2", "--materialize"), "--gpus > 1 counts only")):
         r = run(phjoin, *args)

@@ -298,10 +298,18 @@ def test_one_process_several_gpus(phj, oracle, gpus):
                     assert res["matches"] == want and res["gpus"] == gpus, (name, partitions, chunks, res, want)
                 res = e.join_host(R, S)
                 assert res["matches"] == want and res["h2d_bytes"] == 16 * (R.shape[0] + S.shape[0])
-    with pytest.raises(phj.PhjError):
-        phj.Engine("no-partitioning", num_gpus=gpus)
+    # the no-partitioning joiner over the same GPUs: every GPU builds the whole table and probes its row shard
+    for flags in (0, phj.FLAG_CHAINED_TABLE):
+        with phj.Engine("no-partitioning", num_gpus=gpus, flags=flags) as e:
+            for name, (R, S) in cases.items():
+                e.upload(R, S)
+                res = e.join()
+                assert res["matches"] == oracle.count_by_sort(R, S) and res["gpus"] == gpus, (name, flags, res)
+            assert e.join_host(R, S)["matches"] == oracle.count_by_sort(R, S)
     with pytest.raises(phj.PhjError):
         phj.Engine("radix-partitioning", partitions=gpus // 2 or 3, num_gpus=gpus)
+    with pytest.raises(phj.PhjError):
+        phj.Engine("no-partitioning", partitions=64, num_gpus=gpus)
 
 
 @pytest.mark.gpu
