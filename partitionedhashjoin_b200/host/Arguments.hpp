@@ -42,7 +42,8 @@ inline std::string HelpText() {
          "  --radix-bits arg                      b1,b2: bits of partitioning pass 1 and 2.\n"
          "  --device arg (=0)                     CUDA device.\n"
          "  --gpus arg (=1)                       Number of GPUs (1 .. 16). Radix join: sharded by partition,\n"
-         "                                        --partitions then = GPUs x partitions per GPU (<= 256).\n"
+         "                                        --partitions then = GPUs x partitions per GPU (<= 256;\n"
+         "                                        default: the largest multiple of the GPUs up to 64).\n"
          "                                        No-partitioning join: every GPU builds the whole table and\n"
          "                                        probes its share of the secondary relation.\n"
          "  --repeat arg (=1)                     Joins per run; the fastest is reported.\n"
@@ -176,6 +177,10 @@ inline Common::Configuration Parse(int argc, char** argv, bool* help) {
     if (c.Gpu.Gpus < 1) throw std::invalid_argument("--gpus must be at least 1");
     if (c.Gpu.Gpus > 1 && c.Gpu.Materialize)
         throw std::invalid_argument("--gpus > 1 counts only: --materialize needs one GPU.");
+    // The reference's default of 32 partitions is not GPUs x partitions per GPU for every GPU count (3, 5, 6, 7):
+    // without -p the sharded join takes the library's own default, the largest multiple of the GPU count <= 64.
+    if (c.Gpu.Gpus > 1 && c.Gpu.Gpus <= 64 && c.JoinType == Common::JoinAlgorithmType::RadixParitioning && !get("partitions"))
+        c.RadixClusteringConfig.NumberOfPartitions = 64 / static_cast<size_t>(c.Gpu.Gpus) * static_cast<size_t>(c.Gpu.Gpus);
     return c;
 }
 

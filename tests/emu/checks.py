@@ -4,7 +4,7 @@ scheduler over the g++-compiled kernel headers). Started by tests/test_emulated.
 at the emulated build; compares with the oracle exactly as the `-m gpu` tests do on the B200, at sizes the emulator
 finishes in seconds. Not a product path and not a source of numbers.
 
-    python tests/emu/checks.py single | group | ranks <world>
+    python tests/emu/checks.py single | group | cli | ranks <world>
 """
 import json
 import os
@@ -226,10 +226,36 @@ def check_ranks(world):
     return [f"{world} ranks: counts, windows tuple by tuple, re-size, hot digits vs plain exchange"]
 
 
+def check_cli():
+    """The C++ host mirror (host/main.cpp: the reference's CLI and joiner classes) linked against the emulated engine:
+    every joiner, the streamed upload, the joined table, --gpus N for both joiners incl. a GPU count that is not a power
+    of two. The CLI joins generator data (every probe key has a build match), so the logged count is |secondary|."""
+    import subprocess
+    exe = os.path.join(HERE, "_build", "phjoin_emu")
+    out = os.path.join(HERE, "_build", "cli_result.json")
+    runs = [("radix-partitioning", ["-p", "256"]), ("radix-partitioning", ["-p", "100", "--hash", "murmur3"]),
+            ("no-partitioning", []), ("no-partitioning", ["--table", "separate-chaining"]),
+            ("radix-partitioning", ["-p", "64", "--stream-upload"]), ("radix-partitioning", ["-p", "64", "--materialize"]),
+            ("radix-partitioning", ["--gpus", "2"]), ("radix-partitioning", ["--gpus", "3"]),
+            ("radix-partitioning", ["--gpus", "6", "-p", "12"]), ("no-partitioning", ["--gpus", "2"]),
+            ("no-partitioning", ["--gpus", "5", "--table", "separate-chaining"])]
+    for join, extra in runs:
+        r = subprocess.run([exe, "--join", join, "--primary", "6000", "--secondary", "50000", "--skew", "1.25", "--log", "debug",
+                            "-f", out, *extra], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "Joined 50000 tuples." in r.stderr, (join, extra, r.returncode, r.stderr[-600:])
+        d = json.load(open(out))
+        want_type = "RadixParitioning" if join.startswith("radix") else "NoPartitioning"
+        assert d["parameters"]["Type"] == want_type and int(d["results"]["probe"]) >= 0, d
+    r = subprocess.run([exe, "--join", "radix-partitioning", "--gpus", "3", "-p", "64"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 1 and "multiple of the 3 GPUs" in r.stderr, r.stderr[-400:]
+    return [f"{len(runs)} CLI runs logged the expected count"]
+
+
 def main():
     t0 = time.time()
     what = sys.argv[1]
-    done = {"single": check_single, "group": check_group}[what]() if what != "ranks" else check_ranks(int(sys.argv[2]))
+    done = {"single": check_single, "group": check_group, "cli": check_cli}[what]() if what != "ranks" \
+        else check_ranks(int(sys.argv[2]))
     print(json.dumps({"check": " ".join(sys.argv[1:]), "ok": True, "seconds": round(time.time() - t0, 1), "done": done}))
 
 

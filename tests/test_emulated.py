@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 BUILD = os.path.join(EMU, "_build")
 WORLDS = [2, 3, 4, 6, 8]
-CHECKS = {"single": ["single"], "group": ["group"], **{f"ranks{w}": ["ranks", str(w)] for w in WORLDS}}
+CHECKS = {"single": ["single"], "group": ["group"], "cli": ["cli"], **{f"ranks{w}": ["ranks", str(w)] for w in WORLDS}}
 
 
 @pytest.fixture(scope="module")
@@ -76,6 +76,12 @@ def test_one_process_sharded_join_on_emulated_gpus(emulated_runs):
     (3 and 6 GPUs: the split digit is hash % digits, not a bit field of the hash)."""
     line = finished(emulated_runs, "group")
     assert {f"{w} GPUs ok" for w in WORLDS} <= set(line["done"])
+
+
+def test_cli_on_the_emulated_engine(emulated_runs):
+    """host/main.cpp (the reference's CLI + the C++ joiner classes) linked against the emulated engine: all joiners,
+    --stream-upload, --materialize, --gpus N for the radix and the no-partitioning join (N = 2, 3, 5, 6)."""
+    finished(emulated_runs, "cli")
 
 
 @pytest.mark.parametrize("world", WORLDS)
