@@ -133,13 +133,15 @@ def check_group():
     on uniform and heavy-hitter keys, re-uploads that grow the windows, the one-call host join."""
     import _cases
     phj, oracle = load()
-    cases = dict(_cases.adversarial_cases())
-    R = _cases.sequential(8000)
-    S = np.empty(70_001, dtype=phj.TUPLE_DTYPE)
-    phj.fill_zipf(S, 1.25, 1, 16_000, 4242, 7)   # half of the key range misses R; key 1 is 22 % of S
+    keep = ("dup_build_keys", "extreme_keys", "all_probe_equal_hit", "tiny_build", "build_smaller_than_fanout",
+            "empty_probe", "random64")
+    cases = {k: v for k, v in _cases.adversarial_cases().items() if k in keep}
+    R = _cases.sequential(6000)
+    S = np.empty(40_001, dtype=phj.TUPLE_DTYPE)
+    phj.fill_zipf(S, 1.25, 1, 12_000, 4242, 7)   # half of the key range misses R; key 1 is 22 % of S
     cases["zipf125_half_miss"] = (R, S)
-    cases["random_larger"] = (_cases.tuples(_cases.splitmix64(30_000, 51).astype(np.int64) % 20_011),
-                              _cases.tuples(_cases.splitmix64(90_000, 52).astype(np.int64) % 30_011))
+    cases["random_larger"] = (_cases.tuples(_cases.splitmix64(20_000, 51).astype(np.int64) % 15_013),
+                              _cases.tuples(_cases.splitmix64(50_000, 52).astype(np.int64) % 20_011))
     done, n = [], 0
     for gpus in (2, 3, 4, 6, 8):  # 3 and 6: the split digit is hash % digits instead of a bit field
         for partitions, chunks, flags in ((0, 0, 0), (gpus, 3, phj.FLAG_COUNT_PIECEWISE),
@@ -155,7 +157,7 @@ def check_group():
                 res = e.join_host(R, S)
                 assert res["matches"] == oracle.count_by_sort(R, S)
         # the no-partitioning joiner over the same GPUs: whole build relation everywhere, probe rows sharded
-        for flags in (0, phj.FLAG_CHAINED_TABLE):
+        for flags in ((0, phj.FLAG_CHAINED_TABLE) if gpus in (2, 3) else (0,)):
             with phj.Engine("no-partitioning", num_gpus=gpus, flags=flags) as e:
                 for name, (Rc, Sc) in cases.items():
                     e.upload(Rc, Sc)
@@ -199,9 +201,9 @@ def check_ranks(world):
     import _cases
     phj, oracle = load()
     import _dist_gpu_worker as worker
-    keys_r = _cases.splitmix64(9_000, 21).astype(np.int64) % 7_001
-    keys_s = np.where(_cases.splitmix64(48_000, 22) % np.uint64(10) < 3, 4242,
-                      _cases.splitmix64(48_000, 23) % np.uint64(10_501)).astype(np.int64)
+    keys_r = _cases.splitmix64(6_000, 21).astype(np.int64) % 4_001
+    keys_s = np.where(_cases.splitmix64(30_000, 22) % np.uint64(10) < 3, 4242,
+                      _cases.splitmix64(30_000, 23) % np.uint64(6_007)).astype(np.int64)
     R, S = _cases.tuples(keys_r), _cases.tuples(keys_s)
     want = oracle.count_by_sort(R, S)
     dist = worker.dist = ThreadDist(world)   # the module-level name check_library_join hands to ShardedJoin

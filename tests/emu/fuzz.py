@@ -112,6 +112,15 @@ def one(seed, phj, oracle, cases):
         if rng.integers(0, 3) == 0:
             flags |= phj.FLAG_NO_HOT_DIGITS
         desc.update(algo="sharded", gpus=gpus, P=P, chunks=chunks, flags=flags)
+        if rng.integers(0, 5) == 0:  # the no-partitioning joiner over the same GPUs (build side replicated)
+            table = int(rng.choice([0, phj.FLAG_CHAINED_TABLE]))
+            desc.update(algo="npj replicas", flags=table)
+            with phj.Engine("no-partitioning", num_gpus=gpus, hash=hash_name, hash_seed=seed_p, flags=table) as e:
+                e.upload(R, S)
+                res = e.join()
+                assert res["matches"] == want and res["gpus"] == gpus, (desc, res["matches"], want)
+                assert e.join_host(R, S)["matches"] == want, (desc, "join_host")
+            return desc
         with phj.Engine("radix-partitioning", partitions=P, split_chunks=chunks, num_gpus=gpus, hash=hash_name,
                         hash_seed=seed_p, flags=flags) as e:
             e.upload(R, S)
