@@ -7,9 +7,11 @@
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <unistd.h>
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "cuda_emu.h"
@@ -238,9 +240,24 @@ extern "C" __attribute__((visibility("default"))) int emu_run_kernel(void (*tram
                     for (int i = 3; i <= 8; ++i) top[-i] = 0;
                     f.sp = top - 8;
                 }
+                // Order in which runnable fibers get their turn. Any order is a legal execution (threads only meet at
+                // rendezvous points), so a kernel that passes only in one of them relies on something CUDA does not
+                // promise: PHJ_EMU_SCHED = forward (default) | reverse | random (a new permutation every sweep).
+                static const int sched = [] {
+                    const char* v = getenv("PHJ_EMU_SCHED");
+                    return !v ? 0 : !strcmp(v, "reverse") ? 1 : !strcmp(v, "random") ? 2 : 0;
+                }();
+                uint64_t rnd = 0x9E3779B97F4A7C15ull * (x + 1) + y * 1315423911ull + z;
                 while (m->ndone < nthreads) {
                     bool progress = false;
-                    for (int t = 0; t < nthreads; ++t) {
+                    if (sched == 2) {  // a cheap permutation: t -> (a * t + b) mod nthreads with a odd (nthreads is even
+                        rnd = rnd * 6364136223846793005ull + 1442695040888963407ull;  // or 1 .. 1024: gcd(a, n) = 1
+                    }                                                                  // for powers of two and most n)
+                    const uint32_t a = sched == 2 ? (uint32_t)(rnd >> 33) | 1u : 1u, b = sched == 2 ? (uint32_t)(rnd >> 13) : 0u;
+                    const bool perm_ok = sched != 2 || std::__gcd<uint32_t>(a % (uint32_t)nthreads, (uint32_t)nthreads) == 1;
+                    for (int i = 0; i < nthreads; ++i) {
+                        const int t = sched == 1 ? nthreads - 1 - i
+                                      : (sched == 2 && perm_ok) ? (int)(((uint64_t)a * (uint32_t)i + b) % (uint32_t)nthreads) : i;
                         Fiber& f = m->fibers[t];
                         if (f.state == kDone) continue;
                         if (f.state == kWaitWarp && m->warps[f.warp].gen == f.wait_gen) continue;
