@@ -61,6 +61,12 @@ extern thread_local Ctx ctx;  // of the fiber that is running on this OS thread
 // (valid until the caller's next collective) and, in *live, the lanes that took part.
 const uint64_t* warp_gather(uint64_t v, uint32_t* live);
 void cta_barrier();
+// cp.async.bulk shared -> global, modelled as LATE as the PTX rules allow: the copy is only recorded at issue and
+// carried out when the issuing thread waits for its bulk groups (wait_group[.read] 0) -- so a kernel that reuses the
+// shared-memory source before that wait writes wrong data here, as it may on the device. A thread that exits with
+// copies still pending aborts the run (the stores of an exited CTA are not guaranteed to have been read).
+void bulk_defer(void* gdst, const void* ssrc, uint32_t bytes);
+void bulk_complete();
 }  // namespace emu
 
 #define threadIdx (emu::ctx.tid)

@@ -27,12 +27,19 @@ constexpr int kMaxThreads = 1024;
 
 enum State : int { kReady, kWaitWarp, kWaitCta, kDone };
 
+struct BulkOp {
+    void* dst;
+    const void* src;
+    uint32_t bytes;
+};
+
 struct Fiber {
     void* sp;
     State state;
     uint32_t wait_gen;
     uint3 tid;
     unsigned lane, warp;
+    std::vector<BulkOp> bulk;  // cp.async.bulk stores issued and not yet waited for
 };
 
 struct Warp {
@@ -108,6 +115,11 @@ void fiber_main() {
     ctx.tid = f->tid;
     ctx.lane = f->lane;
     m->tramp(m->args);
+    if (!f->bulk.empty()) {
+        fprintf(stderr, "emu: thread (%u,%u,%u) of block (%u,%u,%u) exited with %zu bulk stores it never waited for\n",
+                f->tid.x, f->tid.y, f->tid.z, ctx.bid.x, ctx.bid.y, ctx.bid.z, f->bulk.size());
+        abort();
+    }
     // the thread has exited: it counts as arrived at every later rendezvous
     f->state = kDone;
     ++m->ndone;
@@ -175,6 +187,16 @@ const uint64_t* warp_gather(uint64_t v, uint32_t* live) {
     return w.vals[g & 1];
 }
 
+void bulk_defer(void* gdst, const void* ssrc, uint32_t bytes) {
+    tl_machine->cur->bulk.push_back(BulkOp{gdst, ssrc, bytes});
+}
+
+void bulk_complete() {
+    Fiber* f = tl_machine->cur;
+    for (const BulkOp& op : f->bulk) memcpy(op.dst, op.src, op.bytes);
+    f->bulk.clear();
+}
+
 void cta_barrier() {
     Machine* m = tl_machine;
     Fiber* f = m->cur;
@@ -230,6 +252,7 @@ extern "C" __attribute__((visibility("default"))) int emu_run_kernel(void (*tram
                 for (int t = 0; t < nthreads; ++t) {
                     Fiber& f = m->fibers[t];
                     f.state = kReady;
+                    f.bulk.clear();
                     f.tid = uint3{(unsigned)t % bx, ((unsigned)t / bx) % by, (unsigned)t / (bx * by)};
                     f.lane = (unsigned)t & 31;
                     f.warp = (unsigned)t >> 5;

@@ -1,7 +1,7 @@
 // emu_ptx_helpers.h -- TEST INFRASTRUCTURE: host versions of the inline-PTX helper block of phj_kernels.cuh (the
 // block between `#ifndef PHJ_PTX_HELPERS_PROVIDED` and its `#endif`), same names and signatures. Loads and stores
-// become plain accesses, the TMA bulk store a memcpy that completes at once, the bulk-group waits and the proxy
-// fence no-ops, bar.warp.sync a warp rendezvous.
+// become plain accesses, the TMA bulk store a copy that happens when its thread waits for its bulk groups (the latest
+// moment the PTX rules allow), the proxy fence a no-op, bar.warp.sync a warp rendezvous.
 #pragma once
 #include <time.h>
 
@@ -36,10 +36,10 @@ inline void cta_sync() {
     __syncwarp();
     __syncthreads();
 }
-inline void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) { memcpy(gdst, ssrc, bytes); }
+inline void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) { emu::bulk_defer(gdst, ssrc, bytes); }
 inline void bulk_commit() {}
-inline void bulk_wait_read0() {}
-inline void bulk_wait_all0() {}
+inline void bulk_wait_read0() { emu::bulk_complete(); }
+inline void bulk_wait_all0() { emu::bulk_complete(); }
 inline void fence_proxy_async_smem() {}
 
 }  // namespace phj

@@ -89,7 +89,7 @@ def one(seed, phj, oracle, cases):
                     pos = np.searchsorted(ku, S["id"])
                     hit = (pos < ku.shape[0]) & (ku[np.minimum(pos, max(ku.shape[0] - 1, 0))] == S["id"]) if ku.shape[0] else np.zeros(n_s, bool)
                     rows = int(kc[pos[hit]].sum()) if ku.shape[0] else 0
-                if op == 2 and rows <= 2_000_000:  # the joined table
+                if op == 2 and rows <= 300_000:  # the joined table
                     rm = e.join_materialize()
                     ref = cases.sorted_rows(oracle.join_materialize(R, S))
                     assert rm["joined_tuples"] == ref.shape[0] == rows, (desc, rm["joined_tuples"], ref.shape[0], rows)
@@ -151,6 +151,8 @@ def main():
             if os.environ.get("PHJ_FUZZ_TRACE"):
                 traceback.print_exc()
         done += 1
+        if done % 50 == 0:
+            print(f"  ... {done} runs, {failed} failed, {time.time() - t0:.0f} s", flush=True)
     print(f"seeds {first}..{first + done - 1}: {done} runs, {failed} failed, {time.time() - t0:.0f} s", flush=True)
     sys.exit(1 if failed else 0)
 
