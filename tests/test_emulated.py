@@ -33,7 +33,11 @@ def emulated_runs():
     env["PHJ_LIB"] = os.path.join(BUILD, "libphj_emu_engine.so")
     env["LD_LIBRARY_PATH"] = BUILD + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     env.pop("PHJ_KERNEL_TIMES", None)
-    procs = {name: subprocess.Popen([sys.executable, os.path.join(EMU, "checks.py"), *argv], env=env,
+    # every order in which the runnable threads of a CTA take their turn is a legal execution: the checks are spread
+    # over the emulator's three (tests/emu/README.md)
+    order = {"group": "random", "ranks3": "reverse", "ranks8": "random", "ranks4": "reverse"}
+    procs = {name: subprocess.Popen([sys.executable, os.path.join(EMU, "checks.py"), *argv],
+                                    env={**env, "PHJ_EMU_SCHED": order.get(name, "forward")},
                                     stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
              for name, argv in CHECKS.items()}
     yield procs
