@@ -25,8 +25,8 @@ CHECKS = {"single": ["single"], "group": ["group"], "cli": ["cli"], **{f"ranks{w
 @pytest.fixture(scope="module")
 def emulated_runs():
     """Builds tests/emu/_build (incremental) and starts every check at once, each in its own process."""
-    if not shutil.which("nvcc"):
-        pytest.skip("nvcc is needed to compile the engine's host side")
+    if not shutil.which("nvcc") or not os.path.exists("/usr/bin/g++") or not shutil.which("make"):
+        pytest.skip("nvcc, make and /usr/bin/g++ are needed to compile the emulated build")
     r = subprocess.run(["make", "-C", EMU], capture_output=True, text=True)
     assert r.returncode == 0, f"tests/emu does not build:\n{r.stdout[-2000:]}\n{r.stderr[-3000:]}"
     env = dict(os.environ)
