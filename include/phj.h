@@ -316,6 +316,9 @@ int phj_dist_upload(phj_dist* d, const phj_tuple* build, size_t n_build, const p
 int phj_dist_bind_device(phj_dist* d, const void* d_build, size_t n_build, const void* d_probe, size_t n_probe);
 int phj_dist_join(phj_dist* d, phj_result* out);
 int phj_dist_kernel_times(phj_dist* d, const char** names, uint64_t* ns, uint32_t cap);
+/* Which kernels of the following joins get CUDA events around them, as phj_kernel_timing: null = none, "" = all,
+ * else those whose name contains `filter`. */
+int phj_dist_kernel_timing(phj_dist* d, const char* filter);
 /* Same launches with their begin / end device times relative to the join's first event (needs
  * PHJ_KERNEL_TIMES=1): shows which kernels of the two streams ran side by side. */
 int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, uint64_t* end_ns, uint32_t cap);

@@ -159,6 +159,7 @@ SIGNATURES = {
     "phj_dist_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "phj_dist_join": (C.c_int, [C.c_void_p, C.POINTER(PhjResult)]),
     "phj_dist_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]),
+    "phj_dist_kernel_timing": (C.c_int, [C.c_void_p, C.c_char_p]),
     "phj_dist_kernel_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.c_uint32]),
     "phj_dist_measure_peer_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),

@@ -1016,6 +1016,11 @@ int phj_dist_kernel_times(phj_dist* d, const char** names, uint64_t* ns, uint32_
     return d ? phj_kernel_times(d->split, names, ns, cap) : 0;
 }
 
+int phj_dist_kernel_timing(phj_dist* d, const char* filter) {
+    if (!d) return fail(PHJ_ERR_INVALID, "handle is null");
+    return phj_kernel_timing(d->split, filter);
+}
+
 int phj_dist_kernel_trace(phj_dist* d, const char** names, uint64_t* begin_ns, uint64_t* end_ns, uint32_t cap) {
     if (!d) return 0;
     phj_handle* h = d->split;
