@@ -95,6 +95,18 @@ def check_single():
                 same_partitioning(got, gb, wt, wb, rel.shape[0])
                 layouts += 1
         lap(f"layout {P} {bits} {flags:#x}")
+    # the exchange step on its own (PHJ_ALGO_SHARD_SPLIT): a digit count that is a bit field of the hash, and two that
+    # are not (what 3 and 6 GPUs x their local partitions give)
+    for P in (64, 63, 60):
+        with phj.Engine("shard-split", partitions=P, hash_seed=SEED_P) as e:
+            e.upload(R, S)
+            e.join()
+            for which, rel in ((0, R), (1, S)):
+                got, gb = e.read_partitions(which, P)
+                wt, wb = oracle.radix_partition(rel, P, 0, SEED_P, workers=1)
+                same_partitioning(got, gb, wt, wb, rel.shape[0])
+                layouts += 1
+    lap("shard-split layouts")
     done.append(f"{layouts} partitioned relations bit-identical to the oracle's")
 
     # the joined table against the oracle's GetAll join, as a multiset
