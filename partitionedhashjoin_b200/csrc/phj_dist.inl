@@ -364,22 +364,34 @@ int dist_size(phj_dist* D) {
                 grow_any = true;
                 if (r == D->rank) grow_mine[w] = true;
             }
-    if (grow_any || !D->peer[0][D->rank]) {
+    // An allocation that fails on ONE GPU must not leave the others waiting in the next collective: failures are
+    // recorded, all ranks agree on them (one word, all-reduced), and either everybody goes on or everybody returns.
+    int alloc_rc = PHJ_OK;
+    auto device_alloc = [&](void** p, size_t bytes, const char* what) {
+        *p = nullptr;
+        const cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) return true;
+        cudaGetLastError();
+        *p = nullptr;
+        alloc_rc = fail(PHJ_ERR_NOMEM, "GPU %d: no memory for %s of the sharded join (%zu bytes): %s", D->device, what,
+                        bytes, cudaGetErrorString(e));
+        return false;
+    };
+    const bool remap = grow_any || !D->peer[0][D->rank];
+    if (remap) {
         if ((rc = dist_close_peers(D)) != PHJ_OK) return rc;
         if ((rc = dist_host_barrier(D)) != PHJ_OK) return rc;  // nobody maps a window that is about to go
         for (int w = 0; w < 2; ++w)
             if (grow_mine[w] || !D->win[w]) {
                 if (D->win[w]) PHJ_CUDA(cudaFree(D->win[w]));
                 D->win[w] = nullptr;
-                PHJ_CUDA(cudaMalloc(&D->win[w], D->caps[w][D->rank] * 16));
-                if (!D->group) {
+                if (device_alloc(&D->win[w], D->caps[w][D->rank] * 16, w ? "the probe window" : "the build window") &&
+                    !D->group) {
                     cudaIpcMemHandle_t hd;
                     PHJ_CUDA(cudaIpcGetMemHandle(&hd, D->win[w]));
                     memcpy(D->win_handle[w], &hd, 64);
                 }
             }
-        if ((rc = dist_exchange_windows(D)) != PHJ_OK) return rc;
-        ++D->resizes;
     }
     // tables: load <= 0.5 at the largest build partition seen (duplicates only lower it), 10 % to spare
     uint32_t rb = 64;
@@ -389,10 +401,27 @@ int dist_size(phj_dist* D) {
         if (want > D->cap_pt || !D->d_pt) {
             if (D->d_pt) PHJ_CUDA(cudaFree(D->d_pt));
             D->d_pt = nullptr;
-            PHJ_CUDA(cudaMalloc(&D->d_pt, want * 8));
-            D->cap_pt = want;
+            D->cap_pt = 0;
+            if (device_alloc(reinterpret_cast<void**>(&D->d_pt), want * 8, "the partition tables")) D->cap_pt = want;
         }
         D->region_buckets = rb;
+    }
+    {
+        NcclApi* nc = nccl_api();
+        D->h_flags[0] = alloc_rc != PHJ_OK;
+        PHJ_CUDA(cudaMemcpyAsync(D->d_flags + 9, D->h_flags, 8, cudaMemcpyHostToDevice, h->stream));
+        PHJ_NCCL(nc->AllReduce(D->d_flags + 9, D->d_flags + 9, 1, ncclUint64, ncclSum, D->comm, h->stream));
+        PHJ_CUDA(cudaMemcpyAsync(D->h_flags, D->d_flags + 9, 8, cudaMemcpyDeviceToHost, h->stream));
+        PHJ_CUDA(cudaStreamSynchronize(h->stream));
+        if (D->h_flags[0]) {
+            if (alloc_rc != PHJ_OK) return alloc_rc;
+            return fail(PHJ_ERR_NOMEM, "sharded join: %llu of the %d GPUs could not allocate their windows or tables",
+                        (unsigned long long)D->h_flags[0], W);
+        }
+    }
+    if (remap) {
+        if ((rc = dist_exchange_windows(D)) != PHJ_OK) return rc;
+        ++D->resizes;
     }
     D->max_keys = D->region_buckets * 3;
     D->sized = true;
@@ -776,15 +805,21 @@ int group_run(phj_group* g, const std::function<int(int)>& f) {
         w->cv.notify_all();
     }
     int rc = PHJ_OK;
+    std::string first, all;
     for (int r = 0; r < g->world; ++r) {
         phj_group::Worker* w = g->workers[r];
         std::unique_lock<std::mutex> lk(w->m);
         w->cv.wait(lk, [&] { return w->done; });
-        if (w->rc != PHJ_OK && rc == PHJ_OK) {
+        if (w->rc == PHJ_OK) continue;
+        if (rc == PHJ_OK) {
             rc = w->rc;
-            g_error = "GPU " + std::to_string(r) + ": " + w->error;
+            first = w->error;
+        } else if (w->error == first || all.size() > 600) {
+            continue;  // the ranks that only learnt of another rank's failure all say the same
         }
+        all += (all.empty() ? "" : "; ") + ("GPU " + std::to_string(r) + ": " + w->error);
     }
+    if (rc != PHJ_OK) g_error = all;
     return rc;
 }
 

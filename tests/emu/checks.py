@@ -4,7 +4,7 @@ scheduler over the g++-compiled kernel headers). Started by tests/test_emulated.
 at the emulated build; compares with the oracle exactly as the `-m gpu` tests do on the B200, at sizes the emulator
 finishes in seconds. Not a product path and not a source of numbers.
 
-    python tests/emu/checks.py single | group | cli | ranks <world>
+    python tests/emu/checks.py single | group | cli | failure | ranks <world>
 """
 import json
 import os
@@ -182,6 +182,35 @@ def check_group():
     return done
 
 
+def check_failure():
+    """An allocation that fails on ONE of the GPUs of a sharded join: every rank must come back with an error (the
+    ranks agree on the failure before the next collective) instead of the others waiting for the one that gave up; the
+    handle works again once memory is there."""
+    import _cases
+    phj, oracle = load()
+    R = _cases.sequential(5000)
+    S = np.empty(60_000, dtype=phj.TUPLE_DTYPE)
+    phj.fill_zipf(S, 0.5, 1, 8000, 99, 4)
+    want = oracle.count_by_sort(R, S)
+    done = []
+    for gpus, victim in ((4, 2), (3, 0)):
+        with phj.Engine("radix-partitioning", num_gpus=gpus) as e:
+            e.upload(R, S)
+            os.environ["PHJ_EMU_FAIL_MALLOC"] = f"{victim}:100000"   # the probe window of that GPU (~ 270 KB)
+            try:
+                try:
+                    e.join()
+                    raise AssertionError("the join went through although a window could not be allocated")
+                except phj.PhjError as exc:
+                    assert exc.status == 4 and f"GPU {victim}" in str(exc) and "no memory for" in str(exc), str(exc)
+            finally:
+                del os.environ["PHJ_EMU_FAIL_MALLOC"]
+            for _ in range(2):
+                assert e.join()["matches"] == want
+        done.append(f"{gpus} GPUs: a failed window allocation on GPU {victim} is an error on every rank, then recovers")
+    return done
+
+
 class ThreadDist:
     """What multigpu.ShardedJoin needs of torch.distributed, between threads: the NCCL id travels from rank 0."""
 
@@ -268,7 +297,7 @@ def check_cli():
 def main():
     t0 = time.time()
     what = sys.argv[1]
-    done = {"single": check_single, "group": check_group, "cli": check_cli}[what]() if what != "ranks" \
+    done = {"single": check_single, "group": check_group, "cli": check_cli, "failure": check_failure}[what]() if what != "ranks" \
         else check_ranks(int(sys.argv[2]))
     print(json.dumps({"check": " ".join(sys.argv[1:]), "ok": True, "seconds": round(time.time() - t0, 1), "done": done}))
 

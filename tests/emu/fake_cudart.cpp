@@ -182,6 +182,14 @@ const char* cudaGetErrorString(cudaError_t e) {
 // ---- memory -------------------------------------------------------------------------------------------
 cudaError_t cudaMalloc(void** p, size_t bytes) {
     *p = nullptr;
+    // failure injection for the tests: PHJ_EMU_FAIL_MALLOC = "<device>:<bytes>" makes allocations of at least that many
+    // bytes fail on that device (read on every call, so a test can switch it on and off)
+    if (const char* f = getenv("PHJ_EMU_FAIL_MALLOC")) {
+        int dev = -1;
+        unsigned long long min_bytes = 0;
+        if (sscanf(f, "%d:%llu", &dev, &min_bytes) == 2 && dev == tl_device && bytes >= min_bytes)
+            return cudaErrorMemoryAllocation;
+    }
     if (posix_memalign(p, 256, bytes ? bytes : 1) != 0) return cudaErrorMemoryAllocation;
     memset(*p, 0xA5, bytes < 4096 ? bytes : 4096);  // device memory is not zeroed: make the start of it visibly so
     return cudaSuccess;

@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 BUILD = os.path.join(EMU, "_build")
 WORLDS = [2, 3, 4, 6, 8]
-CHECKS = {"single": ["single"], "group": ["group"], "cli": ["cli"], **{f"ranks{w}": ["ranks", str(w)] for w in WORLDS}}
+CHECKS = {"single": ["single"], "group": ["group"], "cli": ["cli"], "failure": ["failure"],
+          **{f"ranks{w}": ["ranks", str(w)] for w in WORLDS}}
 
 
 @pytest.fixture(scope="module")
@@ -86,6 +87,12 @@ def test_cli_on_the_emulated_engine(emulated_runs):
     """host/main.cpp (the reference's CLI + the C++ joiner classes) linked against the emulated engine: all joiners,
     --stream-upload, --materialize, --gpus N for the radix and the no-partitioning join (N = 2, 3, 5, 6)."""
     finished(emulated_runs, "cli")
+
+
+def test_failed_allocation_on_one_gpu_is_an_error_everywhere(emulated_runs):
+    """The sizing pass of the sharded join: a window that one GPU cannot allocate makes every rank return an error
+    (they agree on it before the next collective) instead of leaving the others waiting; the handle recovers."""
+    finished(emulated_runs, "failure")
 
 
 @pytest.mark.parametrize("world", WORLDS)
