@@ -504,7 +504,7 @@ int dist_enqueue_join(phj_dist* D) {
         probe_sms = std::min(std::max(probe_sms, sms / 5), sms / 2);
         scatter_cap = D->cfg.split_ctas ? std::min<uint32_t>(D->cfg.split_ctas, sms - 1) : sms - probe_sms;
         scatter_cap = std::max<uint32_t>(scatter_cap, 1);
-        grid_l = (sms - scatter_cap) * 6;  // pt_probe: 256 threads x <= 40 registers = 6 CTAs per SM
+        grid_l = std::max<uint32_t>(sms - scatter_cap, 1) * 6;  // pt_probe: 256 threads x <= 40 registers = 6 CTAs per SM
     }
     {
         KernelScope ks(h, "pt_clear", 1, sb);

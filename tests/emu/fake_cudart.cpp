@@ -32,6 +32,7 @@ std::map<const void*, Tramp> g_tramps;
 FindFn g_find = nullptr;
 RunFn g_run = nullptr;
 thread_local int tl_device = 0;
+thread_local cudaError_t tl_last_error = cudaSuccess;  // of a kernel launch: `<<<>>>` has no return value
 
 struct CallConfig {
     dim3 grid, block;
@@ -102,7 +103,19 @@ cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, vo
     return cudaSuccess;
 }
 
+static cudaError_t launch_kernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem);
+
 cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
+    const cudaError_t e = launch_kernel(func, grid, block, args, smem);
+    if (e != cudaSuccess) {
+        tl_last_error = e;  // what cudaGetLastError() reports, as on the device
+        fprintf(stderr, "emu: kernel launch failed with error %d (grid %u x %u x %u, block %u, %zu bytes of shared memory)\n",
+                (int)e, grid.x, grid.y, grid.z, block.x * block.y * block.z, smem);
+    }
+    return e;
+}
+
+static cudaError_t launch_kernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem) {
     Tramp tramp = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_mutex);
@@ -172,7 +185,11 @@ cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
 }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) {
+    const cudaError_t e = tl_last_error;
+    tl_last_error = cudaSuccess;
+    return e;
+}
 const char* cudaGetErrorString(cudaError_t e) {
     static thread_local char buf[64];
     snprintf(buf, sizeof(buf), "emulated CUDA runtime: error %d", (int)e);
