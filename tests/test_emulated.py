@@ -37,7 +37,7 @@ def emulated_runs():
     # every order in which the runnable threads of a CTA take their turn is a legal execution: the checks are spread
     # over the emulator's three (tests/emu/README.md)
     order = {"group": "random", "ranks3": "reverse", "ranks8": "random", "ranks4": "reverse"}
-    sms = {"ranks8": "148", "ranks2": "148"}  # the B200's SM count (its segment and grid shapes); 2 elsewhere: small grids
+    sms = {"ranks8": "148"}  # the B200's SM count (its segment and grid shapes); 2 elsewhere: small grids
     procs = {name: subprocess.Popen([sys.executable, os.path.join(EMU, "checks.py"), *argv],
                                     env={**env, "PHJ_EMU_SCHED": order.get(name, "forward"),
                                          "PHJ_EMU_SMS": sms.get(name, "2")},
