@@ -783,6 +783,24 @@ def scaled_other_config(phj, dist, torch, rank, world, local, args, joins=3):
             "digits": lay["digits"], "chunks": lay["chunks"]}
 
 
+def shuffle_scatter_dram_traffic(world):
+    """DRAM bytes (read + write) of the NVLink scatter over one rank's whole shard, from the ncu capture of that launch
+    (tools/ncu_split.py -> profiles/r02r_ncu_split_summary.md: GPU 0 as rank 0 of 8, the other seven ranks' windows on a
+    second GPU). The capture stands for 8 ranks: the share written locally is 1 / world. Returns (bytes or None, source)."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02r_ncu_split_summary.md")
+    if world != 8 or not os.path.exists(path):
+        return None, None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    total = 0.0
+    for line in open(path):
+        m = re.match(r"\* DRAM (read|write): ([0-9.]+) (\w+)", line)
+        if m and m.group(3) in scale:
+            total += float(m.group(2)) * scale[m.group(3)]
+    return (total or None), "profiles/r02r_ncu_split_summary.md"
+
+
 def _allreduce(dist, torch, local, values, op=None):
     t = torch.tensor(values, dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
@@ -1019,7 +1037,9 @@ def bench(args, dist, rank, world, local, make_inputs, workload_config, ClockSam
             "roofline": {"bound": "hbm", "kernel": "radix_scatter[shuffle] (rank 0, all launches of a join; NVLink-bound "
                                                    "for N > 1: see `shuffle`)", "unit": "GB/s", "peak": peak,
                          "peak_source": peak_src, "achieved": alg_bytes / max(scat_ms, 1e-9) / 1e6,
-                         "frac": alg_bytes / max(scat_ms, 1e-9) / 1e6 / peak, "traffic": None,
+                         "frac": alg_bytes / max(scat_ms, 1e-9) / 1e6 / peak,
+                         "traffic": shuffle_scatter_dram_traffic(world)[0] if mode == "library" and not scaled else None,
+                         "traffic_source": shuffle_scatter_dram_traffic(world)[1] if mode == "library" and not scaled else None,
                          "algorithmic_bytes_per_join_per_gpu": alg_bytes, "ms_per_join": scat_ms},
             "phases_ms_rank0": {k[:-3]: v / args.steps / 1e6 for k, v in sums.items()},
             # medians over the warm-up joins (which time every kernel) and, for the scatter, the timed steps

@@ -76,3 +76,13 @@ def test_gpu_arm_fails_loudly_without_a_gpu(phj):
     r = run_bench("--steps", "1", "--warmup", "1", "--quick")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout), (r.returncode, r.stderr[-300:])
     assert not any(line.startswith("{") for line in r.stdout.splitlines())
+
+
+def test_shuffle_traffic_comes_from_the_split_scatter_capture():
+    """roofline.traffic of the 8-GPU line: DRAM read + write of the NVLink scatter from profiles/r02r_ncu_split_summary.md
+    (the shard is read once, 1 / 8 of it is written locally); no capture for other GPU counts, so none is claimed."""
+    from partitionedhashjoin_b200 import multigpu
+    traffic, source = multigpu.shuffle_scatter_dram_traffic(8)
+    shard = 16.0 * 210_000_000
+    assert source and os.path.exists(os.path.join(ROOT, source)) and 1.0 * shard < traffic < 1.25 * shard
+    assert multigpu.shuffle_scatter_dram_traffic(4) == (None, None)
